@@ -1,0 +1,388 @@
+/*
+ * rafting_b200.h — C ABI of the B200-native batched Multi-Raft hot path.
+ *
+ * Drop-in boundary for curioloop/rafting's per-context EventLoop path
+ * (reference: src/main/java/io/lubricant/consensus/raft/, abbreviated M/ below).
+ * The reference has no FFI of its own (100 % Java); every entry point below names the
+ * Java surface it replaces.  Plain pointers and sizes only: no torch / C++ types.
+ *
+ *   Java surface replaced                                   entry point here
+ *   ------------------------------------------------------  ---------------------------
+ *   ContextManager.start / RaftRoutine ctor                 rafting_engine_create
+ *     (M/context/ContextManager.java:46-55, RaftRoutine.java:44-50)
+ *   ContextManager.close                                     rafting_engine_destroy
+ *   ContextManager.buildContext + RaftContext.initialize    rafting_group_open[_bulk]
+ *     (ContextManager.java:57-106, RaftContext.java:91-113)
+ *   ContextManager.exitContext / RaftContext.close          rafting_group_close
+ *   ContextEventLoop.execute(event[,urgent])                rafting_lease + rafting_step
+ *     (M/support/EventLoop.java:41-101) — one step == the event loops of ALL groups
+ *     draining one batch, in the canonical serial order described in DESIGN.md §3
+ *   RaftParticipant.{appendEntries,preVote,requestVote,     group-op kinds RAFTING_OP_*
+ *     installSnapshot,onTimeout} (M/RaftParticipant.java:14-49)
+ *   RaftStub.process -> Leader.acceptCommand                RAFTING_OP_SUBMIT
+ *     (M/command/RaftStub.java:79-91, Leader.java:128-140)
+ *   Async callbacks registered by Leader.replicateLog,      lane-event kinds RAFTING_EV_*
+ *     Follower.prepareElection, Candidate.startElection
+ *     (Leader.java:174-188,218-237; Follower.java:258-270; Candidate.java:112-134)
+ *   RaftService.{appendEntries,installSnapshot,preVote,     outbox plan / ballot records
+ *     requestVote} *outbound* calls (M/RaftService.java:22-61)
+ *   RaftLog.{epoch,last,lastCommitted,get(i).term()}        rafting_state_export / rafting_log_term
+ *     (M/command/RaftLog.java:72-132, storage/RocksLog.java:92-128)
+ *   RaftLog.flush (compaction / snapshot epoch move)        RAFTING_OP_FLUSH
+ *   (new, north_star) cross-shard commitIndex summary       rafting_commit_slice / rafting_allgather_commit
+ *
+ * All functions return 0 (RAFTING_OK) or a negative rafting_status_t; they never throw and never
+ * call back into the caller.  Per-event protocol errors (the reference's AssertionError /
+ * AbstractMethodError / IllegalStateException, which its event loop logs and drops —
+ * M/support/EventLoopGroup.java:40-44) are reported per event in the outbox and in the group's
+ * sticky error word, never as the call's return value.
+ */
+#ifndef RAFTING_B200_H
+#define RAFTING_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAFTING_ABI_VERSION 1u
+
+/* ------------------------------------------------------------------------------------------ */
+/* status codes (call level)                                                                  */
+/* ------------------------------------------------------------------------------------------ */
+typedef enum rafting_status {
+    RAFTING_OK            =  0,
+    RAFTING_E_INVAL       = -1,  /* bad argument (IllegalArgumentException)                    */
+    RAFTING_E_NOMEM       = -2,
+    RAFTING_E_CUDA        = -3,  /* CUDA runtime failure; rafting_last_error() has the text    */
+    RAFTING_E_CLOSED      = -4,  /* engine/group closed (IllegalStateException "log closed")   */
+    RAFTING_E_CAPACITY    = -5,  /* max_groups / max_rows / entry pool exceeded                */
+    RAFTING_E_NODEVICE    = -6,  /* no CUDA device: the product path has no CPU fallback       */
+    RAFTING_E_BUSY        = -7,  /* lease outstanding / step in flight                         */
+    RAFTING_E_NCCL        = -8
+} rafting_status_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* per-event error codes (outbox + sticky per-group word). One code per throw site.           */
+/* ------------------------------------------------------------------------------------------ */
+enum {
+    RAFTING_EV_OK                    = 0,
+    RAFTING_ERR_MATCH_ROLLBACK       = 1,  /* AbstractMethodError, Leadership.java:76-81          */
+    RAFTING_ERR_IMPOSSIBLE_REPL      = 2,  /* AssertionError, Leader.java:251-253                  */
+    RAFTING_ERR_COMMIT_ROLLBACK      = 3,  /* AssertionError, RocksLog.java:101-103                */
+    RAFTING_ERR_TRY_COMMIT_FAILED    = 4,  /* NPE on get(major)==null, caught+logged Leader.java:277 */
+    RAFTING_ERR_LEADER_SELF_AE       = 5,  /* Leader.java:71-73                                    */
+    RAFTING_ERR_TWO_LEADERS          = 6,  /* Leader.java:79-81                                    */
+    RAFTING_ERR_LEADER_VOTE_SELF     = 7,  /* Leader.java:104                                      */
+    RAFTING_ERR_FOLLOWER_TWO_LEADERS = 8,  /* Follower.java:48-50                                  */
+    RAFTING_ERR_INDEX_TERM_ZERO      = 9,  /* Follower.java:179-181                                */
+    RAFTING_ERR_EPOCH_TERM_MISMATCH  = 10, /* Follower.java:184-186                                */
+    RAFTING_ERR_IMPOSSIBLE_LOG       = 11, /* Follower.java:199-204                                */
+    RAFTING_ERR_CANDIDATE_SELF_RV    = 12, /* Candidate.java:53-55                                 */
+    RAFTING_ERR_CANDIDATE_VOTE_SELF  = 13, /* Candidate.java:64-66                                 */
+    RAFTING_ERR_IS_BEFORE_AE         = 14, /* RaftMember.java:62-64, Follower.java:138-139         */
+    RAFTING_ERR_LEADER_UNCHANGED     = 15, /* Membership.java:89                                   */
+    RAFTING_ERR_BALLOT_MISMATCH      = 16, /* Membership.java:103-105                              */
+    RAFTING_ERR_LOG_NOT_FOLLOW_EPOCH = 17, /* RocksLog.java:175-177                                */
+    RAFTING_ERR_LOG_NOT_CONTINUOUS   = 18, /* RocksLog.java:185-187                                */
+    RAFTING_ERR_LOG_START            = 19, /* Leader.java:202-204                                  */
+    RAFTING_ERR_LOG_VACANCY          = 20, /* RocksLog.java:161-163                                */
+    RAFTING_ERR_FLUSH_RANGE          = 21, /* IndexOutOfBoundsException, RocksLog.java:230-233     */
+    RAFTING_ERR_TERM_RUNS_OVERFLOW   = 22, /* engine capacity: > RAFTING_TERM_RUNS term changes    */
+    RAFTING_ERR_LOG_SHAPE            = 23, /* degenerate store shape outside the engine's domain   */
+    RAFTING_ERR_NOT_LEADER           = 24, /* NotLeaderException, RaftStub.java:88-90              */
+    RAFTING_ERR_NOT_READY            = 25, /* NotReadyException, RaftStub.java:83-87               */
+    RAFTING_ERR_BAD_EVENT            = 26, /* malformed event (unknown kind / lane)                */
+    RAFTING_ERR_CLOSED_GROUP         = 27  /* ObsoleteContextException / !stillRunning             */
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* constants mirrored from the reference                                                      */
+/* ------------------------------------------------------------------------------------------ */
+#define RAFTING_REPLICATE_LIMIT 50   /* Leadership.java:10 */
+#define RAFTING_IN_FLIGHT_LIMIT 20   /* Leadership.java:11 */
+#define RAFTING_TIMER_TIMEOUT  (-1)  /* TimerTicket.java:13 */
+#define RAFTING_TIMER_FENCING  (-2)  /* TimerTicket.java:14 */
+#define RAFTING_TIMER_INVALID  (-3)  /* TimerTicket.java:15 */
+#define RAFTING_TERM_RUNS        8   /* engine: run-length term table depth per group          */
+#define RAFTING_MAX_REPLICAS    33   /* follower lanes per group <= 32 (one warp)              */
+
+enum { RAFTING_ROLE_FOLLOWER = 0, RAFTING_ROLE_CANDIDATE = 1, RAFTING_ROLE_LEADER = 2 };
+
+/* ------------------------------------------------------------------------------------------ */
+/* config — mirrors M/support/RaftConfig.java:187-198 + the hard-coded constants              */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct rafting_cfg {
+    uint32_t struct_size;           /* sizeof(rafting_cfg_t), ABI guard                        */
+    uint32_t replicas;              /* R = RaftCluster.size(); follower lanes F = R-1          */
+    uint32_t local_slot;            /* this node's slot in the sorted node table, 0..R-1       */
+    uint32_t max_groups;            /* capacity G                                              */
+    uint32_t max_rows;              /* rows per step                                           */
+    uint32_t entry_pool_cap;        /* int64 term slots for inbound AE entries, per step       */
+    int32_t  pre_vote;              /* RaftConfig.preVote()                                    */
+    int32_t  avail_critical_point;  /* metrics/avail-critical-point                            */
+    int64_t  recovery_cool_down_ms; /* metrics/recovery-cool-down                              */
+    int64_t  heartbeat_ms;          /* RaftConfig.heartbeatInterval()                          */
+    int64_t  broadcast_ms;          /* RaftConfig.broadcastTimeout() (informational)           */
+    int64_t  election_ms;           /* E = round(election*tick); timeouts are drawn in [E, 2E]  */
+    uint64_t timer_seed;            /* seed of the counter-based draw used when an event carries none */
+    int32_t  device;                /* CUDA ordinal                                            */
+    uint32_t flags;                 /* reserved, 0                                             */
+} rafting_cfg_t;
+
+/*
+ * Election-timeout draws.  The reference draws ThreadLocalRandom.nextInt(E, 2E+1) at every
+ * non-muted resetTimer (RaftConfig.java:187-190), which makes its output non-deterministic; for a
+ * bit-exact batch semantics the draw is an INPUT.  Group ops carry one draw (op_nr.y, used for every
+ * reset inside that op; 0 = use the counter-based draw); role changes triggered by lane events and
+ * by timer sweeps use the counter-based draw below, keyed by (seed, gid, incarnation of the new role).
+ */
+#if defined(__CUDACC__)
+#define RAFTING_HD __host__ __device__
+#else
+#define RAFTING_HD
+#endif
+RAFTING_HD static inline uint64_t rafting_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+RAFTING_HD static inline int64_t rafting_draw(uint64_t seed, uint32_t gid, uint32_t incarnation, int64_t election_ms) {
+    uint64_t h = rafting_splitmix64(seed ^ ((uint64_t)gid * 0xD6E8FEB86659FD93ull) ^ ((uint64_t)incarnation << 32));
+    if (election_ms <= 0) return 1;
+    return election_ms + (int64_t)(h % (uint64_t)(election_ms + 1));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* batch layout                                                                               */
+/*                                                                                            */
+/* A step carries `rows` rows over `n` groups (n = n_active, or every open group when         */
+/* gids == NULL).  Row r holds, per group, at most ONE group op followed by at most ONE lane  */
+/* event per follower lane f = 0..F-1.  Canonical serial order per group:      */
+/*     for r in rows: [timer sweep if row_now[r] != 0]; op(r); ev(r,0); ev(r,1); ... ev(r,F-1) */
+/* Follower lane f stands for node slot (f < local_slot ? f : f + 1).                         */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct rafting_i64x2 { int64_t x, y; } rafting_i64x2_t;
+
+/* group-op kinds (op_meta bits 0..7) */
+enum {
+    RAFTING_OP_NONE         = 0,
+    RAFTING_OP_SUBMIT       = 1,  /* RaftStub.process: isReady -> newEntry x count -> replicateLog(false)
+                                     count = bits 16..31 (>=1; count==1 is exactly Leader.acceptCommand;
+                                     count>1 is the batched-submit extension, one replicateLog at the end).
+                                     a = bitmask of follower lanes whose RaftService is unavailable      */
+    RAFTING_OP_TIMEOUT      = 2,  /* timer fired: electionTimeout / keepAlive (RaftRoutine.java:53-77).
+                                     a = unavailable-lane mask (used by heartbeat / vote broadcast)      */
+    RAFTING_OP_AE_REQUEST   = 3,  /* inbound appendEntries: peer=leader slot, a=term, b=prevLogIndex,
+                                     c=prevLogTerm, d=leaderCommit, count=n entries, ent=pool offset;
+                                     entries are (prevLogIndex_first + i, ent_terms[ent+i]) with
+                                     first index = e (see op_e): contiguous by construction            */
+    RAFTING_OP_PREVOTE_REQ  = 4,  /* inbound preVote: peer=candidate, a=term, b=lastLogIndex, c=lastLogTerm */
+    RAFTING_OP_VOTE_REQ     = 5,  /* inbound requestVote: same fields                                    */
+    RAFTING_OP_IS_REQUEST   = 6,  /* inbound installSnapshot: peer=leader, a=term, b=lastIncludedIndex,
+                                     c=lastIncludedTerm, d=host result of RaftContext.installSnapshot   */
+    RAFTING_OP_FLUSH        = 7,  /* RaftLog.flush(b=index, c=term) — compaction / snapshot epoch move  */
+    RAFTING_OP_KIND_MAX     = 8
+};
+#define RAFTING_OP_KIND(m)   ((uint32_t)(m) & 0xffu)
+#define RAFTING_OP_PEER(m)   (((uint32_t)(m) >> 8) & 0xffu)
+#define RAFTING_OP_COUNT(m)  (((uint32_t)(m) >> 16) & 0xffffu)
+#define RAFTING_OP_MAKE(kind, peer, count) \
+    ((uint32_t)(kind) | ((uint32_t)(peer) << 8) | ((uint32_t)(count) << 16))
+
+/* lane-event kinds (ev_meta bits 0..3) */
+enum {
+    RAFTING_EV_NONE     = 0,
+    RAFTING_EV_AE_ACK   = 1,  /* AE-Echo,  Leader.java:218-237 */
+    RAFTING_EV_IS_ACK   = 2,  /* IS-Echo,  Leader.java:174-188 */
+    RAFTING_EV_PV_REPLY = 3,  /* PV-Echo,  Follower.java:258-270 */
+    RAFTING_EV_RV_REPLY = 4   /* RV-Echo,  Candidate.java:112-134 */
+};
+/* outcome taxonomy of Async callbacks (M/transport/rpc/Async.java:239-254) */
+enum { RAFTING_OUT_OK = 0, RAFTING_OUT_ERROR = 1, RAFTING_OUT_CANCELED = 2 };
+/* ev_meta: bits 0..3 kind | 4..5 outcome | 6 success | 32..63 incarnation of the role object that sent the RPC */
+#define RAFTING_EVM_MAKE(kind, outcome, success, incarnation) \
+    ((uint64_t)(kind) | ((uint64_t)(outcome) << 4) | ((uint64_t)((success) ? 1 : 0) << 6) | \
+     ((uint64_t)(uint32_t)(incarnation) << 32))
+#define RAFTING_EVM_KIND(m)     ((uint32_t)((m) & 0xfu))
+#define RAFTING_EVM_OUTCOME(m)  ((uint32_t)(((m) >> 4) & 0x3u))
+#define RAFTING_EVM_SUCCESS(m)  ((uint32_t)(((m) >> 6) & 0x1u))
+#define RAFTING_EVM_INC(m)      ((uint32_t)((m) >> 32))
+
+/*
+ * Inbox: SoA columns.  Index of group column = r * n + i ; of lane column = (r * n + i) * F + f.
+ * Any op_* pointer may be NULL when op_meta is NULL (no group ops in the step); ev_* likewise.
+ */
+typedef struct rafting_inbox {
+    uint32_t rows;                 /* rows in this step (<= cfg.max_rows)                        */
+    uint32_t n_active;             /* 0 = dense over gid 0..G-1, else length of gids[]           */
+    const uint32_t* gids;          /* optional compacted active list (strictly increasing)       */
+    const int64_t*  row_now;       /* [rows] optional: != 0 => timer sweep at that time first    */
+    /* group ops */
+    const uint64_t*        op_meta; /* lo32 RAFTING_OP_MAKE(...), hi32 entry-pool offset          */
+    const rafting_i64x2_t* op_nr;   /* (now_ms, election-timeout draw ms)                         */
+    const rafting_i64x2_t* op_ab;   /* (a, b)                                                     */
+    const rafting_i64x2_t* op_cd;   /* (c, d)                                                     */
+    const int64_t*         op_e;    /* AE request: index of entries[0]                            */
+    const int64_t*         ent_terms; /* entry-term pool                                          */
+    uint32_t               ent_count;
+    uint32_t               _pad;
+    /* lane events */
+    const uint64_t*        ev_meta; /* RAFTING_EVM_MAKE(...)                                      */
+    const rafting_i64x2_t* ev_tn;   /* (respTerm, now_ms)                                         */
+    const rafting_i64x2_t* ev_el;   /* AE/IS ack: (epochAtSend, lastIndexAtSend); votes: unused   */
+} rafting_inbox_t;
+
+/* plan kinds (plan_meta bits 0..3) */
+enum { RAFTING_PLAN_NONE = 0, RAFTING_PLAN_AE = 1, RAFTING_PLAN_IS = 2,
+       RAFTING_PLAN_SKIP_INFLIGHT = 3, RAFTING_PLAN_UNAVAILABLE = 4 };
+/* plan_meta: bits 0..3 kind | 4 heartbeat | 16..31 entry count | 32..63 incarnation */
+#define RAFTING_PLM_KIND(m)   ((uint32_t)((m) & 0xfu))
+#define RAFTING_PLM_HB(m)     ((uint32_t)(((m) >> 4) & 1u))
+#define RAFTING_PLM_COUNT(m)  ((uint32_t)(((m) >> 16) & 0xffffu))
+#define RAFTING_PLM_INC(m)    ((uint32_t)((m) >> 32))
+
+/* ballot kinds (ballot_meta bits 0..3) */
+enum { RAFTING_BALLOT_NONE = 0, RAFTING_BALLOT_PREVOTE = 1, RAFTING_BALLOT_VOTE = 2 };
+
+/* reply: rep_meta bit 0 valid | bit 1 success | bits 8..15 per-event error code (reply suppressed if != 0) */
+#define RAFTING_REP_VALID(m)   ((uint32_t)((m) & 1u))
+#define RAFTING_REP_SUCCESS(m) ((uint32_t)(((m) >> 1) & 1u))
+#define RAFTING_REP_ERR(m)     ((uint32_t)(((m) >> 8) & 0xffu))
+
+/*
+ * Outbox: what the Java pump thread turns back into Netty writes / fsyncs / applies.
+ * Row-indexed columns mirror the inbox; group-indexed columns are end-of-step snapshots.
+ */
+typedef struct rafting_outbox {
+    /* per (row, group): reply to an inbound RPC, or op status                                   */
+    uint32_t*        rep_meta;
+    int64_t*         rep_term;     /* RaftResponse.term()                                        */
+    /* per (row, group, lane): outbound AppendEntries / InstallSnapshot (Leader.replicateLog)    */
+    uint64_t*        plan_meta;
+    rafting_i64x2_t* plan_pp;      /* AE: (prevLogIndex, prevLogTerm); IS: (epoch.index, epoch.term) */
+    rafting_i64x2_t* plan_lc;      /* (lastIndex == lastIndexAtSend, leaderCommit)               */
+    int64_t*         plan_epoch;   /* epoch.index at send == epochAtSend                          */
+    /* per (row, group): outbound PreVote / RequestVote broadcast                                */
+    uint64_t*        ballot_meta;  /* bits 0..3 kind | 32..63 incarnation of the asking role object */
+    int64_t*         ballot_term;  /* term argument of the RPC                                    */
+    rafting_i64x2_t* ballot_last;  /* (lastLogIndex, lastLogTerm)                                 */
+    /* per group, end of step                                                                    */
+    int64_t*         commit_index; /* RaftLog.lastCommitted()                                     */
+    int64_t*         current_term; /* RaftParticipant.currentTerm()                               */
+    uint32_t*        role_word;    /* bits 0..1 role | 8..15 votedFor+1 | 16..23 currentLeader+1 |
+                                      bit 24 timeoutDetected | bit 25 leader isReady(now of last op) |
+                                      bit 30 persist-dirty | bit 31 commit-dirty                  */
+    uint32_t*        incarnation;
+    uint32_t*        err_word;     /* lo16 last per-event error code, hi16 error count (sticky)   */
+} rafting_outbox_t;
+
+/* restored per-group state handed to group_open (StableLock.restore + RaftLog state)            */
+typedef struct rafting_group_init {
+    int64_t term;          /* Persistence.term                                                   */
+    int32_t ballot;        /* Persistence.ballot as node slot, -1 = null                         */
+    int32_t _pad;
+    int64_t epoch_index, epoch_term;   /* RaftLog.epoch()                                         */
+    int64_t first_index;   /* lowest stored key (epoch_index or epoch_index+1), ignored if empty */
+    int64_t last_index;    /* RaftLog.last().index, or < first_index for an empty store           */
+    int64_t last_term;     /* every restored entry is given this term (single run)                */
+    int64_t commit_index;  /* volatile in the reference (RocksLog.java:50): 0 after restart       */
+    int64_t now_ms;        /* time of RaftContext.initialize                                      */
+    int64_t rand_ms;       /* election-timeout draw for the initial resetTimer                    */
+} rafting_group_init_t;
+
+/* full per-group state for parity checks / checkpoint (RaftContext.initialize restores from it) */
+typedef struct rafting_follower_state {   /* Leadership.State, Leadership.java:26-38 */
+    int64_t last_request, request_success, request_failure;
+    int32_t request_in_flight, recent_rejection, recent_failure;
+    int32_t pending_installation;
+    int64_t last_epoch, next_index, match_index;
+} rafting_follower_state_t;
+
+typedef struct rafting_group_state {
+    uint32_t alive;
+    uint32_t role;
+    int64_t  current_term;
+    int32_t  voted_for;            /* node slot or -1 */
+    int32_t  current_leader;       /* node slot or -1 */
+    uint32_t incarnation;
+    uint32_t timeout_detected;
+    uint32_t leader_prepared;      /* Leader.followerStatus != null */
+    int32_t  votes;                /* tally of the live election / pre-vote round */
+    uint32_t elected_inc;          /* incarnation of the last elected Candidate (0 = none) */
+    uint32_t elected_aborted;
+    int64_t  elected_term;
+    int64_t  timer;                /* TimerTicket deadline (non-leader) / next heartbeat due (leader) */
+    int64_t  commit_index;
+    int64_t  epoch_index, epoch_term;
+    int64_t  first_index, last_index;   /* stored key range; empty when last_index < first_index */
+    int64_t  last_term;
+    uint32_t term_runs;            /* number of term runs in the stored range */
+    uint32_t err_word;
+    uint64_t log_digest;           /* FNV-1a over (index, term) of every stored entry */
+    uint32_t n_followers;
+    uint32_t _pad;
+    rafting_follower_state_t followers[RAFTING_MAX_REPLICAS - 1];
+} rafting_group_state_t;
+
+typedef struct rafting_engine rafting_engine_t;
+
+/* lease: pinned host staging columns sized for (rows x n groups); valid until the matching step */
+typedef struct rafting_lease {
+    rafting_inbox_t  in;    /* const-cast to fill; pointers are into pinned host memory */
+    rafting_outbox_t out;   /* filled by rafting_step */
+} rafting_lease_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* entry points                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+uint32_t    rafting_abi_version(void);
+const char* rafting_last_error(void);                         /* thread-local text of the last failure */
+
+int rafting_engine_create (const rafting_cfg_t* cfg, rafting_engine_t** out);
+int rafting_engine_destroy(rafting_engine_t* e);
+
+/* open group(s): gid is caller-chosen (dense 0..max_groups-1) so shards keep group order */
+int rafting_group_open     (rafting_engine_t* e, uint32_t gid, const rafting_group_init_t* init);
+int rafting_group_open_bulk(rafting_engine_t* e, uint32_t first_gid, uint32_t count,
+                            const rafting_group_init_t* inits /* [count] */);
+int rafting_group_close    (rafting_engine_t* e, uint32_t gid);
+
+/* host path: fill lease->in (pinned), call step; H2D + kernels + D2H happen inside the call */
+int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_t ent_count,
+                  rafting_lease_t* out);
+int rafting_step (rafting_engine_t* e, rafting_lease_t* lease);          /* synchronous         */
+int rafting_step_begin(rafting_engine_t* e, rafting_lease_t* lease);     /* async: enqueue      */
+int rafting_step_wait (rafting_engine_t* e, rafting_lease_t* lease);     /* async: outbox ready */
+
+/* device path: inbox/outbox columns already resident in HBM (pointers are device pointers).
+   `stream` is a cudaStream_t (0 = engine's stream). No host copies, no sync. */
+int rafting_step_device(rafting_engine_t* e, const rafting_inbox_t* in_dev,
+                        const rafting_outbox_t* out_dev, void* stream);
+
+/* parity / checkpoint */
+int rafting_state_export(rafting_engine_t* e, uint32_t gid, rafting_group_state_t* out);
+int rafting_state_digest(rafting_engine_t* e, uint32_t first_gid, uint32_t count,
+                         uint64_t* digests /* [count], host */);
+int rafting_log_term    (rafting_engine_t* e, uint32_t gid, int64_t index, int64_t* term /* -1 = null */);
+
+/* multi-GPU summary: device pointer of this shard's commitIndex[G_local] (int64), and the
+   NCCL all-gather of it into a [world * G_local] device buffer owned by the engine */
+int rafting_commit_slice(rafting_engine_t* e, void** dev_ptr, uint32_t* count);
+int rafting_comm_init   (rafting_engine_t* e, int rank, int world, const void* nccl_unique_id, size_t id_len);
+int rafting_comm_unique_id(void* out, size_t* len);
+int rafting_allgather_commit(rafting_engine_t* e, int64_t* host_out /* [world*G], may be NULL */,
+                             void** dev_out);
+
+/* introspection used by bench/tests */
+int rafting_engine_stream(rafting_engine_t* e, void** cuda_stream);
+int rafting_engine_counters(rafting_engine_t* e, uint64_t* kernel_launches, uint64_t* events_processed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAFTING_B200_H */
