@@ -217,6 +217,11 @@ enum { RAFTING_OUT_OK = 0, RAFTING_OUT_ERROR = 1, RAFTING_OUT_CANCELED = 2 };
  * Inbox: SoA columns.  Index of group column = r * n + i ; of lane column = (r * n + i) * F + f.
  * Any op_* pointer may be NULL when op_meta is NULL (no group ops in the step); ev_* likewise.
  */
+/* inbox flags: NO_REQUESTS promises the step holds no inbound-request ops (AE/PREVOTE/VOTE/IS
+   requests, FLUSH); the engine then runs the leaner kernel variant, and any such op found anyway is
+   answered with RAFTING_ERR_BAD_EVENT */
+#define RAFTING_INBOX_NO_REQUESTS 1u
+
 typedef struct rafting_inbox {
     uint32_t rows;                 /* rows in this step (<= cfg.max_rows)                        */
     uint32_t n_active;             /* 0 = dense over gid 0..G-1, else length of gids[]           */
@@ -230,7 +235,7 @@ typedef struct rafting_inbox {
     const int64_t*         op_e;    /* AE request: index of entries[0]                            */
     const int64_t*         ent_terms; /* entry-term pool                                          */
     uint32_t               ent_count;
-    uint32_t               _pad;
+    uint32_t               flags;   /* RAFTING_INBOX_* promises about the batch content              */
     /* lane events */
     const uint64_t*        ev_meta; /* RAFTING_EVM_MAKE(...)                                      */
     const rafting_i64x2_t* ev_tn;   /* (respTerm, now_ms)                                         */
@@ -366,9 +371,15 @@ int rafting_step_device(rafting_engine_t* e, const rafting_inbox_t* in_dev,
 
 /* parity / checkpoint */
 int rafting_state_export(rafting_engine_t* e, uint32_t gid, rafting_group_state_t* out);
+int rafting_state_export_bulk(rafting_engine_t* e, uint32_t first_gid, uint32_t count,
+                              rafting_group_state_t* out /* [count], host */);
 int rafting_state_digest(rafting_engine_t* e, uint32_t first_gid, uint32_t count,
                          uint64_t* digests /* [count], host */);
 int rafting_log_term    (rafting_engine_t* e, uint32_t gid, int64_t index, int64_t* term /* -1 = null */);
+/* in-HBM checkpoint of every table (RaftContext.initialize restores from StableLock + RaftLog; here
+   the whole shard is snapshotted / rolled back at once).  One shadow copy per engine. */
+int rafting_checkpoint(rafting_engine_t* e);
+int rafting_restore   (rafting_engine_t* e);
 
 /* multi-GPU summary: device pointer of this shard's commitIndex[G_local] (int64), and the
    NCCL all-gather of it into a [world * G_local] device buffer owned by the engine */
@@ -381,6 +392,7 @@ int rafting_allgather_commit(rafting_engine_t* e, int64_t* host_out /* [world*G]
 /* introspection used by bench/tests */
 int rafting_engine_stream(rafting_engine_t* e, void** cuda_stream);
 int rafting_engine_counters(rafting_engine_t* e, uint64_t* kernel_launches, uint64_t* events_processed);
+int rafting_abi_sizes(uint32_t* out, uint32_t n);   /* sizeof of the ABI structs as compiled, for binding self-checks */
 
 #ifdef __cplusplus
 }

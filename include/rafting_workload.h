@@ -1,0 +1,39 @@
+/*
+ * rafting_workload.h — synthetic replication streams for tests and bench (rafting_b200/csrc/workload.cu).
+ * Not part of the drop-in boundary: the reference has no counterpart; these entry
+ * points play the remote peers of every group so the BASELINE.json configs can be driven at full size.
+ */
+#ifndef RAFTING_WORKLOAD_H
+#define RAFTING_WORKLOAD_H
+#include "rafting_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rafting_wl_cfg {
+    uint64_t seed;
+    uint32_t rows;          /* inbox rows per step (ticks per step)                       */
+    uint32_t n;             /* groups in the step (dense: the shard's group count)        */
+    uint32_t F;             /* follower lanes                                             */
+    uint32_t gid_base;      /* global id of local group 0 (shard offset) — keys the RNG   */
+    uint32_t max_submit;    /* a in U{0..max_submit} entries per tick                     */
+    uint32_t p_reject_ppm;  /* ok + success=false                                         */
+    uint32_t p_error_ppm;   /* RPC error / timeout                                        */
+    uint32_t p_cancel_ppm;  /* canceled                                                   */
+    int64_t  t0;            /* wall clock of tick 0, ms                                   */
+} rafting_wl_cfg_t;
+
+/* fills in->{op_meta,op_nr,op_ab,ev_meta,ev_tn,ev_el} (those that are non-NULL) for step `step`
+   from the previous step's outbox (NULL: no acks).  on_device != 0: all pointers are device
+   pointers and the generator runs as a kernel on `stream`. */
+int rafting_wl_leader_step(const rafting_wl_cfg_t* w, uint64_t step, const rafting_outbox_t* prev_out,
+                           const rafting_inbox_t* in, int on_device, void* stream);
+
+/* single-row election warm-up: phase 0 TIMEOUT everywhere, 1 grant every PreVote, 2 grant every RequestVote */
+int rafting_wl_election_step(const rafting_wl_cfg_t* w, uint32_t phase, const rafting_outbox_t* prev_out,
+                             const rafting_inbox_t* in, int on_device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

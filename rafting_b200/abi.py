@@ -15,6 +15,7 @@ import ctypes as C
 import numpy as np
 
 ABI_VERSION = 1
+INBOX_NO_REQUESTS = 1
 TERM_RUNS = 8
 MAX_REPLICAS = 33
 I64_MAX = (1 << 63) - 1
@@ -78,7 +79,7 @@ class InboxC(C.Structure):
         ("gids", C.c_void_p), ("row_now", C.c_void_p),
         ("op_meta", C.c_void_p), ("op_nr", C.c_void_p), ("op_ab", C.c_void_p), ("op_cd", C.c_void_p),
         ("op_e", C.c_void_p), ("ent_terms", C.c_void_p),
-        ("ent_count", C.c_uint32), ("_pad", C.c_uint32),
+        ("ent_count", C.c_uint32), ("flags", C.c_uint32),
         ("ev_meta", C.c_void_p), ("ev_tn", C.c_void_p), ("ev_el", C.c_void_p),
     ]
 
@@ -184,6 +185,7 @@ class Inbox:
             self.op_meta = self.op_nr = self.op_ab = self.op_cd = self.op_e = None
         self.ent_terms = np.zeros(max(ent_cap, 1), dtype=np.int64)
         self.ent_count = 0
+        self.flags = 0
         if with_events:
             self.ev_meta = np.zeros((rows, n, F), dtype=np.uint64)
             self.ev_tn = np.zeros((rows, n, F), dtype=I64X2)
@@ -251,6 +253,7 @@ class Inbox:
         c.op_meta, c.op_nr, c.op_ab, c.op_cd, c.op_e = map(_ptr, (self.op_meta, self.op_nr, self.op_ab, self.op_cd, self.op_e))
         c.ent_terms = _ptr(self.ent_terms)
         c.ent_count = self.ent_count
+        c.flags = self.flags
         c.ev_meta, c.ev_tn, c.ev_el = map(_ptr, (self.ev_meta, self.ev_tn, self.ev_el))
         return c
 
@@ -285,17 +288,30 @@ class Outbox:
         return b"".join(getattr(self, name).tobytes() for name, _, _ in self.ROW_COLS)
 
     def equal(self, other: "Outbox", gids=None) -> list[str]:
-        """Names of columns that differ (group columns compared on `gids` if given)."""
+        """Names of columns that differ.  Payload columns are compared only where their meta column
+        says they are valid (rep_term where a reply exists, plan_* where a plan exists, ballot_* where
+        a ballot exists); group columns only on `gids` if given."""
         bad = []
-        for name, _, _ in self.ROW_COLS:
-            if not np.array_equal(getattr(self, name), getattr(other, name)):
-                bad.append(name)
-        for name, _ in self.GROUP_COLS:
+
+        def cmp(name, mask=None):
             a, b = getattr(self, name), getattr(other, name)
-            if gids is not None:
-                a, b = a[gids], b[gids]
+            if mask is not None:
+                a, b = a[mask], b[mask]
             if not np.array_equal(a, b):
                 bad.append(name)
+
+        cmp("rep_meta")
+        cmp("rep_term", (self.rep_meta & 1) != 0)
+        cmp("plan_meta")
+        pm = (self.plan_meta & np.uint64(0xF)) != 0
+        for name in ("plan_pp", "plan_lc", "plan_epoch"):
+            cmp(name, pm)
+        cmp("ballot_meta")
+        bm = self.ballot_meta != 0
+        for name in ("ballot_term", "ballot_last"):
+            cmp(name, bm)
+        for name, _ in self.GROUP_COLS:
+            cmp(name, gids)
         return bad
 
 

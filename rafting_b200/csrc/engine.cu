@@ -1,0 +1,605 @@
+// engine.cu — C-ABI implementation (include/rafting_b200.h) over the sm_100a step kernel.
+//
+// Host-side responsibilities only: table allocation in HBM, pinned staging for the lease/step
+// path, kernel dispatch, state export for parity checks, and the NCCL all-gather of the commit
+// column.  There is NO CPU fallback: without a CUDA device engine_create fails with
+// RAFTING_E_NODEVICE.  Nothing here includes or links oracle/.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "step_kernel.cuh"
+
+using namespace rafting;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(RAFTING_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- NCCL through dlopen: no link-time dependency, the torch-bundled or system libnccl works ----
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void* nccl_comm_t;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(nccl_uid_t*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.h) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) { g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
+    if (!g_nccl.h) return fail(RAFTING_E_NCCL, "dlopen(libnccl.so.2) failed: %s", dlerror());
+    *(void**)&g_nccl.GetUniqueId = dlsym(g_nccl.h, "ncclGetUniqueId");
+    *(void**)&g_nccl.CommInitRank = dlsym(g_nccl.h, "ncclCommInitRank");
+    *(void**)&g_nccl.AllGather = dlsym(g_nccl.h, "ncclAllGather");
+    *(void**)&g_nccl.CommDestroy = dlsym(g_nccl.h, "ncclCommDestroy");
+    *(void**)&g_nccl.GetErrorString = dlsym(g_nccl.h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather)
+        return fail(RAFTING_E_NCCL, "libnccl lacks required symbols");
+    return 0;
+}
+
+// one staged column: pinned host + device copies of the same extent
+struct Col { void* h = nullptr; void* d = nullptr; size_t cap = 0; };
+
+struct rafting_engine {
+    rafting_cfg_t cfg;
+    CfgD dcfg;
+    Tables T;
+    uint32_t G, F;
+    int W;
+    cudaStream_t stream = nullptr;
+    int64_t* commit_all = nullptr;     // [world * G]; T.g_commit points at this rank's slice
+    int rank = 0, world = 1;
+    nccl_comm_t comm = nullptr;
+    int64_t* gather_host = nullptr;
+    // lease staging
+    Col c_gids, c_row_now, c_op_meta, c_op_nr, c_op_ab, c_op_cd, c_op_e, c_ent, c_ev_meta, c_ev_tn, c_ev_el;
+    Col o_rep_meta, o_rep_term, o_plan_meta, o_plan_pp, o_plan_lc, o_plan_epoch, o_ballot_meta, o_ballot_term, o_ballot_last;
+    Col o_commit, o_term, o_role, o_inc, o_err;
+    bool leased = false, inflight = false;
+    uint32_t l_rows = 0, l_n = 0, l_ent = 0; bool l_list = false;
+    uint64_t launches = 0, events = 0;
+    std::vector<void*> dev_allocs;
+    std::vector<size_t> dev_bytes;
+    std::vector<void*> shadow;         // rafting_checkpoint copies, parallel to dev_allocs
+};
+
+static int col_reserve(Col& c, size_t bytes) {
+    if (bytes <= c.cap) return 0;
+    if (c.h) cudaFreeHost(c.h);
+    if (c.d) cudaFree(c.d);
+    c.h = c.d = nullptr; c.cap = 0;
+    size_t cap = bytes + bytes / 4 + 256;
+    CU(cudaHostAlloc(&c.h, cap, cudaHostAllocDefault));
+    CU(cudaMalloc(&c.d, cap));
+    memset(c.h, 0, cap);
+    c.cap = cap;
+    return 0;
+}
+static void col_free(Col& c) { if (c.h) cudaFreeHost(c.h); if (c.d) cudaFree(c.d); c = Col(); }
+
+template <typename T>
+static int dalloc(rafting_engine* e, T** p, size_t count) {
+    void* q = nullptr;
+    size_t bytes = count * sizeof(T); if (bytes == 0) bytes = 16;
+    CU(cudaMalloc(&q, bytes));
+    CU(cudaMemset(q, 0, bytes));
+    e->dev_allocs.push_back(q);
+    e->dev_bytes.push_back(bytes);
+    *p = (T*)q;
+    return 0;
+}
+
+extern "C" uint32_t rafting_abi_version(void) { return RAFTING_ABI_VERSION; }
+extern "C" const char* rafting_last_error(void) { return g_err; }
+
+extern "C" int rafting_engine_create(const rafting_cfg_t* cfg, rafting_engine_t** out) {
+    if (!cfg || !out) return fail(RAFTING_E_INVAL, "null argument");
+    if (cfg->struct_size != sizeof(rafting_cfg_t)) return fail(RAFTING_E_INVAL, "cfg.struct_size %u != %zu", cfg->struct_size, sizeof(rafting_cfg_t));
+    if (cfg->replicas < 2 || cfg->replicas > RAFTING_MAX_REPLICAS || cfg->local_slot >= cfg->replicas || cfg->max_groups == 0)
+        return fail(RAFTING_E_INVAL, "bad replicas/local_slot/max_groups");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(RAFTING_E_NODEVICE, "no CUDA device (%s): the engine has no CPU path", cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(RAFTING_E_INVAL, "device %d out of range", cfg->device);
+    CU(cudaSetDevice(cfg->device));
+    rafting_engine* e = new rafting_engine();
+    e->cfg = *cfg;
+    e->G = cfg->max_groups; e->F = cfg->replicas - 1;
+    int W = 1; while (W < (int)e->F) W <<= 1; e->W = W;
+    e->dcfg.replicas = cfg->replicas; e->dcfg.local_slot = cfg->local_slot;
+    e->dcfg.pre_vote = cfg->pre_vote; e->dcfg.avail_critical_point = cfg->avail_critical_point;
+    e->dcfg.recovery_cool_down_ms = cfg->recovery_cool_down_ms; e->dcfg.heartbeat_ms = cfg->heartbeat_ms;
+    e->dcfg.election_ms = cfg->election_ms; e->dcfg.timer_seed = cfg->timer_seed;
+    int rc = 0;
+    Tables& T = e->T; const size_t G = e->G, F = e->F;
+    T.G = e->G; T.F = e->F;
+    if ((rc = dalloc(e, &T.g_meta, G)) || (rc = dalloc(e, &T.g_term, G)) || (rc = dalloc(e, &e->commit_all, G)) ||
+        (rc = dalloc(e, &T.g_lo, G)) || (rc = dalloc(e, &T.g_hi, G)) || (rc = dalloc(e, &T.g_timer, G)) ||
+        (rc = dalloc(e, &T.g_epoch, G)) || (rc = dalloc(e, &T.g_elect, G)) || (rc = dalloc(e, &T.g_err, G)) ||
+        (rc = dalloc(e, &T.g_runs, G * KRUNS)) || (rc = dalloc(e, &T.l_nm, G * F)) || (rc = dalloc(e, &T.l_es, G * F)) ||
+        (rc = dalloc(e, &T.l_fr, G * F)) || (rc = dalloc(e, &T.l_cnt, G * F))) {
+        rafting_engine_destroy(e); return rc;
+    }
+    T.g_commit = e->commit_all;
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        rafting_engine_destroy(e); return fail(RAFTING_E_CUDA, "cudaStreamCreate failed");
+    }
+    *out = e;
+    return RAFTING_OK;
+}
+
+extern "C" int rafting_engine_destroy(rafting_engine_t* e) {
+    if (!e) return RAFTING_OK;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) { cudaStreamSynchronize(e->stream); }
+    if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+    for (void* p : e->dev_allocs) cudaFree(p);
+    for (void* p : e->shadow) cudaFree(p);
+    Col* cols[] = {&e->c_gids, &e->c_row_now, &e->c_op_meta, &e->c_op_nr, &e->c_op_ab, &e->c_op_cd, &e->c_op_e, &e->c_ent,
+                   &e->c_ev_meta, &e->c_ev_tn, &e->c_ev_el, &e->o_rep_meta, &e->o_rep_term, &e->o_plan_meta, &e->o_plan_pp,
+                   &e->o_plan_lc, &e->o_plan_epoch, &e->o_ballot_meta, &e->o_ballot_term, &e->o_ballot_last,
+                   &e->o_commit, &e->o_term, &e->o_role, &e->o_inc, &e->o_err};
+    for (Col* c : cols) col_free(*c);
+    if (e->gather_host) cudaFreeHost(e->gather_host);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return RAFTING_OK;
+}
+
+// ContextManager.buildContext + RaftContext.initialize (RaftContext.java:91-113): the group starts
+// as Follower(restore.term, restore.ballot) — first RaftMember construction (incarnation 1) — with
+// an armed election timer: resetTimer with a null ticket gives max(0 + 1, now + timeout)
+// (RaftRoutine.java:95-107).
+extern "C" int rafting_group_open_bulk(rafting_engine_t* e, uint32_t first, uint32_t count, const rafting_group_init_t* in) {
+    if (!e || !in) return fail(RAFTING_E_INVAL, "null argument");
+    if ((uint64_t)first + count > e->G) return fail(RAFTING_E_CAPACITY, "gid range beyond max_groups");
+    if (count == 0) return RAFTING_OK;
+    CU(cudaSetDevice(e->cfg.device));
+    const size_t F = e->F;
+    std::vector<uint64_t> meta(count); std::vector<int64_t> term(count), commit(count), lo(count), hi(count), timer(count);
+    std::vector<i64x2> epoch(count), elect(count), run0(count); std::vector<uint32_t> err(count, 0);
+    for (uint32_t k = 0; k < count; k++) {
+        const rafting_group_init_t& g = in[k];
+        const bool has = g.last_index >= g.first_index;
+        if (has && g.first_index != g.epoch_index && g.first_index != g.epoch_index + 1)
+            return fail(RAFTING_E_INVAL, "group %u: first_index must be epoch_index or epoch_index+1", first + k);
+        if (g.ballot < -1 || g.ballot >= (int)e->cfg.replicas) return fail(RAFTING_E_INVAL, "group %u: bad ballot", first + k);
+        uint32_t word = RAFTING_ROLE_FOLLOWER | W_ALIVE | ((uint32_t)(g.ballot + 1) << W_BALLOT_SH) | ((has ? 1u : 0u) << W_NRUNS_SH);
+        meta[k] = (uint64_t)word | (1ull << 32);
+        term[k] = g.term; commit[k] = g.commit_index;
+        lo[k] = has ? g.first_index : 1; hi[k] = has ? g.last_index : 0;
+        int64_t draw = g.rand_ms != 0 ? g.rand_ms : rafting_draw(e->cfg.timer_seed, first + k, 1, e->cfg.election_ms);
+        int64_t b = (INT64_MAX - draw < g.now_ms) ? INT64_MAX : g.now_ms + draw;
+        timer[k] = b > 1 ? b : 1;
+        epoch[k].x = g.epoch_index; epoch[k].y = g.epoch_term;
+        elect[k].x = 0; elect[k].y = 0;
+        run0[k].x = has ? g.first_index : 0; run0[k].y = has ? g.last_term : 0;
+    }
+    Tables& T = e->T;
+    CU(cudaMemcpy(T.g_meta + first, meta.data(), count * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(T.g_term + first, term.data(), count * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(T.g_commit + first, commit.data(), count * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(T.g_lo + first, lo.data(), count * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(T.g_hi + first, hi.data(), count * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(T.g_timer + first, timer.data(), count * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(T.g_epoch + first, epoch.data(), count * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(T.g_elect + first, elect.data(), count * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(T.g_err + first, err.data(), count * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(T.g_runs + first, run0.data(), count * 16, cudaMemcpyHostToDevice));
+    for (int k = 1; k < KRUNS; k++) CU(cudaMemset(T.g_runs + (size_t)k * e->G + first, 0, (size_t)count * 16));
+    CU(cudaMemset(T.l_nm + (size_t)first * F, 0, (size_t)count * F * 16));
+    CU(cudaMemset(T.l_es + (size_t)first * F, 0, (size_t)count * F * 16));
+    CU(cudaMemset(T.l_fr + (size_t)first * F, 0, (size_t)count * F * 16));
+    CU(cudaMemset(T.l_cnt + (size_t)first * F, 0, (size_t)count * F * 16));
+    return RAFTING_OK;
+}
+extern "C" int rafting_group_open(rafting_engine_t* e, uint32_t gid, const rafting_group_init_t* init) {
+    return rafting_group_open_bulk(e, gid, 1, init);
+}
+extern "C" int rafting_group_close(rafting_engine_t* e, uint32_t gid) {
+    if (!e || gid >= e->G) return fail(RAFTING_E_INVAL, "bad gid");
+    CU(cudaSetDevice(e->cfg.device));
+    uint64_t m;
+    CU(cudaMemcpy(&m, e->T.g_meta + gid, 8, cudaMemcpyDeviceToHost));
+    m &= ~(uint64_t)W_ALIVE;
+    CU(cudaMemcpy(e->T.g_meta + gid, &m, 8, cudaMemcpyHostToDevice));
+    return RAFTING_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------------------------
+template <int W>
+static void launch_w(rafting_engine* e, const InboxD& in, const OutboxD& out, bool req, cudaStream_t st) {
+    const uint32_t threads = 256;
+    const uint64_t total = (uint64_t)in.n * W;
+    const uint32_t blocks = (uint32_t)((total + threads - 1) / threads);
+    if (blocks == 0) return;
+    if (req) step_kernel<W, true><<<blocks, threads, 0, st>>>(e->T, in, out, e->dcfg);
+    else     step_kernel<W, false><<<blocks, threads, 0, st>>>(e->T, in, out, e->dcfg);
+}
+static int launch_step(rafting_engine* e, const InboxD& in, const OutboxD& out, bool req, cudaStream_t st) {
+    switch (e->W) {
+        case 1: launch_w<1>(e, in, out, req, st); break;
+        case 2: launch_w<2>(e, in, out, req, st); break;
+        case 4: launch_w<4>(e, in, out, req, st); break;
+        case 8: launch_w<8>(e, in, out, req, st); break;
+        case 16: launch_w<16>(e, in, out, req, st); break;
+        default: launch_w<32>(e, in, out, req, st); break;
+    }
+    e->launches++;
+    CU(cudaGetLastError());
+    return RAFTING_OK;
+}
+
+static void to_dev_views(const rafting_inbox_t* in, const rafting_outbox_t* out, uint32_t G, InboxD& di, OutboxD& dout) {
+    di.rows = in->rows; di.n = in->gids ? in->n_active : G; di.gids = in->gids; di.row_now = in->row_now;
+    di.op_meta = in->op_meta; di.op_nr = (const i64x2*)in->op_nr; di.op_ab = (const i64x2*)in->op_ab;
+    di.op_cd = (const i64x2*)in->op_cd; di.op_e = in->op_e; di.ent_terms = in->ent_terms; di.ent_count = in->ent_count;
+    di.ev_meta = in->ev_meta; di.ev_tn = (const i64x2*)in->ev_tn; di.ev_el = (const i64x2*)in->ev_el;
+    dout.rep_meta = out->rep_meta; dout.rep_term = out->rep_term; dout.plan_meta = out->plan_meta;
+    dout.plan_pp = (i64x2*)out->plan_pp; dout.plan_lc = (i64x2*)out->plan_lc; dout.plan_epoch = out->plan_epoch;
+    dout.ballot_meta = out->ballot_meta; dout.ballot_term = out->ballot_term; dout.ballot_last = (i64x2*)out->ballot_last;
+    dout.commit_index = out->commit_index; dout.current_term = out->current_term; dout.role_word = out->role_word;
+    dout.incarnation = out->incarnation; dout.err_word = out->err_word;
+}
+
+extern "C" int rafting_step_device(rafting_engine_t* e, const rafting_inbox_t* in, const rafting_outbox_t* out, void* stream) {
+    if (!e || !in || !out) return fail(RAFTING_E_INVAL, "null argument");
+    if (in->gids && in->n_active > e->G) return fail(RAFTING_E_CAPACITY, "n_active > max_groups");
+    CU(cudaSetDevice(e->cfg.device));
+    InboxD di; OutboxD dout;
+    to_dev_views(in, out, e->G, di, dout);
+    const bool req = !(in->flags & RAFTING_INBOX_NO_REQUESTS);
+    return launch_step(e, di, dout, req, stream ? (cudaStream_t)stream : e->stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// lease / step: pinned host staging, H2D + kernel + D2H inside the call
+// ---------------------------------------------------------------------------------------------
+extern "C" int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_t ent_count, rafting_lease_t* out) {
+    if (!e || !out) return fail(RAFTING_E_INVAL, "null argument");
+    if (e->inflight) return fail(RAFTING_E_BUSY, "a step is in flight");
+    if (rows == 0 || rows > e->cfg.max_rows) return fail(RAFTING_E_CAPACITY, "rows %u > max_rows %u", rows, e->cfg.max_rows);
+    if (n_active > e->G) return fail(RAFTING_E_CAPACITY, "n_active > max_groups");
+    if (ent_count > e->cfg.entry_pool_cap) return fail(RAFTING_E_CAPACITY, "ent_count > entry_pool_cap");
+    CU(cudaSetDevice(e->cfg.device));
+    const size_t n = n_active ? n_active : e->G, R = rows, F = e->F, G = e->G;
+    int rc;
+    if ((rc = col_reserve(e->c_gids, n_active * 4ull)) || (rc = col_reserve(e->c_row_now, R * 8)) ||
+        (rc = col_reserve(e->c_op_meta, R * n * 8)) || (rc = col_reserve(e->c_op_nr, R * n * 16)) ||
+        (rc = col_reserve(e->c_op_ab, R * n * 16)) || (rc = col_reserve(e->c_op_cd, R * n * 16)) ||
+        (rc = col_reserve(e->c_op_e, R * n * 8)) || (rc = col_reserve(e->c_ent, (size_t)ent_count * 8 + 8)) ||
+        (rc = col_reserve(e->c_ev_meta, R * n * F * 8)) || (rc = col_reserve(e->c_ev_tn, R * n * F * 16)) ||
+        (rc = col_reserve(e->c_ev_el, R * n * F * 16)) ||
+        (rc = col_reserve(e->o_rep_meta, R * n * 4)) || (rc = col_reserve(e->o_rep_term, R * n * 8)) ||
+        (rc = col_reserve(e->o_plan_meta, R * n * F * 8)) || (rc = col_reserve(e->o_plan_pp, R * n * F * 16)) ||
+        (rc = col_reserve(e->o_plan_lc, R * n * F * 16)) || (rc = col_reserve(e->o_plan_epoch, R * n * F * 8)) ||
+        (rc = col_reserve(e->o_ballot_meta, R * n * 8)) || (rc = col_reserve(e->o_ballot_term, R * n * 8)) ||
+        (rc = col_reserve(e->o_ballot_last, R * n * 16)) ||
+        (rc = col_reserve(e->o_commit, G * 8)) || (rc = col_reserve(e->o_term, G * 8)) ||
+        (rc = col_reserve(e->o_role, G * 4)) || (rc = col_reserve(e->o_inc, G * 4)) || (rc = col_reserve(e->o_err, G * 4)))
+        return rc;
+    memset(out, 0, sizeof(*out));
+    rafting_inbox_t& in = out->in;
+    in.rows = rows; in.n_active = n_active;
+    in.gids = n_active ? (const uint32_t*)e->c_gids.h : nullptr;
+    in.row_now = (const int64_t*)e->c_row_now.h;
+    memset(e->c_row_now.h, 0, R * 8);
+    in.op_meta = (const uint64_t*)e->c_op_meta.h; in.op_nr = (const rafting_i64x2_t*)e->c_op_nr.h;
+    in.op_ab = (const rafting_i64x2_t*)e->c_op_ab.h; in.op_cd = (const rafting_i64x2_t*)e->c_op_cd.h;
+    in.op_e = (const int64_t*)e->c_op_e.h; in.ent_terms = (const int64_t*)e->c_ent.h; in.ent_count = ent_count;
+    in.ev_meta = (const uint64_t*)e->c_ev_meta.h; in.ev_tn = (const rafting_i64x2_t*)e->c_ev_tn.h;
+    in.ev_el = (const rafting_i64x2_t*)e->c_ev_el.h;
+    rafting_outbox_t& o = out->out;
+    o.rep_meta = (uint32_t*)e->o_rep_meta.h; o.rep_term = (int64_t*)e->o_rep_term.h;
+    o.plan_meta = (uint64_t*)e->o_plan_meta.h; o.plan_pp = (rafting_i64x2_t*)e->o_plan_pp.h;
+    o.plan_lc = (rafting_i64x2_t*)e->o_plan_lc.h; o.plan_epoch = (int64_t*)e->o_plan_epoch.h;
+    o.ballot_meta = (uint64_t*)e->o_ballot_meta.h; o.ballot_term = (int64_t*)e->o_ballot_term.h;
+    o.ballot_last = (rafting_i64x2_t*)e->o_ballot_last.h;
+    o.commit_index = (int64_t*)e->o_commit.h; o.current_term = (int64_t*)e->o_term.h;
+    o.role_word = (uint32_t*)e->o_role.h; o.incarnation = (uint32_t*)e->o_inc.h; o.err_word = (uint32_t*)e->o_err.h;
+    e->leased = true; e->l_rows = rows; e->l_n = (uint32_t)n; e->l_ent = ent_count; e->l_list = n_active != 0;
+    return RAFTING_OK;
+}
+
+// A lease column the caller set to NULL is "absent": not copied, and the kernel sees NULL.
+#define H2D(col, hostptr, bytes)                                                                         \
+    ((hostptr) ? (cudaMemcpyAsync((col).d, (col).h, (bytes), cudaMemcpyHostToDevice, e->stream), (col).d) : nullptr)
+
+extern "C" int rafting_step_begin(rafting_engine_t* e, rafting_lease_t* L) {
+    if (!e || !L) return fail(RAFTING_E_INVAL, "null argument");
+    if (!e->leased) return fail(RAFTING_E_INVAL, "no lease outstanding");
+    if (e->inflight) return fail(RAFTING_E_BUSY, "a step is in flight");
+    if (L->in.rows == 0 || L->in.rows > e->l_rows) return fail(RAFTING_E_CAPACITY, "rows beyond the lease");
+    if (L->in.ent_count > e->l_ent) return fail(RAFTING_E_CAPACITY, "ent_count beyond the lease");
+    CU(cudaSetDevice(e->cfg.device));
+    const size_t n = e->l_n, R = L->in.rows, F = e->F, G = e->G;
+    const rafting_inbox_t& in = L->in;
+    InboxD di; memset(&di, 0, sizeof(di));
+    di.rows = in.rows; di.n = (uint32_t)n;
+    di.gids = e->l_list ? (const uint32_t*)H2D(e->c_gids, in.gids, n * 4) : nullptr;
+    if (e->l_list && !di.gids) return fail(RAFTING_E_INVAL, "active-list lease without gids");
+    bool sweep = false;
+    if (in.row_now) for (size_t r = 0; r < R; r++) sweep |= in.row_now[r] != 0;
+    di.row_now = sweep ? (const int64_t*)H2D(e->c_row_now, in.row_now, R * 8) : nullptr;
+    di.op_meta = (const uint64_t*)H2D(e->c_op_meta, in.op_meta, R * n * 8);
+    if (di.op_meta) {
+        di.op_nr = (const i64x2*)H2D(e->c_op_nr, in.op_nr, R * n * 16);
+        di.op_ab = (const i64x2*)H2D(e->c_op_ab, in.op_ab, R * n * 16);
+        di.op_cd = (const i64x2*)H2D(e->c_op_cd, in.op_cd, R * n * 16);
+        di.op_e = (const int64_t*)H2D(e->c_op_e, in.op_e, R * n * 8);
+        if (!di.op_nr) return fail(RAFTING_E_INVAL, "op_meta without op_nr");
+        if (in.ent_count) di.ent_terms = (const int64_t*)H2D(e->c_ent, in.ent_terms, (size_t)in.ent_count * 8);
+        di.ent_count = in.ent_count;
+    }
+    di.ev_meta = (const uint64_t*)H2D(e->c_ev_meta, in.ev_meta, R * n * F * 8);
+    if (di.ev_meta) {
+        di.ev_tn = (const i64x2*)H2D(e->c_ev_tn, in.ev_tn, R * n * F * 16);
+        di.ev_el = (const i64x2*)H2D(e->c_ev_el, in.ev_el, R * n * F * 16);
+        if (!di.ev_tn) return fail(RAFTING_E_INVAL, "ev_meta without ev_tn");
+    }
+    const rafting_outbox_t& o = L->out;
+    OutboxD dout; memset(&dout, 0, sizeof(dout));
+    const bool ops = di.op_meta || di.row_now;
+    if (o.rep_meta && ops) { dout.rep_meta = (uint32_t*)e->o_rep_meta.d; dout.rep_term = (int64_t*)e->o_rep_term.d; }
+    if (o.plan_meta && ops) {
+        dout.plan_meta = (uint64_t*)e->o_plan_meta.d; dout.plan_pp = (i64x2*)e->o_plan_pp.d;
+        dout.plan_lc = (i64x2*)e->o_plan_lc.d; dout.plan_epoch = (int64_t*)e->o_plan_epoch.d;
+    }
+    if (o.ballot_meta) { dout.ballot_meta = (uint64_t*)e->o_ballot_meta.d; dout.ballot_term = (int64_t*)e->o_ballot_term.d; dout.ballot_last = (i64x2*)e->o_ballot_last.d; }
+    if (o.commit_index) dout.commit_index = (int64_t*)e->o_commit.d;
+    if (o.current_term) dout.current_term = (int64_t*)e->o_term.d;
+    if (o.role_word) dout.role_word = (uint32_t*)e->o_role.d;
+    if (o.incarnation) dout.incarnation = (uint32_t*)e->o_inc.d;
+    if (o.err_word) dout.err_word = (uint32_t*)e->o_err.d;
+    const bool req = !(in.flags & RAFTING_INBOX_NO_REQUESTS);
+    int rc = launch_step(e, di, dout, req, e->stream);
+    if (rc) return rc;
+#define D2H(col, devptr, bytes) if (devptr) cudaMemcpyAsync((col).h, (col).d, (bytes), cudaMemcpyDeviceToHost, e->stream)
+    D2H(e->o_rep_meta, dout.rep_meta, R * n * 4); D2H(e->o_rep_term, dout.rep_term, R * n * 8);
+    D2H(e->o_plan_meta, dout.plan_meta, R * n * F * 8); D2H(e->o_plan_pp, dout.plan_pp, R * n * F * 16);
+    D2H(e->o_plan_lc, dout.plan_lc, R * n * F * 16); D2H(e->o_plan_epoch, dout.plan_epoch, R * n * F * 8);
+    D2H(e->o_ballot_meta, dout.ballot_meta, R * n * 8); D2H(e->o_ballot_term, dout.ballot_term, R * n * 8);
+    D2H(e->o_ballot_last, dout.ballot_last, R * n * 16);
+    D2H(e->o_commit, dout.commit_index, G * 8); D2H(e->o_term, dout.current_term, G * 8);
+    D2H(e->o_role, dout.role_word, G * 4); D2H(e->o_inc, dout.incarnation, G * 4); D2H(e->o_err, dout.err_word, G * 4);
+#undef D2H
+    CU(cudaGetLastError());
+    e->inflight = true;
+    return RAFTING_OK;
+}
+extern "C" int rafting_step_wait(rafting_engine_t* e, rafting_lease_t* L) {
+    (void)L;
+    if (!e) return fail(RAFTING_E_INVAL, "null argument");
+    if (!e->inflight) return RAFTING_OK;
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    e->inflight = false;
+    return RAFTING_OK;
+}
+extern "C" int rafting_step(rafting_engine_t* e, rafting_lease_t* L) {
+    int rc = rafting_step_begin(e, L);
+    if (rc) return rc;
+    return rafting_step_wait(e, L);
+}
+
+// ---------------------------------------------------------------------------------------------
+// state export (parity checks / checkpoint)
+// ---------------------------------------------------------------------------------------------
+static uint64_t fnv1a(uint64_t h, uint64_t v) {
+    for (int i = 0; i < 8; i++) { h ^= (v >> (8 * i)) & 0xff; h *= 0x100000001B3ull; }
+    return h;
+}
+extern "C" int rafting_state_export_bulk(rafting_engine_t* e, uint32_t first, uint32_t count, rafting_group_state_t* out) {
+    if (!e || !out) return fail(RAFTING_E_INVAL, "null argument");
+    if ((uint64_t)first + count > e->G) return fail(RAFTING_E_CAPACITY, "gid range beyond max_groups");
+    if (count == 0) return RAFTING_OK;
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    const size_t F = e->F; const Tables& T = e->T;
+    std::vector<uint64_t> meta(count); std::vector<int64_t> term(count), commit(count), lo(count), hi(count), timer(count);
+    std::vector<i64x2> epoch(count), elect(count), runs((size_t)count * KRUNS), nm(count * F), es(count * F), fr(count * F);
+    std::vector<int4> cnt(count * F); std::vector<uint32_t> err(count);
+    CU(cudaMemcpy(meta.data(), T.g_meta + first, count * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(term.data(), T.g_term + first, count * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(commit.data(), T.g_commit + first, count * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(lo.data(), T.g_lo + first, count * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hi.data(), T.g_hi + first, count * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(timer.data(), T.g_timer + first, count * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(epoch.data(), T.g_epoch + first, count * 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(elect.data(), T.g_elect + first, count * 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(err.data(), T.g_err + first, count * 4, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < KRUNS; k++)
+        CU(cudaMemcpy(runs.data() + (size_t)k * count, T.g_runs + (size_t)k * e->G + first, count * 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(nm.data(), T.l_nm + (size_t)first * F, count * F * 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(es.data(), T.l_es + (size_t)first * F, count * F * 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(fr.data(), T.l_fr + (size_t)first * F, count * F * 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cnt.data(), T.l_cnt + (size_t)first * F, count * F * 16, cudaMemcpyDeviceToHost));
+    for (uint32_t k = 0; k < count; k++) {
+        rafting_group_state_t& o = out[k];
+        memset(&o, 0, sizeof(o));
+        const uint32_t w = (uint32_t)meta[k];
+        const int nr = (int)((w >> W_NRUNS_SH) & 0xf);
+        o.alive = (w & W_ALIVE) ? 1 : 0; o.role = w & W_ROLE_MASK; o.current_term = term[k];
+        o.voted_for = (int)((w >> W_BALLOT_SH) & 0xff) - 1; o.current_leader = (int)((w >> W_LEADER_SH) & 0xff) - 1;
+        o.incarnation = (uint32_t)(meta[k] >> 32);
+        o.timeout_detected = (w & W_TIMEOUT_DET) ? 1 : 0; o.leader_prepared = (w & W_PREPARED) ? 1 : 0;
+        o.votes = (int32_t)((uint64_t)elect[k].y >> 32); o.elected_inc = (uint32_t)(uint64_t)elect[k].y;
+        o.elected_aborted = (w & W_ELECT_ABORT) ? 1 : 0; o.elected_term = elect[k].x;
+        o.timer = timer[k]; o.commit_index = commit[k]; o.epoch_index = epoch[k].x; o.epoch_term = epoch[k].y;
+        uint64_t h = 0xCBF29CE484222325ull;
+        if (nr > 0) {
+            o.first_index = lo[k]; o.last_index = hi[k]; o.last_term = runs[k].y;
+            for (int r = nr - 1; r >= 0; r--) {
+                const i64x2& run = runs[(size_t)r * count + k];
+                int64_t start = (r == nr - 1) ? lo[k] : run.x;    // the oldest run starts at the lowest stored key
+                h = fnv1a(h, (uint64_t)start); h = fnv1a(h, (uint64_t)run.y);
+            }
+            h = fnv1a(h, (uint64_t)hi[k]);
+        } else { o.first_index = 1; o.last_index = 0; o.last_term = 0; }
+        o.term_runs = (uint32_t)nr; o.err_word = err[k]; o.log_digest = h; o.n_followers = (uint32_t)F;
+        if (o.role == RAFTING_ROLE_LEADER && o.leader_prepared) {
+            for (size_t f = 0; f < F; f++) {
+                rafting_follower_state_t& d = o.followers[f]; const size_t li = (size_t)k * F + f;
+                d.next_index = nm[li].x; d.match_index = nm[li].y; d.last_epoch = es[li].x; d.request_success = es[li].y;
+                d.request_failure = fr[li].x; d.last_request = fr[li].y;
+                d.request_in_flight = cnt[li].x; d.recent_rejection = cnt[li].y; d.recent_failure = cnt[li].z;
+                d.pending_installation = cnt[li].w;
+            }
+        }
+    }
+    return RAFTING_OK;
+}
+extern "C" int rafting_state_export(rafting_engine_t* e, uint32_t gid, rafting_group_state_t* out) {
+    return rafting_state_export_bulk(e, gid, 1, out);
+}
+extern "C" int rafting_state_digest(rafting_engine_t* e, uint32_t first, uint32_t count, uint64_t* digests) {
+    if (!digests) return fail(RAFTING_E_INVAL, "null argument");
+    const uint32_t chunk = 4096;
+    std::vector<rafting_group_state_t> buf(chunk);
+    for (uint32_t off = 0; off < count; off += chunk) {
+        uint32_t c = count - off < chunk ? count - off : chunk;
+        int rc = rafting_state_export_bulk(e, first + off, c, buf.data());
+        if (rc) return rc;
+        for (uint32_t k = 0; k < c; k++) {
+            const unsigned char* p = (const unsigned char*)&buf[k];
+            uint64_t h = 0xCBF29CE484222325ull;
+            const size_t used = offsetof(rafting_group_state_t, followers) + sizeof(rafting_follower_state_t) * e->F;
+            for (size_t b = 0; b < used; b++) { h ^= p[b]; h *= 0x100000001B3ull; }
+            digests[off + k] = h;
+        }
+    }
+    return RAFTING_OK;
+}
+extern "C" int rafting_log_term(rafting_engine_t* e, uint32_t gid, int64_t index, int64_t* term) {
+    if (!e || gid >= e->G || !term) return fail(RAFTING_E_INVAL, "bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    uint64_t meta; int64_t lo, hi; i64x2 runs[KRUNS];
+    CU(cudaMemcpy(&meta, e->T.g_meta + gid, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&lo, e->T.g_lo + gid, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&hi, e->T.g_hi + gid, 8, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < KRUNS; k++) CU(cudaMemcpy(&runs[k], e->T.g_runs + (size_t)k * e->G + gid, 16, cudaMemcpyDeviceToHost));
+    const int nr = (int)(((uint32_t)meta >> W_NRUNS_SH) & 0xf);
+    *term = -1;
+    if (nr == 0 || index < lo || index > hi) return RAFTING_OK;
+    for (int k = 0; k < nr; k++) if (index >= runs[k].x || k == nr - 1) { *term = runs[k].y; break; }
+    return RAFTING_OK;
+}
+
+extern "C" int rafting_checkpoint(rafting_engine_t* e) {
+    if (!e) return fail(RAFTING_E_INVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    while (e->shadow.size() < e->dev_allocs.size()) {
+        void* q = nullptr;
+        CU(cudaMalloc(&q, e->dev_bytes[e->shadow.size()]));
+        e->shadow.push_back(q);
+    }
+    for (size_t i = 0; i < e->dev_allocs.size(); i++)
+        CU(cudaMemcpyAsync(e->shadow[i], e->dev_allocs[i], e->dev_bytes[i], cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return RAFTING_OK;
+}
+extern "C" int rafting_restore(rafting_engine_t* e) {
+    if (!e) return fail(RAFTING_E_INVAL, "null argument");
+    if (e->shadow.size() != e->dev_allocs.size()) return fail(RAFTING_E_INVAL, "no checkpoint taken (or tables re-homed since)");
+    CU(cudaSetDevice(e->cfg.device));
+    for (size_t i = 0; i < e->dev_allocs.size(); i++)
+        CU(cudaMemcpyAsync(e->dev_allocs[i], e->shadow[i], e->dev_bytes[i], cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return RAFTING_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU commitIndex summary
+// ---------------------------------------------------------------------------------------------
+extern "C" int rafting_commit_slice(rafting_engine_t* e, void** dev_ptr, uint32_t* count) {
+    if (!e || !dev_ptr || !count) return fail(RAFTING_E_INVAL, "null argument");
+    *dev_ptr = e->T.g_commit; *count = e->G;
+    return RAFTING_OK;
+}
+extern "C" int rafting_comm_unique_id(void* out, size_t* len) {
+    if (!out || !len || *len < sizeof(nccl_uid_t)) return fail(RAFTING_E_INVAL, "buffer too small (need 128)");
+    int rc = nccl_load(); if (rc) return rc;
+    nccl_uid_t id;
+    int nr = g_nccl.GetUniqueId(&id);
+    if (nr) return fail(RAFTING_E_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+    memcpy(out, &id, sizeof(id)); *len = sizeof(id);
+    return RAFTING_OK;
+}
+// Shards are contiguous gid blocks: rank r owns global groups [r*G, (r+1)*G).  The commit column is
+// re-homed INSIDE the gather buffer so the step kernel writes its slice straight into the
+// all-gather send position (in-place ncclAllGather, no staging copy).
+extern "C" int rafting_comm_init(rafting_engine_t* e, int rank, int world, const void* uid, size_t id_len) {
+    if (!e || world < 1 || rank < 0 || rank >= world) return fail(RAFTING_E_INVAL, "bad rank/world");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    int64_t* buf = nullptr;
+    int rc = dalloc(e, &buf, (size_t)world * e->G); if (rc) return rc;
+    CU(cudaMemcpy(buf + (size_t)rank * e->G, e->T.g_commit, (size_t)e->G * 8, cudaMemcpyDeviceToDevice));
+    e->commit_all = buf; e->T.g_commit = buf + (size_t)rank * e->G;
+    e->rank = rank; e->world = world;
+    if (world > 1) {
+        if (!uid || id_len != sizeof(nccl_uid_t)) return fail(RAFTING_E_INVAL, "unique id must be 128 bytes");
+        rc = nccl_load(); if (rc) return rc;
+        nccl_uid_t id; memcpy(&id, uid, sizeof(id));
+        int nr = g_nccl.CommInitRank(&e->comm, world, id, rank);
+        if (nr) return fail(RAFTING_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+    }
+    return RAFTING_OK;
+}
+extern "C" int rafting_allgather_commit(rafting_engine_t* e, int64_t* host_out, void** dev_out) {
+    if (!e) return fail(RAFTING_E_INVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    if (e->world > 1) {
+        if (!e->comm) return fail(RAFTING_E_NCCL, "communicator not initialised");
+        int nr = g_nccl.AllGather(e->T.g_commit, e->commit_all, e->G, /*ncclInt64*/ 4, e->comm, e->stream);
+        if (nr) return fail(RAFTING_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+    }
+    if (dev_out) *dev_out = e->commit_all;
+    if (host_out) {
+        CU(cudaMemcpyAsync(host_out, e->commit_all, (size_t)e->world * e->G * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    return RAFTING_OK;
+}
+
+extern "C" int rafting_engine_stream(rafting_engine_t* e, void** s) {
+    if (!e || !s) return fail(RAFTING_E_INVAL, "null argument");
+    *s = e->stream; return RAFTING_OK;
+}
+extern "C" int rafting_engine_counters(rafting_engine_t* e, uint64_t* launches, uint64_t* events) {
+    if (!e) return fail(RAFTING_E_INVAL, "null argument");
+    if (launches) *launches = e->launches;
+    if (events) *events = e->events;
+    return RAFTING_OK;
+}
+// compile-time layout facts for tests/test_abi.py
+extern "C" int rafting_abi_sizes(uint32_t* out, uint32_t n) {
+    const uint32_t v[] = {(uint32_t)sizeof(rafting_cfg_t), (uint32_t)sizeof(rafting_inbox_t), (uint32_t)sizeof(rafting_outbox_t),
+                          (uint32_t)sizeof(rafting_group_init_t), (uint32_t)sizeof(rafting_follower_state_t),
+                          (uint32_t)sizeof(rafting_group_state_t), (uint32_t)sizeof(rafting_lease_t)};
+    for (uint32_t i = 0; i < n && i < 7; i++) out[i] = v[i];
+    return 7;
+}

@@ -1,0 +1,314 @@
+"""Host-side mirror of the reference's plug points over the C ABI (librafting_b200.so).
+
+`Engine` stands where the reference's ContextManager + the three ContextLoop threads stand
+(M/context/ContextManager.java:46-106, M/support/EventLoopGroup.java:32-80): it owns every
+RaftContext hosted by this node/GPU shard and drains one batch of their events per `step`.
+The method names follow the reference where one exists:
+
+    open_group / close_group   ContextManager.createContext / exitContext (+ RaftContext.initialize)
+    step(inbox) -> outbox      one turn of every group's ContextEventLoop
+    export(gid)                RaftContext.participant() / RaftLog.{epoch,last,lastCommitted} / Leadership.State
+    log_term(gid, i)           RaftLog.get(i).term()
+    allgather_commit()         (new) cross-shard commitIndex summary
+
+This module is ctypes only: no torch, no numpy math on the data path, and NO CPU FALLBACK — if the
+shared library or a CUDA device is missing it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_LIB = None
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librafting_b200.so")
+
+STATUS = {0: "OK", -1: "E_INVAL", -2: "E_NOMEM", -3: "E_CUDA", -4: "E_CLOSED", -5: "E_CAPACITY",
+          -6: "E_NODEVICE", -7: "E_BUSY", -8: "E_NCCL"}
+
+EXPORTS = [
+    "rafting_abi_version", "rafting_last_error", "rafting_engine_create", "rafting_engine_destroy",
+    "rafting_group_open", "rafting_group_open_bulk", "rafting_group_close", "rafting_lease", "rafting_step",
+    "rafting_step_begin", "rafting_step_wait", "rafting_step_device", "rafting_state_export",
+    "rafting_state_export_bulk", "rafting_state_digest", "rafting_log_term", "rafting_commit_slice",
+    "rafting_comm_init", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_engine_stream",
+    "rafting_engine_counters", "rafting_abi_sizes", "rafting_checkpoint", "rafting_restore",
+]
+
+
+class RaftingError(RuntimeError):
+    def __init__(self, rc: int, what: str):
+        self.rc = rc
+        msg = lib().rafting_last_error().decode(errors="replace") if _LIB is not None else ""
+        super().__init__(f"{what}: {STATUS.get(rc, rc)} {msg}")
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def lib():
+    """Loads the in-tree CUDA library. Raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: run `python -m rafting_b200._build` (or __graft_entry__.build()). "
+                "The engine has no CPU path.")
+        L = C.CDLL(_LIB_PATH)
+        L.rafting_abi_version.restype = C.c_uint32
+        L.rafting_last_error.restype = C.c_char_p
+        L.rafting_engine_create.argtypes = [C.POINTER(abi.Cfg), C.POINTER(C.c_void_p)]
+        L.rafting_engine_destroy.argtypes = [C.c_void_p]
+        L.rafting_group_open.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.GroupInit)]
+        L.rafting_group_open_bulk.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.rafting_group_close.argtypes = [C.c_void_p, C.c_uint32]
+        L.rafting_lease.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(abi.LeaseC)]
+        L.rafting_step.argtypes = [C.c_void_p, C.POINTER(abi.LeaseC)]
+        L.rafting_step_begin.argtypes = [C.c_void_p, C.POINTER(abi.LeaseC)]
+        L.rafting_step_wait.argtypes = [C.c_void_p, C.POINTER(abi.LeaseC)]
+        L.rafting_step_device.argtypes = [C.c_void_p, C.POINTER(abi.InboxC), C.POINTER(abi.OutboxC), C.c_void_p]
+        L.rafting_state_export.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.GroupState)]
+        L.rafting_state_export_bulk.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.rafting_state_digest.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.rafting_log_term.argtypes = [C.c_void_p, C.c_uint32, C.c_int64, C.POINTER(C.c_int64)]
+        L.rafting_commit_slice.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+        L.rafting_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+        L.rafting_comm_unique_id.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+        L.rafting_allgather_commit.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.rafting_engine_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.rafting_engine_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.rafting_abi_sizes.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
+        L.rafting_checkpoint.argtypes = [C.c_void_p]
+        L.rafting_restore.argtypes = [C.c_void_p]
+        if L.rafting_abi_version() != abi.ABI_VERSION:
+            raise RuntimeError("librafting_b200.so ABI version mismatch")
+        _LIB = L
+    return _LIB
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RaftingError(rc, what)
+
+
+def _np_view(ptr: int, dtype, shape):
+    """numpy view over pinned host memory owned by the engine."""
+    n = int(np.prod(shape)) if len(shape) else 1
+    if n == 0 or not ptr:
+        return np.zeros(shape, dtype=dtype)
+    dt = np.dtype(dtype)
+    buf = (C.c_char * (n * dt.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
+
+class Engine:
+    def __init__(self, cfg: abi.Cfg):
+        self.cfg = cfg
+        self.F = cfg.replicas - 1
+        self.G = cfg.max_groups
+        h = C.c_void_p()
+        _check(lib().rafting_engine_create(C.byref(cfg), C.byref(h)), "rafting_engine_create")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().rafting_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- lifecycle -------------------------------------------------------------------------
+    def open_group(self, gid: int, **kw):
+        gi = abi.GroupInit()
+        d = dict(term=0, ballot=-1, epoch_index=0, epoch_term=0, first_index=1, last_index=0, last_term=0,
+                 commit_index=0, now_ms=0, rand_ms=1000)
+        d.update(kw)
+        for k, v in d.items():
+            setattr(gi, k, v)
+        _check(lib().rafting_group_open(self._h, gid, C.byref(gi)), "rafting_group_open")
+
+    def open_bulk(self, first_gid: int, inits: np.ndarray):
+        inits = np.ascontiguousarray(inits, dtype=abi.GROUP_INIT_DTYPE)
+        _check(lib().rafting_group_open_bulk(self._h, first_gid, len(inits), inits.ctypes.data), "rafting_group_open_bulk")
+
+    def close_group(self, gid: int):
+        _check(lib().rafting_group_close(self._h, gid), "rafting_group_close")
+
+    # ---- host path: lease -> fill pinned columns -> step (H2D + kernel + D2H inside) ----------
+    def lease(self, rows: int, n_active: int = 0, ent_count: int = 0) -> "Lease":
+        lc = abi.LeaseC()
+        _check(lib().rafting_lease(self._h, rows, n_active, ent_count, C.byref(lc)), "rafting_lease")
+        return Lease(self, lc, rows, n_active if n_active else self.G)
+
+    def step(self, inbox: abi.Inbox, threads: int = 1) -> abi.Outbox:
+        """Same call shape as oracle.binding.Oracle.step: numpy inbox in, numpy outbox out."""
+        n = inbox.n
+        lease = self.lease(inbox.rows, 0 if inbox.gids is None else len(inbox.gids), inbox.ent_count)
+        lease.fill_from(inbox)
+        lease.run()
+        return lease.outbox_copy()
+
+    # ---- device path -------------------------------------------------------------------------
+    def step_device(self, inbox_c: abi.InboxC, outbox_c: abi.OutboxC, stream: int = 0):
+        _check(lib().rafting_step_device(self._h, C.byref(inbox_c), C.byref(outbox_c), C.c_void_p(stream)),
+               "rafting_step_device")
+
+    # ---- introspection -----------------------------------------------------------------------
+    def export(self, gid: int) -> abi.GroupState:
+        st = abi.GroupState()
+        _check(lib().rafting_state_export(self._h, gid, C.byref(st)), "rafting_state_export")
+        return st
+
+    def export_bulk(self, first: int, count: int):
+        arr = (abi.GroupState * count)()
+        _check(lib().rafting_state_export_bulk(self._h, first, count, C.cast(arr, C.c_void_p)), "rafting_state_export_bulk")
+        return arr
+
+    def digest(self, first: int, count: int) -> np.ndarray:
+        out = np.zeros(count, dtype=np.uint64)
+        _check(lib().rafting_state_digest(self._h, first, count, out.ctypes.data), "rafting_state_digest")
+        return out
+
+    def log_term(self, gid: int, index: int) -> int:
+        t = C.c_int64()
+        _check(lib().rafting_log_term(self._h, gid, index, C.byref(t)), "rafting_log_term")
+        return t.value
+
+    def checkpoint(self):
+        _check(lib().rafting_checkpoint(self._h), "rafting_checkpoint")
+
+    def restore(self):
+        _check(lib().rafting_restore(self._h), "rafting_restore")
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        _check(lib().rafting_engine_stream(self._h, C.byref(s)), "rafting_engine_stream")
+        return s.value or 0
+
+    def counters(self) -> tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(lib().rafting_engine_counters(self._h, C.byref(a), C.byref(b)), "rafting_engine_counters")
+        return a.value, b.value
+
+    # ---- multi-GPU summary ---------------------------------------------------------------------
+    def commit_slice(self) -> tuple[int, int]:
+        p, n = C.c_void_p(), C.c_uint32()
+        _check(lib().rafting_commit_slice(self._h, C.byref(p), C.byref(n)), "rafting_commit_slice")
+        return p.value, n.value
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        n = C.c_size_t(128)
+        _check(lib().rafting_comm_unique_id(buf, C.byref(n)), "rafting_comm_unique_id")
+        return buf.raw[:n.value]
+
+    def comm_init(self, rank: int, world: int, uid: bytes | None):
+        if uid is None:
+            _check(lib().rafting_comm_init(self._h, rank, world, None, 0), "rafting_comm_init")
+        else:
+            b = C.create_string_buffer(uid, len(uid))
+            _check(lib().rafting_comm_init(self._h, rank, world, b, len(uid)), "rafting_comm_init")
+        self.rank, self.world = rank, world
+
+    def allgather_commit(self, to_host: bool = True):
+        world = getattr(self, "world", 1)
+        dev = C.c_void_p()
+        if to_host:
+            out = np.zeros(world * self.G, dtype=np.int64)
+            _check(lib().rafting_allgather_commit(self._h, out.ctypes.data, C.byref(dev)), "rafting_allgather_commit")
+            return out
+        _check(lib().rafting_allgather_commit(self._h, None, C.byref(dev)), "rafting_allgather_commit")
+        return dev.value
+
+
+class Lease:
+    """Pinned host staging for one step (rafting_lease_t): numpy views over the engine's buffers."""
+
+    IN_OPS = (("op_meta", np.uint64), ("op_nr", abi.I64X2), ("op_ab", abi.I64X2), ("op_cd", abi.I64X2), ("op_e", np.int64))
+    IN_EVS = (("ev_meta", np.uint64), ("ev_tn", abi.I64X2), ("ev_el", abi.I64X2))
+
+    def __init__(self, eng: Engine, lc: abi.LeaseC, rows: int, n: int):
+        self.eng, self.c, self.rows, self.n = eng, lc, rows, n
+        F, G = eng.F, eng.G
+        i = lc.inbox
+        self._orig = {name: getattr(i, name) for name, _ in self.IN_OPS + self.IN_EVS}
+        self._orig["row_now"] = i.row_now
+        self.gids = _np_view(i.gids, np.uint32, (i.n_active,)) if i.n_active else None
+        self.row_now = _np_view(i.row_now, np.int64, (rows,))
+        for name, dt in self.IN_OPS:
+            setattr(self, name, _np_view(getattr(i, name), dt, (rows, n)))
+        self.ent_terms = _np_view(i.ent_terms, np.int64, (max(i.ent_count, 1),))
+        for name, dt in self.IN_EVS:
+            setattr(self, name, _np_view(getattr(i, name), dt, (rows, n, F)))
+        o = lc.outbox
+        self.out = abi.Outbox.__new__(abi.Outbox)
+        self.out.rows, self.out.n, self.out.F, self.out.G = rows, n, F, G
+        for name, dt, lane in abi.Outbox.ROW_COLS:
+            shape = (rows, n, F) if lane else (rows, n)
+            setattr(self.out, name, _np_view(getattr(o, name), dt, shape))
+        for name, dt in abi.Outbox.GROUP_COLS:
+            setattr(self.out, name, _np_view(getattr(o, name), dt, (G,)))
+
+    def use(self, ops: bool = True, events: bool = True, flags: int = 0):
+        """Declare which column families this step carries (absent ones are neither copied nor read)."""
+        i = self.c.inbox
+        for name, _ in self.IN_OPS:
+            setattr(i, name, self._orig[name] if ops else None)
+        for name, _ in self.IN_EVS:
+            setattr(i, name, self._orig[name] if events else None)
+        i.flags = flags
+        self._ops = ops
+
+    def fill_from(self, ib: abi.Inbox):
+        if ib.gids is not None:
+            self.gids[:] = ib.gids
+        self.c.inbox.rows = ib.rows
+        if ib.row_now is not None:
+            self.row_now[:ib.rows] = ib.row_now
+        else:
+            self.row_now[:] = 0
+        self.use(ops=ib.op_meta is not None, events=ib.ev_meta is not None, flags=ib.flags)
+        if ib.op_meta is not None:
+            for name, _ in self.IN_OPS:
+                getattr(self, name)[:ib.rows] = getattr(ib, name)
+        if ib.ent_count:
+            self.ent_terms[:ib.ent_count] = ib.ent_terms[:ib.ent_count]
+        self.c.inbox.ent_count = ib.ent_count
+        if ib.ev_meta is not None:
+            for name, _ in self.IN_EVS:
+                getattr(self, name)[:ib.rows] = getattr(ib, name)
+
+    def run(self):
+        _check(lib().rafting_step(self.eng._h, C.byref(self.c)), "rafting_step")
+
+    def begin(self):
+        _check(lib().rafting_step_begin(self.eng._h, C.byref(self.c)), "rafting_step_begin")
+
+    def wait(self):
+        _check(lib().rafting_step_wait(self.eng._h, C.byref(self.c)), "rafting_step_wait")
+
+    def outbox_copy(self) -> abi.Outbox:
+        o = abi.Outbox.__new__(abi.Outbox)
+        o.rows, o.n, o.F, o.G = self.out.rows, self.out.n, self.out.F, self.out.G
+        rows = self.c.inbox.rows
+        sweep = bool(self.row_now[:rows].any())
+        for name, _, _ in abi.Outbox.ROW_COLS:
+            col = getattr(self.out, name)[:rows].copy()
+            # without group ops (and without a sweep) the engine neither produces nor copies back the
+            # reply / plan families: they read as "nothing" (zero meta)
+            if not (getattr(self, "_ops", True) or sweep) and name in ("rep_meta", "plan_meta"):
+                col[...] = 0
+            setattr(o, name, col)
+        o.rows = rows
+        for name, _ in abi.Outbox.GROUP_COLS:
+            setattr(o, name, getattr(self.out, name).copy())
+        return o

@@ -1,0 +1,120 @@
+"""Parity of the CUDA engine against the CPU oracle, through the C ABI (rafting_lease/rafting_step).
+
+Bit-exact is the bar: every outbox column and every exported state byte must match on the same
+seeded stream.  All tests here need a B200 (`-m gpu`)."""
+import numpy as np
+import pytest
+
+from oracle import binding
+from rafting_b200 import abi, workload
+from tests import harness
+from tests import test_oracle_kat as kat
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine_mod():
+    from rafting_b200 import engine
+    engine.lib()
+    return engine
+
+
+def _scenarios():
+    return sorted(n for n in dir(kat) if n.startswith("test_") and callable(getattr(kat, n)))
+
+
+SINGLE_GROUP = [n for n in _scenarios() if n not in (
+    "test_major_position_table", "test_major_indices_random", "test_backoff_step_matches_double_math", "test_is_better")]
+
+
+@pytest.mark.parametrize("name", SINGLE_GROUP)
+def test_kat_scenarios_on_engine(engine_mod, monkeypatch, name):
+    """Every hand-derived known-answer scenario of tests/test_oracle_kat.py, run on the GPU engine."""
+    monkeypatch.setattr(kat, "SUT_FACTORY", engine_mod.Engine)
+    getattr(kat, name)()
+
+
+def _pair(engine_mod, G, R, rows, local_slot=0, pre_vote=True, ent=0, terms_mod=7, **cfgkw):
+    cfg = abi.make_cfg(replicas=R, local_slot=local_slot, max_groups=G, max_rows=rows, pre_vote=pre_vote,
+                       entry_pool_cap=ent, **cfgkw)
+    o, e = binding.Oracle(cfg), engine_mod.Engine(cfg)
+    init = harness.init_array(G, terms=np.arange(G) % terms_mod)
+    o.open_bulk(0, init)
+    e.open_bulk(0, init)
+    return cfg, o, e
+
+
+@pytest.mark.parametrize("R,G,rows", [(3, 4096, 8), (5, 2048, 4), (2, 512, 3), (4, 777, 5), (7, 300, 2), (9, 130, 2), (33, 40, 2)])
+def test_leader_stream_parity(engine_mod, R, G, rows):
+    """configs #2/#4 shape at reduced size: election warm-up, then the leader steady-state stream."""
+    cfg, o, e = _pair(engine_mod, G, R, rows)
+    w1 = workload.make_wl(0x5EED0002, 1, G, R - 1)
+    w = workload.make_wl(0x5EED0002, rows, G, R - 1, p_reject_ppm=60_000, p_error_ppm=20_000, p_cancel_ppm=20_000)
+    oo, oe = harness.elect_all(o, w1), harness.elect_all(e, w1)
+    harness.assert_outbox_equal(oo, oe, where="after election")
+    assert ((oe.role_word & 3) == abi.ROLE_LEADER).all()
+    last = harness.run_leader_workload([o, e], w, steps=14)
+    harness.assert_states_equal(o, e, range(0, G, max(1, G // 257)), R - 1, where="end of stream")
+    assert last.commit_index.min() > 0
+    # bulk digest path agrees with per-group export
+    d = e.digest(0, G)
+    assert len(set(d.tolist())) > 1
+
+
+@pytest.mark.parametrize("R,local_slot,pre_vote,seed", [(3, 0, True, 1), (3, 2, False, 2), (5, 2, True, 3), (4, 1, True, 4), (7, 6, False, 5)])
+def test_fuzz_parity_all_event_kinds(engine_mod, R, local_slot, pre_vote, seed):
+    """Random mix of every op and lane-event kind (requests, votes, snapshots, flushes, acks, forged
+    and stale replies), steered by the oracle's state so that every role and error path is reached."""
+    G, rows = 48, 3
+    cfg, o, e = _pair(engine_mod, G, R, rows, local_slot=local_slot, pre_vote=pre_vote, ent=rows * G * 8, terms_mod=3)
+    fz = harness.Fuzzer(cfg, o, seed=seed, rows=rows)
+    out = None
+    roles, errs = set(), set()
+    for k in range(60):
+        ib = fz.make(out)
+        out = o.step(ib)
+        oe = e.step(ib)
+        harness.assert_outbox_equal(out, oe, where=f"fuzz step {k}")
+        roles |= set((out.role_word & 3).tolist())
+        errs |= set(((out.rep_meta >> 8) & 0xFF).ravel().tolist())
+        if k % 10 == 9:
+            harness.assert_states_equal(o, e, range(G), R - 1, where=f"fuzz step {k}")
+    assert roles == {0, 1, 2}
+    assert len(errs) > 3
+
+
+def test_active_list_and_sweep_parity(engine_mod):
+    G, R, rows = 512, 3, 2
+    cfg, o, e = _pair(engine_mod, G, R, rows)
+    w1 = workload.make_wl(7, 1, G, R - 1)
+    harness.elect_all(o, w1), harness.elect_all(e, w1)
+    # compacted active list: only every third group takes part in this step
+    gids = np.arange(0, G, 3, dtype=np.uint32)
+    ib = abi.Inbox(rows, len(gids), R - 1, gids=gids)
+    for r in range(rows):
+        for i in range(len(gids)):
+            ib.timeout(r, i, harness.T0 + r, rand=0)
+    oo, oe = o.step(ib), e.step(ib)
+    harness.assert_outbox_equal(oo, oe, gids=gids, where="active list")
+    harness.assert_states_equal(o, e, range(G), R - 1, where="active list")
+    # sweep rows: leaders whose keepAlive is due fire, others do not
+    for now in (harness.T0 + 100, harness.T0 + 301, harness.T0 + 5000):
+        ib = abi.Inbox(1, G, R - 1, sweep=True, with_ops=False)
+        ib.row_now[0] = now
+        oo, oe = o.step(ib), e.step(ib)
+        harness.assert_outbox_equal(oo, oe, where=f"sweep {now}")
+    harness.assert_states_equal(o, e, range(G), R - 1, where="sweep")
+
+
+def test_closed_group_and_capacity_errors(engine_mod):
+    cfg, o, e = _pair(engine_mod, 8, 3, 2)
+    o.close_group(3), e.close_group(3)
+    ib = abi.Inbox(1, 8, 2)
+    for i in range(8):
+        ib.timeout(0, i, harness.T0)
+    harness.assert_outbox_equal(o.step(ib), e.step(ib))
+    with pytest.raises(engine_mod.RaftingError):
+        e.lease(3)                       # rows > max_rows
+    with pytest.raises(engine_mod.RaftingError):
+        engine_mod.Engine(abi.make_cfg(replicas=1))

@@ -87,14 +87,17 @@ def test_is_better(new, cur, expect):
 # --------------------------------------------------------------------------------------------
 # helpers: drive one group through the batch interface
 # --------------------------------------------------------------------------------------------
+SUT_FACTORY = binding.Oracle     # tests/test_engine_gpu.py re-runs every scenario below with the CUDA engine
+
+
 class One:
     """One group, R replicas, local slot 0; each call is a one-row step."""
 
     def __init__(self, replicas=3, pre_vote=True, **init):
         self.cfg = abi.make_cfg(replicas=replicas, local_slot=0, max_groups=1, max_rows=1, pre_vote=pre_vote,
-                                heartbeat_ms=300, election_ms=900)
+                                heartbeat_ms=300, election_ms=900, entry_pool_cap=64)
         self.F = replicas - 1
-        self.o = binding.Oracle(self.cfg)
+        self.o = SUT_FACTORY(self.cfg)
         init.setdefault("now_ms", T0)
         init.setdefault("rand_ms", 1000)
         self.o.open_group(0, **init)
