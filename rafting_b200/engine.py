@@ -279,7 +279,11 @@ class Lease:
         self.use(ops=ib.op_meta is not None, events=ib.ev_meta is not None, flags=ib.flags)
         if ib.op_meta is not None:
             for name, _ in self.IN_OPS:
-                getattr(self, name)[:ib.rows] = getattr(ib, name)
+                col = getattr(ib, name)
+                if col is None:                      # e.g. op_cd / op_e absent in a NO_REQUESTS step
+                    setattr(self.c.inbox, name, None)
+                else:
+                    getattr(self, name)[:ib.rows] = col
         if ib.ent_count:
             self.ent_terms[:ib.ent_count] = ib.ent_terms[:ib.ent_count]
         self.c.inbox.ent_count = ib.ent_count
