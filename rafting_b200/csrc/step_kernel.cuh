@@ -382,7 +382,8 @@ template <int W>
 __device__ __forceinline__ bool leader_ready(GS& g, const Ctx& c, const LS& s) {          // Leader.java:52-64
     bool r = c.lv && state_ready(s, c.cfg->avail_critical_point, c.cfg->recovery_cool_down_ms, c.now);
     int cnt = __popc(sub_ballot(c, r, W));
-    bool ready = (g.word & W_PREPARED) && (1 + cnt > (int)c.F / 2);
+    // the Java loop only returns true from inside `isReady(..) && ++ready > half`: at least one follower must be ready
+    bool ready = (g.word & W_PREPARED) && cnt >= 1 && (1 + cnt > (int)c.F / 2);
     g.word = ready ? (g.word | W_READY) : (g.word & ~W_READY);
     return ready;
 }
