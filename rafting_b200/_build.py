@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librafting_b200.so")
 SOURCES = ["engine.cu", "workload.cu"]
-HEADERS = ["step_kernel.cuh", "tables.cuh", os.path.join("..", "..", "include", "rafting_b200.h"),
+HEADERS = ["step_kernel.cuh", "handlers.cuh", "tables.cuh", os.path.join("..", "..", "include", "rafting_b200.h"),
            os.path.join("..", "..", "include", "rafting_workload.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -38,7 +38,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB, "-ldl"]
+    extra = os.environ.get("RAFTING_NVCC_EXTRA", "").split()      # e.g. -DRAFTING_MINBLOCKS=5 for tuning runs
+    cmd = [nvcc()] + NVCC_FLAGS + extra + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB, "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:

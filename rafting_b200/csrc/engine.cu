@@ -62,6 +62,7 @@ struct Col { void* h = nullptr; void* d = nullptr; size_t cap = 0; };
 struct rafting_engine {
     rafting_cfg_t cfg;
     CfgD dcfg;
+    CfgD* d_cfg = nullptr;            // device copy for the slow path (the fast path reads the kernel-param copy)
     Tables T;
     uint32_t G, F;
     int W;
@@ -141,6 +142,10 @@ extern "C" int rafting_engine_create(const rafting_cfg_t* cfg, rafting_engine_t*
         rafting_engine_destroy(e); return rc;
     }
     T.g_commit = e->commit_all;
+    if ((rc = dalloc(e, &e->d_cfg, 1))) { rafting_engine_destroy(e); return rc; }
+    if (cudaMemcpy(e->d_cfg, &e->dcfg, sizeof(CfgD), cudaMemcpyHostToDevice) != cudaSuccess) {
+        rafting_engine_destroy(e); return fail(RAFTING_E_CUDA, "cfg upload failed");
+    }
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
         rafting_engine_destroy(e); return fail(RAFTING_E_CUDA, "cudaStreamCreate failed");
     }
@@ -230,22 +235,21 @@ extern "C" int rafting_group_close(rafting_engine_t* e, uint32_t gid) {
 // kernel dispatch
 // ---------------------------------------------------------------------------------------------
 template <int W>
-static void launch_w(rafting_engine* e, const InboxD& in, const OutboxD& out, bool req, cudaStream_t st) {
-    const uint32_t threads = 256;
+static void launch_w(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
+    const uint32_t threads = 128;
     const uint64_t total = (uint64_t)in.n * W;
     const uint32_t blocks = (uint32_t)((total + threads - 1) / threads);
     if (blocks == 0) return;
-    if (req) step_kernel<W, true><<<blocks, threads, 0, st>>>(e->T, in, out, e->dcfg);
-    else     step_kernel<W, false><<<blocks, threads, 0, st>>>(e->T, in, out, e->dcfg);
+    step_kernel<W><<<blocks, threads, 0, st>>>(e->T, in, out, e->d_cfg, e->dcfg);
 }
-static int launch_step(rafting_engine* e, const InboxD& in, const OutboxD& out, bool req, cudaStream_t st) {
+static int launch_step(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
     switch (e->W) {
-        case 1: launch_w<1>(e, in, out, req, st); break;
-        case 2: launch_w<2>(e, in, out, req, st); break;
-        case 4: launch_w<4>(e, in, out, req, st); break;
-        case 8: launch_w<8>(e, in, out, req, st); break;
-        case 16: launch_w<16>(e, in, out, req, st); break;
-        default: launch_w<32>(e, in, out, req, st); break;
+        case 1: launch_w<1>(e, in, out, st); break;
+        case 2: launch_w<2>(e, in, out, st); break;
+        case 4: launch_w<4>(e, in, out, st); break;
+        case 8: launch_w<8>(e, in, out, st); break;
+        case 16: launch_w<16>(e, in, out, st); break;
+        default: launch_w<32>(e, in, out, st); break;
     }
     e->launches++;
     CU(cudaGetLastError());
@@ -255,7 +259,7 @@ static int launch_step(rafting_engine* e, const InboxD& in, const OutboxD& out, 
 static void to_dev_views(const rafting_inbox_t* in, const rafting_outbox_t* out, uint32_t G, InboxD& di, OutboxD& dout) {
     di.rows = in->rows; di.n = in->gids ? in->n_active : G; di.gids = in->gids; di.row_now = in->row_now;
     di.op_meta = in->op_meta; di.op_nr = (const i64x2*)in->op_nr; di.op_ab = (const i64x2*)in->op_ab;
-    di.op_cd = (const i64x2*)in->op_cd; di.op_e = in->op_e; di.ent_terms = in->ent_terms; di.ent_count = in->ent_count;
+    di.op_cd = (const i64x2*)in->op_cd; di.op_e = in->op_e; di.ent_terms = in->ent_terms; di.ent_count = in->ent_count; di.flags = in->flags;
     di.ev_meta = in->ev_meta; di.ev_tn = (const i64x2*)in->ev_tn; di.ev_el = (const i64x2*)in->ev_el;
     dout.rep_meta = out->rep_meta; dout.rep_term = out->rep_term; dout.plan_meta = out->plan_meta;
     dout.plan_pp = (i64x2*)out->plan_pp; dout.plan_lc = (i64x2*)out->plan_lc; dout.plan_epoch = out->plan_epoch;
@@ -270,8 +274,7 @@ extern "C" int rafting_step_device(rafting_engine_t* e, const rafting_inbox_t* i
     CU(cudaSetDevice(e->cfg.device));
     InboxD di; OutboxD dout;
     to_dev_views(in, out, e->G, di, dout);
-    const bool req = !(in->flags & RAFTING_INBOX_NO_REQUESTS);
-    return launch_step(e, di, dout, req, stream ? (cudaStream_t)stream : e->stream);
+    return launch_step(e, di, dout, stream ? (cudaStream_t)stream : e->stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -373,8 +376,8 @@ extern "C" int rafting_step_begin(rafting_engine_t* e, rafting_lease_t* L) {
     if (o.role_word) dout.role_word = (uint32_t*)e->o_role.d;
     if (o.incarnation) dout.incarnation = (uint32_t*)e->o_inc.d;
     if (o.err_word) dout.err_word = (uint32_t*)e->o_err.d;
-    const bool req = !(in.flags & RAFTING_INBOX_NO_REQUESTS);
-    int rc = launch_step(e, di, dout, req, e->stream);
+    di.flags = in.flags;
+    int rc = launch_step(e, di, dout, e->stream);
     if (rc) return rc;
 #define D2H(col, devptr, bytes) if (devptr) cudaMemcpyAsync((col).h, (col).d, (bytes), cudaMemcpyDeviceToHost, e->stream)
     D2H(e->o_rep_meta, dout.rep_meta, R * n * 4); D2H(e->o_rep_term, dout.rep_term, R * n * 8);

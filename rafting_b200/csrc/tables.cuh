@@ -68,6 +68,7 @@ struct InboxD {
     const int64_t*  op_e;
     const int64_t*  ent_terms;
     uint32_t        ent_count;
+    uint32_t        flags;
     const uint64_t* ev_meta;
     const i64x2*    ev_tn;
     const i64x2*    ev_el;
