@@ -230,32 +230,37 @@ __device__ __noinline__ uint32_t slow_events(const KArgs* ka, uint32_t i, uint32
 }
 
 // quorum index over (new matchIndex for lanes <= upto, old for lanes > upto): what Leader.tryCommit
-// sees right after lane `upto`'s ack in the serial order (Leader.java:247-261, Leadership.java:116-130)
+// sees right after lane `upto`'s ack in the serial order (Leader.java:247-261, Leadership.java:116-130).
+// Executed by the WHOLE warp (full-mask shuffles of width W): every sub-warp gets its own answer.
 template <int W>
 __device__ __forceinline__ void quorum_after(const Lite& k, int64_t oldM, int64_t newM, int upto, int64_t& full, int64_t& major) {
     const int F = (int)k.F;
     const int64_t mine = k.lane <= upto ? newM : oldM;
+    if (W == 1) { full = major = mine; return; }
     if (W == 2) {                                   // R = 3: sorted = [min, max]
-        const int64_t other = shfl64(k.mask, mine, k.lane ^ 1, W);
+        const int64_t other = shfl64(0xffffffffu, mine, k.lane ^ 1, W);
         full = mine < other ? mine : other; major = mine < other ? other : mine;
         return;
     }
     int64_t mn = I64MAX; int rank = 0;
 #pragma unroll
     for (int j = 0; j < W; j++) {
-        const int64_t mj = shfl64(k.mask, mine, j, W);
+        const int64_t mj = shfl64(0xffffffffu, mine, j, W);
         if (j < F) { mn = mj < mn ? mj : mn; rank += (mj < mine) || (mj == mine && j < k.lane); }
     }
-    unsigned b = __ballot_sync(k.mask, k.lv && rank == F / 2);
+    const unsigned b = __ballot_sync(0xffffffffu, k.lv && rank == F / 2);
     const unsigned sel = W == 32 ? b : ((b >> k.sub0) & ((1u << W) - 1u));
-    full = mn; major = shfl64(k.mask, mine, __ffs(sel) - 1, W);
+    full = mn; major = shfl64(0xffffffffu, mine, __ffs(sel) - 1, W);
+}
+__device__ __forceinline__ unsigned sub_bits(const Lite& k, unsigned b, int W) {
+    return W == 32 ? b : ((b >> k.sub0) & ((1u << W) - 1u));
 }
 
 #ifndef RAFTING_MINBLOCKS
 #define RAFTING_MINBLOCKS 7
 #endif
 #ifndef RAFTING_STAGES
-#define RAFTING_STAGES 3
+#define RAFTING_STAGES 2
 #endif
 constexpr int TPB = 128;                 // threads per block
 constexpr int NST = RAFTING_STAGES;      // input rows staged in shared memory (NST-1 rows in flight per thread)
@@ -279,6 +284,9 @@ struct __align__(16) Stage {             // one staged input row of this block
     uint64_t ev_meta[TPB];
 };
 
+// Control flow is WARP-UNIFORM: every collective (ballot / shuffle) is executed by all 32 lanes with
+// the full mask, per-group decisions are predicates, and the generic slow path is entered by the whole
+// warp when any of its groups needs it (the generic handlers are correct for every group state).
 template <int W>
 __global__ void __launch_bounds__(TPB, RAFTING_MINBLOCKS)
 step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, CfgD cfg) {
@@ -288,20 +296,22 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
     __syncthreads();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i = tid / W;
-    if (i >= in.n) return;                                   // whole sub-warps leave together
+    if ((tid & ~31u) / W >= in.n) return;                    // whole warps beyond the batch leave together
     const uint32_t F = T.F;
-    const uint32_t gid = in.gids ? in.gids[i] : i;
-    if (gid >= T.G) return;
+    uint32_t gid = 0; bool valid = i < in.n;
+    if (valid) { gid = in.gids ? in.gids[i] : i; if (gid >= T.G) { valid = false; gid = 0; } }
     const Lite k = make_lite<W>(T, cfgp, gid);
-    const int lane = k.lane; const bool lv = k.lv;
+    const int lane = k.lane; const bool lv = valid && k.lv;
     const uint32_t tl = threadIdx.x, gl = threadIdx.x / W;   // this thread's / this group's slot in a stage
+    constexpr unsigned FULL = 0xffffffffu;
 
     // ---- hot group scalars + this lane's follower slot live in registers for the whole batch ----
     GS g; LS s;
-    load_hot(T, gid, g); g.dirty = 0; g.electTerm = 0; g.electInc = 0; g.votes = 0;
+    g.word = 0; g.inc = 0; g.err = 0; g.term = g.commit = g.lo = g.hi = g.timer = g.epochIndex = g.epochTerm = g.r0s = g.r0t = 0;
+    if (valid) load_hot(T, gid, g);
+    g.dirty = 0; g.electTerm = 0; g.electInc = 0; g.votes = 0;
     const size_t li0 = (size_t)gid * F + (uint32_t)lane;
     zero_lane(s); if (lv) load_lane(T, li0, s);
-    const bool alive = (g.word & W_ALIVE) != 0;
     const bool hasOps = in.op_meta != nullptr, hasEv = in.ev_meta != nullptr;
 
     // ---- asynchronous staging of the input rows (cp.async, no registers held): the group op is
@@ -309,7 +319,7 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
 #define RAFTING_ISSUE(R_)                                                                                  \
     {                                                                                                      \
         const uint32_t r_ = (R_);                                                                          \
-        if (r_ < in.rows) {                                                                                \
+        if (r_ < in.rows && valid) {                                                                       \
             Stage<W>& st_ = stage[r_ % NST];                                                               \
             const size_t gi_ = (size_t)r_ * in.n + i;                                                      \
             if (hasOps) {                                                                                  \
@@ -332,72 +342,131 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
         const size_t gi = (size_t)r * in.n + i;
         RAFTING_ISSUE(r + NST - 1);
         cp_async_wait<NST - 1>();                            // row r has landed
-        __syncwarp(k.mask);                                  // ... including the parts sibling lanes fetched
+        __syncwarp();                                        // ... including the parts sibling lanes fetched
         const Stage<W>& st = stage[r % NST];
-        uint64_t opm = 0; int64_t opNow = 0, opUnavail = 0;
-        if (hasOps) { opm = st.op_meta[gl]; opNow = st.op_nr[gl].x; if (in.op_ab) opUnavail = st.op_ab[gl].x; }
+        const bool alive = valid && (g.word & W_ALIVE) != 0;
 
         // ================= group op =================
-        const int64_t sweep = in.row_now ? in.row_now[r] : 0;
-        uint32_t kind = RAFTING_OP_NONE, meta = 0;
-        int64_t now = 0;
+        const int64_t sweep = in.row_now ? in.row_now[r] : 0;             // grid-uniform
+        uint32_t meta = 0, kind = RAFTING_OP_NONE; int64_t now = 0; uint64_t unavail = 0;
+        if (sweep == 0 && hasOps && valid) {
+            meta = (uint32_t)st.op_meta[gl]; kind = RAFTING_OP_KIND(meta); now = st.op_nr[gl].x;
+            if (in.op_ab) unavail = (uint64_t)st.op_ab[gl].x;
+        }
+        bool slowOp;                                          // this group's op needs the generic handler
         if (sweep != 0) {
-            if (alive) {
-                const bool due = (role_of(g) == RAFTING_ROLE_LEADER) ? (g.timer <= sweep)
-                                 : (g.timer > 0 && g.timer != I64MAX && g.timer <= sweep);
-                if (due) { kind = RAFTING_OP_TIMEOUT; now = sweep; }
-            }
-        } else if (hasOps) { meta = (uint32_t)opm; kind = RAFTING_OP_KIND(meta); now = opNow; }
-        bool wroteRep = false;
-        if (kind != RAFTING_OP_NONE) {
-            const bool leader = alive && role_of(g) == RAFTING_ROLE_LEADER;
-            const uint64_t unavail = sweep != 0 ? 0ull : (uint64_t)opUnavail;
-            bool fast = false; int err = 0;
-            RowOut ro; ro.pm = 0; ro.pe = 0; ro.pp.x = ro.pp.y = ro.lc.x = ro.lc.y = 0;
+            const bool due = alive && ((role_of(g) == RAFTING_ROLE_LEADER) ? (g.timer <= sweep)
+                                       : (g.timer > 0 && g.timer != I64MAX && g.timer <= sweep));
+            kind = due ? (uint32_t)RAFTING_OP_TIMEOUT : (uint32_t)RAFTING_OP_NONE;
+            slowOp = due;
+        } else {
             const bool hbeat = kind == RAFTING_OP_TIMEOUT;
-            if (leader && (hbeat || (kind == RAFTING_OP_SUBMIT && nruns_of(g) > 0 && g.r0t == g.term))) {
-                // Leader keepAlive -> replicateLog(true)   (RaftRoutine.java:53-62, Leader.java:119-126), or
-                // RaftStub.process -> Leader.acceptCommand -> replicateLog(false) when no new term run is
-                // needed (RaftStub.java:79-91, Leader.java:128-140, RocksLog.java:82-89)
-                fast = true;
-                Ctx c = make_ctx(k, now, 0);
-                bool go = true;
-                if (hbeat) g.timer = (I64MAX - cfg.heartbeat_ms < now) ? I64MAX : now + cfg.heartbeat_ms;   // resetTimer, Leader branch
-                else if (!leader_ready<W>(g, c, s, cfg.avail_critical_point, cfg.recovery_cool_down_ms)) { err = RAFTING_ERR_NOT_READY; go = false; }
-                else { uint32_t count = RAFTING_OP_COUNT(meta); if (count == 0) count = 1; g.hi += count; }
-                if (go) err = replicate_log<W>(g, c, ro, s, hbeat, unavail);
-            }
-            if (fast) {
-                if (err) flag_err(g, err);
-                if (lv && out.plan_meta) {
-                    const size_t li = gi * F + (uint32_t)lane;
-                    out.plan_meta[li] = ro.pm;
-                    if (ro.pm != 0) { out.plan_pp[li] = ro.pp; out.plan_lc[li] = ro.lc; out.plan_epoch[li] = ro.pe; }
-                }
-                if (lane == 0 && out.rep_meta) out.rep_meta[gi] = (uint32_t)err << 8;
-                if (lane == 0 && out.ballot_meta) out.ballot_meta[gi] = 0;
-                wroteRep = true;
+            const bool fastOk = alive && role_of(g) == RAFTING_ROLE_LEADER && (g.word & W_PREPARED) &&
+                                (hbeat || (kind == RAFTING_OP_SUBMIT && nruns_of(g) > 0 && g.r0t == g.term));
+            slowOp = kind != RAFTING_OP_NONE && !fastOk;
+        }
+        const bool opHere = kind != RAFTING_OP_NONE;
+        // ---- fast op, computed tentatively (nothing is mutated until the warp agrees to stay fast) ----
+        // Leader keepAlive -> replicateLog(true) (RaftRoutine.java:53-62, Leader.java:119-126), or
+        // RaftStub.process -> Leader.acceptCommand -> replicateLog(false) (RaftStub.java:79-91, Leader.java:128-140)
+        const bool P = opHere && !slowOp;
+        const bool hbeat = kind == RAFTING_OP_TIMEOUT;
+        const unsigned rb = __ballot_sync(FULL, P && lv && state_ready(s, cfg.avail_critical_point, cfg.recovery_cool_down_ms, now));
+        const int rcnt = __popc(sub_bits(k, rb, W));
+        const bool ready = rcnt >= 1 && (1 + rcnt > (int)F / 2);             // Leader.isReady, Leader.java:52-64
+        const bool go = P && (hbeat || ready);
+        uint32_t count = RAFTING_OP_COUNT(meta); if (count == 0) count = 1;
+        const int64_t hiN = g.hi + ((go && !hbeat) ? (int64_t)count : 0);   // RocksLog.newEntry x count, same term run
+        // Leader.replicateLog for this lane's follower (Leader.java:142-245), pure part
+        int e = 0; uint64_t pm = 0; i64x2 pp = {0, 0}, lc = {0, 0}; int dInflight = 0; bool failStat = false;
+        if (go && lv) {
+            const uint64_t hbBit = hbeat ? (1ull << 4) : 0ull, incBits = (uint64_t)g.inc << 32;
+            if ((unavail >> lane) & 1ull) { failStat = true; pm = RAFTING_PLAN_UNAVAILABLE | hbBit | incBits; }
+            else if (s.inflight > RAFTING_IN_FLIGHT_LIMIT / (hbeat ? 10 : 1)) pm = RAFTING_PLAN_SKIP_INFLIGHT | hbBit | incBits;
+            else if (s.pending) {
+                pm = RAFTING_PLAN_IS | hbBit | incBits; pp.x = g.epochIndex; pp.y = g.epochTerm; lc.x = g.epochIndex; lc.y = g.commit;
+                dInflight = 1;
             } else {
-                // hand the state over through the tables, run the generic handler, take it back
-                if (lane == 0) { store_hot(T, gid, g); if (out.ballot_meta) out.ballot_meta[gi] = 0; }
-                if (lv) store_lane(T, li0, s);
-                __syncwarp(k.mask);
-                const uint32_t dirty = slow_op<W>(&ka, i, gid, r, kind, sweep, g.dirty);
-                __syncwarp(k.mask);
-                load_hot(T, gid, g); g.dirty = dirty; if (lv) load_lane(T, li0, s);
-                wroteRep = true;                            // slow_op stored every column and wrote the row's outputs
+                int64_t prevTerm = g.epochTerm, prevIndex = g.epochIndex, lastIndex;
+                const int64_t nm1 = (int64_t)((uint64_t)s.next - 1u);
+                const int64_t nextIndex = nm1 > g.epochIndex ? nm1 : g.epochIndex;
+                int64_t idx = nextIndex, len = (RAFTING_REPLICATE_LIMIT >> (hbeat ? 1 : 0)) + 1;
+                if (idx == g.epochIndex) { idx++; len--; }                   // RocksLog.batch, RocksLog.java:134-137
+                int64_t eFirst = 0, eCount = 0;
+                if (len > 0 && nruns_of(g) > 0) {
+                    const int64_t hiKey = idx + len - 1;
+                    if (idx < g.lo && g.lo <= hiKey) e = RAFTING_ERR_LOG_VACANCY;
+                    else {
+                        const int64_t a = idx > g.lo ? idx : g.lo, b = hiKey < hiN ? hiKey : hiN;
+                        if (a <= b) { eFirst = a; eCount = b - a + 1; }
+                    }
+                }
+                uint32_t cnt = 0;
+                if (eCount > 0) {
+                    if (eFirst == nextIndex) {                               // Leader.java:198-201
+                        int64_t t = g.r0t;
+                        if (eFirst < g.r0s) {                                // older term run: walk the table (rare)
+                            bool found = false;
+#pragma unroll 1
+                            for (int q = 1; q < nruns_of(g); q++) {
+                                const i64x2 run = k.runs[(size_t)q * k.G];
+                                if (!found && eFirst >= run.x) { t = run.y; found = true; }
+                            }
+                        }
+                        prevTerm = t; prevIndex = eFirst; eFirst++; eCount--;
+                    } else if (eFirst != g.epochIndex + 1) e = RAFTING_ERR_LOG_START;
+                    lastIndex = (eCount == 0) ? prevIndex : eFirst + eCount - 1;
+                    cnt = (uint32_t)eCount;
+                } else lastIndex = g.epochIndex;
+                pm = RAFTING_PLAN_AE | hbBit | ((uint64_t)cnt << 16) | incBits;
+                pp.x = prevIndex; pp.y = prevTerm; lc.x = lastIndex; lc.y = g.commit;
+                dInflight = 1;
             }
         }
-        if (!wroteRep) {
-            if (lv && out.plan_meta) out.plan_meta[gi * F + (uint32_t)lane] = 0;
-            if (lane == 0 && out.rep_meta) out.rep_meta[gi] = 0;
-            if (lane == 0 && out.ballot_meta) out.ballot_meta[gi] = 0;
+        // the AssertionErrors inside replicateLog abort the follower loop midway: keep those rows serial
+        const bool warpSlowOp = __any_sync(FULL, slowOp || e != 0);
+        if (!warpSlowOp) {
+            // ---- commit the fast op ----
+            if (P) {
+                if (hbeat) g.timer = (I64MAX - cfg.heartbeat_ms < now) ? I64MAX : now + cfg.heartbeat_ms;   // resetTimer, Leader branch
+                else { g.word = ready ? (g.word | W_READY) : (g.word & ~W_READY); if (!ready) flag_err(g, RAFTING_ERR_NOT_READY); }
+                g.hi = hiN;
+                if (go && lv) {
+                    if (now > s.lastReq) s.lastReq = now;                    // Leader.java:158
+                    if (failStat) stat_failure(s, now, true, false);         // Leader.java:241-243
+                    s.inflight += dInflight;
+                }
+            }
+            if (lv && out.plan_meta) {
+                const size_t li = gi * F + (uint32_t)lane;
+                out.plan_meta[li] = pm;
+                if (pm != 0) { out.plan_pp[li] = pp; out.plan_lc[li] = lc; out.plan_epoch[li] = g.epochIndex; }
+            }
+            if (valid && lane == 0) {
+                if (out.rep_meta) out.rep_meta[gi] = (P && !hbeat && !ready) ? ((uint32_t)RAFTING_ERR_NOT_READY << 8) : 0u;
+                if (out.ballot_meta) out.ballot_meta[gi] = 0;
+            }
+        } else {
+            // ---- the whole warp hands its state over through the tables and runs the generic handler ----
+            if (valid && lane == 0) { store_hot(T, gid, g); if (out.ballot_meta) out.ballot_meta[gi] = 0; }
+            if (lv) store_lane(T, li0, s);
+            __syncwarp();
+            uint32_t dirty = g.dirty;
+            if (valid && opHere) dirty = slow_op<W>(&ka, i, gid, r, kind, sweep, g.dirty);
+            else {
+                if (lv && out.plan_meta) out.plan_meta[gi * F + (uint32_t)lane] = 0;
+                if (valid && lane == 0 && out.rep_meta) out.rep_meta[gi] = 0;
+            }
+            __syncwarp();
+            if (valid) { load_hot(T, gid, g); g.dirty = dirty; }
+            if (lv) load_lane(T, li0, s);
         }
 
         // ================= lane events =================
-        if (hasEv && (g.word & W_ALIVE)) {
+        if (hasEv) {
             uint64_t em = 0; i64x2 etn = {0, 0}, eel = {0, 0};
-            if (lv) { em = st.ev_meta[tl]; etn = st.ev_tn[tl]; if (in.ev_el) eel = st.ev_el[tl]; }
+            const bool aliveNow = valid && (g.word & W_ALIVE) != 0;
+            if (lv && aliveNow) { em = st.ev_meta[tl]; etn = st.ev_tn[tl]; if (in.ev_el) eel = st.ev_el[tl]; }
             const uint32_t ek = RAFTING_EVM_KIND(em);
             const bool present = ek != RAFTING_EV_NONE;
             const bool isAck = ek == RAFTING_EV_AE_ACK || ek == RAFTING_EV_IS_ACK;
@@ -405,65 +474,71 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
             // per-lane classification of what the serial order would do with this lane's event
             const bool live = present && isAck && leaderLive && RAFTING_EVM_INC(em) == g.inc;
             const bool okOutcome = RAFTING_EVM_OUTCOME(em) == RAFTING_OUT_OK;
-            const bool stepDown = live && okOutcome && etn.x > g.term;
-            const bool oddKind = present && !isAck;           // vote replies / unknown kinds: generic path
+            const bool stepDown = live && okOutcome && etn.x > g.term;      // Leader.java:178-180,224-226
+            const bool oddKind = present && !isAck;                         // vote replies / unknown kinds
             // the only per-event error of an ack is "match index should not rollback" (Leadership.java:76-81):
             // known before anything is applied, and rare, so such rows keep the serial bookkeeping
-            const bool rollback = live && okOutcome && (ek == RAFTING_EV_IS_ACK ? eel.x : eel.y) < s.match;
-            unsigned anyB = __ballot_sync(k.mask, present);
-            unsigned slowB = __ballot_sync(k.mask, oddKind || stepDown || rollback);
-            if (W != 32) { anyB = (anyB >> k.sub0) & ((1u << W) - 1u); slowB = (slowB >> k.sub0) & ((1u << W) - 1u); }
-            if (anyB && slowB == 0) {
-                if (leaderLive) {
-                    const int64_t oldMatch = s.match; bool trig = false;
-                    if (live) {
-                        // ---- concurrent application of the acks (disjoint Leadership.State objects) ----
-                        s.inflight--;
-                        if (okOutcome) {
-                            const bool success = RAFTING_EVM_SUCCESS(em) != 0, snap = ek == RAFTING_EV_IS_ACK;
-                            stat_success(s, etn.y, !success);
-                            update_index(s, eel.x, snap ? eel.x : eel.y, success, snap);
-                            trig = !snap && success;
-                        } else stat_failure(s, etn.y, RAFTING_EVM_OUTCOME(em) == RAFTING_OUT_ERROR, false);
-                    }
-                    // ---- Leader.tryCommit after each successful AE ack, in lane order ----
-                    unsigned tb = __ballot_sync(k.mask, trig);
-                    if (W != 32) tb = (tb >> k.sub0) & ((1u << W) - 1u);
-                    while (tb) {
-                        const int f = __ffs(tb) - 1; tb &= tb - 1;
-                        int64_t full, major;
-                        quorum_after<W>(k, oldMatch, s.match, f, full, major);
-                        int cerr = 0;
-                        if (full > major) cerr = RAFTING_ERR_IMPOSSIBLE_REPL;
-                        else if (major != 0) {
-                            Ctx c = make_ctx(k, 0, 0);
-                            int64_t t;
-                            if (!term_at(g, c, major, t)) flag_err(g, RAFTING_ERR_TRY_COMMIT_FAILED);
-                            else {
-                                const int64_t ci = (t == g.term) ? major : full;
-                                if (ci != 0 && ci != g.commit) cerr = commit_log(g, ci);
+            const bool snap = ek == RAFTING_EV_IS_ACK;
+            const bool rollback = live && okOutcome && (snap ? eel.x : eel.y) < s.match;
+            const bool warpSlowEv = __any_sync(FULL, oddKind || stepDown || rollback);
+            if (!warpSlowEv) {
+                // ---- AE-Echo / IS-Echo of all lanes applied concurrently (disjoint Leadership.State objects,
+                //      Leader.java:174-188,218-237); acks for a dead Leader object are dropped ----
+                const int64_t oldMatch = s.match; bool trig = false;
+                if (live) {
+                    s.inflight--;
+                    if (okOutcome) {
+                        const bool success = RAFTING_EVM_SUCCESS(em) != 0;
+                        stat_success(s, etn.y, !success);
+                        update_index(s, eel.x, snap ? eel.x : eel.y, success, snap);
+                        trig = !snap && success;
+                    } else stat_failure(s, etn.y, RAFTING_EVM_OUTCOME(em) == RAFTING_OUT_ERROR, false);
+                }
+                // ---- Leader.tryCommit after each successful AE ack, in lane order (Leader.java:247-280) ----
+                const unsigned tb = __ballot_sync(FULL, trig);
+                if (tb) {
+                    const unsigned myTb = sub_bits(k, tb, W);
+#pragma unroll
+                    for (int f = 0; f < W; f++) {
+                        if (f < (int)F) {
+                            int64_t full, major;
+                            quorum_after<W>(k, oldMatch, s.match, f, full, major);
+                            if ((myTb >> f) & 1u) {
+                                int cerr = 0;
+                                if (full > major) cerr = RAFTING_ERR_IMPOSSIBLE_REPL;
+                                else if (major != 0) {
+                                    Ctx c = make_ctx(k, 0, 0);
+                                    int64_t t;
+                                    if (!term_at(g, c, major, t)) flag_err(g, RAFTING_ERR_TRY_COMMIT_FAILED);
+                                    else {
+                                        const int64_t ci = (t == g.term) ? major : full;
+                                        if (ci != 0 && ci != g.commit) cerr = commit_log(g, ci);
+                                    }
+                                }
+                                if (cerr) flag_err(g, cerr);
                             }
                         }
-                        if (cerr) flag_err(g, cerr);
                     }
                 }
-                // not a prepared Leader and only acks present: each is addressed to a dead Leadership.State -> dropped
-            } else if (anyB) {
-                if (lane == 0) store_hot(T, gid, g);
+            } else {
+                if (valid && lane == 0) store_hot(T, gid, g);
                 if (lv) store_lane(T, li0, s);
-                __syncwarp(k.mask);
-                const uint32_t dirty = slow_events<W>(&ka, i, gid, r, g.dirty);
-                __syncwarp(k.mask);
-                load_hot(T, gid, g); g.dirty = dirty; if (lv) load_lane(T, li0, s);
+                __syncwarp();
+                uint32_t dirty = g.dirty;
+                const unsigned pb = sub_bits(k, __ballot_sync(FULL, present), W);
+                if (valid && pb != 0) dirty = slow_events<W>(&ka, i, gid, r, g.dirty);
+                __syncwarp();
+                if (valid) { load_hot(T, gid, g); g.dirty = dirty; }
+                if (lv) load_lane(T, li0, s);
             }
         }
-        __syncwarp(k.mask);                                  // siblings are done with this stage before it is refilled
+        __syncwarp();                                        // siblings are done with this stage before it is refilled
     }
     cp_async_wait<0>();
 
     // ---- write back: the columns the fast path can change; the slow path stored the rest itself ----
     if (lv) store_lane(T, li0, s);
-    if (lane == 0) {
+    if (valid && lane == 0) {
         store_hot(T, gid, g);
         if (out.commit_index) out.commit_index[gid] = g.commit;
         if (out.current_term) out.current_term[gid] = g.term;
