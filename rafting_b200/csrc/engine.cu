@@ -234,23 +234,30 @@ extern "C" int rafting_group_close(rafting_engine_t* e, uint32_t gid) {
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch
 // ---------------------------------------------------------------------------------------------
-template <int W>
-static void launch_w(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
-    const uint32_t threads = 128;
-    const uint64_t total = (uint64_t)in.n * W;
-    const uint32_t blocks = (uint32_t)((total + threads - 1) / threads);
-    if (blocks == 0) return;
-    step_kernel<W><<<blocks, threads, 0, st>>>(e->T, in, out, e->d_cfg, e->dcfg);
+// follower-slot bound FT and staging depth NST per replica count: R=2 -> <1,3>, R=3 -> <2,3>,
+// R<=5 -> <4,3>, R<=9 -> <8,2>, larger clusters keep their slots in local memory and read the inbox directly
+template <int FT, int NST>
+static int launch_t(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
+    const size_t smem = NST > 0 ? (size_t)NST * sizeof(Stage<FT>) : 0;
+    static bool configured[64] = {false};
+    if (smem > 0 && !configured[e->cfg.device & 63]) {
+        CU(cudaFuncSetAttribute(step_kernel<FT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[e->cfg.device & 63] = true;
+    }
+    const uint32_t blocks = (in.n + TPB - 1) / TPB;
+    if (blocks == 0) return RAFTING_OK;
+    step_kernel<FT, NST><<<blocks, TPB, smem, st>>>(e->T, in, out, e->d_cfg, e->dcfg);
+    return RAFTING_OK;
 }
 static int launch_step(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
-    switch (e->W) {
-        case 1: launch_w<1>(e, in, out, st); break;
-        case 2: launch_w<2>(e, in, out, st); break;
-        case 4: launch_w<4>(e, in, out, st); break;
-        case 8: launch_w<8>(e, in, out, st); break;
-        case 16: launch_w<16>(e, in, out, st); break;
-        default: launch_w<32>(e, in, out, st); break;
-    }
+    int rc;
+    const uint32_t F = e->F;
+    if (F == 1) rc = launch_t<1, 3>(e, in, out, st);
+    else if (F == 2) rc = launch_t<2, 3>(e, in, out, st);
+    else if (F <= 4) rc = launch_t<4, 3>(e, in, out, st);
+    else if (F <= 8) rc = launch_t<8, 2>(e, in, out, st);
+    else rc = launch_t<32, 0>(e, in, out, st);
+    if (rc) return rc;
     e->launches++;
     CU(cudaGetLastError());
     return RAFTING_OK;

@@ -1,10 +1,9 @@
 // handlers.cuh — device-side restatement of the reference's per-event handlers (used by step_kernel.cuh).
 //
-// Replaces, for all groups at once, the reference's per-context EventLoop path
-// (M/support/EventLoop.java:87-101 + the RaftParticipant handlers and Async callbacks it runs):
-//   K1 ack_quorum_commit : AE-Echo / IS-Echo + Leadership.State.{statSuccess,statFailure,updateIndex,
-//                          majorIndices} + Leader.tryCommit + RocksLog.markCommitted
-//                          (Leader.java:174-188,218-237,247-280; Leadership.java:53-130; RocksLog.java:100-109)
+// One THREAD owns one group (RaftContext) for the whole batch: the group scalars (GS) and the
+// Leadership.State of every follower (LS[F]) live in that thread's registers.  Everything here is
+// plain sequential code per group — the reference's own execution model (one event loop turn at a
+// time per context, M/support/EventLoop.java:87-101) — and parallelism comes from the number of groups.
 //   K2 vote_tally        : RV-Echo / PV-Echo + Membership.isBetter (Candidate.java:112-134,
 //                          Follower.java:249-270, Membership.java:74-108)
 //   K3 ae_request_check  : *.appendEntries, logContains, purgeEntries, RocksLog.conflict/truncate/append
@@ -12,14 +11,7 @@
 //   K4 vote_request_check: *.preVote / requestVote / installSnapshot, logUpToDate
 //                          (Follower.java:91-153,193-207; Candidate.java:43-72; Leader.java:88-111; RaftMember.java:61-66)
 //   K5 timer_sweep       : RaftRoutine.resetTimer / electionTimeout / keepAlive (RaftRoutine.java:53-130)
-//   K6 replicate_plan    : Leader.prepareReplication / replicateLog / isReady (Leader.java:30-64,142-245)
-// fused into one kernel because they share the same per-group state and the same serial order.
-//
-// Mapping: one sub-warp of W lanes per group (W = pow2 >= F = R-1).  Lane f owns Leadership.State of
-// follower f in registers for the whole batch; every lane carries an identical copy of the group
-// scalars.  Lane events are loaded coalesced (one per lane), broadcast inside the sub-warp with
-// shuffles and applied in lane order, which is the canonical serial order.  The quorum index is a
-// rank-select over the sub-warp's matchIndex registers (shuffles), votes/readiness are ballots.
+// K1 (ack_quorum_commit) and K6 (replicate_plan) touch the follower slots and live in step_kernel.cuh.
 // Pure integer work: the roofline is HBM bandwidth, no tensor cores.
 #pragma once
 #include "tables.cuh"
@@ -39,27 +31,18 @@ struct LS {                       // Leadership.State of this lane's follower
     int64_t next, match, lastEpoch, reqSucc, reqFail, lastReq;
     int32_t inflight, rej, fail, pending;
 };
-struct RowOut {                   // outputs of the current row, written once at row end
-    uint64_t pm; i64x2 pp, lc; int64_t pe;   // per lane
-    uint64_t bm; int64_t bt; i64x2 bl;       // per group
+struct RowOut {                   // ballot emitted by the current row (written once at row end)
+    uint64_t bm; int64_t bt; i64x2 bl;
 };
 struct Ctx {
     const CfgD* cfg;
     i64x2*   runs;                // &g_runs[gid], stride G
     uint32_t gid, F, G;
-    unsigned mask;                // member mask of this sub-warp
-    int      lane, sub0;          // lane inside the sub-warp, first warp-lane of the sub-warp
-    bool     lv;                  // lane < F
     int64_t  now, draw;
 };
 struct Reply { int valid, success; int64_t term; };
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int64_t shfl64(unsigned mask, int64_t v, int src, int W) {
-    int lo = __shfl_sync(mask, (int)(uint32_t)(uint64_t)v, src, W);
-    int hi = __shfl_sync(mask, (int)(uint32_t)((uint64_t)v >> 32), src, W);
-    return (int64_t)(((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo);
-}
 __device__ __forceinline__ int role_of(const GS& g) { return (int)(g.word & W_ROLE_MASK); }
 __device__ __forceinline__ int ballot_of(const GS& g) { return (int)((g.word >> W_BALLOT_SH) & 0xff) - 1; }
 __device__ __forceinline__ int leader_of(const GS& g) { return (int)((g.word >> W_LEADER_SH) & 0xff) - 1; }
@@ -75,10 +58,6 @@ __device__ __forceinline__ int majority(const Ctx& c) { return (int)c.cfg->repli
 __device__ __forceinline__ void flag_err(GS& g, int code) {
     uint32_t cnt = (g.err >> 16) + 1; if (cnt > 0xffffu) cnt = 0xffffu;
     g.err = (cnt << 16) | (uint32_t)code;
-}
-__device__ __forceinline__ unsigned sub_ballot(const Ctx& c, bool p, int W) {
-    unsigned b = __ballot_sync(c.mask, p);
-    return W == 32 ? b : ((b >> c.sub0) & ((1u << W) - 1u));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -98,12 +77,11 @@ __device__ __forceinline__ bool term_at(const GS& g, const Ctx& c, int64_t idx, 
 }
 __device__ __noinline__ void push_run(GS& g, const Ctx& c, int64_t start, int64_t term) {
     const int n = nruns_of(g);
-    if (c.lane == 0 && n >= 1) {
+    if (n >= 1) {
         for (int k = n - 1; k >= 1; k--) c.runs[(size_t)(k + 1) * c.G] = c.runs[(size_t)k * c.G];
         i64x2 r; r.x = g.r0s; r.y = g.r0t;
         c.runs[(size_t)1 * c.G] = r;
     }
-    __syncwarp(c.mask);
     g.r0s = start; g.r0t = term;
     if (n == 0) g.lo = start;
     set_nruns(g, n + 1);
@@ -112,10 +90,7 @@ __device__ __noinline__ void pop_run(GS& g, const Ctx& c) {
     const int n = nruns_of(g);
     if (n <= 1) { set_nruns(g, 0); return; }
     i64x2 r = c.runs[(size_t)1 * c.G];
-    __syncwarp(c.mask);
-    if (c.lane == 0)
-        for (int k = 1; k <= n - 2; k++) c.runs[(size_t)k * c.G] = c.runs[(size_t)(k + 1) * c.G];
-    __syncwarp(c.mask);
+    for (int k = 1; k <= n - 2; k++) c.runs[(size_t)k * c.G] = c.runs[(size_t)(k + 1) * c.G];
     g.r0s = r.x; g.r0t = r.y;
     set_nruns(g, n - 1);
 }
@@ -140,10 +115,9 @@ __device__ __noinline__ int log_flush(GS& g, const Ctx& c, int64_t index, int64_
                     i64x2 r = c.runs[(size_t)k * c.G];
                     if (keep == n && r.x <= index) {
                         keep = k + 1;
-                        if (c.lane == 0) { r.x = index; c.runs[(size_t)k * c.G] = r; }
+                        r.x = index; c.runs[(size_t)k * c.G] = r;
                     }
                 }
-                __syncwarp(c.mask);
                 set_nruns(g, keep);
             }
             g.lo = index;
@@ -280,155 +254,8 @@ __device__ __forceinline__ int commit_log(GS& g, int64_t ci) {
     return 0;
 }
 
-// Leader.tryCommit + Leadership.State.majorIndices — Leader.java:247-280, Leadership.java:116-130.
-// Rank-select over the sub-warp's matchIndex registers: the element of rank F/2 (ties broken by
-// lane) is sorted[F/2]; the minimum is sorted[0].
-template <int W>
-__device__ __forceinline__ int try_commit(GS& g, const Ctx& c, int64_t myMatch) {
-    const int F = (int)c.F;
-    int64_t full = I64MAX; int rank = 0;
-#pragma unroll
-    for (int j = 0; j < W; j++) {
-        int64_t mj = shfl64(c.mask, myMatch, j, W);
-        if (j < F) {
-            full = mj < full ? mj : full;
-            rank += (mj < myMatch) || (mj == myMatch && j < c.lane);
-        }
-    }
-    unsigned sel = sub_ballot(c, c.lv && rank == F / 2, W);
-    int64_t major = shfl64(c.mask, myMatch, __ffs(sel) - 1, W);
-    if (full > major) return RAFTING_ERR_IMPOSSIBLE_REPL;
-    if (major != 0) {
-        int64_t t;
-        if (!term_at(g, c, major, t)) { flag_err(g, RAFTING_ERR_TRY_COMMIT_FAILED); return 0; }
-        int64_t ci = (t == g.term) ? major : full;
-        if (ci != 0 && ci != g.commit) return commit_log(g, ci);
-    }
-    return 0;
-}
-
-// Leader.prepareReplication + replicateLog — Leader.java:30-50,142-245.  Lane-parallel: each lane
-// plans its own follower; the (unreachable under the store invariants) AssertionErrors of
-// RocksLog.batch abort the followers after the failing one, as the sequential loop would.
-template <int W>
-__device__ __forceinline__ int replicate_log(GS& g, const Ctx& c, RowOut& ro, LS& s, bool heartbeat, uint64_t unavail) {
-    if (!(g.word & W_PREPARED)) {
-        int64_t li, lt; last_or_epoch(g, li, lt);
-        s.next = (int64_t)((uint64_t)li + 1u); s.match = 0; s.lastEpoch = g.epochIndex;
-        s.reqSucc = 0; s.reqFail = 0; s.lastReq = 0; s.inflight = 0; s.rej = 0; s.fail = 0; s.pending = 0;
-        g.word |= W_PREPARED;
-    }
-    const int64_t epochIndex = g.epochIndex, epochTerm = g.epochTerm, leaderCommit = g.commit, now = c.now;
-    const uint64_t hb = heartbeat ? (1ull << 4) : 0ull;
-    const uint64_t incBits = (uint64_t)g.inc << 32;
-    // tentative per-lane result
-    int e = 0; uint64_t pm = 0; i64x2 pp = {0, 0}, lc = {0, 0};
-    int dInflight = 0; bool fail = false;
-    if (c.lv) {
-        if ((unavail >> c.lane) & 1ull) { fail = true; pm = RAFTING_PLAN_UNAVAILABLE | hb | incBits; }
-        else if (s.inflight > RAFTING_IN_FLIGHT_LIMIT / (heartbeat ? 10 : 1)) pm = RAFTING_PLAN_SKIP_INFLIGHT | hb | incBits;
-        else if (s.pending) {
-            pm = RAFTING_PLAN_IS | hb | incBits; pp.x = epochIndex; pp.y = epochTerm; lc.x = epochIndex; lc.y = leaderCommit;
-            dInflight = 1;
-        } else {
-            int64_t prevTerm = epochTerm, prevIndex = epochIndex, lastIndex;
-            const int64_t nm1 = (int64_t)((uint64_t)s.next - 1u);
-            const int64_t nextIndex = nm1 > epochIndex ? nm1 : epochIndex;
-            const int fetch = RAFTING_REPLICATE_LIMIT >> (heartbeat ? 1 : 0);
-            int64_t idx = nextIndex, len = fetch + 1;
-            if (idx == epochIndex) { idx++; len--; }                         // RocksLog.java:134-137
-            int64_t eFirst = 0, eCount = 0;
-            if (len > 0 && nruns_of(g) > 0) {
-                const int64_t hiKey = idx + len - 1;
-                if (idx < g.lo && g.lo <= hiKey) e = RAFTING_ERR_LOG_VACANCY; // RocksLog.java:161-163
-                else {
-                    const int64_t a = idx > g.lo ? idx : g.lo, b = hiKey < g.hi ? hiKey : g.hi;
-                    if (a <= b) { eFirst = a; eCount = b - a + 1; }
-                }
-            }
-            if (!e) {
-                uint32_t count = 0;
-                if (eCount > 0) {
-                    if (eFirst == nextIndex) {                               // Leader.java:198-201
-                        int64_t t = 0; term_at(g, c, eFirst, t);
-                        prevTerm = t; prevIndex = eFirst; eFirst++; eCount--;
-                    } else if (eFirst != epochIndex + 1) e = RAFTING_ERR_LOG_START;   // :202-204
-                    lastIndex = (eCount == 0) ? prevIndex : eFirst + eCount - 1;
-                    count = (uint32_t)eCount;
-                } else lastIndex = epochIndex;                               // :210-212
-                if (!e) {
-                    pm = RAFTING_PLAN_AE | hb | ((uint64_t)count << 16) | incBits;
-                    pp.x = prevIndex; pp.y = prevTerm; lc.x = lastIndex; lc.y = leaderCommit;
-                    dInflight = 1;
-                }
-            }
-        }
-    }
-    const unsigned errs = sub_ballot(c, c.lv && e != 0, W);
-    const int fe = errs ? __ffs(errs) - 1 : W;                               // first failing follower
-    if (c.lv && c.lane <= fe) {
-        if (now > s.lastReq) s.lastReq = now;                                // Leader.java:158
-        if (c.lane < fe) {
-            if (fail) stat_failure(s, now, true, false);                     // :241-243
-            s.inflight += dInflight;
-            ro.pm = pm; ro.pp = pp; ro.lc = lc; ro.pe = epochIndex;
-        }
-    }
-    if (errs) return __shfl_sync(c.mask, e, fe, W);
-    return 0;
-}
-
-template <int W>
-__device__ __forceinline__ bool leader_ready(GS& g, const Ctx& c, const LS& s, int32_t crit, int64_t cool) {   // Leader.java:52-64
-    bool r = c.lv && state_ready(s, crit, cool, c.now);
-    int cnt = __popc(sub_ballot(c, r, W));
-    // the Java loop only returns true from inside `isReady(..) && ++ready > half`: at least one follower must be ready
-    bool ready = (g.word & W_PREPARED) && cnt >= 1 && (1 + cnt > (int)c.F / 2);
-    g.word = ready ? (g.word | W_READY) : (g.word & ~W_READY);
-    return ready;
-}
-
-// RaftStub.process -> Leader.acceptCommand -> RocksLog.newEntry — RaftStub.java:79-91, Leader.java:128-140, RocksLog.java:82-89
-template <int W>
-__device__ __forceinline__ int op_submit(GS& g, const Ctx& c, RowOut& ro, LS& s, uint32_t count, uint64_t unavail) {
-    if (role_of(g) != RAFTING_ROLE_LEADER) return RAFTING_ERR_NOT_LEADER;
-    if (!leader_ready<W>(g, c, s, c.cfg->avail_critical_point, c.cfg->recovery_cool_down_ms)) return RAFTING_ERR_NOT_READY;
-    if (count == 0) count = 1;
-    const bool has = nruns_of(g) > 0;
-    if (!has && g.epochIndex != 0) return RAFTING_ERR_LOG_SHAPE;
-    if ((!has || g.r0t != g.term) && nruns_of(g) >= KRUNS) return RAFTING_ERR_TERM_RUNS_OVERFLOW;
-    const int64_t index = has ? g.hi + 1 : 1;
-    if (has && g.r0t == g.term) g.hi = index + count - 1;
-    else { push_run(g, c, index, g.term); g.hi = index + count - 1; }
-    return replicate_log<W>(g, c, ro, s, false, unavail);
-}
-
-// RaftRoutine.keepAlive / electionTimeout + onTimeout — RaftRoutine.java:53-77, Leader.java:119-126,
-// Follower.java:156-168,223-279, Candidate.java:82-88
-template <int W>
-__device__ __forceinline__ int op_timeout(GS& g, const Ctx& c, RowOut& ro, LS& s, uint64_t unavail) {
-    if (role_of(g) == RAFTING_ROLE_LEADER) {
-        reset_timer(g, c, false, false);
-        return replicate_log<W>(g, c, ro, s, true, unavail);
-    }
-    if (!(g.timer > 0)) return 0;
-    g.timer = RAFTING_TIMER_TIMEOUT;
-    if (role_of(g) == RAFTING_ROLE_FOLLOWER && c.cfg->pre_vote) {
-        const int64_t t = g.term;
-        int err = switch_to(g, c, ro, RAFTING_ROLE_FOLLOWER, g.term, ballot_of(g));
-        if (err) return err;
-        if (role_of(g) == RAFTING_ROLE_FOLLOWER && g.term == t) {            // prepareElection
-            g.word |= W_TIMEOUT_DET;
-            g.votes = 1;
-            emit_ballot(g, c, ro, RAFTING_BALLOT_PREVOTE, (int64_t)((uint64_t)g.term + 1u));
-        }
-        return 0;
-    }
-    return switch_to(g, c, ro, RAFTING_ROLE_CANDIDATE, (int64_t)((uint64_t)g.term + 1u), (int)c.cfg->local_slot);
-}
-
 // ---------------------------------------------------------------------------------------------
-// inbound requests (compiled only into the REQ variant of the kernel)
+// inbound requests
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int log_contains(const GS& g, const Ctx& c, int64_t index, int64_t term) {   // Follower.java:177-191
     if (index == 0 && term == 0) return 1;
