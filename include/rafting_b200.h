@@ -392,6 +392,7 @@ int rafting_allgather_commit(rafting_engine_t* e, int64_t* host_out /* [world*G]
 /* introspection used by bench/tests */
 int rafting_engine_stream(rafting_engine_t* e, void** cuda_stream);
 int rafting_engine_counters(rafting_engine_t* e, uint64_t* kernel_launches, uint64_t* events_processed);
+int64_t rafting_backoff_step(int32_t recent_rejection);   /* integer form of round(ln(e + r)), Leadership.java:105 */
 int rafting_abi_sizes(uint32_t* out, uint32_t n);   /* sizeof of the ABI structs as compiled, for binding self-checks */
 
 #ifdef __cplusplus

@@ -605,6 +605,8 @@ extern "C" int rafting_engine_counters(rafting_engine_t* e, uint64_t* launches, 
     if (events) *events = e->events;
     return RAFTING_OK;
 }
+// the kernel's integer form of round(ln(e + r)) (Leadership.java:105), exposed so a CPU test can check it against libm
+extern "C" int64_t rafting_backoff_step(int32_t r) { return rafting::backoff_step(r); }
 // compile-time layout facts for tests/test_abi.py
 extern "C" int rafting_abi_sizes(uint32_t* out, uint32_t n) {
     const uint32_t v[] = {(uint32_t)sizeof(rafting_cfg_t), (uint32_t)sizeof(rafting_inbox_t), (uint32_t)sizeof(rafting_outbox_t),

@@ -154,7 +154,7 @@ __device__ __forceinline__ bool state_ready(const LS& s, int32_t crit, int64_t c
 }
 // round(ln(e + r)) as an integer threshold table (Leadership.java:105); verified against libm by
 // tests/test_backoff_table.py for every boundary and every r < 2^16
-__device__ __forceinline__ int64_t backoff_step(int32_t r) {
+__host__ __device__ __forceinline__ int64_t backoff_step(int32_t r) {
     if (r < 0) return 0;   // unreachable: ln of a negative argument is NaN, Math.round(NaN) == 0
     if (r <= 1) return 1;        if (r <= 9) return 2;         if (r <= 30) return 3;
     if (r <= 87) return 4;       if (r <= 241) return 5;       if (r <= 662) return 6;
