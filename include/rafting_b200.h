@@ -362,7 +362,14 @@ int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_
                   rafting_lease_t* out);
 int rafting_step (rafting_engine_t* e, rafting_lease_t* lease);          /* synchronous         */
 int rafting_step_begin(rafting_engine_t* e, rafting_lease_t* lease);     /* async: enqueue      */
-int rafting_step_wait (rafting_engine_t* e, rafting_lease_t* lease);     /* async: outbox ready */
+int rafting_step_wait (rafting_engine_t* e, rafting_lease_t* lease);     /* async: outbox ready; ends the lease */
+/* Up to TWO leases may be outstanding (two slots): begin(A); fill B; begin(B); wait(A); ... overlaps
+   the H2D of one step, the kernel of another and the D2H of a third.
+   Caller-owned buffers (e.g. the transport's pinned receive pool, north_star "Netty feeds pinned
+   staging buffers"): same pipeline, host pointers supplied by the caller; pin them for real overlap. */
+int rafting_step_begin_host(rafting_engine_t* e, uint32_t slot /* 0|1 */, const rafting_inbox_t* in_host,
+                            const rafting_outbox_t* out_host);
+int rafting_step_wait_slot (rafting_engine_t* e, uint32_t slot);
 
 /* device path: inbox/outbox columns already resident in HBM (pointers are device pointers).
    `stream` is a cudaStream_t (0 = engine's stream). No host copies, no sync. */

@@ -59,6 +59,7 @@ static int nccl_load() {
 // one staged column: pinned host + device copies of the same extent
 struct Col { void* h = nullptr; void* d = nullptr; size_t cap = 0; };
 
+struct HostPath;
 struct rafting_engine {
     rafting_cfg_t cfg;
     CfgD dcfg;
@@ -71,12 +72,7 @@ struct rafting_engine {
     int rank = 0, world = 1;
     nccl_comm_t comm = nullptr;
     int64_t* gather_host = nullptr;
-    // lease staging
-    Col c_gids, c_row_now, c_op_meta, c_op_nr, c_op_ab, c_op_cd, c_op_e, c_ent, c_ev_meta, c_ev_tn, c_ev_el;
-    Col o_rep_meta, o_rep_term, o_plan_meta, o_plan_pp, o_plan_lc, o_plan_epoch, o_ballot_meta, o_ballot_term, o_ballot_last;
-    Col o_commit, o_term, o_role, o_inc, o_err;
-    bool leased = false, inflight = false;
-    uint32_t l_rows = 0, l_n = 0, l_ent = 0; bool l_list = false;
+    struct HostPath* host = nullptr;  // slots, copy streams (created on first use)
     uint64_t launches = 0, events = 0;
     std::vector<void*> dev_allocs;
     std::vector<size_t> dev_bytes;
@@ -109,6 +105,7 @@ static int dalloc(rafting_engine* e, T** p, size_t count) {
     return 0;
 }
 
+static void rafting_hostpath_release(rafting_engine* e);
 extern "C" uint32_t rafting_abi_version(void) { return RAFTING_ABI_VERSION; }
 extern "C" const char* rafting_last_error(void) { return g_err; }
 
@@ -160,11 +157,7 @@ extern "C" int rafting_engine_destroy(rafting_engine_t* e) {
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void* p : e->dev_allocs) cudaFree(p);
     for (void* p : e->shadow) cudaFree(p);
-    Col* cols[] = {&e->c_gids, &e->c_row_now, &e->c_op_meta, &e->c_op_nr, &e->c_op_ab, &e->c_op_cd, &e->c_op_e, &e->c_ent,
-                   &e->c_ev_meta, &e->c_ev_tn, &e->c_ev_el, &e->o_rep_meta, &e->o_rep_term, &e->o_plan_meta, &e->o_plan_pp,
-                   &e->o_plan_lc, &e->o_plan_epoch, &e->o_ballot_meta, &e->o_ballot_term, &e->o_ballot_last,
-                   &e->o_commit, &e->o_term, &e->o_role, &e->o_inc, &e->o_err};
-    for (Col* c : cols) col_free(*c);
+    rafting_hostpath_release(e);
     if (e->gather_host) cudaFreeHost(e->gather_host);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -285,128 +278,231 @@ extern "C" int rafting_step_device(rafting_engine_t* e, const rafting_inbox_t* i
 }
 
 // ---------------------------------------------------------------------------------------------
-// lease / step: pinned host staging, H2D + kernel + D2H inside the call
+// host path.  Two SLOTS, each with its own device staging (and, for leases, engine-owned pinned
+// buffers), and three streams: H2D copies, the step kernel, D2H copies.  A step in slot s is
+//   s_h2d: inbox columns -> device staging          (event h2d[s])
+//   stream: wait h2d[s]; step kernel                (event kernel[s])
+//   s_d2h: wait kernel[s]; outbox columns -> host   (event done[s])
+// so while slot A's kernel runs, slot B's inputs travel up and the previous outbox travels down (PCIe
+// is full duplex).  Kernels of successive steps stay ordered on `stream`: that is the serial order.
 // ---------------------------------------------------------------------------------------------
+enum { PER_GI = 0, PER_LI = 1, PER_ACTIVE = 2, PER_ROW = 3, PER_ENT = 4, PER_G = 5 };
+struct ColDesc { size_t off; uint32_t elem; int per; };
+#define INCOL(f, elem, per) {offsetof(rafting_inbox_t, f), elem, per}
+#define OUTCOL(f, elem, per) {offsetof(rafting_outbox_t, f), elem, per}
+static const ColDesc IN_COLS[] = {
+    INCOL(gids, 4, PER_ACTIVE), INCOL(row_now, 8, PER_ROW), INCOL(op_meta, 8, PER_GI), INCOL(op_nr, 16, PER_GI),
+    INCOL(op_ab, 16, PER_GI), INCOL(op_cd, 16, PER_GI), INCOL(op_e, 8, PER_GI), INCOL(ent_terms, 8, PER_ENT),
+    INCOL(ev_meta, 8, PER_LI), INCOL(ev_tn, 16, PER_LI), INCOL(ev_el, 16, PER_LI)};
+static const ColDesc OUT_COLS[] = {
+    OUTCOL(rep_meta, 4, PER_GI), OUTCOL(rep_term, 8, PER_GI), OUTCOL(plan_meta, 8, PER_LI), OUTCOL(plan_pp, 16, PER_LI),
+    OUTCOL(plan_lc, 16, PER_LI), OUTCOL(plan_epoch, 8, PER_LI), OUTCOL(ballot_meta, 8, PER_GI), OUTCOL(ballot_term, 8, PER_GI),
+    OUTCOL(ballot_last, 16, PER_GI), OUTCOL(commit_index, 8, PER_G), OUTCOL(current_term, 8, PER_G), OUTCOL(role_word, 4, PER_G),
+    OUTCOL(incarnation, 4, PER_G), OUTCOL(err_word, 4, PER_G)};
+constexpr int N_IN = sizeof(IN_COLS) / sizeof(IN_COLS[0]), N_OUT = sizeof(OUT_COLS) / sizeof(OUT_COLS[0]);
+
+static size_t col_bytes(const ColDesc& c, size_t rows, size_t n, size_t F, size_t G, size_t nact, size_t ent) {
+    switch (c.per) {
+        case PER_GI: return rows * n * c.elem;
+        case PER_LI: return rows * n * F * c.elem;
+        case PER_ACTIVE: return nact * c.elem;
+        case PER_ROW: return rows * c.elem;
+        case PER_ENT: return ent * c.elem;
+        default: return G * c.elem;
+    }
+}
+template <typename S> static const void*& in_ptr(S* st, const ColDesc& c) { return *(const void**)((char*)st + c.off); }
+template <typename S> static void*& out_ptr(S* st, const ColDesc& c) { return *(void**)((char*)st + c.off); }
+
+struct Slot {
+    Col in[N_IN], out[N_OUT];                 // .d device staging, .h pinned host (leases only)
+    cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
+    bool leased = false, inflight = false;
+    uint32_t rows = 0, n = 0, ent = 0; bool list = false;
+};
+struct HostPath {
+    Slot slot[2];
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    bool ready = false;
+};
+static HostPath* hp(rafting_engine* e) { if (!e->host) e->host = new HostPath(); return e->host; }
+
+static int dev_reserve(Col& c, size_t bytes, bool pinned) {
+    if (bytes > c.cap || (pinned && !c.h)) {
+        if (c.h) cudaFreeHost(c.h);
+        if (c.d) cudaFree(c.d);
+        c.h = c.d = nullptr; c.cap = 0;
+        const size_t cap = bytes + bytes / 4 + 256;
+        CU(cudaMalloc(&c.d, cap));
+        if (pinned) { CU(cudaHostAlloc(&c.h, cap, cudaHostAllocDefault)); memset(c.h, 0, cap); }
+        c.cap = cap;
+    }
+    return 0;
+}
+static int hostpath_init(rafting_engine* e) {
+    HostPath* H = hp(e);
+    if (H->ready) return 0;
+    CU(cudaStreamCreateWithFlags(&H->s_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&H->s_d2h, cudaStreamNonBlocking));
+    for (Slot& s : H->slot) {
+        CU(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.ev_kernel, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    }
+    H->ready = true;
+    return 0;
+}
+static void hostpath_free(rafting_engine* e) {
+    HostPath* H = hp(e);
+    for (Slot& s : H->slot) {
+        for (Col& c : s.in) col_free(c);
+        for (Col& c : s.out) col_free(c);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
+    if (H->s_h2d) cudaStreamDestroy(H->s_h2d);
+    if (H->s_d2h) cudaStreamDestroy(H->s_d2h);
+}
+
+static void rafting_hostpath_release(rafting_engine* e) { if (e->host) { hostpath_free(e); delete e->host; e->host = nullptr; } }
+
+// enqueue one step in `slot`: `in` / `out` hold HOST pointers (pinned for real overlap)
+static int step_enqueue(rafting_engine* e, uint32_t slot, const rafting_inbox_t* in, const rafting_outbox_t* out) {
+    HostPath* H = hp(e); Slot& S = H->slot[slot];
+    if (S.inflight) return fail(RAFTING_E_BUSY, "slot %u has a step in flight", slot);
+    const size_t rows = in->rows, F = e->F, G = e->G;
+    const bool list = in->gids != nullptr;
+    const size_t n = list ? in->n_active : G;
+    if (rows == 0 || rows > e->cfg.max_rows) return fail(RAFTING_E_CAPACITY, "rows %zu beyond max_rows %u", rows, e->cfg.max_rows);
+    if (n > G) return fail(RAFTING_E_CAPACITY, "n_active > max_groups");
+    if (in->ent_count > e->cfg.entry_pool_cap) return fail(RAFTING_E_CAPACITY, "ent_count > entry_pool_cap");
+    bool sweep = false;
+    if (in->row_now) for (size_t r = 0; r < rows; r++) sweep |= in->row_now[r] != 0;
+    if (in->op_meta && !in->op_nr) return fail(RAFTING_E_INVAL, "op_meta without op_nr");
+    if (in->ev_meta && !in->ev_tn) return fail(RAFTING_E_INVAL, "ev_meta without ev_tn");
+    rafting_inbox_t din = *in; rafting_outbox_t dout; memset(&dout, 0, sizeof(dout));
+    // ---- H2D ----
+    for (int k = 0; k < N_IN; k++) {
+        const ColDesc& c = IN_COLS[k];
+        const void* hsrc = in_ptr(in, c);
+        bool use = hsrc != nullptr;
+        if (c.per == PER_GI && !in->op_meta) use = false;                    // op family absent
+        if (c.per == PER_LI && !in->ev_meta) use = false;                    // event family absent
+        if (c.per == PER_ROW && !sweep) use = false;
+        if (c.per == PER_ENT && (in->ent_count == 0 || !in->op_meta)) use = false;
+        const size_t bytes = use ? col_bytes(c, rows, n, F, G, in->n_active, in->ent_count) : 0;
+        if (!use || bytes == 0) { in_ptr(&din, c) = nullptr; continue; }
+        int rc = dev_reserve(S.in[k], bytes, false); if (rc) return rc;
+        CU(cudaMemcpyAsync(S.in[k].d, hsrc, bytes, cudaMemcpyHostToDevice, H->s_h2d));
+        in_ptr(&din, c) = S.in[k].d;
+    }
+    CU(cudaEventRecord(S.ev_h2d, H->s_h2d));
+    // ---- kernel ----
+    const bool ops = din.op_meta || din.row_now;
+    for (int k = 0; k < N_OUT; k++) {
+        const ColDesc& c = OUT_COLS[k];
+        void* hdst = out_ptr(out, c);
+        bool use = hdst != nullptr;
+        const bool repOrPlan = c.off <= offsetof(rafting_outbox_t, plan_epoch);
+        if (repOrPlan && !ops) use = false;                                  // nothing can produce replies / plans
+        if (!use) continue;
+        int rc = dev_reserve(S.out[k], col_bytes(c, rows, n, F, G, 0, 0), false); if (rc) return rc;
+        out_ptr(&dout, c) = S.out[k].d;
+    }
+    CU(cudaStreamWaitEvent(e->stream, S.ev_h2d, 0));
+    InboxD di; OutboxD dov;
+    to_dev_views(&din, &dout, e->G, di, dov);
+    int rc = launch_step(e, di, dov, e->stream); if (rc) return rc;
+    CU(cudaEventRecord(S.ev_kernel, e->stream));
+    // ---- D2H ----
+    CU(cudaStreamWaitEvent(H->s_d2h, S.ev_kernel, 0));
+    for (int k = 0; k < N_OUT; k++) {
+        const ColDesc& c = OUT_COLS[k];
+        void* dsrc = out_ptr(&dout, c);
+        if (!dsrc) continue;
+        CU(cudaMemcpyAsync(out_ptr(out, c), dsrc, col_bytes(c, rows, n, F, G, 0, 0), cudaMemcpyDeviceToHost, H->s_d2h));
+    }
+    CU(cudaEventRecord(S.ev_done, H->s_d2h));
+    S.inflight = true;
+    return RAFTING_OK;
+}
+static int slot_wait(rafting_engine* e, uint32_t slot) {
+    Slot& S = hp(e)->slot[slot];
+    if (!S.inflight) return RAFTING_OK;
+    CU(cudaEventSynchronize(S.ev_done));
+    S.inflight = false;
+    return RAFTING_OK;
+}
+
+extern "C" int rafting_step_begin_host(rafting_engine_t* e, uint32_t slot, const rafting_inbox_t* in_host, const rafting_outbox_t* out_host) {
+    if (!e || !in_host || !out_host || slot > 1) return fail(RAFTING_E_INVAL, "bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    int rc = hostpath_init(e); if (rc) return rc;
+    return step_enqueue(e, slot, in_host, out_host);
+}
+extern "C" int rafting_step_wait_slot(rafting_engine_t* e, uint32_t slot) {
+    if (!e || slot > 1) return fail(RAFTING_E_INVAL, "bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    return slot_wait(e, slot);
+}
+
+// lease = engine-owned pinned columns of a free slot
 extern "C" int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_t ent_count, rafting_lease_t* out) {
     if (!e || !out) return fail(RAFTING_E_INVAL, "null argument");
-    if (e->inflight) return fail(RAFTING_E_BUSY, "a step is in flight");
     if (rows == 0 || rows > e->cfg.max_rows) return fail(RAFTING_E_CAPACITY, "rows %u > max_rows %u", rows, e->cfg.max_rows);
     if (n_active > e->G) return fail(RAFTING_E_CAPACITY, "n_active > max_groups");
     if (ent_count > e->cfg.entry_pool_cap) return fail(RAFTING_E_CAPACITY, "ent_count > entry_pool_cap");
     CU(cudaSetDevice(e->cfg.device));
-    const size_t n = n_active ? n_active : e->G, R = rows, F = e->F, G = e->G;
-    int rc;
-    if ((rc = col_reserve(e->c_gids, n_active * 4ull)) || (rc = col_reserve(e->c_row_now, R * 8)) ||
-        (rc = col_reserve(e->c_op_meta, R * n * 8)) || (rc = col_reserve(e->c_op_nr, R * n * 16)) ||
-        (rc = col_reserve(e->c_op_ab, R * n * 16)) || (rc = col_reserve(e->c_op_cd, R * n * 16)) ||
-        (rc = col_reserve(e->c_op_e, R * n * 8)) || (rc = col_reserve(e->c_ent, (size_t)ent_count * 8 + 8)) ||
-        (rc = col_reserve(e->c_ev_meta, R * n * F * 8)) || (rc = col_reserve(e->c_ev_tn, R * n * F * 16)) ||
-        (rc = col_reserve(e->c_ev_el, R * n * F * 16)) ||
-        (rc = col_reserve(e->o_rep_meta, R * n * 4)) || (rc = col_reserve(e->o_rep_term, R * n * 8)) ||
-        (rc = col_reserve(e->o_plan_meta, R * n * F * 8)) || (rc = col_reserve(e->o_plan_pp, R * n * F * 16)) ||
-        (rc = col_reserve(e->o_plan_lc, R * n * F * 16)) || (rc = col_reserve(e->o_plan_epoch, R * n * F * 8)) ||
-        (rc = col_reserve(e->o_ballot_meta, R * n * 8)) || (rc = col_reserve(e->o_ballot_term, R * n * 8)) ||
-        (rc = col_reserve(e->o_ballot_last, R * n * 16)) ||
-        (rc = col_reserve(e->o_commit, G * 8)) || (rc = col_reserve(e->o_term, G * 8)) ||
-        (rc = col_reserve(e->o_role, G * 4)) || (rc = col_reserve(e->o_inc, G * 4)) || (rc = col_reserve(e->o_err, G * 4)))
-        return rc;
+    int rc = hostpath_init(e); if (rc) return rc;
+    HostPath* H = hp(e);
+    int sl = -1;
+    for (int k = 0; k < 2; k++) if (!H->slot[k].leased && !H->slot[k].inflight) { sl = k; break; }
+    if (sl < 0) return fail(RAFTING_E_BUSY, "both slots are leased or in flight");
+    Slot& S = H->slot[sl];
+    const size_t n = n_active ? n_active : e->G, F = e->F, G = e->G;
     memset(out, 0, sizeof(*out));
-    rafting_inbox_t& in = out->in;
-    in.rows = rows; in.n_active = n_active;
-    in.gids = n_active ? (const uint32_t*)e->c_gids.h : nullptr;
-    in.row_now = (const int64_t*)e->c_row_now.h;
-    memset(e->c_row_now.h, 0, R * 8);
-    in.op_meta = (const uint64_t*)e->c_op_meta.h; in.op_nr = (const rafting_i64x2_t*)e->c_op_nr.h;
-    in.op_ab = (const rafting_i64x2_t*)e->c_op_ab.h; in.op_cd = (const rafting_i64x2_t*)e->c_op_cd.h;
-    in.op_e = (const int64_t*)e->c_op_e.h; in.ent_terms = (const int64_t*)e->c_ent.h; in.ent_count = ent_count;
-    in.ev_meta = (const uint64_t*)e->c_ev_meta.h; in.ev_tn = (const rafting_i64x2_t*)e->c_ev_tn.h;
-    in.ev_el = (const rafting_i64x2_t*)e->c_ev_el.h;
-    rafting_outbox_t& o = out->out;
-    o.rep_meta = (uint32_t*)e->o_rep_meta.h; o.rep_term = (int64_t*)e->o_rep_term.h;
-    o.plan_meta = (uint64_t*)e->o_plan_meta.h; o.plan_pp = (rafting_i64x2_t*)e->o_plan_pp.h;
-    o.plan_lc = (rafting_i64x2_t*)e->o_plan_lc.h; o.plan_epoch = (int64_t*)e->o_plan_epoch.h;
-    o.ballot_meta = (uint64_t*)e->o_ballot_meta.h; o.ballot_term = (int64_t*)e->o_ballot_term.h;
-    o.ballot_last = (rafting_i64x2_t*)e->o_ballot_last.h;
-    o.commit_index = (int64_t*)e->o_commit.h; o.current_term = (int64_t*)e->o_term.h;
-    o.role_word = (uint32_t*)e->o_role.h; o.incarnation = (uint32_t*)e->o_inc.h; o.err_word = (uint32_t*)e->o_err.h;
-    e->leased = true; e->l_rows = rows; e->l_n = (uint32_t)n; e->l_ent = ent_count; e->l_list = n_active != 0;
+    for (int k = 0; k < N_IN; k++) {
+        const ColDesc& c = IN_COLS[k];
+        const size_t bytes = col_bytes(c, rows, n, F, G, n_active, (size_t)ent_count + 1);
+        if ((rc = dev_reserve(S.in[k], bytes, true))) return rc;
+        in_ptr(&out->in, c) = (c.per == PER_ACTIVE && n_active == 0) ? nullptr : S.in[k].h;
+    }
+    memset(S.in[1].h, 0, (size_t)rows * 8);                                  // row_now: no sweep unless the caller sets it
+    for (int k = 0; k < N_OUT; k++) {
+        const ColDesc& c = OUT_COLS[k];
+        if ((rc = dev_reserve(S.out[k], col_bytes(c, rows, n, F, G, 0, 0), true))) return rc;
+        out_ptr(&out->out, c) = S.out[k].h;
+    }
+    out->in.rows = rows; out->in.n_active = n_active; out->in.ent_count = ent_count;
+    S.leased = true; S.rows = rows; S.n = (uint32_t)n; S.ent = ent_count; S.list = n_active != 0;
     return RAFTING_OK;
 }
-
-// A lease column the caller set to NULL is "absent": not copied, and the kernel sees NULL.
-#define H2D(col, hostptr, bytes)                                                                         \
-    ((hostptr) ? (cudaMemcpyAsync((col).d, (col).h, (bytes), cudaMemcpyHostToDevice, e->stream), (col).d) : nullptr)
-
+static int lease_slot(rafting_engine* e, const rafting_lease_t* L) {
+    HostPath* H = hp(e);
+    for (int k = 0; k < 2; k++)
+        if (H->slot[k].leased && L->out.commit_index == (int64_t*)H->slot[k].out[9].h) return k;
+    return -1;
+}
 extern "C" int rafting_step_begin(rafting_engine_t* e, rafting_lease_t* L) {
     if (!e || !L) return fail(RAFTING_E_INVAL, "null argument");
-    if (!e->leased) return fail(RAFTING_E_INVAL, "no lease outstanding");
-    if (e->inflight) return fail(RAFTING_E_BUSY, "a step is in flight");
-    if (L->in.rows == 0 || L->in.rows > e->l_rows) return fail(RAFTING_E_CAPACITY, "rows beyond the lease");
-    if (L->in.ent_count > e->l_ent) return fail(RAFTING_E_CAPACITY, "ent_count beyond the lease");
     CU(cudaSetDevice(e->cfg.device));
-    const size_t n = e->l_n, R = L->in.rows, F = e->F, G = e->G;
-    const rafting_inbox_t& in = L->in;
-    InboxD di; memset(&di, 0, sizeof(di));
-    di.rows = in.rows; di.n = (uint32_t)n;
-    di.gids = e->l_list ? (const uint32_t*)H2D(e->c_gids, in.gids, n * 4) : nullptr;
-    if (e->l_list && !di.gids) return fail(RAFTING_E_INVAL, "active-list lease without gids");
-    bool sweep = false;
-    if (in.row_now) for (size_t r = 0; r < R; r++) sweep |= in.row_now[r] != 0;
-    di.row_now = sweep ? (const int64_t*)H2D(e->c_row_now, in.row_now, R * 8) : nullptr;
-    di.op_meta = (const uint64_t*)H2D(e->c_op_meta, in.op_meta, R * n * 8);
-    if (di.op_meta) {
-        di.op_nr = (const i64x2*)H2D(e->c_op_nr, in.op_nr, R * n * 16);
-        di.op_ab = (const i64x2*)H2D(e->c_op_ab, in.op_ab, R * n * 16);
-        di.op_cd = (const i64x2*)H2D(e->c_op_cd, in.op_cd, R * n * 16);
-        di.op_e = (const int64_t*)H2D(e->c_op_e, in.op_e, R * n * 8);
-        if (!di.op_nr) return fail(RAFTING_E_INVAL, "op_meta without op_nr");
-        if (in.ent_count) di.ent_terms = (const int64_t*)H2D(e->c_ent, in.ent_terms, (size_t)in.ent_count * 8);
-        di.ent_count = in.ent_count;
-    }
-    di.ev_meta = (const uint64_t*)H2D(e->c_ev_meta, in.ev_meta, R * n * F * 8);
-    if (di.ev_meta) {
-        di.ev_tn = (const i64x2*)H2D(e->c_ev_tn, in.ev_tn, R * n * F * 16);
-        di.ev_el = (const i64x2*)H2D(e->c_ev_el, in.ev_el, R * n * F * 16);
-        if (!di.ev_tn) return fail(RAFTING_E_INVAL, "ev_meta without ev_tn");
-    }
-    const rafting_outbox_t& o = L->out;
-    OutboxD dout; memset(&dout, 0, sizeof(dout));
-    const bool ops = di.op_meta || di.row_now;
-    if (o.rep_meta && ops) { dout.rep_meta = (uint32_t*)e->o_rep_meta.d; dout.rep_term = (int64_t*)e->o_rep_term.d; }
-    if (o.plan_meta && ops) {
-        dout.plan_meta = (uint64_t*)e->o_plan_meta.d; dout.plan_pp = (i64x2*)e->o_plan_pp.d;
-        dout.plan_lc = (i64x2*)e->o_plan_lc.d; dout.plan_epoch = (int64_t*)e->o_plan_epoch.d;
-    }
-    if (o.ballot_meta) { dout.ballot_meta = (uint64_t*)e->o_ballot_meta.d; dout.ballot_term = (int64_t*)e->o_ballot_term.d; dout.ballot_last = (i64x2*)e->o_ballot_last.d; }
-    if (o.commit_index) dout.commit_index = (int64_t*)e->o_commit.d;
-    if (o.current_term) dout.current_term = (int64_t*)e->o_term.d;
-    if (o.role_word) dout.role_word = (uint32_t*)e->o_role.d;
-    if (o.incarnation) dout.incarnation = (uint32_t*)e->o_inc.d;
-    if (o.err_word) dout.err_word = (uint32_t*)e->o_err.d;
-    di.flags = in.flags;
-    int rc = launch_step(e, di, dout, e->stream);
-    if (rc) return rc;
-#define D2H(col, devptr, bytes) if (devptr) cudaMemcpyAsync((col).h, (col).d, (bytes), cudaMemcpyDeviceToHost, e->stream)
-    D2H(e->o_rep_meta, dout.rep_meta, R * n * 4); D2H(e->o_rep_term, dout.rep_term, R * n * 8);
-    D2H(e->o_plan_meta, dout.plan_meta, R * n * F * 8); D2H(e->o_plan_pp, dout.plan_pp, R * n * F * 16);
-    D2H(e->o_plan_lc, dout.plan_lc, R * n * F * 16); D2H(e->o_plan_epoch, dout.plan_epoch, R * n * F * 8);
-    D2H(e->o_ballot_meta, dout.ballot_meta, R * n * 8); D2H(e->o_ballot_term, dout.ballot_term, R * n * 8);
-    D2H(e->o_ballot_last, dout.ballot_last, R * n * 16);
-    D2H(e->o_commit, dout.commit_index, G * 8); D2H(e->o_term, dout.current_term, G * 8);
-    D2H(e->o_role, dout.role_word, G * 4); D2H(e->o_inc, dout.incarnation, G * 4); D2H(e->o_err, dout.err_word, G * 4);
-#undef D2H
-    CU(cudaGetLastError());
-    e->inflight = true;
-    return RAFTING_OK;
+    const int sl = lease_slot(e, L);
+    if (sl < 0) return fail(RAFTING_E_INVAL, "not an outstanding lease");
+    Slot& S = hp(e)->slot[sl];
+    if (L->in.rows == 0 || L->in.rows > S.rows) return fail(RAFTING_E_CAPACITY, "rows beyond the lease");
+    if (L->in.ent_count > S.ent) return fail(RAFTING_E_CAPACITY, "ent_count beyond the lease");
+    if (S.list != (L->in.gids != nullptr)) return fail(RAFTING_E_INVAL, "active-list lease without gids (or the reverse)");
+    return step_enqueue(e, (uint32_t)sl, &L->in, &L->out);
 }
 extern "C" int rafting_step_wait(rafting_engine_t* e, rafting_lease_t* L) {
-    (void)L;
-    if (!e) return fail(RAFTING_E_INVAL, "null argument");
-    if (!e->inflight) return RAFTING_OK;
+    if (!e || !L) return fail(RAFTING_E_INVAL, "null argument");
     CU(cudaSetDevice(e->cfg.device));
-    CU(cudaStreamSynchronize(e->stream));
-    e->inflight = false;
-    return RAFTING_OK;
+    const int sl = lease_slot(e, L);
+    if (sl < 0) return fail(RAFTING_E_INVAL, "not an outstanding lease");
+    int rc = slot_wait(e, (uint32_t)sl);
+    hp(e)->slot[sl].leased = false;                                          // the lease ends with its step
+    return rc;
 }
 extern "C" int rafting_step(rafting_engine_t* e, rafting_lease_t* L) {
     int rc = rafting_step_begin(e, L);

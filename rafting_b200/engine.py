@@ -36,6 +36,7 @@ EXPORTS = [
     "rafting_state_export_bulk", "rafting_state_digest", "rafting_log_term", "rafting_commit_slice",
     "rafting_comm_init", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_engine_stream",
     "rafting_engine_counters", "rafting_abi_sizes", "rafting_checkpoint", "rafting_restore",
+    "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_backoff_step",
 ]
 
 
@@ -82,6 +83,8 @@ def lib():
         L.rafting_engine_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.rafting_engine_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.rafting_abi_sizes.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
+        L.rafting_step_begin_host.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.InboxC), C.POINTER(abi.OutboxC)]
+        L.rafting_step_wait_slot.argtypes = [C.c_void_p, C.c_uint32]
         L.rafting_checkpoint.argtypes = [C.c_void_p]
         L.rafting_restore.argtypes = [C.c_void_p]
         if L.rafting_abi_version() != abi.ABI_VERSION:
@@ -155,6 +158,13 @@ class Engine:
         lease.fill_from(inbox)
         lease.run()
         return lease.outbox_copy()
+
+    # ---- host path with caller-owned (pinned) buffers, two slots -------------------------------
+    def step_begin_host(self, slot: int, inbox_c: abi.InboxC, outbox_c: abi.OutboxC):
+        _check(lib().rafting_step_begin_host(self._h, slot, C.byref(inbox_c), C.byref(outbox_c)), "rafting_step_begin_host")
+
+    def step_wait_slot(self, slot: int):
+        _check(lib().rafting_step_wait_slot(self._h, slot), "rafting_step_wait_slot")
 
     # ---- device path -------------------------------------------------------------------------
     def step_device(self, inbox_c: abi.InboxC, outbox_c: abi.OutboxC, stream: int = 0):

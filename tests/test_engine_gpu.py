@@ -118,3 +118,37 @@ def test_closed_group_and_capacity_errors(engine_mod):
         e.lease(3)                       # rows > max_rows
     with pytest.raises(engine_mod.RaftingError):
         engine_mod.Engine(abi.make_cfg(replicas=1))
+
+
+def test_two_slot_host_pipeline_matches_oracle(engine_mod):
+    """rafting_step_begin_host / rafting_step_wait_slot with caller-owned buffers, two steps in flight:
+    the stream is pre-recorded (oracle run), then replayed through alternating slots without waiting for
+    the previous step, and every outbox and the final state must still equal the serial oracle run."""
+    G, R, rows, steps = 1024, 3, 4, 10
+    cfg, o, e = _pair(engine_mod, G, R, rows)
+    w1 = workload.make_wl(3, 1, G, R - 1)
+    w = workload.make_wl(3, rows, G, R - 1)
+    harness.elect_all(o, w1), harness.elect_all(e, w1)
+    inboxes, want = [], []
+    prev = None
+    for k in range(steps):
+        ib = workload.leader_inbox_host(w, k, prev)
+        prev = o.step(ib)
+        inboxes.append(ib); want.append(prev)
+    got = [abi.Outbox(rows, G, R - 1, G) for _ in range(steps)]
+    keep = []
+    for k in range(steps):
+        sl = k % 2
+        if k >= 2:
+            e.step_wait_slot(sl)
+        ic, oc = inboxes[k].as_c(), got[k].as_c()
+        keep.append((ic, oc))
+        e.step_begin_host(sl, ic, oc)
+    e.step_wait_slot(0), e.step_wait_slot(1)
+    for k in range(steps):
+        harness.assert_outbox_equal(want[k], got[k], where=f"pipelined step {k}")
+    harness.assert_states_equal(o, e, range(0, G, 13), R - 1, where="after the pipelined replay")
+    # two leases can be outstanding at once, a third is refused
+    l0, l1 = e.lease(rows), e.lease(rows)
+    with pytest.raises(engine_mod.RaftingError):
+        e.lease(rows)
