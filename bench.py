@@ -296,6 +296,11 @@ def run_engine(args):
                 e.step_device(ics[k], ocs[k], stream_ptr)
             torch.cuda.synchronize()
 
+        # untimed: touch both slots once so their device staging exists before the clock starts
+        rewind()
+        for sl in range(2):
+            e.step_begin_host(sl, host_in[sl][1], host_out[sl][1])
+        e.step_wait_slot(0); e.step_wait_slot(1)
         # (1) throughput: two slots in flight — H2D of step j+1, kernel of step j and D2H of step j-1 overlap
         rewind(); barrier()
         t0 = time.perf_counter()
