@@ -257,6 +257,8 @@ def run_engine(args):
         evs[2 + 2 * j].record(ext)
         if world > 1:
             e.allgather_commit(to_host=False)
+    if world > 1:
+        e.allgather_join()                      # the timed region ends when the last summary has been gathered
     evs[2 * K + 1].record(ext)
     torch.cuda.synchronize(); barrier()
     total_ms = evs[0].elapsed_time(evs[2 * K + 1])
@@ -355,7 +357,7 @@ def run_engine(args):
                        "acks_per_step_per_gpu": acks_per_launch,
                        "inputs": f"every step reads a distinct pre-generated inbox resident in HBM "
                                  f"({inboxes[0].nbytes() / 1e6:.0f} MB inbox + {outs[0].nbytes() / 1e6:.0f} MB outbox per step, > L2), no L2 flush needed",
-                       "collective": "ncclAllGather of commitIndex[G] after every step" if world > 1 else "none (1 GPU)",
+                       "collective": "ncclAllGather of commitIndex[G] after every step, on its own stream behind the producing kernel" if world > 1 else "none (1 GPU)",
                        "bit_exact_replay": replay_ok},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

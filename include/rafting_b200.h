@@ -394,7 +394,8 @@ int rafting_commit_slice(rafting_engine_t* e, void** dev_ptr, uint32_t* count);
 int rafting_comm_init   (rafting_engine_t* e, int rank, int world, const void* nccl_unique_id, size_t id_len);
 int rafting_comm_unique_id(void* out, size_t* len);
 int rafting_allgather_commit(rafting_engine_t* e, int64_t* host_out /* [world*G], may be NULL */,
-                             void** dev_out);
+                             void** dev_out);       /* asynchronous on its own stream unless host_out != NULL */
+int rafting_allgather_join  (rafting_engine_t* e);  /* the step stream waits for the gathers enqueued so far */
 
 /* introspection used by bench/tests */
 int rafting_engine_stream(rafting_engine_t* e, void** cuda_stream);

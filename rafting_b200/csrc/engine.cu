@@ -71,6 +71,8 @@ struct rafting_engine {
     int64_t* commit_all = nullptr;     // [world * G]; T.g_commit points at this rank's slice
     int rank = 0, world = 1;
     nccl_comm_t comm = nullptr;
+    cudaStream_t s_comm = nullptr;     // the summary all-gather runs here, off the kernels' critical path
+    cudaEvent_t ev_step = nullptr, ev_comm = nullptr;
     int64_t* gather_host = nullptr;
     struct HostPath* host = nullptr;  // slots, copy streams (created on first use)
     uint64_t launches = 0, events = 0;
@@ -154,6 +156,7 @@ extern "C" int rafting_engine_destroy(rafting_engine_t* e) {
     if (!e) return RAFTING_OK;
     cudaSetDevice(e->cfg.device);
     if (e->stream) { cudaStreamSynchronize(e->stream); }
+    if (e->s_comm) { cudaStreamSynchronize(e->s_comm); cudaStreamDestroy(e->s_comm); cudaEventDestroy(e->ev_step); cudaEventDestroy(e->ev_comm); }
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void* p : e->dev_allocs) cudaFree(p);
     for (void* p : e->shadow) cudaFree(p);
@@ -675,19 +678,39 @@ extern "C" int rafting_comm_init(rafting_engine_t* e, int rank, int world, const
     }
     return RAFTING_OK;
 }
+// The all-gather is enqueued on its own stream behind the kernel that produced the slice, so the NEXT
+// step kernel does not wait for it (the gathered vector is a monotone summary: each entry is the group's
+// commitIndex at or after the step the gather was issued for).  With host_out the call synchronises and
+// the vector is exactly the state after the last enqueued step.
 extern "C" int rafting_allgather_commit(rafting_engine_t* e, int64_t* host_out, void** dev_out) {
     if (!e) return fail(RAFTING_E_INVAL, "null argument");
     CU(cudaSetDevice(e->cfg.device));
+    if (!e->s_comm) {
+        CU(cudaStreamCreateWithFlags(&e->s_comm, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(e->ev_step, e->stream));
+    CU(cudaStreamWaitEvent(e->s_comm, e->ev_step, 0));
     if (e->world > 1) {
         if (!e->comm) return fail(RAFTING_E_NCCL, "communicator not initialised");
-        int nr = g_nccl.AllGather(e->T.g_commit, e->commit_all, e->G, /*ncclInt64*/ 4, e->comm, e->stream);
+        int nr = g_nccl.AllGather(e->T.g_commit, e->commit_all, e->G, /*ncclInt64*/ 4, e->comm, e->s_comm);
         if (nr) return fail(RAFTING_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
     }
     if (dev_out) *dev_out = e->commit_all;
     if (host_out) {
-        CU(cudaMemcpyAsync(host_out, e->commit_all, (size_t)e->world * e->G * 8, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpyAsync(host_out, e->commit_all, (size_t)e->world * e->G * 8, cudaMemcpyDeviceToHost, e->s_comm));
+        CU(cudaStreamSynchronize(e->s_comm));
     }
+    return RAFTING_OK;
+}
+// makes the step stream wait for every all-gather enqueued so far (e.g. before a timing event or a restore)
+extern "C" int rafting_allgather_join(rafting_engine_t* e) {
+    if (!e) return fail(RAFTING_E_INVAL, "null argument");
+    if (!e->s_comm) return RAFTING_OK;
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaEventRecord(e->ev_comm, e->s_comm));
+    CU(cudaStreamWaitEvent(e->stream, e->ev_comm, 0));
     return RAFTING_OK;
 }
 

@@ -36,7 +36,7 @@ EXPORTS = [
     "rafting_state_export_bulk", "rafting_state_digest", "rafting_log_term", "rafting_commit_slice",
     "rafting_comm_init", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_engine_stream",
     "rafting_engine_counters", "rafting_abi_sizes", "rafting_checkpoint", "rafting_restore",
-    "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_backoff_step",
+    "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_backoff_step", "rafting_allgather_join",
 ]
 
 
@@ -80,6 +80,7 @@ def lib():
         L.rafting_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.rafting_comm_unique_id.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         L.rafting_allgather_commit.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.rafting_allgather_join.argtypes = [C.c_void_p]
         L.rafting_engine_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.rafting_engine_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.rafting_abi_sizes.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
@@ -238,6 +239,10 @@ class Engine:
             return out
         _check(lib().rafting_allgather_commit(self._h, None, C.byref(dev)), "rafting_allgather_commit")
         return dev.value
+
+
+    def allgather_join(self):
+        _check(lib().rafting_allgather_join(self._h), "rafting_allgather_join")
 
 
 class Lease:
