@@ -284,6 +284,8 @@ typedef struct rafting_outbox {
                                       bit 30 persist-dirty | bit 31 commit-dirty                  */
     uint32_t*        incarnation;
     uint32_t*        err_word;     /* lo16 last per-event error code, hi16 error count (sticky)   */
+    rafting_i64x2_t* last_entry;   /* RaftLog.last(): (index, term); (epoch.index, epoch.term) when the store is empty
+                                      — what Follower.prepareElection / Candidate.startElection would send */
 } rafting_outbox_t;
 
 /* restored per-group state handed to group_open (StableLock.restore + RaftLog state)            */

@@ -21,7 +21,11 @@ typedef struct rafting_wl_cfg {
     uint32_t p_error_ppm;   /* RPC error / timeout                                        */
     uint32_t p_cancel_ppm;  /* canceled                                                   */
     int64_t  t0;            /* wall clock of tick 0, ms                                   */
+    uint32_t local_slot;    /* this node's slot (peer ids of inbound requests avoid it)   */
+    uint32_t _pad;
 } rafting_wl_cfg_t;
+
+#define RAFTING_WL_POOL_TERMS (256u * 50u)   /* entry-term pool of the mixed stream: 50 copies of every term < 256 */
 
 /* fills in->{op_meta,op_nr,op_ab,ev_meta,ev_tn,ev_el} (those that are non-NULL) for step `step`
    from the previous step's outbox (NULL: no acks).  on_device != 0: all pointers are device
@@ -32,6 +36,15 @@ int rafting_wl_leader_step(const rafting_wl_cfg_t* w, uint64_t step, const rafti
 /* single-row election warm-up: phase 0 TIMEOUT everywhere, 1 grant every PreVote, 2 grant every RequestVote */
 int rafting_wl_election_step(const rafting_wl_cfg_t* w, uint32_t phase, const rafting_outbox_t* prev_out,
                              const rafting_inbox_t* in, int on_device, void* stream);
+
+/* config #3 — RequestVote storm with PreVote; config #5 — mixed leader churn + InstallSnapshot catch-up.
+   Both need in->op_cd / in->op_e as well; the mixed stream also needs in->ent_terms filled by
+   rafting_wl_fill_term_pool and in->ent_count = RAFTING_WL_POOL_TERMS. */
+int rafting_wl_vote_step (const rafting_wl_cfg_t* w, uint64_t step, const rafting_outbox_t* prev_out,
+                          const rafting_inbox_t* in, int on_device, void* stream);
+int rafting_wl_mixed_step(const rafting_wl_cfg_t* w, uint64_t step, const rafting_outbox_t* prev_out,
+                          const rafting_inbox_t* in, int on_device, void* stream);
+int rafting_wl_fill_term_pool(int64_t* pool, uint32_t capacity, int on_device, void* stream);
 
 #ifdef __cplusplus
 }

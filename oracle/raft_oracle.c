@@ -955,6 +955,7 @@ static void step_group(orc_engine_t* e, const rafting_inbox_t* in, const rafting
     if (out->role_word)    out->role_word[gid] = role_word(g);
     if (out->incarnation)  out->incarnation[gid] = g->incarnation;
     if (out->err_word)     out->err_word[gid] = g->errWord;
+    if (out->last_entry)   last_or_epoch(&g->log, &out->last_entry[gid].x, &out->last_entry[gid].y);
 }
 
 typedef struct { orc_engine_t* e; const rafting_inbox_t* in; const rafting_outbox_t* out;

@@ -90,7 +90,7 @@ class OutboxC(C.Structure):
         ("plan_meta", C.c_void_p), ("plan_pp", C.c_void_p), ("plan_lc", C.c_void_p), ("plan_epoch", C.c_void_p),
         ("ballot_meta", C.c_void_p), ("ballot_term", C.c_void_p), ("ballot_last", C.c_void_p),
         ("commit_index", C.c_void_p), ("current_term", C.c_void_p), ("role_word", C.c_void_p),
-        ("incarnation", C.c_void_p), ("err_word", C.c_void_p),
+        ("incarnation", C.c_void_p), ("err_word", C.c_void_p), ("last_entry", C.c_void_p),
     ]
 
 
@@ -266,7 +266,7 @@ class Outbox:
                 ("plan_epoch", np.int64, True),
                 ("ballot_meta", np.uint64, False), ("ballot_term", np.int64, False), ("ballot_last", I64X2, False))
     GROUP_COLS = (("commit_index", np.int64), ("current_term", np.int64), ("role_word", np.uint32),
-                  ("incarnation", np.uint32), ("err_word", np.uint32))
+                  ("incarnation", np.uint32), ("err_word", np.uint32), ("last_entry", I64X2))
 
     def __init__(self, rows: int, n: int, F: int, G: int):
         self.rows, self.n, self.F, self.G = rows, n, F, G

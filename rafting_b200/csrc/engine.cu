@@ -81,18 +81,6 @@ struct rafting_engine {
     std::vector<void*> shadow;         // rafting_checkpoint copies, parallel to dev_allocs
 };
 
-static int col_reserve(Col& c, size_t bytes) {
-    if (bytes <= c.cap) return 0;
-    if (c.h) cudaFreeHost(c.h);
-    if (c.d) cudaFree(c.d);
-    c.h = c.d = nullptr; c.cap = 0;
-    size_t cap = bytes + bytes / 4 + 256;
-    CU(cudaHostAlloc(&c.h, cap, cudaHostAllocDefault));
-    CU(cudaMalloc(&c.d, cap));
-    memset(c.h, 0, cap);
-    c.cap = cap;
-    return 0;
-}
 static void col_free(Col& c) { if (c.h) cudaFreeHost(c.h); if (c.d) cudaFree(c.d); c = Col(); }
 
 template <typename T>
@@ -268,7 +256,7 @@ static void to_dev_views(const rafting_inbox_t* in, const rafting_outbox_t* out,
     dout.plan_pp = (i64x2*)out->plan_pp; dout.plan_lc = (i64x2*)out->plan_lc; dout.plan_epoch = out->plan_epoch;
     dout.ballot_meta = out->ballot_meta; dout.ballot_term = out->ballot_term; dout.ballot_last = (i64x2*)out->ballot_last;
     dout.commit_index = out->commit_index; dout.current_term = out->current_term; dout.role_word = out->role_word;
-    dout.incarnation = out->incarnation; dout.err_word = out->err_word;
+    dout.incarnation = out->incarnation; dout.err_word = out->err_word; dout.last_entry = (i64x2*)out->last_entry;
 }
 
 extern "C" int rafting_step_device(rafting_engine_t* e, const rafting_inbox_t* in, const rafting_outbox_t* out, void* stream) {
@@ -301,7 +289,7 @@ static const ColDesc OUT_COLS[] = {
     OUTCOL(rep_meta, 4, PER_GI), OUTCOL(rep_term, 8, PER_GI), OUTCOL(plan_meta, 8, PER_LI), OUTCOL(plan_pp, 16, PER_LI),
     OUTCOL(plan_lc, 16, PER_LI), OUTCOL(plan_epoch, 8, PER_LI), OUTCOL(ballot_meta, 8, PER_GI), OUTCOL(ballot_term, 8, PER_GI),
     OUTCOL(ballot_last, 16, PER_GI), OUTCOL(commit_index, 8, PER_G), OUTCOL(current_term, 8, PER_G), OUTCOL(role_word, 4, PER_G),
-    OUTCOL(incarnation, 4, PER_G), OUTCOL(err_word, 4, PER_G)};
+    OUTCOL(incarnation, 4, PER_G), OUTCOL(err_word, 4, PER_G), OUTCOL(last_entry, 16, PER_G)};
 constexpr int N_IN = sizeof(IN_COLS) / sizeof(IN_COLS[0]), N_OUT = sizeof(OUT_COLS) / sizeof(OUT_COLS[0]);
 
 static size_t col_bytes(const ColDesc& c, size_t rows, size_t n, size_t F, size_t G, size_t nact, size_t ent) {

@@ -570,6 +570,7 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
                              ((g.dirty & 1u) << 30) | (((g.dirty >> 1) & 1u) << 31);
     if (out.incarnation) out.incarnation[gid] = g.inc;
     if (out.err_word) out.err_word[gid] = g.err;
+    if (out.last_entry) { i64x2 v; last_or_epoch(g, v.x, v.y); out.last_entry[gid] = v; }
 }
 
 }  // namespace rafting

@@ -11,7 +11,7 @@ _IN_COLS = (("op_meta", 8, False), ("op_nr", 16, False), ("op_ab", 16, False), (
 _OUT_ROW = (("rep_meta", 4, False), ("rep_term", 8, False), ("plan_meta", 8, True), ("plan_pp", 16, True),
             ("plan_lc", 16, True), ("plan_epoch", 8, True), ("ballot_meta", 8, False), ("ballot_term", 8, False),
             ("ballot_last", 16, False))
-_OUT_GRP = (("commit_index", 8), ("current_term", 8), ("role_word", 4), ("incarnation", 4), ("err_word", 4))
+_OUT_GRP = (("commit_index", 8), ("current_term", 8), ("role_word", 4), ("incarnation", 4), ("err_word", 4), ("last_entry", 16))
 
 
 class DevInbox:

@@ -18,16 +18,17 @@ class WlCfg(C.Structure):
     _fields_ = [
         ("seed", C.c_uint64), ("rows", C.c_uint32), ("n", C.c_uint32), ("F", C.c_uint32), ("gid_base", C.c_uint32),
         ("max_submit", C.c_uint32), ("p_reject_ppm", C.c_uint32), ("p_error_ppm", C.c_uint32),
-        ("p_cancel_ppm", C.c_uint32), ("t0", C.c_int64),
+        ("p_cancel_ppm", C.c_uint32), ("t0", C.c_int64), ("local_slot", C.c_uint32), ("_pad", C.c_uint32),
     ]
 
 
 def make_wl(seed, rows, n, F, gid_base=0, max_submit=4, p_reject_ppm=20_000, p_error_ppm=5_000,
-            p_cancel_ppm=5_000, t0=T0_MS) -> WlCfg:
+            p_cancel_ppm=5_000, t0=T0_MS, local_slot=0) -> WlCfg:
     """Defaults = config #2 of SURVEY.md §8(d): 97 % ok/success, 2 % ok/reject, 0.5 % error, 0.5 % canceled."""
     w = WlCfg()
     w.seed, w.rows, w.n, w.F, w.gid_base = seed, rows, n, F, gid_base
     w.max_submit, w.p_reject_ppm, w.p_error_ppm, w.p_cancel_ppm, w.t0 = max_submit, p_reject_ppm, p_error_ppm, p_cancel_ppm, t0
+    w.local_slot = local_slot
     return w
 
 
@@ -38,6 +39,9 @@ def _bind():
                                              C.c_int, C.c_void_p]
         L.rafting_wl_election_step.argtypes = [C.POINTER(WlCfg), C.c_uint32, C.POINTER(abi.OutboxC), C.POINTER(abi.InboxC),
                                                C.c_int, C.c_void_p]
+        for fn in (L.rafting_wl_vote_step, L.rafting_wl_mixed_step):
+            fn.argtypes = [C.POINTER(WlCfg), C.c_uint64, C.POINTER(abi.OutboxC), C.POINTER(abi.InboxC), C.c_int, C.c_void_p]
+        L.rafting_wl_fill_term_pool.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L._wl_bound = True
     return L
 
@@ -76,4 +80,29 @@ def election_inbox_host(w: WlCfg, phase: int, prev_out: abi.Outbox | None) -> ab
     election_step(w, phase, None if prev_out is None else prev_out.as_c(), ic)
     ib.op_cd = None
     ib.op_e = None
+    return ib
+
+
+POOL_TERMS = 256 * 50
+
+
+def vote_inbox_host(w: WlCfg, step: int, prev_out: abi.Outbox | None) -> abi.Inbox:
+    """config #3 (RequestVote storm, PreVote on): one host inbox."""
+    ib = abi.Inbox(w.rows, w.n, w.F)
+    rc = _bind().rafting_wl_vote_step(C.byref(w), step, None if prev_out is None else C.byref(prev_out.as_c()),
+                                      C.byref(ib.as_c()), 0, None)
+    if rc:
+        raise RuntimeError(f"rafting_wl_vote_step rc={rc}")
+    return ib
+
+
+def mixed_inbox_host(w: WlCfg, step: int, prev_out: abi.Outbox | None) -> abi.Inbox:
+    """config #5 (mixed leader churn + InstallSnapshot catch-up): one host inbox."""
+    ib = abi.Inbox(w.rows, w.n, w.F, ent_cap=POOL_TERMS)
+    _bind().rafting_wl_fill_term_pool(ib.ent_terms.ctypes.data, POOL_TERMS, 0, None)
+    ib.ent_count = POOL_TERMS
+    rc = _bind().rafting_wl_mixed_step(C.byref(w), step, None if prev_out is None else C.byref(prev_out.as_c()),
+                                       C.byref(ib.as_c()), 0, None)
+    if rc:
+        raise RuntimeError(f"rafting_wl_mixed_step rc={rc}")
     return ib

@@ -152,3 +152,40 @@ def test_two_slot_host_pipeline_matches_oracle(engine_mod):
     l0, l1 = e.lease(rows), e.lease(rows)
     with pytest.raises(engine_mod.RaftingError):
         e.lease(rows)
+
+
+@pytest.mark.parametrize("R,G", [(5, 3000), (3, 2000)])
+def test_vote_storm_parity(engine_mod, R, G):
+    """config #3 shape at reduced size through the generic (slow-path) handlers."""
+    rows = 2
+    cfg = abi.make_cfg(replicas=R, local_slot=1, max_groups=G, max_rows=rows, entry_pool_cap=workload.POOL_TERMS)
+    o, e = binding.Oracle(cfg), engine_mod.Engine(cfg)
+    init = harness.init_array(G, terms=1 + np.arange(G) % 5)
+    init["last_index"] = 100 + np.arange(G) % 50
+    init["last_term"] = 1 + np.arange(G) % 5
+    o.open_bulk(0, init), e.open_bulk(0, init)
+    w = workload.make_wl(0x5EED0003, rows, G, R - 1, local_slot=1)
+    out = None
+    for k in range(10):
+        ib = workload.vote_inbox_host(w, k, out)
+        out = o.step(ib)
+        harness.assert_outbox_equal(out, e.step(ib), where=f"vote round {k}")
+    harness.assert_states_equal(o, e, range(0, G, 7), R - 1, where="vote storm end")
+
+
+def test_mixed_churn_parity(engine_mod):
+    """config #5 shape at reduced size: fast path and slow path interleave inside one batch."""
+    G, R, rows = 4096, 3, 4
+    cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=rows, entry_pool_cap=workload.POOL_TERMS)
+    o, e = binding.Oracle(cfg), engine_mod.Engine(cfg)
+    init = harness.init_array(G, terms=np.arange(G) % 7)
+    o.open_bulk(0, init), e.open_bulk(0, init)
+    w1 = workload.make_wl(0x5EED0005, 1, G, R - 1)
+    harness.elect_all(o, w1), harness.elect_all(e, w1)
+    w = workload.make_wl(0x5EED0005, rows, G, R - 1)
+    out = None
+    for k in range(50):
+        ib = workload.mixed_inbox_host(w, k, out)
+        out = o.step(ib)
+        harness.assert_outbox_equal(out, e.step(ib), where=f"mixed step {k}")
+    harness.assert_states_equal(o, e, range(0, G, 5), R - 1, where="mixed end")

@@ -59,3 +59,57 @@ def test_fuzz_is_deterministic_and_exercises_all_roles():
         roles |= set((out.role_word & 3).tolist())
     harness.assert_states_equal(a, b, range(G), R - 1)
     assert roles == {0, 1, 2}
+
+
+def _vote_setup(G, R, local_slot=2):
+    cfg = abi.make_cfg(replicas=R, local_slot=local_slot, max_groups=G, max_rows=2, entry_pool_cap=workload.POOL_TERMS)
+    init = harness.init_array(G, terms=1 + np.arange(G) % 5)
+    init["last_index"] = 100 + np.arange(G) % 50
+    init["last_term"] = 1 + np.arange(G) % 5
+    return cfg, init
+
+
+def test_vote_storm_stream_threads_agree_and_elects_leaders():
+    """config #3 shape at reduced size: PreVote on, 5 replicas, grant/higher-term/timeout mix."""
+    G, R = 600, 5
+    cfg, init = _vote_setup(G, R)
+    a, b = binding.Oracle(cfg), binding.Oracle(cfg)
+    a.open_bulk(0, init), b.open_bulk(0, init)
+    w = workload.make_wl(0x5EED0003, 2, G, R - 1, local_slot=2)
+    out = None
+    seen_roles = set()
+    for k in range(8):
+        ib = workload.vote_inbox_host(w, k, out)
+        out = a.step(ib, threads=1)
+        harness.assert_outbox_equal(out, b.step(ib, threads=3), where=f"vote round {k}")
+        seen_roles |= set((out.role_word & 3).tolist())
+    harness.assert_states_equal(a, b, range(G), R - 1)
+    assert seen_roles == {0, 1, 2}
+    leaders = ((out.role_word & 3) == abi.ROLE_LEADER).sum()
+    assert G * 0.2 < leaders < G
+    assert (out.current_term >= init["term"]).all()              # terms never go back
+
+
+def test_mixed_churn_stream_threads_agree_and_covers_paths():
+    """config #5 shape at reduced size: steady leaders + churn (step-down, follower AE, re-election) +
+    catch-up (flush, InstallSnapshot)."""
+    G, R, rows = 700, 3, 4
+    cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=rows, entry_pool_cap=workload.POOL_TERMS)
+    a, b = binding.Oracle(cfg), binding.Oracle(cfg)
+    init = harness.init_array(G, terms=np.arange(G) % 7)
+    a.open_bulk(0, init), b.open_bulk(0, init)
+    w1 = workload.make_wl(0x5EED0005, 1, G, R - 1)
+    harness.elect_all(a, w1), harness.elect_all(b, w1)
+    w = workload.make_wl(0x5EED0005, rows, G, R - 1)
+    out = None
+    op_kinds, plan_kinds = set(), set()
+    for k in range(40):
+        ib = workload.mixed_inbox_host(w, k, out)
+        out = a.step(ib, threads=1)
+        harness.assert_outbox_equal(out, b.step(ib, threads=2), where=f"mixed step {k}")
+        op_kinds |= set((ib.op_meta & 0xFF).ravel().tolist())
+        plan_kinds |= set((out.plan_meta & 0xF).ravel().tolist())
+    harness.assert_states_equal(a, b, range(G), R - 1)
+    assert {abi.OP_SUBMIT, abi.OP_TIMEOUT, abi.OP_AE_REQUEST, abi.OP_FLUSH} <= op_kinds
+    assert {abi.PLAN_AE, abi.PLAN_IS} <= plan_kinds
+    assert any(a.export(g).epoch_index > 0 for g in range(G))
