@@ -235,6 +235,7 @@ static int launch_t(rafting_engine* e, const InboxD& in, const OutboxD& out, cud
 }
 static int launch_step(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
     int rc;
+    if ((uint64_t)in.rows * in.n * e->F >= (1ull << 32)) return fail(RAFTING_E_CAPACITY, "rows * groups * followers must stay below 2^32 per step");
     const uint32_t F = e->F;
     if (F == 1) rc = launch_t<1, 3>(e, in, out, st);
     else if (F == 2) rc = launch_t<2, 3>(e, in, out, st);

@@ -84,7 +84,7 @@ __device__ __forceinline__ void store_lane(const Tables& T, size_t li, const LS&
 template <int FT>
 __device__ __forceinline__ bool leader_ready(GS& g, const LS (&s)[FT], int F, int32_t crit, int64_t cool, int64_t now) {
     int cnt = 0;
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
     for (int f = 0; f < FT; f++) if (f < F && state_ready(s[f], crit, cool, now)) cnt++;
     // the Java loop only returns true from inside `isReady(..) && ++ready > half` (Leader.java:55-62)
     const bool ready = (g.word & W_PREPARED) && cnt >= 1 && (1 + cnt > F / 2);
@@ -105,7 +105,7 @@ template <int FT>
 __device__ __forceinline__ int replicate_log(GS& g, const Ctx& c, LS (&s)[FT], int F, bool heartbeat, uint64_t unavail, const PlanSink& o) {
     if (!(g.word & W_PREPARED)) {                                            // prepareReplication, Leader.java:30-50
         int64_t li, lt; last_or_epoch(g, li, lt);
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
         for (int f = 0; f < FT; f++) {
             s[f].next = (int64_t)((uint64_t)li + 1u); s[f].match = 0; s[f].lastEpoch = g.epochIndex;
             s[f].reqSucc = 0; s[f].reqFail = 0; s[f].lastReq = 0; s[f].inflight = 0; s[f].rej = 0; s[f].fail = 0; s[f].pending = 0;
@@ -115,49 +115,54 @@ __device__ __forceinline__ int replicate_log(GS& g, const Ctx& c, LS (&s)[FT], i
     const int64_t epochIndex = g.epochIndex, epochTerm = g.epochTerm, leaderCommit = g.commit, now = c.now;
     const uint64_t hb = heartbeat ? (1ull << 4) : 0ull, incBits = (uint64_t)g.inc << 32;
     const int limit = RAFTING_IN_FLIGHT_LIMIT / (heartbeat ? 10 : 1);        // :162
-    const int fetch = RAFTING_REPLICATE_LIMIT >> (heartbeat ? 1 : 0);        // :194
+    const int64_t fetch = RAFTING_REPLICATE_LIMIT >> (heartbeat ? 1 : 0);    // :194
     const bool nonEmpty = nruns_of(g) > 0;
     int err = 0;
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
     for (int f = 0; f < FT; f++) {
         if (f >= F) break;
-        if (err) { put_plan(o, f, 0, 0, 0, 0, 0, 0); continue; }             // an Error aborted the follower loop
         LS& x = s[f];
-        if (now > x.lastReq) x.lastReq = now;                                // :158
-        if ((unavail >> f) & 1ull) {                                         // :241-243
-            stat_failure(x, now, true, false);
-            put_plan(o, f, RAFTING_PLAN_UNAVAILABLE | hb | incBits, 0, 0, 0, 0, epochIndex);
-            continue;
-        }
-        if (x.inflight > limit) { put_plan(o, f, RAFTING_PLAN_SKIP_INFLIGHT | hb | incBits, 0, 0, 0, 0, epochIndex); continue; }   // :163-166
-        if (x.pending) {                                                     // :168-190
-            put_plan(o, f, RAFTING_PLAN_IS | hb | incBits, epochIndex, epochTerm, epochIndex, leaderCommit, epochIndex);
-            x.inflight++;
-            continue;
-        }
-        int64_t prevTerm = epochTerm, prevIndex = epochIndex, lastIndex;     // :192
+        // ---- the AppendEntries plan, computed branch-free (most followers take this path) ----
+        // RaftLog.batch(max(nextIndex-1, epoch.index), fetch+1), RocksLog.java:131-166, over the contiguous
+        // stored range [lo, hi]; then Leader.java:196-212.  With `has` = batch non-empty, a = first returned
+        // index, b = last returned index:  prev = (a, term(a)) if a == nextIndex else epoch;
+        // entries = (prev, b];  lastIndex = has ? b : epoch.index.
         const int64_t nm1 = (int64_t)((uint64_t)x.next - 1u);
         const int64_t nextIndex = nm1 > epochIndex ? nm1 : epochIndex;       // :193
-        int64_t idx = nextIndex, len = fetch + 1;
-        if (idx == epochIndex) { idx++; len--; }                             // RocksLog.batch, RocksLog.java:134-137
-        int64_t eFirst = 0, eCount = 0;
-        if (len > 0 && nonEmpty) {
-            const int64_t hiKey = idx + len - 1;
-            if (idx < g.lo && g.lo <= hiKey) { err = RAFTING_ERR_LOG_VACANCY; put_plan(o, f, 0, 0, 0, 0, 0, 0); continue; }   // RocksLog.java:161-163
-            const int64_t a = idx > g.lo ? idx : g.lo, b = hiKey < g.hi ? hiKey : g.hi;
-            if (a <= b) { eFirst = a; eCount = b - a + 1; }
+        const bool atEpoch = nextIndex == epochIndex;
+        const int64_t idx = nextIndex + (atEpoch ? 1 : 0), len = fetch + (atEpoch ? 0 : 1);
+        const int64_t hiKey = idx + len - 1;
+        const int64_t a = idx > g.lo ? idx : g.lo, b = hiKey < g.hi ? hiKey : g.hi;
+        const bool scan = nonEmpty && len > 0;
+        const bool vacancy = scan && idx < g.lo && g.lo <= hiKey;            // RocksLog.java:161-163
+        const bool has = scan && a <= b;
+        const bool isPrev = has && a == nextIndex;                           // :198-201
+        const bool badStart = has && !isPrev && a != epochIndex + 1;         // :202-204
+        int64_t prevTerm = epochTerm;
+        if (isPrev) {
+            prevTerm = g.r0t;
+            if (a < g.r0s) { int64_t t = 0; term_at(g, c, a, t); prevTerm = t; }   // older term run: walk the table (rare)
         }
-        uint32_t count = 0;
-        if (eCount > 0) {                                                    // :196
-            if (eFirst == nextIndex) {                                       // :198-201
-                int64_t t = 0; term_at(g, c, eFirst, t);
-                prevTerm = t; prevIndex = eFirst; eFirst++; eCount--;
-            } else if (eFirst != epochIndex + 1) { err = RAFTING_ERR_LOG_START; put_plan(o, f, 0, 0, 0, 0, 0, 0); continue; }   // :202-204
-            lastIndex = (eCount == 0) ? prevIndex : eFirst + eCount - 1;     // :205-209
-            count = (uint32_t)eCount;
-        } else lastIndex = epochIndex;                                       // :210-212
-        put_plan(o, f, RAFTING_PLAN_AE | hb | ((uint64_t)count << 16) | incBits, prevIndex, prevTerm, lastIndex, leaderCommit, epochIndex);   // :216
-        x.inflight++;                                                        // :217
+        const int64_t prevIndex = isPrev ? a : epochIndex;
+        const int64_t lastIndex = has ? b : epochIndex;
+        const uint64_t count = has ? (uint64_t)(b - a + (isPrev ? 0 : 1)) : 0ull;
+        // ---- which RPC, in the order Leader.replicateLog tests them ----
+        const bool unav = ((unavail >> f) & 1ull) != 0;                      // :241-243
+        const bool skip = !unav && x.inflight > limit;                       // :163-166
+        const bool snap = !unav && !skip && x.pending != 0;                  // :168-190
+        const bool ae = !unav && !skip && !snap;
+        const int e = ae ? (vacancy ? RAFTING_ERR_LOG_VACANCY : (badStart ? RAFTING_ERR_LOG_START : 0)) : 0;
+        if (err) { put_plan(o, f, 0, 0, 0, 0, 0, 0); continue; }             // an Error already aborted the follower loop
+        if (now > x.lastReq) x.lastReq = now;                                // :158
+        if (e) { err = e; put_plan(o, f, 0, 0, 0, 0, 0, 0); continue; }
+        if (unav) stat_failure(x, now, true, false);
+        x.inflight += (snap || ae) ? 1 : 0;                                  // :173, :217
+        const uint64_t kindBits = unav ? (uint64_t)RAFTING_PLAN_UNAVAILABLE : skip ? (uint64_t)RAFTING_PLAN_SKIP_INFLIGHT
+                                  : snap ? (uint64_t)RAFTING_PLAN_IS : (uint64_t)RAFTING_PLAN_AE;
+        const uint64_t pm = kindBits | hb | incBits | (ae ? (count << 16) : 0ull);
+        const int64_t p0 = ae ? prevIndex : (snap ? epochIndex : 0), p1 = ae ? prevTerm : (snap ? epochTerm : 0);
+        const int64_t l0 = ae ? lastIndex : (snap ? epochIndex : 0), l1 = (ae || snap) ? leaderCommit : 0;
+        put_plan(o, f, pm, p0, p1, l0, l1, epochIndex);                      // :172, :216
     }
     return err;
 }
@@ -166,16 +171,16 @@ __device__ __forceinline__ int replicate_log(GS& g, const Ctx& c, LS (&s)[FT], i
 template <int FT>
 __device__ __forceinline__ int try_commit(GS& g, const Ctx& c, const LS (&s)[FT], int F) {
     int64_t full = I64MAX, major = 0;
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
     for (int a = 0; a < FT; a++) if (a < F) full = s[a].match < full ? s[a].match : full;
     if (FT == 1) major = s[0].match;
     else if (FT == 2) { if (F == 2) major = s[0].match > s[1].match ? s[0].match : s[1].match; else major = s[0].match; }
     else {
         // sorted[F/2] by rank selection (ties broken by position), small F: O(F^2) compares in registers
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
         for (int a = 0; a < FT; a++) {
             int rank = 0;
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
             for (int b = 0; b < FT; b++) if (b < F) rank += (s[b].match < s[a].match) || (s[b].match == s[a].match && b < a);
             if (a < F && rank == F / 2) major = s[a].match;
         }
@@ -357,9 +362,12 @@ __device__ __noinline__ uint32_t slow_row(const KArgs* ka, uint32_t i, uint32_t 
 // the kernel
 // ---------------------------------------------------------------------------------------------
 #ifndef RAFTING_MINBLOCKS
-#define RAFTING_MINBLOCKS 4
+#define RAFTING_MINBLOCKS 8
 #endif
-constexpr int TPB = 128;                 // threads (= groups) per block
+#ifndef RAFTING_TPB
+#define RAFTING_TPB 64
+#endif
+constexpr int TPB = RAFTING_TPB;         // threads (= groups) per block: 64K groups / 64 = 1024 blocks = 6.9 per SM (balanced)
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -403,7 +411,7 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
     GS g; LS s[FT];
     load_hot(T, gid, g); g.dirty = 0; g.electTerm = 0; g.electInc = 0; g.votes = 0;
     const size_t li0 = (size_t)gid * T.F;
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
     for (int f = 0; f < FT; f++) {
         s[f].next = s[f].match = s[f].lastEpoch = s[f].reqSucc = s[f].reqFail = s[f].lastReq = 0;
         s[f].inflight = s[f].rej = s[f].fail = s[f].pending = 0;
@@ -416,14 +424,14 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
         const uint32_t r_ = (R_);                                                                          \
         if (r_ < in.rows) {                                                                                \
             auto& st_ = stage[r_ % (NST > 0 ? NST : 1)];                                                                   \
-            const size_t gi_ = (size_t)r_ * in.n + i;                                                      \
+            const uint32_t gi_ = r_ * in.n + i;                                                            \
             if (hasOps) {                                                                                  \
                 cp_async8(&st_.op_meta[tl], in.op_meta + gi_); cp_async16(&st_.op_nr[tl], in.op_nr + gi_);  \
                 if (in.op_ab) cp_async16(&st_.op_ab[tl], in.op_ab + gi_);                                  \
             }                                                                                              \
             if (hasEv) {                                                                                   \
-                _Pragma("unroll") for (int f_ = 0; f_ < FT; f_++) if (f_ < F) {                            \
-                    const size_t li_ = gi_ * T.F + f_;                                                     \
+                _Pragma("unroll 8") for (int f_ = 0; f_ < FT; f_++) if (f_ < F) {                            \
+                    const uint32_t li_ = gi_ * T.F + f_;                                                   \
                     cp_async8(&st_.ev_meta[tl * FT + f_], in.ev_meta + li_);                               \
                     cp_async16(&st_.ev_tn[tl * FT + f_], in.ev_tn + li_);                                  \
                     if (in.ev_el) cp_async16(&st_.ev_el[tl * FT + f_], in.ev_el + li_);                    \
@@ -432,11 +440,11 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
         }                                                                                                  \
         cp_async_commit();                                                                                 \
     }
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
     for (int p = 0; p < NST - 1; p++) RAFTING_ISSUE((uint32_t)p);
 
     for (uint32_t r = 0; r < in.rows; r++) {
-        const size_t gi = (size_t)r * in.n + i;
+        const uint32_t gi = r * in.n + i;                    // rows * n * F < 2^32 is checked by the host
         RAFTING_ISSUE(r + (uint32_t)(NST > 0 ? NST - 1 : 0));
         if (STAGED) cp_async_wait<(NST > 0 ? NST - 1 : 0)>();  // row r has landed (this thread's own copies)
         const auto& st = stage[STAGED ? r % (NST > 0 ? NST : 1) : 0];
@@ -459,7 +467,7 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
             slowOp = kind != RAFTING_OP_NONE && !fastOk;
         }
         PlanSink o; o.pm = nullptr; o.pp = nullptr; o.lc = nullptr; o.pe = nullptr;
-        if (out.plan_meta) { o.pm = out.plan_meta + gi * T.F; o.pp = out.plan_pp + gi * T.F; o.lc = out.plan_lc + gi * T.F; o.pe = out.plan_epoch + gi * T.F; }
+        if (out.plan_meta) { const uint32_t pl = gi * T.F; o.pm = out.plan_meta + pl; o.pp = out.plan_pp + pl; o.lc = out.plan_lc + pl; o.pe = out.plan_epoch + pl; }
         uint32_t repMeta = 0;
         if (kind != RAFTING_OP_NONE && !slowOp) {
             // Leader keepAlive -> replicateLog(true) (RaftRoutine.java:53-62, Leader.java:119-126), or
@@ -472,20 +480,20 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
             else { uint32_t count = RAFTING_OP_COUNT(meta); if (count == 0) count = 1; g.hi += count; }
             if (go) err = replicate_log<FT>(g, c, s, F, kind == RAFTING_OP_TIMEOUT, unavail, o);
             else if (o.pm) {
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
                 for (int f = 0; f < FT; f++) if (f < F) o.pm[f] = 0;
             }
             if (err) flag_err(g, err);
             repMeta = (uint32_t)err << 8;
         } else if (!slowOp && o.pm) {
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
             for (int f = 0; f < FT; f++) if (f < F) o.pm[f] = 0;
         }
 
         // ================= lane events: classify =================
         bool anyEv = false, slowEv = false;
         if (hasEv && alive) {
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
             for (int f = 0; f < FT; f++) {
                 if (f >= F) break;
                 const uint64_t em = STAGED ? st.ev_meta[tl * FT + f] : in.ev_meta[gi * T.F + f];
@@ -500,11 +508,11 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
             if (!slowOp && out.rep_meta) out.rep_meta[gi] = repMeta;      // the op (if any) already ran inline
             if (out.ballot_meta) out.ballot_meta[gi] = 0;
             store_hot(T, gid, g);
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
             for (int f = 0; f < FT; f++) if (f < F) store_lane(T, li0 + f, s[f]);
             const uint32_t dirty = slow_row<FT>(&ka, i, gid, r, kind, sweep, (slowOp ? 1u : 0u) | (anyEv ? 2u : 0u), 0u, g.dirty);
             load_hot(T, gid, g); g.dirty = dirty;
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
             for (int f = 0; f < FT; f++) if (f < F) load_lane(T, li0 + f, s[f]);
             continue;
         }
@@ -515,7 +523,7 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
         if (anyEv) {
             const bool leaderLive = role_of(g) == RAFTING_ROLE_LEADER && (g.word & W_PREPARED);
             int bailAt = -1;
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
             for (int f = 0; f < FT; f++) {
                 if (f >= F) break;
                 const uint64_t em = STAGED ? st.ev_meta[tl * FT + f] : in.ev_meta[gi * T.F + f];
@@ -547,11 +555,11 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
             }
             if (bailAt >= 0) {
                 store_hot(T, gid, g);
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
                 for (int f = 0; f < FT; f++) if (f < F) store_lane(T, li0 + f, s[f]);
                 const uint32_t dirty = slow_row<FT>(&ka, i, gid, r, 0u, 0, 2u, (uint32_t)bailAt, g.dirty);
                 load_hot(T, gid, g); g.dirty = dirty;
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
                 for (int f = 0; f < FT; f++) if (f < F) load_lane(T, li0 + f, s[f]);
             }
         }
@@ -559,7 +567,7 @@ step_kernel(Tables T, InboxD in, OutboxD out, const CfgD* __restrict__ cfgp, Cfg
     if (STAGED) cp_async_wait<0>();
 
     // ---- write back: the columns the fast path can change; the slow path stored the rest itself ----
-#pragma unroll
+#pragma unroll (FT <= 8 ? FT : 1)
     for (int f = 0; f < FT; f++) if (f < F) store_lane(T, li0 + f, s[f]);
     store_hot(T, gid, g);
     if (out.commit_index) out.commit_index[gid] = g.commit;
