@@ -225,12 +225,18 @@ static int launch_t(rafting_engine* e, const InboxD& in, const OutboxD& out, cud
     const size_t smem = NST > 0 ? (size_t)NST * sizeof(Stage<FT>) : 0;
     static bool configured[64] = {false};
     if (smem > 0 && !configured[e->cfg.device & 63]) {
-        CU(cudaFuncSetAttribute(step_kernel<FT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(unrolled::step_kernel<FT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[e->cfg.device & 63] = true;
     }
     const uint32_t blocks = (in.n + TPB - 1) / TPB;
     if (blocks == 0) return RAFTING_OK;
-    step_kernel<FT, NST><<<blocks, TPB, smem, st>>>(e->T, in, out, e->d_cfg, e->dcfg);
+    unrolled::step_kernel<FT, NST><<<blocks, TPB, smem, st>>>(e->T, in, out, e->d_cfg, e->dcfg);
+    return RAFTING_OK;
+}
+static int launch_looped(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
+    const uint32_t blocks = (in.n + TPB - 1) / TPB;
+    if (blocks == 0) return RAFTING_OK;
+    looped::step_kernel<32, 0><<<blocks, TPB, 0, st>>>(e->T, in, out, e->d_cfg, e->dcfg);
     return RAFTING_OK;
 }
 static int launch_step(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
@@ -241,7 +247,7 @@ static int launch_step(rafting_engine* e, const InboxD& in, const OutboxD& out, 
     else if (F == 2) rc = launch_t<2, 3>(e, in, out, st);
     else if (F <= 4) rc = launch_t<4, 3>(e, in, out, st);
     else if (F <= 8) rc = launch_t<8, 2>(e, in, out, st);
-    else rc = launch_t<32, 0>(e, in, out, st);
+    else rc = launch_looped(e, in, out, st);
     if (rc) return rc;
     e->launches++;
     CU(cudaGetLastError());
