@@ -55,6 +55,18 @@ def b_ack(R):                      # B_ack(R) = 184 + 8 (R - 2
     return 184 + 8 * (R - 2)
 
 
+def measured_traffic(G, R, rows):
+    """DRAM bytes per launch from the committed ncu --set full capture (only valid for the profiled shape)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        if (G, R, rows) == (65536, 3, 16):
+            return float(t["traffic_bytes_per_launch"]), t["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -348,6 +360,7 @@ def run_engine(args):
         peak, peak_src = measured_peak()
         acks_per_launch = acks_timed / K
         achieved = acks_per_launch * b_ack(R) / (float(np.mean(kern_ms)) * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(G, R, rows)
         value = acks_all / (total_ms_max * 1e-3)
         line = {
             "metric": "AppendEntries/sec across Raft groups", "value": value, "unit": "acks/s",
@@ -361,8 +374,9 @@ def run_engine(args):
                        "bit_exact_replay": replay_ok},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_ack": b_ack(R),
-                         "kernel_ms": float(np.mean(kern_ms)), "kernel": "rafting::step_kernel<W,false>"},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "bytes_per_ack": b_ack(R), "algorithmic_bytes_per_launch": acks_per_launch * b_ack(R),
+                         "kernel_ms": float(np.mean(kern_ms)), "kernel": "rafting::unrolled::step_kernel<FT=R-1,NST=3>"},
             "clocks": sampler.summary(),
         }
         if e2e:
