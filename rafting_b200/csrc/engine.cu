@@ -244,7 +244,10 @@ static int launch_step(rafting_engine* e, const InboxD& in, const OutboxD& out, 
     if ((uint64_t)in.rows * in.n * e->F >= (1ull << 32)) return fail(RAFTING_E_CAPACITY, "rows * groups * followers must stay below 2^32 per step");
     const uint32_t F = e->F;
     if (F == 1) rc = launch_t<1, 3>(e, in, out, st);
-    else if (F == 2) rc = launch_t<2, 3>(e, in, out, st);
+#ifndef RAFTING_NST2
+#define RAFTING_NST2 3
+#endif
+    else if (F == 2) rc = launch_t<2, RAFTING_NST2>(e, in, out, st);
     else if (F <= 4) rc = launch_t<4, 3>(e, in, out, st);
     else if (F <= 8) rc = launch_t<8, 2>(e, in, out, st);
     else rc = launch_looped(e, in, out, st);
