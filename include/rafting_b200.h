@@ -390,6 +390,25 @@ int rafting_log_term    (rafting_engine_t* e, uint32_t gid, int64_t index, int64
 int rafting_checkpoint(rafting_engine_t* e);
 int rafting_restore   (rafting_engine_t* e);
 
+/* ---- HBM-resident segmented entry buffer with async pinned-host spill (rafting_b200/csrc/seglog.cuh) ----
+   Payload side of RaftLog (M/command/RaftLog.java:72-132; RocksLog.java:82-242): newEntry/append ->
+   rafting_log_append; get/batch -> rafting_log_read / rafting_log_gather.  truncate/flush need no call:
+   a record is visible iff its index lies in the group's stored key range kept by the step kernel. */
+typedef struct rafting_entry_ref {
+    uint32_t gid;
+    uint32_t len;        /* payload bytes; 0xffffffff in gather output = not stored */
+    int64_t  index, term;
+    uint64_t blob_off;   /* offset of the payload inside the accompanying blob (8-byte aligned on output) */
+} rafting_entry_ref_t;
+int rafting_log_config(rafting_engine_t* e, uint32_t segment_bytes, uint32_t hbm_segments, uint32_t ring_slots /* pow2 */);
+int rafting_log_append(rafting_engine_t* e, const rafting_entry_ref_t* refs, uint32_t n, const void* blob, size_t blob_bytes);
+int rafting_log_read  (rafting_engine_t* e, uint32_t gid, int64_t first_index, uint32_t max_n,
+                       rafting_entry_ref_t* refs_out, void* blob_out, size_t blob_cap, uint32_t* n_out);
+int rafting_log_gather(rafting_engine_t* e, uint32_t n_ranges, const uint32_t* gids, const int64_t* firsts,
+                       const uint32_t* counts, rafting_entry_ref_t* refs_out, uint32_t refs_cap,
+                       void* blob_out, size_t blob_cap, uint32_t* n_out, size_t* bytes_out);
+int rafting_log_stats (rafting_engine_t* e, uint64_t* out /* appended, head, spilled_bytes, hbm_hits, cold_hits, indexed */, uint32_t n);
+
 /* multi-GPU summary: device pointer of this shard's commitIndex[G_local] (int64), and the
    NCCL all-gather of it into a [world * G_local] device buffer owned by the engine */
 int rafting_commit_slice(rafting_engine_t* e, void** dev_ptr, uint32_t* count);

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librafting_b200.so")
 SOURCES = ["engine.cu", "workload.cu"]
-HEADERS = ["step_kernel.cuh", "step_body.inc", "handlers.cuh", "tables.cuh", os.path.join("..", "..", "include", "rafting_b200.h"),
+HEADERS = ["step_kernel.cuh", "step_body.inc", "seglog.cuh", "handlers.cuh", "tables.cuh", os.path.join("..", "..", "include", "rafting_b200.h"),
            os.path.join("..", "..", "include", "rafting_workload.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -60,6 +60,7 @@ static int nccl_load() {
 struct Col { void* h = nullptr; void* d = nullptr; size_t cap = 0; };
 
 struct HostPath;
+namespace rafting { struct SegLog; }
 struct rafting_engine {
     rafting_cfg_t cfg;
     CfgD dcfg;
@@ -75,6 +76,8 @@ struct rafting_engine {
     cudaEvent_t ev_step = nullptr, ev_comm = nullptr;
     int64_t* gather_host = nullptr;
     struct HostPath* host = nullptr;  // slots, copy streams (created on first use)
+    struct rafting::SegLog* seglog = nullptr;   // HBM entry buffer (seglog.cuh), created by rafting_log_config
+    cudaEvent_t ev_seg = nullptr;
     uint64_t launches = 0, events = 0;
     std::vector<void*> dev_allocs;
     std::vector<size_t> dev_bytes;
@@ -96,6 +99,7 @@ static int dalloc(rafting_engine* e, T** p, size_t count) {
 }
 
 static void rafting_hostpath_release(rafting_engine* e);
+static void seglog_release(rafting_engine* e);
 extern "C" uint32_t rafting_abi_version(void) { return RAFTING_ABI_VERSION; }
 extern "C" const char* rafting_last_error(void) { return g_err; }
 
@@ -149,6 +153,8 @@ extern "C" int rafting_engine_destroy(rafting_engine_t* e) {
     for (void* p : e->dev_allocs) cudaFree(p);
     for (void* p : e->shadow) cudaFree(p);
     rafting_hostpath_release(e);
+    seglog_release(e);
+    if (e->ev_seg) cudaEventDestroy(e->ev_seg);
     if (e->gather_host) cudaFreeHost(e->gather_host);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -732,3 +738,5 @@ extern "C" int rafting_abi_sizes(uint32_t* out, uint32_t n) {
     for (uint32_t i = 0; i < n && i < 7; i++) out[i] = v[i];
     return 7;
 }
+
+#include "seglog.cuh"

@@ -37,6 +37,7 @@ EXPORTS = [
     "rafting_comm_init", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_engine_stream",
     "rafting_engine_counters", "rafting_abi_sizes", "rafting_checkpoint", "rafting_restore",
     "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_backoff_step", "rafting_allgather_join",
+    "rafting_log_config", "rafting_log_append", "rafting_log_read", "rafting_log_gather", "rafting_log_stats",
 ]
 
 
@@ -81,6 +82,13 @@ def lib():
         L.rafting_comm_unique_id.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         L.rafting_allgather_commit.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.rafting_allgather_join.argtypes = [C.c_void_p]
+        L.rafting_log_config.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.rafting_log_append.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
+        L.rafting_log_read.argtypes = [C.c_void_p, C.c_uint32, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t,
+                                       C.POINTER(C.c_uint32)]
+        L.rafting_log_gather.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                         C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]
+        L.rafting_log_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.rafting_engine_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.rafting_engine_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.rafting_abi_sizes.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
@@ -240,6 +248,59 @@ class Engine:
         _check(lib().rafting_allgather_commit(self._h, None, C.byref(dev)), "rafting_allgather_commit")
         return dev.value
 
+
+    # ---- HBM segmented entry buffer (payload side of RaftLog) ------------------------------------
+    ENTRY_REF = np.dtype([("gid", "<u4"), ("len", "<u4"), ("index", "<i8"), ("term", "<i8"), ("blob_off", "<u8")])
+
+    def log_config(self, segment_bytes=1 << 18, hbm_segments=64, ring_slots=64):
+        _check(lib().rafting_log_config(self._h, segment_bytes, hbm_segments, ring_slots), "rafting_log_config")
+
+    def log_append(self, entries):
+        """entries: iterable of (gid, index, term, payload bytes) — RocksLog.newEntry / append (RocksLog.java:82-89,169-196)."""
+        entries = list(entries)
+        refs = np.zeros(len(entries), dtype=self.ENTRY_REF)
+        blob = bytearray()
+        for k, (gid, index, term, payload) in enumerate(entries):
+            refs[k] = (gid, len(payload), index, term, len(blob))
+            blob += payload
+            blob += b"\0" * (-len(blob) % 8)
+        buf = np.frombuffer(bytes(blob) or b"\0" * 8, dtype=np.uint8)
+        _check(lib().rafting_log_append(self._h, refs.ctypes.data, len(refs), buf.ctypes.data, len(blob)), "rafting_log_append")
+
+    def log_read(self, gid, first_index, max_n, blob_cap=1 << 20):
+        """RaftLog.batch(first_index, max_n) payload side (RocksLog.java:131-166): [(index, term, bytes)]."""
+        refs = np.zeros(max(max_n, 1), dtype=self.ENTRY_REF)
+        blob = np.zeros(blob_cap, dtype=np.uint8)
+        n = C.c_uint32()
+        _check(lib().rafting_log_read(self._h, gid, first_index, max_n, refs.ctypes.data, blob.ctypes.data, blob_cap, C.byref(n)),
+               "rafting_log_read")
+        return [(int(r["index"]), int(r["term"]), blob[int(r["blob_off"]):int(r["blob_off"]) + int(r["len"])].tobytes())
+                for r in refs[:n.value]]
+
+    def log_gather(self, ranges, blob_cap=1 << 24):
+        """ranges: [(gid, first, count)] -> [(gid, index, term, bytes | None)] in request order."""
+        g = np.array([r[0] for r in ranges], dtype=np.uint32)
+        f = np.array([r[1] for r in ranges], dtype=np.int64)
+        c = np.array([r[2] for r in ranges], dtype=np.uint32)
+        cap = int(c.sum()) + 1
+        refs = np.zeros(cap, dtype=self.ENTRY_REF)
+        blob = np.zeros(blob_cap, dtype=np.uint8)
+        n, nb = C.c_uint32(), C.c_size_t()
+        _check(lib().rafting_log_gather(self._h, len(ranges), g.ctypes.data, f.ctypes.data, c.ctypes.data, refs.ctypes.data, cap,
+                                        blob.ctypes.data, blob_cap, C.byref(n), C.byref(nb)), "rafting_log_gather")
+        out = []
+        for r in refs[:n.value]:
+            if int(r["len"]) == 0xFFFFFFFF:
+                out.append((int(r["gid"]), int(r["index"]), 0, None))
+            else:
+                out.append((int(r["gid"]), int(r["index"]), int(r["term"]),
+                            blob[int(r["blob_off"]):int(r["blob_off"]) + int(r["len"])].tobytes()))
+        return out
+
+    def log_stats(self) -> dict:
+        v = np.zeros(6, dtype=np.uint64)
+        lib().rafting_log_stats(self._h, v.ctypes.data, 6)
+        return dict(zip(("appended", "head", "spilled_bytes", "hbm_hits", "cold_hits", "indexed"), v.tolist()))
 
     def allgather_join(self):
         _check(lib().rafting_allgather_join(self._h), "rafting_allgather_join")

@@ -1,0 +1,75 @@
+"""HBM segmented entry buffer (payload side of RaftLog) against the dict restatement of RocksLog
+(oracle/payload_model.py): batched appends with overwrites, reads bounded by the group's stored key range,
+truncation through a conflicting AppendEntries, and enough data to wrap the HBM segment ring so that old
+entries come back from the pinned-host cold tier — byte for byte."""
+import numpy as np
+import pytest
+
+from oracle.payload_model import PayloadLog
+from rafting_b200 import abi
+from tests import harness
+
+pytestmark = pytest.mark.gpu
+
+
+def _payload(rng, gid, index, term):
+    n = int(rng.integers(0, 200))
+    return bytes(rng.integers(0, 256, size=n, dtype=np.uint8)) + f"|{gid}:{index}:{term}".encode()
+
+
+def test_append_read_gather_truncate_and_spill():
+    from rafting_b200 import engine
+    G, R = 64, 3
+    cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=1, entry_pool_cap=64)
+    e = engine.Engine(cfg)
+    init = harness.init_array(G, terms=1)
+    init["last_index"] = 300                     # stored keys 1..300, one term run
+    init["last_term"] = 1
+    e.open_bulk(0, init)
+    e.log_config(segment_bytes=8192, hbm_segments=4, ring_slots=16)     # tiny arena: 32 KiB, forces spills
+    rng = np.random.default_rng(5)
+    models = [PayloadLog() for _ in range(G)]
+    # batched appends, several rounds, with overwrites of the tail (a re-sent AppendEntries suffix)
+    for rnd in range(6):
+        batch = []
+        for gid in range(G):
+            lo = rnd * 40 + 1
+            for index in range(max(1, lo - 5), lo + 40):
+                p = _payload(rng, gid, index, 1)
+                batch.append((gid, index, 1, p))
+                models[gid].put(index, 1, p)
+        rng.shuffle(batch)                       # order inside a batch is irrelevant except for duplicates
+        seen = {}
+        for k, (gid, index, _, p) in enumerate(batch):
+            seen[(gid, index)] = p
+        for (gid, index), p in seen.items():
+            models[gid].put(index, 1, p)
+        e.log_append(batch)
+    st = e.log_stats()
+    assert st["spilled_bytes"] > 0 and st["appended"] == 6 * G * 45
+    # point/batch reads, everywhere in the log (old indexes live in the cold tier by now)
+    for gid in (0, 7, 63):
+        for first, n in ((1, 10), (37, 50), (230, 20), (236, 80)):
+            assert e.log_read(gid, first, n) == models[gid].batch(first, n), (gid, first, n)
+    assert e.log_stats()["cold_hits"] > 0
+    # gather = the AE plans of a step, many groups at once; beyond the stored keys -> not stored
+    ranges = [(gid, int(rng.integers(1, 230)), int(rng.integers(1, 12))) for gid in range(G)] + [(3, 238, 10)]
+    got = e.log_gather(ranges)
+    want = []
+    for gid, first, cnt in ranges:
+        for i in range(first, first + cnt):
+            want.append((gid, i, models[gid].kv[i][0], models[gid].kv[i][1]) if i in models[gid].kv else (gid, i, 0, None))
+    assert got == want
+    assert e.log_stats()["hbm_hits"] > 0
+    # a conflicting AppendEntries truncates the follower's log: the payload of the dropped suffix disappears
+    ib = abi.Inbox(1, G, R - 1, ent_cap=8)
+    ib.ae_request(0, 5, harness.T0, 1, 2, 100, 1, [2, 2], leader_commit=0)      # entries 101,102 at term 2: conflict at 101
+    e.step(ib)
+    s = e.export(5)
+    assert (s.last_index, s.last_term) == (102, 2)
+    models[5].truncate(101)
+    p101, p102 = b"new-101", b"new-102"
+    e.log_append([(5, 101, 2, p101), (5, 102, 2, p102)])
+    models[5].put(101, 2, p101), models[5].put(102, 2, p102)
+    assert e.log_read(5, 95, 20) == models[5].batch(95, 20)
+    assert e.log_read(5, 103, 5) == []
