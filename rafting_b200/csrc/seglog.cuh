@@ -155,19 +155,24 @@ extern "C" int rafting_log_append(rafting_engine_t* e, const rafting_entry_ref_t
     SegLog* L = e->seglog;
     CU(cudaSetDevice(e->cfg.device));
     if (!e->ev_seg) CU(cudaEventCreateWithFlags(&e->ev_seg, cudaEventDisableTiming));
-    // layout pass: records never straddle a segment
+    // layout pass: records never straddle a segment; a batch that would not fit the arena is cut and the
+    // remainder appended by a second pass
     std::vector<uint64_t> locs(n);
     uint64_t head = L->head, total = 0;
+    const uint64_t room = (uint64_t)L->seg_bytes * (L->nseg - 1);
+    const uint32_t n_all = n;
     for (uint32_t i = 0; i < n; i++) {
         if (refs[i].gid >= e->G) return fail(RAFTING_E_INVAL, "ref %u: gid out of range", i);
         if ((uint64_t)refs[i].blob_off + refs[i].len > blob_bytes) return fail(RAFTING_E_INVAL, "ref %u: payload beyond the blob", i);
         const uint64_t rec = sizeof(SegHdr) + (((uint64_t)refs[i].len + 7) & ~7ull);
         if (rec > L->seg_bytes) return fail(RAFTING_E_CAPACITY, "ref %u: record larger than a segment", i);
-        if (head / L->seg_bytes != (head + rec - 1) / L->seg_bytes) head = (head / L->seg_bytes + 1) * L->seg_bytes;   // skip the tail
-        locs[i] = head; head += rec;
+        uint64_t h2 = head;
+        if (h2 / L->seg_bytes != (h2 + rec - 1) / L->seg_bytes) h2 = (h2 / L->seg_bytes + 1) * L->seg_bytes;   // skip the tail
+        if (h2 + rec - L->head > room) { n = i; break; }
+        locs[i] = h2; head = h2 + rec;
     }
+    if (n == 0) return fail(RAFTING_E_CAPACITY, "arena too small for a single record batch");
     total = head - L->head;
-    if (total > (uint64_t)L->seg_bytes * (L->nseg - 1)) return fail(RAFTING_E_CAPACITY, "append batch larger than the arena minus one segment");
     // staging image = [span of bytes head..new head) + headers array + locs array
     const size_t hdr_bytes = (size_t)n * sizeof(SegHdr), loc_bytes = (size_t)n * 8;
     const size_t need = total + hdr_bytes + loc_bytes + 64;
@@ -214,6 +219,7 @@ extern "C" int rafting_log_append(rafting_engine_t* e, const rafting_entry_ref_t
                                                                          L->ring_index, L->ring_loc, L->ring_len, L->K, e->G);
     CU(cudaGetLastError());
     L->head = head; L->appended += n;
+    if (n < n_all) return rafting_log_append(e, refs + n, n_all - n, blob, blob_bytes);
     return RAFTING_OK;
 }
 
