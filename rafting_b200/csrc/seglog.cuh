@@ -46,6 +46,8 @@ struct SegLog {
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     cudaStream_t s_spill = nullptr;
     uint64_t appended = 0, spilled_bytes = 0, hbm_hits = 0, cold_hits = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;    // device time of the last gather's kernels
+    float last_gather_kernel_ms = 0; uint64_t last_gather_bytes = 0;
 };
 
 static inline uint64_t seg_key(uint32_t gid, int64_t index) { return ((uint64_t)gid << 40) ^ (uint64_t)index; }
@@ -106,6 +108,7 @@ static void seglog_release(rafting_engine* e) {
     if (L->stage) cudaFreeHost(L->stage);
     if (L->d_req) cudaFree(L->d_req);
     if (L->d_out) cudaFree(L->d_out);
+    if (L->t0) { cudaEventDestroy(L->t0); cudaEventDestroy(L->t1); }
     delete L; e->seglog = nullptr;
 }
 
@@ -323,16 +326,21 @@ extern "C" int rafting_log_gather(rafting_engine_t* e, uint32_t n_ranges, const 
         }
         uint32_t* d_lens = (uint32_t*)((uint8_t*)L->d_req + req_bytes);
         CU(cudaMemcpyAsync(L->d_req, req.data(), req_bytes, cudaMemcpyHostToDevice, e->stream));
+        if (!L->t0) { CU(cudaEventCreate(&L->t0)); CU(cudaEventCreate(&L->t1)); }
+        CU(cudaEventRecord(L->t0, e->stream));
         const uint64_t oldest = newest + 1 >= L->nseg ? (newest + 1 - L->nseg) * (uint64_t)L->seg_bytes : 0;
         rafting::seglog_probe_kernel<<<(nq + 255) / 256, 256, 0, e->stream>>>((const GatherReq*)L->d_req, nq, L->ring_index, L->ring_loc,
                                                                                L->ring_len, L->K, oldest, d_lens);
         rafting::seglog_copy_kernel<<<(nq * 32 + 255) / 256, 256, 0, e->stream>>>((const GatherReq*)L->d_req, nq, L->ring_loc, L->ring_len, L->K,
                                                                                   L->arena, (uint64_t)L->seg_bytes * L->nseg, d_lens, L->d_out);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(L->t1, e->stream));
         std::vector<uint32_t> lens(nq);
         CU(cudaMemcpyAsync(lens.data(), d_lens, len_bytes, cudaMemcpyDeviceToHost, e->stream));
         CU(cudaMemcpyAsync(blob_out, L->d_out, used, cudaMemcpyDeviceToHost, e->stream));
         CU(cudaStreamSynchronize(e->stream));
+        CU(cudaEventElapsedTime(&L->last_gather_kernel_ms, L->t0, L->t1));
+        L->last_gather_bytes = used;
         // ring misses (the slot now belongs to a newer index of the same group): direct copy from the arena
         for (uint32_t k = 0; k < nq; k++) {
             if (lens[k] != 0xffffffffu) { L->hbm_hits++; continue; }
@@ -355,7 +363,8 @@ extern "C" int rafting_log_gather(rafting_engine_t* e, uint32_t n_ranges, const 
 extern "C" int rafting_log_stats(rafting_engine_t* e, uint64_t* out, uint32_t n) {
     if (!e || !e->seglog || !out) return fail(RAFTING_E_INVAL, "entry buffer not configured");
     SegLog* L = e->seglog;
-    const uint64_t v[] = {L->appended, L->head, L->spilled_bytes, L->hbm_hits, L->cold_hits, (uint64_t)L->index.size()};
-    for (uint32_t i = 0; i < n && i < 6; i++) out[i] = v[i];
-    return 6;
+    const uint64_t v[] = {L->appended, L->head, L->spilled_bytes, L->hbm_hits, L->cold_hits, (uint64_t)L->index.size(),
+                          (uint64_t)(L->last_gather_kernel_ms * 1e6), L->last_gather_bytes};
+    for (uint32_t i = 0; i < n && i < 8; i++) out[i] = v[i];
+    return 8;
 }

@@ -298,9 +298,10 @@ class Engine:
         return out
 
     def log_stats(self) -> dict:
-        v = np.zeros(6, dtype=np.uint64)
-        lib().rafting_log_stats(self._h, v.ctypes.data, 6)
-        return dict(zip(("appended", "head", "spilled_bytes", "hbm_hits", "cold_hits", "indexed"), v.tolist()))
+        v = np.zeros(8, dtype=np.uint64)
+        lib().rafting_log_stats(self._h, v.ctypes.data, 8)
+        return dict(zip(("appended", "head", "spilled_bytes", "hbm_hits", "cold_hits", "indexed", "gather_kernel_ns",
+                         "gather_bytes"), v.tolist()))
 
     def allgather_join(self):
         _check(lib().rafting_allgather_join(self._h), "rafting_allgather_join")
