@@ -263,7 +263,7 @@ class Engine:
         for k, (gid, index, term, payload) in enumerate(entries):
             refs[k] = (gid, len(payload), index, term, len(blob))
             blob += payload
-            blob += b"\0" * (-len(blob) % 8)
+            blob += b"\0" * (-len(blob) % 16)
         buf = np.frombuffer(bytes(blob) or b"\0" * 8, dtype=np.uint8)
         _check(lib().rafting_log_append(self._h, refs.ctypes.data, len(refs), buf.ctypes.data, len(blob)), "rafting_log_append")
 

@@ -41,7 +41,7 @@ def main():
     g = np.arange(G, dtype=np.uint32); f = np.full(G, per_group - 15, dtype=np.int64); c = np.full(G, 16, dtype=np.uint32)
     cap = G * 16 + 1
     out_refs = np.zeros(cap, dtype=engine.Engine.ENTRY_REF)
-    out_blob = np.zeros(G * 16 * payload + 4096, dtype=np.uint8)
+    out_blob = np.zeros(G * 16 * (payload + 16) + 4096, dtype=np.uint8)
     n, nb = C.c_uint32(), C.c_size_t()
     best = None
     for _ in range(5):
@@ -60,7 +60,7 @@ def main():
         peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         peak = 6650.0
-    moved = 2 * nb.value + n.value * (24 + 28)          # payload read + written, ring slot + request per entry
+    moved = 2 * nb.value + n.value * (32 + 8 + 24 + 4)   # payload read + written; header, ring slot, request, length per entry
     print(json.dumps({
         "what": "HBM segmented entry buffer", "groups": G, "entries": int(len(refs)), "payload_bytes": payload,
         "append": {"seconds": t_append, "entries_per_s": len(refs) / t_append, "GBps_host_to_hbm": blob.nbytes / t_append / 1e9,
