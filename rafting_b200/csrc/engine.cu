@@ -228,21 +228,32 @@ extern "C" int rafting_group_close(rafting_engine_t* e, uint32_t gid) {
 // R<=5 -> <4,3>, R<=9 -> <8,2>, larger clusters keep their slots in local memory and read the inbox directly
 template <int FT, int NST>
 static int launch_t(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
-    const size_t smem = NST > 0 ? (size_t)NST * sizeof(Stage<FT>) : 0;
+    const size_t smem = NST > 0 ? (size_t)NST * sizeof(Stage<FT>) + 64 : 0;
     static bool configured[64] = {false};
     if (smem > 0 && !configured[e->cfg.device & 63]) {
-        CU(cudaFuncSetAttribute(unrolled::step_kernel<FT, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(unrolled::step_kernel<FT, NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (NST > 0) CU(cudaFuncSetAttribute(unrolled::step_kernel<FT, (NST > 0 ? NST : 1), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[e->cfg.device & 63] = true;
     }
-    const uint32_t blocks = (in.n + TPB - 1) / TPB;
+    const uint32_t blocks = (in.n + TPB - 1) / TPB, full = in.n / TPB;
     if (blocks == 0) return RAFTING_OK;
-    unrolled::step_kernel<FT, NST><<<blocks, TPB, smem, st>>>(e->T, in, out, e->d_cfg, e->dcfg);
+    // TMA bulk staging needs full blocks, F == FT and 16-byte aligned column slices on every row
+    auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+    const bool bulk = NST > 0 && e->F == (uint32_t)FT && full > 0 && (in.n % 2 == 0 || in.rows == 1) &&
+                      al16(in.op_meta) && al16(in.op_nr) && al16(in.op_ab) && al16(in.ev_meta) && al16(in.ev_tn) && al16(in.ev_el) &&
+                      !getenv("RAFTING_NO_BULK");
+    if (bulk) {
+        unrolled::step_kernel<FT, (NST > 0 ? NST : 1), true><<<full, TPB, smem, st>>>(e->T, in, out, e->d_cfg, e->dcfg, 0u);
+        if (blocks > full) unrolled::step_kernel<FT, NST, false><<<blocks - full, TPB, smem, st>>>(e->T, in, out, e->d_cfg, e->dcfg, full);
+    } else {
+        unrolled::step_kernel<FT, NST, false><<<blocks, TPB, smem, st>>>(e->T, in, out, e->d_cfg, e->dcfg, 0u);
+    }
     return RAFTING_OK;
 }
 static int launch_looped(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
     const uint32_t blocks = (in.n + TPB - 1) / TPB;
     if (blocks == 0) return RAFTING_OK;
-    looped::step_kernel<32, 0><<<blocks, TPB, 0, st>>>(e->T, in, out, e->d_cfg, e->dcfg);
+    looped::step_kernel<32, 0, false><<<blocks, TPB, 64, st>>>(e->T, in, out, e->d_cfg, e->dcfg, 0u);
     return RAFTING_OK;
 }
 static int launch_step(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
