@@ -228,7 +228,7 @@ extern "C" int rafting_group_close(rafting_engine_t* e, uint32_t gid) {
 // R<=5 -> <4,3>, R<=9 -> <8,2>, larger clusters keep their slots in local memory and read the inbox directly
 template <int FT, int NST>
 static int launch_t(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
-    const size_t smem = NST > 0 ? (size_t)NST * sizeof(Stage<FT>) + 64 : 0;
+    const size_t smem = NST > 0 ? (size_t)NST * sizeof(Stage<FT>) + (size_t)NST * (TPB / 32) * 8 + 16 : 0;
     static bool configured[64] = {false};
     if (smem > 0 && !configured[e->cfg.device & 63]) {
         CU(cudaFuncSetAttribute(unrolled::step_kernel<FT, NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
