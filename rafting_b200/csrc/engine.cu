@@ -241,7 +241,7 @@ static int launch_t(rafting_engine* e, const InboxD& in, const OutboxD& out, cud
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
     const bool bulk = NST > 0 && e->F == (uint32_t)FT && full > 0 && (in.n % 2 == 0 || in.rows == 1) &&
                       al16(in.op_meta) && al16(in.op_nr) && al16(in.op_ab) && al16(in.ev_meta) && al16(in.ev_tn) && al16(in.ev_el) &&
-                      !getenv("RAFTING_NO_BULK");
+                      getenv("RAFTING_BULK_STAGING") != nullptr;   // opt-in: measured slower than per-thread cp.async
     if (bulk) {
         unrolled::step_kernel<FT, (NST > 0 ? NST : 1), true><<<full, TPB, smem, st>>>(e->T, in, out, e->d_cfg, e->dcfg, 0u);
         if (blocks > full) unrolled::step_kernel<FT, NST, false><<<blocks - full, TPB, smem, st>>>(e->T, in, out, e->d_cfg, e->dcfg, full);
