@@ -365,11 +365,11 @@ int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_
 int rafting_step (rafting_engine_t* e, rafting_lease_t* lease);          /* synchronous         */
 int rafting_step_begin(rafting_engine_t* e, rafting_lease_t* lease);     /* async: enqueue      */
 int rafting_step_wait (rafting_engine_t* e, rafting_lease_t* lease);     /* async: outbox ready; ends the lease */
-/* Up to TWO leases may be outstanding (two slots): begin(A); fill B; begin(B); wait(A); ... overlaps
+/* Up to RAFTING_HOST_SLOTS (4) leases may be outstanding: begin(A); fill B; begin(B); wait(A); ... overlaps
    the H2D of one step, the kernel of another and the D2H of a third.
    Caller-owned buffers (e.g. the transport's pinned receive pool, north_star "Netty feeds pinned
    staging buffers"): same pipeline, host pointers supplied by the caller; pin them for real overlap. */
-int rafting_step_begin_host(rafting_engine_t* e, uint32_t slot /* 0|1 */, const rafting_inbox_t* in_host,
+int rafting_step_begin_host(rafting_engine_t* e, uint32_t slot /* 0..3 */, const rafting_inbox_t* in_host,
                             const rafting_outbox_t* out_host);
 int rafting_step_wait_slot (rafting_engine_t* e, uint32_t slot);
 

@@ -17,6 +17,10 @@
 
 using namespace rafting;
 
+#ifndef RAFTING_HOST_SLOTS
+#define RAFTING_HOST_SLOTS 4        // steps that may be in flight on the host path
+#endif
+
 static thread_local char g_err[512] = "";
 static int fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
@@ -283,7 +287,7 @@ static void to_dev_views(const rafting_inbox_t* in, const rafting_outbox_t* out,
     dout.plan_pp = (i64x2*)out->plan_pp; dout.plan_lc = (i64x2*)out->plan_lc; dout.plan_epoch = out->plan_epoch;
     dout.ballot_meta = out->ballot_meta; dout.ballot_term = out->ballot_term; dout.ballot_last = (i64x2*)out->ballot_last;
     dout.commit_index = out->commit_index; dout.current_term = out->current_term; dout.role_word = out->role_word;
-    dout.incarnation = out->incarnation; dout.err_word = out->err_word; dout.last_entry = (i64x2*)out->last_entry;
+    dout.incarnation = out->incarnation; dout.err_word = out->err_word; dout.last_entry = (i64x2*)out->last_entry; dout.flags = nullptr;
 }
 
 extern "C" int rafting_step_device(rafting_engine_t* e, const rafting_inbox_t* in, const rafting_outbox_t* out, void* stream) {
@@ -333,13 +337,15 @@ template <typename S> static const void*& in_ptr(S* st, const ColDesc& c) { retu
 template <typename S> static void*& out_ptr(S* st, const ColDesc& c) { return *(void**)((char*)st + c.off); }
 
 struct Slot {
-    Col in[N_IN], out[N_OUT];                 // .d device staging, .h pinned host (leases only)
+    Col in[N_IN], out[N_OUT];
+    uint32_t* d_flags = nullptr; uint32_t* h_flags = nullptr;   // [0] ballots emitted, [1] valid replies (device / pinned host)
+    rafting_outbox_t host_out; rafting_outbox_t dev_out; size_t rows_ = 0, n_ = 0;   // of the step in flight (for the sparse columns)                 // .d device staging, .h pinned host (leases only)
     cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
     bool leased = false, inflight = false;
     uint32_t rows = 0, n = 0, ent = 0; bool list = false;
 };
 struct HostPath {
-    Slot slot[2];
+    Slot slot[RAFTING_HOST_SLOTS];
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     bool ready = false;
 };
@@ -366,6 +372,8 @@ static int hostpath_init(rafting_engine* e) {
         CU(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_kernel, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+        CU(cudaMalloc((void**)&s.d_flags, 16));
+        CU(cudaHostAlloc((void**)&s.h_flags, 16, cudaHostAllocDefault));
     }
     H->ready = true;
     return 0;
@@ -378,6 +386,8 @@ static void hostpath_free(rafting_engine* e) {
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
+        if (s.d_flags) cudaFree(s.d_flags);
+        if (s.h_flags) cudaFreeHost(s.h_flags);
     }
     if (H->s_h2d) cudaStreamDestroy(H->s_h2d);
     if (H->s_d2h) cudaStreamDestroy(H->s_d2h);
@@ -429,38 +439,56 @@ static int step_enqueue(rafting_engine* e, uint32_t slot, const rafting_inbox_t*
         out_ptr(&dout, c) = S.out[k].d;
     }
     CU(cudaStreamWaitEvent(e->stream, S.ev_h2d, 0));
+    CU(cudaMemsetAsync(S.d_flags, 0, 16, e->stream));
     InboxD di; OutboxD dov;
     to_dev_views(&din, &dout, e->G, di, dov);
+    dov.flags = S.d_flags;
     int rc = launch_step(e, di, dov, e->stream); if (rc) return rc;
     CU(cudaEventRecord(S.ev_kernel, e->stream));
-    // ---- D2H ----
+    // ---- D2H: dense columns always; the payload of the SPARSE families (rep_term, ballot_term, ballot_last —
+    //      meaningful only where a reply / ballot exists, i.e. never in leader steady state) only if the kernel
+    //      counted any, which the host learns from two flag words at wait time ----
     CU(cudaStreamWaitEvent(H->s_d2h, S.ev_kernel, 0));
     for (int k = 0; k < N_OUT; k++) {
         const ColDesc& c = OUT_COLS[k];
         void* dsrc = out_ptr(&dout, c);
         if (!dsrc) continue;
+        const bool sparse = c.off == offsetof(rafting_outbox_t, rep_term) || c.off == offsetof(rafting_outbox_t, ballot_term) ||
+                            c.off == offsetof(rafting_outbox_t, ballot_last);
+        if (sparse) continue;
         CU(cudaMemcpyAsync(out_ptr(out, c), dsrc, col_bytes(c, rows, n, F, G, 0, 0), cudaMemcpyDeviceToHost, H->s_d2h));
     }
+    CU(cudaMemcpyAsync(S.h_flags, S.d_flags, 16, cudaMemcpyDeviceToHost, H->s_d2h));
     CU(cudaEventRecord(S.ev_done, H->s_d2h));
+    S.host_out = *out; S.dev_out = dout; S.rows_ = rows; S.n_ = n;
     S.inflight = true;
     return RAFTING_OK;
 }
 static int slot_wait(rafting_engine* e, uint32_t slot) {
-    Slot& S = hp(e)->slot[slot];
+    HostPath* H = hp(e); Slot& S = H->slot[slot];
     if (!S.inflight) return RAFTING_OK;
     CU(cudaEventSynchronize(S.ev_done));
     S.inflight = false;
+    // sparse families: fetch their payload columns only when the step produced ballots / valid replies
+    const size_t gi_cnt = S.rows_ * S.n_;
+    if (S.h_flags[0]) {
+        if (S.dev_out.ballot_term) CU(cudaMemcpyAsync(S.host_out.ballot_term, S.dev_out.ballot_term, gi_cnt * 8, cudaMemcpyDeviceToHost, H->s_d2h));
+        if (S.dev_out.ballot_last) CU(cudaMemcpyAsync(S.host_out.ballot_last, S.dev_out.ballot_last, gi_cnt * 16, cudaMemcpyDeviceToHost, H->s_d2h));
+    }
+    if (S.h_flags[1] && S.dev_out.rep_term)
+        CU(cudaMemcpyAsync(S.host_out.rep_term, S.dev_out.rep_term, gi_cnt * 8, cudaMemcpyDeviceToHost, H->s_d2h));
+    if (S.h_flags[0] || S.h_flags[1]) CU(cudaStreamSynchronize(H->s_d2h));
     return RAFTING_OK;
 }
 
 extern "C" int rafting_step_begin_host(rafting_engine_t* e, uint32_t slot, const rafting_inbox_t* in_host, const rafting_outbox_t* out_host) {
-    if (!e || !in_host || !out_host || slot > 1) return fail(RAFTING_E_INVAL, "bad argument");
+    if (!e || !in_host || !out_host || slot >= RAFTING_HOST_SLOTS) return fail(RAFTING_E_INVAL, "bad argument");
     CU(cudaSetDevice(e->cfg.device));
     int rc = hostpath_init(e); if (rc) return rc;
     return step_enqueue(e, slot, in_host, out_host);
 }
 extern "C" int rafting_step_wait_slot(rafting_engine_t* e, uint32_t slot) {
-    if (!e || slot > 1) return fail(RAFTING_E_INVAL, "bad argument");
+    if (!e || slot >= RAFTING_HOST_SLOTS) return fail(RAFTING_E_INVAL, "bad argument");
     CU(cudaSetDevice(e->cfg.device));
     return slot_wait(e, slot);
 }
@@ -475,8 +503,8 @@ extern "C" int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_acti
     int rc = hostpath_init(e); if (rc) return rc;
     HostPath* H = hp(e);
     int sl = -1;
-    for (int k = 0; k < 2; k++) if (!H->slot[k].leased && !H->slot[k].inflight) { sl = k; break; }
-    if (sl < 0) return fail(RAFTING_E_BUSY, "both slots are leased or in flight");
+    for (int k = 0; k < RAFTING_HOST_SLOTS; k++) if (!H->slot[k].leased && !H->slot[k].inflight) { sl = k; break; }
+    if (sl < 0) return fail(RAFTING_E_BUSY, "every slot is leased or in flight");
     Slot& S = H->slot[sl];
     const size_t n = n_active ? n_active : e->G, F = e->F, G = e->G;
     memset(out, 0, sizeof(*out));
@@ -498,7 +526,7 @@ extern "C" int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_acti
 }
 static int lease_slot(rafting_engine* e, const rafting_lease_t* L) {
     HostPath* H = hp(e);
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < RAFTING_HOST_SLOTS; k++)
         if (H->slot[k].leased && L->out.commit_index == (int64_t*)H->slot[k].out[9].h) return k;
     return -1;
 }

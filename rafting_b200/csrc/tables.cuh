@@ -79,6 +79,7 @@ struct OutboxD {
     uint64_t* ballot_meta; int64_t* ballot_term; i64x2* ballot_last;
     int64_t* commit_index; int64_t* current_term; uint32_t* role_word; uint32_t* incarnation; uint32_t* err_word;
     i64x2* last_entry;
+    uint32_t* flags;          // engine-internal: [0] += ballots emitted, [1] += valid replies (host path's sparse D2H)
 };
 struct CfgD {
     uint32_t replicas, local_slot;

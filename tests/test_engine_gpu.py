@@ -137,19 +137,21 @@ def test_two_slot_host_pipeline_matches_oracle(engine_mod):
         inboxes.append(ib); want.append(prev)
     got = [abi.Outbox(rows, G, R - 1, G) for _ in range(steps)]
     keep = []
+    NSL = 3
     for k in range(steps):
-        sl = k % 2
-        if k >= 2:
+        sl = k % NSL
+        if k >= NSL:
             e.step_wait_slot(sl)
         ic, oc = inboxes[k].as_c(), got[k].as_c()
         keep.append((ic, oc))
         e.step_begin_host(sl, ic, oc)
-    e.step_wait_slot(0), e.step_wait_slot(1)
+    for sl in range(NSL):
+        e.step_wait_slot(sl)
     for k in range(steps):
         harness.assert_outbox_equal(want[k], got[k], where=f"pipelined step {k}")
     harness.assert_states_equal(o, e, range(0, G, 13), R - 1, where="after the pipelined replay")
-    # two leases can be outstanding at once, a third is refused
-    l0, l1 = e.lease(rows), e.lease(rows)
+    # RAFTING_HOST_SLOTS (4) leases can be outstanding at once, one more is refused
+    held = [e.lease(rows) for _ in range(4)]
     with pytest.raises(engine_mod.RaftingError):
         e.lease(rows)
 
