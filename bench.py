@@ -218,8 +218,10 @@ def run_engine(args):
         prev_c = oc
     outs = [devbatch.DevOutbox(rows, G, F, G, dev) for _ in range(2)]
     n_rec = W + K
-    inboxes = [devbatch.DevInbox(rows, G, F, dev) for _ in range(n_rec)]
-    settle = devbatch.DevInbox(rows, G, F, dev)
+    # the leader stream never marks a follower unavailable: the op_ab column (its only field used by SUBMIT / TIMEOUT)
+    # is omitted from the batch, as a shim would do
+    inboxes = [devbatch.DevInbox(rows, G, F, dev, unavail=False) for _ in range(n_rec)]
+    settle = devbatch.DevInbox(rows, G, F, dev, unavail=False)
     SETTLE = 3
     prev_out = None
     for k in range(SETTLE):

@@ -49,7 +49,7 @@ RAFTING_HD inline void leader_cell(const rafting_wl_cfg_t& w, const Cols& c, uin
         const uint32_t a = (uint32_t)(key(w.seed, gid, tick, 0, 1) % (uint64_t)(w.max_submit + 1));
         c.op_meta[gi] = a ? RAFTING_OP_MAKE(RAFTING_OP_SUBMIT, 0, a) : RAFTING_OP_MAKE(RAFTING_OP_TIMEOUT, 0, 0);
         c.op_nr[gi].x = now; c.op_nr[gi].y = 0;
-        c.op_ab[gi].x = 0; c.op_ab[gi].y = 0;
+        if (c.op_ab) { c.op_ab[gi].x = 0; c.op_ab[gi].y = 0; }     // no unavailable follower in this stream: the column may be omitted
     }
     if (c.ev_meta) {
         for (uint32_t f = 0; f < w.F; f++) {
@@ -87,7 +87,7 @@ RAFTING_HD inline void election_cell(const rafting_wl_cfg_t& w, const Cols& c, u
     const int64_t now = w.t0 - 1000 + 10 * (int64_t)phase + (int64_t)(gid % 10u);
     if (c.op_meta) {
         c.op_meta[gi] = phase == 0 ? RAFTING_OP_MAKE(RAFTING_OP_TIMEOUT, 0, 0) : 0;
-        c.op_nr[gi].x = now; c.op_nr[gi].y = 0; c.op_ab[gi].x = 0; c.op_ab[gi].y = 0;
+        c.op_nr[gi].x = now; c.op_nr[gi].y = 0; if (c.op_ab) { c.op_ab[gi].x = 0; c.op_ab[gi].y = 0; }
     }
     if (c.ev_meta) {
         for (uint32_t f = 0; f < w.F; f++) {

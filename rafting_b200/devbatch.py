@@ -15,11 +15,15 @@ _OUT_GRP = (("commit_index", 8), ("current_term", 8), ("role_word", 4), ("incarn
 
 
 class DevInbox:
-    def __init__(self, rows, n, F, device, requests=False):
+    def __init__(self, rows, n, F, device, requests=False, unavail=True):
+        """requests=False omits op_cd/op_e (no inbound-request ops); unavail=False also omits op_ab (its only use in
+        such a step is the unavailable-follower mask of SUBMIT / TIMEOUT: absent == nobody unavailable)."""
         self.rows, self.n, self.F = rows, n, F
         self.t = {}
         for name, sz, lane in _IN_COLS:
             if not requests and name in ("op_cd", "op_e"):
+                continue
+            if not unavail and name == "op_ab":
                 continue
             cnt = rows * n * (F if lane else 1)
             self.t[name] = torch.zeros(cnt * sz, dtype=torch.uint8, device=device)

@@ -62,12 +62,14 @@ def elect_all(sut, w1: workload.WlCfg):
     return out
 
 
-def run_leader_workload(suts, w: workload.WlCfg, steps: int, compare=True, first_step=0, prevs=None):
+def run_leader_workload(suts, w: workload.WlCfg, steps: int, compare=True, first_step=0, prevs=None, drop_ab=False):
     """Drives every SUT in `suts` with the SAME stream, generated from the FIRST sut's outbox
     (after checking the others produced the identical outbox).  Returns the last outboxes."""
     prev = prevs
     for k in range(first_step, first_step + steps):
         ib = workload.leader_inbox_host(w, k, prev)
+        if drop_ab:
+            ib.op_ab = None          # nobody unavailable: the column is simply absent
         outs = [s.step(ib) for s in suts]
         if compare:
             for o in outs[1:]:
