@@ -83,6 +83,9 @@ __device__ __forceinline__ void store_lane(const Tables& T, size_t li, const LS&
 #ifndef RAFTING_MINBLOCKS
 #define RAFTING_MINBLOCKS 8
 #endif
+#ifndef RAFTING_MINBLOCKS4
+#define RAFTING_MINBLOCKS4 1        // FT = 4 (R <= 5)
+#endif
 #ifndef RAFTING_TPB
 #define RAFTING_TPB 64
 #endif
