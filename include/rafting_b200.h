@@ -421,7 +421,8 @@ int rafting_allgather_join  (rafting_engine_t* e);  /* the step stream waits for
 
 /* introspection used by bench/tests */
 int rafting_engine_stream(rafting_engine_t* e, void** cuda_stream);
-int rafting_engine_counters(rafting_engine_t* e, uint64_t* kernel_launches, uint64_t* events_processed);
+int rafting_engine_counters(rafting_engine_t* e, uint64_t* kernel_launches,
+                            uint64_t* events_processed /* reserved: always 0 in this version */);
 int64_t rafting_backoff_step(int32_t recent_rejection);   /* integer form of round(ln(e + r)), Leadership.java:105 */
 int rafting_abi_sizes(uint32_t* out, uint32_t n);   /* sizeof of the ABI structs as compiled, for binding self-checks */
 

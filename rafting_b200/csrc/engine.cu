@@ -71,14 +71,12 @@ struct rafting_engine {
     CfgD* d_cfg = nullptr;            // device copy for the slow path (the fast path reads the kernel-param copy)
     Tables T;
     uint32_t G, F;
-    int W;
     cudaStream_t stream = nullptr;
     int64_t* commit_all = nullptr;     // [world * G]; T.g_commit points at this rank's slice
     int rank = 0, world = 1;
     nccl_comm_t comm = nullptr;
     cudaStream_t s_comm = nullptr;     // the summary all-gather runs here, off the kernels' critical path
     cudaEvent_t ev_step = nullptr, ev_comm = nullptr;
-    int64_t* gather_host = nullptr;
     struct HostPath* host = nullptr;  // slots, copy streams (created on first use)
     struct rafting::SegLog* seglog = nullptr;   // HBM entry buffer (seglog.cuh), created by rafting_log_config
     cudaEvent_t ev_seg = nullptr;
@@ -121,7 +119,6 @@ extern "C" int rafting_engine_create(const rafting_cfg_t* cfg, rafting_engine_t*
     rafting_engine* e = new rafting_engine();
     e->cfg = *cfg;
     e->G = cfg->max_groups; e->F = cfg->replicas - 1;
-    int W = 1; while (W < (int)e->F) W <<= 1; e->W = W;
     e->dcfg.replicas = cfg->replicas; e->dcfg.local_slot = cfg->local_slot;
     e->dcfg.pre_vote = cfg->pre_vote; e->dcfg.avail_critical_point = cfg->avail_critical_point;
     e->dcfg.recovery_cool_down_ms = cfg->recovery_cool_down_ms; e->dcfg.heartbeat_ms = cfg->heartbeat_ms;
@@ -159,7 +156,6 @@ extern "C" int rafting_engine_destroy(rafting_engine_t* e) {
     rafting_hostpath_release(e);
     seglog_release(e);
     if (e->ev_seg) cudaEventDestroy(e->ev_seg);
-    if (e->gather_host) cudaFreeHost(e->gather_host);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return RAFTING_OK;
