@@ -257,27 +257,40 @@ def run_engine(args):
     out_b = outs[0]
     ics = [ib.as_c() for ib in inboxes]
     ocs = [outs[k % 2].as_c() for k in range(n_rec)]
-    for k in range(W):
-        e.step_device(ics[k], ocs[k], stream_ptr)
+    def warm():
+        for k in range(W):
+            e.step_device(ics[k], ocs[k], stream_ptr)
+            if world > 1:
+                e.allgather_commit(to_host=False)
         if world > 1:
-            e.allgather_commit(to_host=False)
-    torch.cuda.synchronize(); barrier()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 2)]
-    evs[0].record(ext)
+            e.allgather_join()
+        torch.cuda.synchronize(); barrier()
+
+    # pass 1 — the metric: K steps back to back, two events around the whole region
+    warm()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext)
     for j in range(K):
-        k = W + j
-        evs[1 + 2 * j].record(ext)
-        e.step_device(ics[k], ocs[k], stream_ptr)
-        evs[2 + 2 * j].record(ext)
+        e.step_device(ics[W + j], ocs[W + j], stream_ptr)
         if world > 1:
             e.allgather_commit(to_host=False)
     if world > 1:
         e.allgather_join()                      # the timed region ends when the last summary has been gathered
-    evs[2 * K + 1].record(ext)
+    ev1.record(ext)
     torch.cuda.synchronize(); barrier()
-    total_ms = evs[0].elapsed_time(evs[2 * K + 1])
-    kern_ms = [evs[1 + 2 * j].elapsed_time(evs[2 + 2 * j]) for j in range(K)]
+    total_ms = ev0.elapsed_time(ev1)
     digest_b = e.digest(0, G)
+    # pass 2 — the same K steps again with an event pair around every kernel (roofline of the dominant kernel)
+    e.restore()
+    warm()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K)]
+    for j in range(K):
+        evs[2 * j].record(ext)
+        e.step_device(ics[W + j], ocs[W + j], stream_ptr)
+        evs[2 * j + 1].record(ext)
+    torch.cuda.synchronize(); barrier()
+    kern_ms = [evs[2 * j].elapsed_time(evs[2 * j + 1]) for j in range(K)]
+
     replay_ok = bool((digest_a == digest_b).all())
     acks_timed = sum(acks_per_step[W:])
     launches0, _ = e.counters()
