@@ -24,7 +24,7 @@
 
 namespace rafting {
 
-struct SegHdr { uint32_t gid, len; int64_t index, term; uint64_t seq; };
+struct alignas(16) SegHdr { uint32_t gid, len; int64_t index, term; uint64_t seq; };
 static_assert(sizeof(SegHdr) == 32, "segment record header");
 
 struct HostLoc { uint64_t off; uint32_t len; int64_t term; };      // len == 0xffffffff: absent
@@ -40,7 +40,8 @@ struct SegLog {
     std::vector<cudaEvent_t> cold_ready;      // spill completion per logical segment
     std::vector<GroupIdx> index;              // authoritative (lengths, terms, cold tier); the device ring is a cache of it
     uint8_t* stage = nullptr; size_t stage_cap = 0;       // pinned staging of one append batch
-    void* d_req = nullptr; size_t d_req_cap = 0;           // device scratch (append: gid/slot/loc triples; gather: requests)
+    void* d_req = nullptr; size_t d_req_cap = 0;           // device scratch (append records / gather requests)
+    uint8_t* d_blob = nullptr; size_t d_blob_cap = 0;      // staged payload blob of the append in flight
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     cudaStream_t s_spill = nullptr;
     uint64_t appended = 0, spilled_bytes = 0, hbm_hits = 0, cold_hits = 0, indexed = 0;
@@ -48,14 +49,31 @@ struct SegLog {
     float last_gather_kernel_ms = 0; uint64_t last_gather_bytes = 0;
 };
 
-struct IndexUpd { uint32_t gid, slot; uint64_t loc1; };            // loc1 = logical offset + 1
-// one thread per appended record.  Logical offsets only grow, so atomicMax makes "the latest put wins"
+struct AppendRec { uint32_t gid, len; int64_t index, term; uint64_t loc; uint64_t src; };   // 40 B per appended entry
+// 8 lanes per appended record: write the header, copy the payload from the staged blob into the arena and
+// publish the record in the group's ring.  Logical offsets only grow, so atomicMax makes "the latest put wins"
 // (RocksDB semantics) hold inside a batch and across batches without any ordering between threads.
-__global__ void seglog_index_kernel(const IndexUpd* __restrict__ upd, uint32_t n, unsigned long long* ring, uint32_t K) {
+__global__ void seglog_scatter_kernel(const AppendRec* __restrict__ recs, uint32_t n, uint64_t seq0, const uint8_t* __restrict__ blob,
+                                      uint8_t* __restrict__ arena, uint64_t arena_bytes, unsigned long long* ring, uint32_t K) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const IndexUpd u = upd[t];
-    atomicMax(&ring[(size_t)u.gid * K + u.slot], (unsigned long long)u.loc1);
+    const uint32_t en = t >> 3, sub = t & 7;
+    if (en >= n) return;
+    const AppendRec r = recs[en];
+    uint8_t* dst = arena + (r.loc % arena_bytes);
+    if (sub == 0) {
+        SegHdr h; h.gid = r.gid; h.len = r.len; h.index = r.index; h.term = r.term; h.seq = seq0 + en;
+        *(int4*)dst = *(const int4*)&h; *(int4*)(dst + 16) = *((const int4*)&h + 1);
+        atomicMax(&ring[(size_t)r.gid * K + ((uint64_t)r.index & (K - 1))], (unsigned long long)(r.loc + 1));
+    }
+    const uint8_t* src = blob + r.src;
+    uint8_t* pay = dst + sizeof(SegHdr);
+    if ((r.src & 15) == 0) {
+        const uint32_t words = r.len >> 4;
+        for (uint32_t i = sub; i < words; i += 8) ((int4*)pay)[i] = ((const int4*)src)[i];
+        for (uint32_t i = (words << 4) + sub; i < r.len; i += 8) pay[i] = src[i];
+    } else {
+        for (uint32_t i = sub; i < r.len; i += 8) pay[i] = src[i];
+    }
 }
 
 struct GatherReq { uint32_t gid; uint32_t slot; int64_t index; uint64_t out_off; };   // slot: position in the reply list
@@ -90,7 +108,7 @@ __global__ void seglog_gather_kernel(const GatherReq* __restrict__ req, uint32_t
 
 }  // namespace rafting
 
-using rafting::SegLog; using rafting::SegHdr; using rafting::HostLoc; using rafting::GatherReq; using rafting::IndexUpd;
+using rafting::SegLog; using rafting::SegHdr; using rafting::HostLoc; using rafting::GatherReq; using rafting::AppendRec;
 
 static void seglog_release(rafting_engine* e) {
     SegLog* L = e->seglog; if (!L) return;
@@ -102,6 +120,7 @@ static void seglog_release(rafting_engine* e) {
     if (L->stage) cudaFreeHost(L->stage);
     if (L->d_req) cudaFree(L->d_req);
     if (L->d_out) cudaFree(L->d_out);
+    if (L->d_blob) cudaFree(L->d_blob);
     if (L->t0) { cudaEventDestroy(L->t0); cudaEventDestroy(L->t1); }
     delete L; e->seglog = nullptr;
 }
@@ -166,67 +185,58 @@ extern "C" int rafting_log_append(rafting_engine_t* e, const rafting_entry_ref_t
     if (!refs || (!blob && blob_bytes)) return fail(RAFTING_E_INVAL, "null argument");
     SegLog* L = e->seglog;
     CU(cudaSetDevice(e->cfg.device));
-    // layout pass: records never straddle a segment; a batch that would not fit the arena is cut and the
-    // remainder appended by a second pass
-    const uint64_t room = (uint64_t)L->seg_bytes * (L->nseg - 1);
-    const uint32_t n_all = n;
-    uint64_t head = L->head;
-    for (uint32_t i = 0; i < n; i++) {
-        if (refs[i].gid >= e->G) return fail(RAFTING_E_INVAL, "ref %u: gid out of range", i);
-        if ((uint64_t)refs[i].blob_off + refs[i].len > blob_bytes) return fail(RAFTING_E_INVAL, "ref %u: payload beyond the blob", i);
-        const uint64_t rec = sizeof(SegHdr) + (((uint64_t)refs[i].len + 15) & ~15ull);
-        if (rec > L->seg_bytes) return fail(RAFTING_E_CAPACITY, "ref %u: record larger than a segment", i);
-        uint64_t h2 = head;
-        if (h2 / L->seg_bytes != (h2 + rec - 1) / L->seg_bytes) h2 = (h2 / L->seg_bytes + 1) * L->seg_bytes;   // skip the tail
-        if (h2 + rec - L->head > room) { n = i; break; }
-        head = h2 + rec;
+    // the payload blob travels to the device once and stays there while the sub-batches below are scattered
+    // (pin it on the host for a truly asynchronous copy)
+    CU(cudaStreamSynchronize(e->stream));                          // previous append done with d_blob / staging
+    if (blob_bytes > L->d_blob_cap) {
+        if (L->d_blob) cudaFree(L->d_blob);
+        L->d_blob_cap = blob_bytes + blob_bytes / 2 + 256;
+        CU(cudaMalloc((void**)&L->d_blob, L->d_blob_cap));
     }
-    if (n == 0) return fail(RAFTING_E_CAPACITY, "arena too small for a single record");
-    const uint64_t total = head - L->head;
-    const size_t upd_bytes = (size_t)n * sizeof(IndexUpd);
-    const size_t need = total + upd_bytes + 64;
-    CU(cudaStreamSynchronize(e->stream));                          // the previous batch has left the staging buffer
-    if (need > L->stage_cap) {
-        if (L->stage) cudaFreeHost(L->stage);
-        L->stage_cap = need + need / 2;
-        CU(cudaHostAlloc((void**)&L->stage, L->stage_cap, cudaHostAllocDefault));
-    }
-    IndexUpd* upd = (IndexUpd*)(L->stage + ((total + 15) & ~15ull));
-    uint64_t cur = L->head;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint64_t rec = sizeof(SegHdr) + (((uint64_t)refs[i].len + 15) & ~15ull);
-        if (cur / L->seg_bytes != (cur + rec - 1) / L->seg_bytes) {
-            const uint64_t nxt = (cur / L->seg_bytes + 1) * L->seg_bytes;
-            memset(L->stage + (cur - L->head), 0, nxt - cur);      // dead tail of the segment
-            cur = nxt;
+    if (blob_bytes) CU(cudaMemcpyAsync(L->d_blob, blob, blob_bytes, cudaMemcpyHostToDevice, e->stream));
+    const uint64_t room = (uint64_t)L->seg_bytes * (L->nseg - 1), arena_bytes = (uint64_t)L->seg_bytes * L->nseg;
+    uint32_t done = 0;
+    while (done < n) {
+        // layout pass (arithmetic only): records never straddle a segment; a sub-batch ends where the arena,
+        // minus one segment, would be exceeded
+        const size_t need = (size_t)(n - done) * sizeof(AppendRec);
+        if (need > L->stage_cap) {
+            CU(cudaStreamSynchronize(e->stream));
+            if (L->stage) cudaFreeHost(L->stage);
+            L->stage_cap = need + need / 2;
+            CU(cudaHostAlloc((void**)&L->stage, L->stage_cap, cudaHostAllocDefault));
+        } else if (done) CU(cudaStreamSynchronize(e->stream));     // the previous sub-batch has left the staging buffer
+        AppendRec* recs = (AppendRec*)L->stage;
+        uint64_t head = L->head; uint32_t m = 0;
+        for (uint32_t i = done; i < n; i++) {
+            if (refs[i].gid >= e->G) return fail(RAFTING_E_INVAL, "ref %u: gid out of range", i);
+            if ((uint64_t)refs[i].blob_off + refs[i].len > blob_bytes) return fail(RAFTING_E_INVAL, "ref %u: payload beyond the blob", i);
+            const uint64_t rec = sizeof(SegHdr) + (((uint64_t)refs[i].len + 15) & ~15ull);
+            if (rec > L->seg_bytes) return fail(RAFTING_E_CAPACITY, "ref %u: record larger than a segment", i);
+            uint64_t h2 = head;
+            if (h2 / L->seg_bytes != (h2 + rec - 1) / L->seg_bytes) h2 = (h2 / L->seg_bytes + 1) * L->seg_bytes;   // skip the tail
+            if (h2 + rec - L->head > room) break;
+            AppendRec& r = recs[m];
+            r.gid = refs[i].gid; r.len = refs[i].len; r.index = refs[i].index; r.term = refs[i].term; r.loc = h2; r.src = refs[i].blob_off;
+            HostLoc hl; hl.off = h2; hl.len = refs[i].len; hl.term = refs[i].term;
+            seglog_put(L, refs[i].gid, refs[i].index, hl);
+            head = h2 + rec; m++;
         }
-        uint8_t* dst = L->stage + (cur - L->head);
-        SegHdr h; h.gid = refs[i].gid; h.len = refs[i].len; h.index = refs[i].index; h.term = refs[i].term; h.seq = L->appended + i;
-        memcpy(dst, &h, sizeof(h));
-        if (refs[i].len) memcpy(dst + sizeof(h), (const uint8_t*)blob + refs[i].blob_off, refs[i].len);
-        upd[i].gid = refs[i].gid; upd[i].slot = (uint32_t)((uint64_t)refs[i].index & (L->K - 1)); upd[i].loc1 = cur + 1;
-        HostLoc hl; hl.off = cur; hl.len = refs[i].len; hl.term = refs[i].term;
-        seglog_put(L, refs[i].gid, refs[i].index, hl);
-        cur += rec;
+        if (m == 0) return fail(RAFTING_E_CAPACITY, "arena too small for a single record");
+        int rc = seglog_spill_for(e, L, head); if (rc) return rc;
+        const size_t rec_bytes = (size_t)m * sizeof(AppendRec);
+        if (rec_bytes > L->d_req_cap) {
+            CU(cudaStreamSynchronize(e->stream));
+            if (L->d_req) cudaFree(L->d_req);
+            L->d_req_cap = rec_bytes * 2;
+            CU(cudaMalloc(&L->d_req, L->d_req_cap));
+        }
+        CU(cudaMemcpyAsync(L->d_req, recs, rec_bytes, cudaMemcpyHostToDevice, e->stream));
+        rafting::seglog_scatter_kernel<<<(uint32_t)(((uint64_t)m * 8 + 255) / 256), 256, 0, e->stream>>>(
+            (const AppendRec*)L->d_req, m, L->appended, L->d_blob, L->arena, arena_bytes, L->ring, L->K);
+        CU(cudaGetLastError());
+        L->head = head; L->appended += m; done += m;
     }
-    int rc = seglog_spill_for(e, L, head); if (rc) return rc;
-    const uint64_t arena_bytes = (uint64_t)L->seg_bytes * L->nseg;
-    uint64_t off = L->head, left = total, src = 0;
-    while (left) {                                                 // H2D of the span, split where it wraps around the arena
-        const uint64_t a = off % arena_bytes, chunk = left < arena_bytes - a ? left : arena_bytes - a;
-        CU(cudaMemcpyAsync(L->arena + a, L->stage + src, chunk, cudaMemcpyHostToDevice, e->stream));
-        off += chunk; src += chunk; left -= chunk;
-    }
-    if (upd_bytes > L->d_req_cap) {
-        if (L->d_req) cudaFree(L->d_req);
-        L->d_req_cap = upd_bytes * 2;
-        CU(cudaMalloc(&L->d_req, L->d_req_cap));
-    }
-    CU(cudaMemcpyAsync(L->d_req, upd, upd_bytes, cudaMemcpyHostToDevice, e->stream));
-    rafting::seglog_index_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>((const IndexUpd*)L->d_req, n, L->ring, L->K);
-    CU(cudaGetLastError());
-    L->head = head; L->appended += n;
-    if (n < n_all) return rafting_log_append(e, refs + n, n_all - n, blob, blob_bytes);
     return RAFTING_OK;
 }
 
