@@ -64,10 +64,10 @@ def main():
     print(json.dumps({
         "what": "HBM segmented entry buffer", "groups": G, "entries": int(len(refs)), "payload_bytes": payload,
         "append": {"seconds": t_append, "entries_per_s": len(refs) / t_append, "GBps_host_to_hbm": blob.nbytes / t_append / 1e9,
-                   "note": "host layout pass + pinned staging + H2D + index kernel + host index, wall clock"},
+                   "note": "layout arithmetic + host index on the host, blob H2D + scatter kernel on the device, wall clock"},
         "gather": {"entries": int(n.value), "payload_bytes": int(nb.value), "kernel_ms": best,
                    "achieved_GBps": moved / (best * 1e-3) / 1e9, "peak_GBps": peak, "frac": moved / (best * 1e-3) / 1e9 / peak,
-                   "bound": "hbm", "note": "probe + copy kernels, CUDA events on the engine stream, best of 5"},
+                   "bound": "hbm", "note": "seglog_gather_kernel, CUDA events on the engine stream, best of 5"},
         "stats": st,
     }))
 
