@@ -301,8 +301,9 @@ def run_engine(args):
     if not args.no_e2e:
         # the transport's pinned receive buffers: one pinned inbox per timed step (filled before the clock
         # starts, as Netty would have decoded them), two pinned outboxes (one per slot)
+        K2 = min(K, 24)                                   # pinned host memory is bounded: at most 24 timed e2e steps
         host_in = []
-        for k in range(W, n_rec):
+        for k in range(W, W + K2):
             cols = {name: t.cpu().pin_memory() for name, t in inboxes[k].t.items()}
             ic = abi.InboxC()
             ic.rows, ic.n_active, ic.flags = rows, 0, abi.INBOX_NO_REQUESTS
@@ -336,7 +337,7 @@ def run_engine(args):
         # (1) throughput: two slots in flight — H2D of step j+1, kernel of step j and D2H of step j-1 overlap
         rewind(); barrier()
         t0 = time.perf_counter()
-        for j in range(K):
+        for j in range(K2):
             sl = j % NSL
             if j >= NSL:
                 e.step_wait_slot(sl)                      # outbox of step j-NSL is readable on the host
@@ -344,11 +345,14 @@ def run_engine(args):
         for sl in range(NSL):
             e.step_wait_slot(sl)
         spent = time.perf_counter() - t0
-        digest_c = e.digest(0, G)
-        e2e_ok = bool((digest_a == digest_c).all())
+        acks_e2e = sum(acks_per_step[W:W + K2])
+        e2e_ok = None                                     # verified only when the e2e pass replays all K steps
+        if K2 == K:
+            digest_c = e.digest(0, G)
+            e2e_ok = bool((digest_a == digest_c).all())
         # (2) latency: one step at a time, host ack in -> commit record readable out
         rewind()
-        for j in range(min(K, 12)):
+        for j in range(min(K2, 12)):
             t1 = time.perf_counter()
             e.step_begin_host(0, host_in[j][1], host_out[0][1])
             e.step_wait_slot(0)
@@ -356,7 +360,10 @@ def run_engine(args):
         t = torch.tensor([spent], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"spent": float(t.item()), "h2d": int(h2d), "d2h": int(d2h), "ok": e2e_ok}
+        ae = torch.tensor([acks_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ae, op=dist.ReduceOp.SUM)
+        e2e = {"spent": float(t.item()), "h2d": int(h2d), "d2h": int(d2h), "ok": e2e_ok, "acks": float(ae.item()), "steps": K2}
     sampler.stop_flag = True
 
     # ---- reduce over ranks ------------------------------------------------------------------------
@@ -404,9 +411,9 @@ def run_engine(args):
             "clocks": sampler.summary(),
         }
         if e2e:
-            ev = acks_all / e2e["spent"]
+            ev = e2e["acks"] / e2e["spent"]
             line["e2e"] = {"value": ev, "unit": "acks/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "bit_exact_replay": e2e["ok"],
+                           "bit_exact_replay": e2e["ok"], "steps": e2e["steps"],
                            "note": "wall clock around K x rafting_step_begin_host/rafting_step_wait_slot with caller-owned pinned "
                                    "buffers, three slots in flight (H2D / kernel / D2H of successive steps overlap); every step's inbox "
                                    "crosses PCIe up and its outbox crosses PCIe down inside the timed region (the payload columns of "
