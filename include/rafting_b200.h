@@ -221,6 +221,10 @@ enum { RAFTING_OUT_OK = 0, RAFTING_OUT_ERROR = 1, RAFTING_OUT_CANCELED = 2 };
    requests, FLUSH); the engine then runs the leaner kernel variant, and any such op found anyway is
    answered with RAFTING_ERR_BAD_EVENT */
 #define RAFTING_INBOX_NO_REQUESTS 1u
+/* COMPACT_GROUPS (only with an active list): the per-group outbox columns (commit_index ... last_entry)
+   are indexed by POSITION in gids[] and hold n_active entries instead of max_groups — a step over a few
+   hundred busy groups then moves kilobytes, not the whole per-group snapshot, across PCIe */
+#define RAFTING_INBOX_COMPACT_GROUPS 2u
 
 typedef struct rafting_inbox {
     uint32_t rows;                 /* rows in this step (<= cfg.max_rows)                        */
@@ -276,7 +280,8 @@ typedef struct rafting_outbox {
     uint64_t*        ballot_meta;  /* bits 0..3 kind | 32..63 incarnation of the asking role object */
     int64_t*         ballot_term;  /* term argument of the RPC                                    */
     rafting_i64x2_t* ballot_last;  /* (lastLogIndex, lastLogTerm)                                 */
-    /* per group, end of step                                                                    */
+    /* per group, end of step: [max_groups] indexed by gid, or [n_active] indexed by position in
+       gids[] under RAFTING_INBOX_COMPACT_GROUPS                                                  */
     int64_t*         commit_index; /* RaftLog.lastCommitted()                                     */
     int64_t*         current_term; /* RaftParticipant.currentTerm()                               */
     uint32_t*        role_word;    /* bits 0..1 role | 8..15 votedFor+1 | 16..23 currentLeader+1 |
@@ -362,6 +367,11 @@ int rafting_group_close    (rafting_engine_t* e, uint32_t gid);
 /* host path: fill lease->in (pinned), call step; H2D + kernels + D2H happen inside the call */
 int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_t ent_count,
                   rafting_lease_t* out);
+/* same, with the inbox flags the step will carry: RAFTING_INBOX_COMPACT_GROUPS sizes the per-group outbox
+   columns for n_active entries.  Every column of a lease lives in one pinned block per direction, so a leased
+   step is one copy up (two with an active list) and one copy down */
+int rafting_lease_ex(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_t ent_count, uint32_t flags,
+                     rafting_lease_t* out);
 int rafting_step (rafting_engine_t* e, rafting_lease_t* lease);          /* synchronous         */
 int rafting_step_begin(rafting_engine_t* e, rafting_lease_t* lease);     /* async: enqueue      */
 int rafting_step_wait (rafting_engine_t* e, rafting_lease_t* lease);     /* async: outbox ready; ends the lease */

@@ -29,7 +29,9 @@ typedef struct rafting_wl_cfg {
 
 /* fills in->{op_meta,op_nr,op_ab,ev_meta,ev_tn,ev_el} (those that are non-NULL) for step `step`
    from the previous step's outbox (NULL: no acks).  on_device != 0: all pointers are device
-   pointers and the generator runs as a kernel on `stream`. */
+   pointers and the generator runs as a kernel on `stream`.  With in->gids the outbox's per-group columns
+   are read by gid, or by position when in->flags has RAFTING_INBOX_COMPACT_GROUPS (prev_out must come
+   from a step with the same flag). */
 int rafting_wl_leader_step(const rafting_wl_cfg_t* w, uint64_t step, const rafting_outbox_t* prev_out,
                            const rafting_inbox_t* in, int on_device, void* stream);
 

@@ -94,7 +94,8 @@ class Oracle:
 
     def step(self, inbox: abi.Inbox, threads: int = 1) -> abi.Outbox:
         n = inbox.n
-        out = abi.Outbox(inbox.rows, n, self.F, self.G)
+        compact = inbox.gids is not None and (inbox.flags & abi.INBOX_COMPACT_GROUPS)
+        out = abi.Outbox(inbox.rows, n, self.F, n if compact else self.G)
         ic, oc = inbox.as_c(), out.as_c()
         rc = lib().orc_step(self._h, C.byref(ic), C.byref(oc), threads)
         if rc:

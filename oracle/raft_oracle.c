@@ -949,13 +949,14 @@ static void step_group(orc_engine_t* e, const rafting_inbox_t* in, const rafting
             }
         }
     }
-    /* end-of-step snapshot columns */
-    if (out->commit_index) out->commit_index[gid] = g->log.commitIndex;
-    if (out->current_term) out->current_term[gid] = g->term;
-    if (out->role_word)    out->role_word[gid] = role_word(g);
-    if (out->incarnation)  out->incarnation[gid] = g->incarnation;
-    if (out->err_word)     out->err_word[gid] = g->errWord;
-    if (out->last_entry)   last_or_epoch(&g->log, &out->last_entry[gid].x, &out->last_entry[gid].y);
+    /* end-of-step snapshot columns: by gid, or by position in the active list (RAFTING_INBOX_COMPACT_GROUPS) */
+    const uint32_t go = (in->gids && (in->flags & RAFTING_INBOX_COMPACT_GROUPS)) ? i : gid;
+    if (out->commit_index) out->commit_index[go] = g->log.commitIndex;
+    if (out->current_term) out->current_term[go] = g->term;
+    if (out->role_word)    out->role_word[go] = role_word(g);
+    if (out->incarnation)  out->incarnation[go] = g->incarnation;
+    if (out->err_word)     out->err_word[go] = g->errWord;
+    if (out->last_entry)   last_or_epoch(&g->log, &out->last_entry[go].x, &out->last_entry[go].y);
 }
 
 typedef struct { orc_engine_t* e; const rafting_inbox_t* in; const rafting_outbox_t* out;

@@ -16,6 +16,7 @@ import numpy as np
 
 ABI_VERSION = 1
 INBOX_NO_REQUESTS = 1
+INBOX_COMPACT_GROUPS = 2
 TERM_RUNS = 8
 MAX_REPLICAS = 33
 I64_MAX = (1 << 63) - 1

@@ -60,9 +60,6 @@ static int nccl_load() {
     return 0;
 }
 
-// one staged column: pinned host + device copies of the same extent
-struct Col { void* h = nullptr; void* d = nullptr; size_t cap = 0; };
-
 struct HostPath;
 namespace rafting { struct SegLog; }
 struct rafting_engine {
@@ -85,8 +82,6 @@ struct rafting_engine {
     std::vector<size_t> dev_bytes;
     std::vector<void*> shadow;         // rafting_checkpoint copies, parallel to dev_allocs
 };
-
-static void col_free(Col& c) { if (c.h) cudaFreeHost(c.h); if (c.d) cudaFree(c.d); c = Col(); }
 
 template <typename T>
 static int dalloc(rafting_engine* e, T** p, size_t count) {
@@ -332,13 +327,48 @@ static size_t col_bytes(const ColDesc& c, size_t rows, size_t n, size_t F, size_
 template <typename S> static const void*& in_ptr(S* st, const ColDesc& c) { return *(const void**)((char*)st + c.off); }
 template <typename S> static void*& out_ptr(S* st, const ColDesc& c) { return *(void**)((char*)st + c.off); }
 
+// Staging layout of one step: every column gets a 256-byte aligned offset inside ONE block, in an order that
+// keeps what a typical step carries adjacent (op + event families first; dense outbox columns before the
+// sparse payload columns).  The device block and — for leases — the pinned host block use the same offsets,
+// so adjacent columns travel in a single cudaMemcpyAsync (a leased leader step is 1 copy up, 1 copy down).
+static const int IN_ORDER[N_IN]   = {2, 3, 8, 9, 10, 4, 5, 6, 7, 0, 1};     // op_meta op_nr ev_meta ev_tn ev_el op_ab op_cd op_e ent gids row_now
+static const int OUT_ORDER[N_OUT] = {0, 2, 3, 4, 5, 6, 9, 10, 11, 12, 13, 14, 1, 7, 8};   // ... dense ..., then rep_term ballot_term ballot_last
+struct Layout { size_t in_off[N_IN], out_off[N_OUT], flags_off, in_total, out_total; };
+// gcols = entries of a per-group outbox column: max_groups, or n under RAFTING_INBOX_COMPACT_GROUPS
+static Layout make_layout(size_t rows, size_t n, size_t F, size_t gcols, size_t nact, size_t ent) {
+    const size_t G = gcols;
+    Layout L; size_t off = 0;
+    for (int q = 0; q < N_IN; q++) { const int k = IN_ORDER[q]; L.in_off[k] = off; off += (col_bytes(IN_COLS[k], rows, n, F, G, nact, ent + 1) + 255) & ~(size_t)255; }
+    L.in_total = off; off = 0;
+    for (int q = 0; q < N_OUT; q++) {
+        const int k = OUT_ORDER[q];
+        if (q == N_OUT - 3) { L.flags_off = off; off += 256; }              // the two flag words sit right after the dense columns
+        L.out_off[k] = off; off += (col_bytes(OUT_COLS[k], rows, n, F, G, 0, 0) + 255) & ~(size_t)255;
+    }
+    L.out_total = off;
+    return L;
+}
+struct Blk { uint8_t* p = nullptr; size_t cap = 0; };
+static int blk_reserve(Blk& b, size_t bytes, bool pinned) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) { if (pinned) cudaFreeHost(b.p); else cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    const size_t cap = bytes + bytes / 4 + 4096;
+    if (pinned) { CU(cudaHostAlloc((void**)&b.p, cap, cudaHostAllocDefault)); memset(b.p, 0, cap); }
+    else CU(cudaMalloc((void**)&b.p, cap));
+    b.cap = cap;
+    return 0;
+}
+
 struct Slot {
-    Col in[N_IN], out[N_OUT];
-    uint32_t* d_flags = nullptr; uint32_t* h_flags = nullptr;   // [0] ballots emitted, [1] valid replies (device / pinned host)
-    rafting_outbox_t host_out; rafting_outbox_t dev_out; size_t rows_ = 0, n_ = 0;   // of the step in flight (for the sparse columns)                 // .d device staging, .h pinned host (leases only)
+    Blk din, dout;                            // device staging (both paths)
+    Blk hin, hout;                            // pinned host staging (leases only), same layout as din / dout
+    uint32_t* h_flags = nullptr;              // pinned landing place of the flag words on the caller-owned path
     cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
     bool leased = false, inflight = false;
-    uint32_t rows = 0, n = 0, ent = 0; bool list = false;
+    uint32_t rows = 0, n = 0, ent = 0; bool list = false, compact = false;
+    void* lease_key = nullptr;                // the lease's commit_index pointer identifies it
+    // of the step in flight (for the sparse columns fetched at wait time)
+    rafting_outbox_t host_out; rafting_outbox_t dev_out; size_t rows_ = 0, n_ = 0; const uint32_t* flags_host = nullptr;
 };
 struct HostPath {
     Slot slot[RAFTING_HOST_SLOTS];
@@ -347,18 +377,6 @@ struct HostPath {
 };
 static HostPath* hp(rafting_engine* e) { if (!e->host) e->host = new HostPath(); return e->host; }
 
-static int dev_reserve(Col& c, size_t bytes, bool pinned) {
-    if (bytes > c.cap || (pinned && !c.h)) {
-        if (c.h) cudaFreeHost(c.h);
-        if (c.d) cudaFree(c.d);
-        c.h = c.d = nullptr; c.cap = 0;
-        const size_t cap = bytes + bytes / 4 + 256;
-        CU(cudaMalloc(&c.d, cap));
-        if (pinned) { CU(cudaHostAlloc(&c.h, cap, cudaHostAllocDefault)); memset(c.h, 0, cap); }
-        c.cap = cap;
-    }
-    return 0;
-}
 static int hostpath_init(rafting_engine* e) {
     HostPath* H = hp(e);
     if (H->ready) return 0;
@@ -368,7 +386,6 @@ static int hostpath_init(rafting_engine* e) {
         CU(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_kernel, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
-        CU(cudaMalloc((void**)&s.d_flags, 16));
         CU(cudaHostAlloc((void**)&s.h_flags, 16, cudaHostAllocDefault));
     }
     H->ready = true;
@@ -377,19 +394,38 @@ static int hostpath_init(rafting_engine* e) {
 static void hostpath_free(rafting_engine* e) {
     HostPath* H = hp(e);
     for (Slot& s : H->slot) {
-        for (Col& c : s.in) col_free(c);
-        for (Col& c : s.out) col_free(c);
+        if (s.din.p) cudaFree(s.din.p);
+        if (s.dout.p) cudaFree(s.dout.p);
+        if (s.hin.p) cudaFreeHost(s.hin.p);
+        if (s.hout.p) cudaFreeHost(s.hout.p);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
-        if (s.d_flags) cudaFree(s.d_flags);
         if (s.h_flags) cudaFreeHost(s.h_flags);
     }
     if (H->s_h2d) cudaStreamDestroy(H->s_h2d);
     if (H->s_d2h) cudaStreamDestroy(H->s_d2h);
 }
-
 static void rafting_hostpath_release(rafting_engine* e) { if (e->host) { hostpath_free(e); delete e->host; e->host = nullptr; } }
+
+// copy list with merging: entries of the engine's own pinned block `hb` (a lease) whose host and device addresses
+// advance by the same amount, with at most one alignment gap between them, become one cudaMemcpyAsync.  Caller-owned
+// buffers are never merged: two of them may be adjacent in the address space and still be separate registrations.
+struct CopyItem { uint8_t* h; uint8_t* d; size_t bytes; };
+static int issue_copies(std::vector<CopyItem>& v, bool to_device, cudaStream_t st, const Blk& hb) {
+    auto own = [&](const CopyItem& c) { return hb.p && c.h >= hb.p && c.h + c.bytes <= hb.p + hb.cap; };
+    size_t i = 0;
+    while (i < v.size()) {
+        uint8_t* h0 = v[i].h; uint8_t* d0 = v[i].d; size_t len = v[i].bytes; size_t j = i + 1;
+        while (own(v[i]) && j < v.size() && own(v[j]) && v[j].h - h0 == v[j].d - d0 && v[j].h >= h0 + len && (size_t)(v[j].h - (h0 + len)) < 256) {
+            len = (size_t)(v[j].h - h0) + v[j].bytes; j++;
+        }
+        if (to_device) CU(cudaMemcpyAsync(d0, h0, len, cudaMemcpyHostToDevice, st));
+        else CU(cudaMemcpyAsync(h0, d0, len, cudaMemcpyDeviceToHost, st));
+        i = j;
+    }
+    return RAFTING_OK;
+}
 
 // enqueue one step in `slot`: `in` / `out` hold HOST pointers (pinned for real overlap)
 static int step_enqueue(rafting_engine* e, uint32_t slot, const rafting_inbox_t* in, const rafting_outbox_t* out) {
@@ -405,10 +441,19 @@ static int step_enqueue(rafting_engine* e, uint32_t slot, const rafting_inbox_t*
     if (in->row_now) for (size_t r = 0; r < rows; r++) sweep |= in->row_now[r] != 0;
     if (in->op_meta && !in->op_nr) return fail(RAFTING_E_INVAL, "op_meta without op_nr");
     if (in->ev_meta && !in->ev_tn) return fail(RAFTING_E_INVAL, "ev_meta without ev_tn");
+    // a leased step keeps the layout of its lease (the pinned block was carved with it)
+    const bool compact = list && (in->flags & RAFTING_INBOX_COMPACT_GROUPS);
+    if (S.leased && compact != S.compact) return fail(RAFTING_E_INVAL, "COMPACT_GROUPS differs from the lease");
+    const size_t gcols = compact ? n : G;
+    const Layout L = S.leased ? make_layout(S.rows, S.n, F, S.compact ? S.n : G, S.list ? S.n : 0, S.ent)
+                              : make_layout(rows, n, F, gcols, in->n_active, in->ent_count);
+    int rc;
+    if ((rc = blk_reserve(S.din, L.in_total, false)) || (rc = blk_reserve(S.dout, L.out_total, false))) return rc;
     rafting_inbox_t din = *in; rafting_outbox_t dout; memset(&dout, 0, sizeof(dout));
     // ---- H2D ----
-    for (int k = 0; k < N_IN; k++) {
-        const ColDesc& c = IN_COLS[k];
+    std::vector<CopyItem> up;
+    for (int q = 0; q < N_IN; q++) {
+        const int k = IN_ORDER[q]; const ColDesc& c = IN_COLS[k];
         const void* hsrc = in_ptr(in, c);
         bool use = hsrc != nullptr;
         if (c.per == PER_GI && !in->op_meta) use = false;                    // op family absent
@@ -417,46 +462,48 @@ static int step_enqueue(rafting_engine* e, uint32_t slot, const rafting_inbox_t*
         if (c.per == PER_ENT && (in->ent_count == 0 || !in->op_meta)) use = false;
         const size_t bytes = use ? col_bytes(c, rows, n, F, G, in->n_active, in->ent_count) : 0;
         if (!use || bytes == 0) { in_ptr(&din, c) = nullptr; continue; }
-        int rc = dev_reserve(S.in[k], bytes, false); if (rc) return rc;
-        CU(cudaMemcpyAsync(S.in[k].d, hsrc, bytes, cudaMemcpyHostToDevice, H->s_h2d));
-        in_ptr(&din, c) = S.in[k].d;
+        CopyItem it; it.h = (uint8_t*)hsrc; it.d = S.din.p + L.in_off[k]; it.bytes = bytes;
+        up.push_back(it);
+        in_ptr(&din, c) = it.d;
     }
+    if ((rc = issue_copies(up, true, H->s_h2d, S.hin))) return rc;
     CU(cudaEventRecord(S.ev_h2d, H->s_h2d));
     // ---- kernel ----
     const bool ops = din.op_meta || din.row_now;
     for (int k = 0; k < N_OUT; k++) {
         const ColDesc& c = OUT_COLS[k];
-        void* hdst = out_ptr(out, c);
-        bool use = hdst != nullptr;
+        bool use = out_ptr(out, c) != nullptr;
         const bool repOrPlan = c.off <= offsetof(rafting_outbox_t, plan_epoch);
         if (repOrPlan && !ops) use = false;                                  // nothing can produce replies / plans
-        if (!use) continue;
-        int rc = dev_reserve(S.out[k], col_bytes(c, rows, n, F, G, 0, 0), false); if (rc) return rc;
-        out_ptr(&dout, c) = S.out[k].d;
+        if (use) out_ptr(&dout, c) = S.dout.p + L.out_off[k];
     }
+    uint32_t* d_flags = (uint32_t*)(S.dout.p + L.flags_off);
     CU(cudaStreamWaitEvent(e->stream, S.ev_h2d, 0));
-    CU(cudaMemsetAsync(S.d_flags, 0, 16, e->stream));
+    CU(cudaMemsetAsync(d_flags, 0, 16, e->stream));
     InboxD di; OutboxD dov;
     to_dev_views(&din, &dout, e->G, di, dov);
-    dov.flags = S.d_flags;
-    int rc = launch_step(e, di, dov, e->stream); if (rc) return rc;
+    dov.flags = d_flags;
+    rc = launch_step(e, di, dov, e->stream); if (rc) return rc;
     CU(cudaEventRecord(S.ev_kernel, e->stream));
     // ---- D2H: dense columns always; the payload of the SPARSE families (rep_term, ballot_term, ballot_last —
     //      meaningful only where a reply / ballot exists, i.e. never in leader steady state) only if the kernel
     //      counted any, which the host learns from two flag words at wait time ----
     CU(cudaStreamWaitEvent(H->s_d2h, S.ev_kernel, 0));
-    for (int k = 0; k < N_OUT; k++) {
-        const ColDesc& c = OUT_COLS[k];
-        void* dsrc = out_ptr(&dout, c);
+    std::vector<CopyItem> down;
+    for (int q = 0; q < N_OUT - 3; q++) {
+        const int k = OUT_ORDER[q]; const ColDesc& c = OUT_COLS[k];
+        uint8_t* dsrc = (uint8_t*)out_ptr(&dout, c);
         if (!dsrc) continue;
-        const bool sparse = c.off == offsetof(rafting_outbox_t, rep_term) || c.off == offsetof(rafting_outbox_t, ballot_term) ||
-                            c.off == offsetof(rafting_outbox_t, ballot_last);
-        if (sparse) continue;
-        CU(cudaMemcpyAsync(out_ptr(out, c), dsrc, col_bytes(c, rows, n, F, G, 0, 0), cudaMemcpyDeviceToHost, H->s_d2h));
+        CopyItem it; it.h = (uint8_t*)out_ptr(out, c); it.d = dsrc; it.bytes = col_bytes(c, rows, n, F, gcols, 0, 0);
+        down.push_back(it);
     }
-    CU(cudaMemcpyAsync(S.h_flags, S.d_flags, 16, cudaMemcpyDeviceToHost, H->s_d2h));
+    // flag words: into the lease's own pinned block when the outbox is leased (merges with the columns), else aside
+    uint32_t* hf = S.h_flags;
+    if (S.leased && S.hout.p && out->commit_index == (int64_t*)(S.hout.p + L.out_off[9])) hf = (uint32_t*)(S.hout.p + L.flags_off);
+    { CopyItem it; it.h = (uint8_t*)hf; it.d = (uint8_t*)d_flags; it.bytes = 16; down.push_back(it); }
+    if ((rc = issue_copies(down, false, H->s_d2h, S.hout))) return rc;
     CU(cudaEventRecord(S.ev_done, H->s_d2h));
-    S.host_out = *out; S.dev_out = dout; S.rows_ = rows; S.n_ = n;
+    S.host_out = *out; S.dev_out = dout; S.rows_ = rows; S.n_ = n; S.flags_host = hf;
     S.inflight = true;
     return RAFTING_OK;
 }
@@ -467,13 +514,14 @@ static int slot_wait(rafting_engine* e, uint32_t slot) {
     S.inflight = false;
     // sparse families: fetch their payload columns only when the step produced ballots / valid replies
     const size_t gi_cnt = S.rows_ * S.n_;
-    if (S.h_flags[0]) {
+    const uint32_t f0 = S.flags_host[0], f1 = S.flags_host[1];
+    if (f0) {
         if (S.dev_out.ballot_term) CU(cudaMemcpyAsync(S.host_out.ballot_term, S.dev_out.ballot_term, gi_cnt * 8, cudaMemcpyDeviceToHost, H->s_d2h));
         if (S.dev_out.ballot_last) CU(cudaMemcpyAsync(S.host_out.ballot_last, S.dev_out.ballot_last, gi_cnt * 16, cudaMemcpyDeviceToHost, H->s_d2h));
     }
-    if (S.h_flags[1] && S.dev_out.rep_term)
+    if (f1 && S.dev_out.rep_term)
         CU(cudaMemcpyAsync(S.host_out.rep_term, S.dev_out.rep_term, gi_cnt * 8, cudaMemcpyDeviceToHost, H->s_d2h));
-    if (S.h_flags[0] || S.h_flags[1]) CU(cudaStreamSynchronize(H->s_d2h));
+    if (f0 || f1) CU(cudaStreamSynchronize(H->s_d2h));
     return RAFTING_OK;
 }
 
@@ -489,9 +537,11 @@ extern "C" int rafting_step_wait_slot(rafting_engine_t* e, uint32_t slot) {
     return slot_wait(e, slot);
 }
 
-// lease = engine-owned pinned columns of a free slot
-extern "C" int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_t ent_count, rafting_lease_t* out) {
+// lease = engine-owned pinned columns of a free slot, carved from one pinned block with the staging layout
+extern "C" int rafting_lease_ex(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_t ent_count, uint32_t flags, rafting_lease_t* out) {
     if (!e || !out) return fail(RAFTING_E_INVAL, "null argument");
+    const bool compact = (flags & RAFTING_INBOX_COMPACT_GROUPS) != 0;
+    if (compact && n_active == 0) return fail(RAFTING_E_INVAL, "COMPACT_GROUPS needs an active list");
     if (rows == 0 || rows > e->cfg.max_rows) return fail(RAFTING_E_CAPACITY, "rows %u > max_rows %u", rows, e->cfg.max_rows);
     if (n_active > e->G) return fail(RAFTING_E_CAPACITY, "n_active > max_groups");
     if (ent_count > e->cfg.entry_pool_cap) return fail(RAFTING_E_CAPACITY, "ent_count > entry_pool_cap");
@@ -503,27 +553,28 @@ extern "C" int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_acti
     if (sl < 0) return fail(RAFTING_E_BUSY, "every slot is leased or in flight");
     Slot& S = H->slot[sl];
     const size_t n = n_active ? n_active : e->G, F = e->F, G = e->G;
+    const Layout L = make_layout(rows, n, F, compact ? n : G, n_active, ent_count);
+    if ((rc = blk_reserve(S.hin, L.in_total, true)) || (rc = blk_reserve(S.hout, L.out_total, true))) return rc;
     memset(out, 0, sizeof(*out));
     for (int k = 0; k < N_IN; k++) {
         const ColDesc& c = IN_COLS[k];
-        const size_t bytes = col_bytes(c, rows, n, F, G, n_active, (size_t)ent_count + 1);
-        if ((rc = dev_reserve(S.in[k], bytes, true))) return rc;
-        in_ptr(&out->in, c) = (c.per == PER_ACTIVE && n_active == 0) ? nullptr : S.in[k].h;
+        in_ptr(&out->in, c) = (c.per == PER_ACTIVE && n_active == 0) ? nullptr : (S.hin.p + L.in_off[k]);
     }
-    memset(S.in[1].h, 0, (size_t)rows * 8);                                  // row_now: no sweep unless the caller sets it
-    for (int k = 0; k < N_OUT; k++) {
-        const ColDesc& c = OUT_COLS[k];
-        if ((rc = dev_reserve(S.out[k], col_bytes(c, rows, n, F, G, 0, 0), true))) return rc;
-        out_ptr(&out->out, c) = S.out[k].h;
-    }
-    out->in.rows = rows; out->in.n_active = n_active; out->in.ent_count = ent_count;
+    memset(S.hin.p + L.in_off[1], 0, (size_t)rows * 8);                     // row_now: no sweep unless the caller sets it
+    for (int k = 0; k < N_OUT; k++) out_ptr(&out->out, OUT_COLS[k]) = S.hout.p + L.out_off[k];
+    out->in.rows = rows; out->in.n_active = n_active; out->in.ent_count = ent_count; out->in.flags = flags;
+    S.compact = compact;
     S.leased = true; S.rows = rows; S.n = (uint32_t)n; S.ent = ent_count; S.list = n_active != 0;
+    S.lease_key = out->out.commit_index;
     return RAFTING_OK;
+}
+extern "C" int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_t ent_count, rafting_lease_t* out) {
+    return rafting_lease_ex(e, rows, n_active, ent_count, 0, out);
 }
 static int lease_slot(rafting_engine* e, const rafting_lease_t* L) {
     HostPath* H = hp(e);
     for (int k = 0; k < RAFTING_HOST_SLOTS; k++)
-        if (H->slot[k].leased && L->out.commit_index == (int64_t*)H->slot[k].out[9].h) return k;
+        if (H->slot[k].leased && L->out.commit_index == (int64_t*)H->slot[k].lease_key) return k;
     return -1;
 }
 extern "C" int rafting_step_begin(rafting_engine_t* e, rafting_lease_t* L) {
@@ -535,6 +586,7 @@ extern "C" int rafting_step_begin(rafting_engine_t* e, rafting_lease_t* L) {
     if (L->in.rows == 0 || L->in.rows > S.rows) return fail(RAFTING_E_CAPACITY, "rows beyond the lease");
     if (L->in.ent_count > S.ent) return fail(RAFTING_E_CAPACITY, "ent_count beyond the lease");
     if (S.list != (L->in.gids != nullptr)) return fail(RAFTING_E_INVAL, "active-list lease without gids (or the reverse)");
+    if (S.list && L->in.n_active > S.n) return fail(RAFTING_E_CAPACITY, "n_active beyond the lease");
     return step_enqueue(e, (uint32_t)sl, &L->in, &L->out);
 }
 extern "C" int rafting_step_wait(rafting_engine_t* e, rafting_lease_t* L) {

@@ -31,6 +31,7 @@ struct Cols {
     const int64_t* current_term; const int64_t* commit_index; const uint32_t* incarnation; const uint32_t* role_word;
     const rafting_i64x2_t* last_entry;
     const uint32_t* gids;
+    bool compact;           // RAFTING_INBOX_COMPACT_GROUPS: the previous outbox's group columns are indexed by position
 };
 
 RAFTING_HD inline uint64_t key(uint64_t seed, uint32_t gid, uint64_t tick, uint32_t lane, uint32_t salt) {
@@ -41,7 +42,7 @@ RAFTING_HD inline uint64_t key(uint64_t seed, uint32_t gid, uint64_t tick, uint3
 
 RAFTING_HD inline void leader_cell(const rafting_wl_cfg_t& w, const Cols& c, uint64_t step, uint32_t r, uint32_t i) {
     const uint32_t gid = c.gids ? c.gids[i] : w.gid_base + i;    // global group id keys the RNG
-    const uint32_t lgid = c.gids ? c.gids[i] : i;                // local id indexes the snapshot columns
+    const uint32_t lgid = (c.gids && !c.compact) ? c.gids[i] : i;                // local id indexes the snapshot columns
     const uint64_t tick = step * w.rows + r;
     const size_t gi = (size_t)r * w.n + i;
     const int64_t now = w.t0 + 10 * (int64_t)tick + (int64_t)(gid % 10u);
@@ -82,7 +83,7 @@ RAFTING_HD inline void leader_cell(const rafting_wl_cfg_t& w, const Cols& c, uin
 // PreVote / RequestVote of the role object that asked (incarnation from the previous outbox)
 RAFTING_HD inline void election_cell(const rafting_wl_cfg_t& w, const Cols& c, uint32_t phase, uint32_t i) {
     const uint32_t gid = c.gids ? c.gids[i] : w.gid_base + i;
-    const uint32_t lgid = c.gids ? c.gids[i] : i;
+    const uint32_t lgid = (c.gids && !c.compact) ? c.gids[i] : i;
     const size_t gi = i;                                           // single row
     const int64_t now = w.t0 - 1000 + 10 * (int64_t)phase + (int64_t)(gid % 10u);
     if (c.op_meta) {
@@ -145,7 +146,7 @@ RAFTING_HD inline uint32_t lane_slot(uint32_t f, uint32_t local) { return f < lo
 // w.p. 0.05; 30 % of the groups also receive an inbound PreVote / RequestVote from a peer candidate.
 RAFTING_HD inline void vote_cell(const rafting_wl_cfg_t& w, const Cols& c, uint64_t step, uint32_t r, uint32_t i) {
     const uint32_t gid = c.gids ? c.gids[i] : w.gid_base + i;
-    const uint32_t lgid = c.gids ? c.gids[i] : i;
+    const uint32_t lgid = (c.gids && !c.compact) ? c.gids[i] : i;
     const uint64_t tick = step * w.rows + r;
     const size_t gi = (size_t)r * w.n + i;
     const int64_t now = w.t0 + 10 * (int64_t)tick + (int64_t)(gid % 10u);
@@ -181,7 +182,7 @@ RAFTING_HD inline void vote_cell(const rafting_wl_cfg_t& w, const Cols& c, uint6
 // Entry terms of an inbound request all equal its term; the pool holds 50 copies of every term < 256.
 RAFTING_HD inline void mixed_cell(const rafting_wl_cfg_t& w, const Cols& c, uint64_t step, uint32_t r, uint32_t i) {
     const uint32_t gid = c.gids ? c.gids[i] : w.gid_base + i;
-    const uint32_t lgid = c.gids ? c.gids[i] : i;
+    const uint32_t lgid = (c.gids && !c.compact) ? c.gids[i] : i;
     const uint64_t tick = step * w.rows + r;
     const size_t gi = (size_t)r * w.n + i;
     const int64_t now = w.t0 + 10 * (int64_t)tick + (int64_t)(gid % 10u);
@@ -272,7 +273,7 @@ Cols make_cols(const rafting_inbox_t* in, const rafting_outbox_t* prev) {
     c.plan_meta = prev ? prev->plan_meta : nullptr; c.plan_lc = prev ? prev->plan_lc : nullptr;
     c.plan_epoch = prev ? prev->plan_epoch : nullptr; c.current_term = prev ? prev->current_term : nullptr;
     c.incarnation = prev ? prev->incarnation : nullptr; c.role_word = prev ? prev->role_word : nullptr;
-    c.gids = in->gids;
+    c.gids = in->gids; c.compact = in->gids && (in->flags & RAFTING_INBOX_COMPACT_GROUPS);
     return c;
 }
 

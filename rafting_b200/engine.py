@@ -31,7 +31,7 @@ STATUS = {0: "OK", -1: "E_INVAL", -2: "E_NOMEM", -3: "E_CUDA", -4: "E_CLOSED", -
 
 EXPORTS = [
     "rafting_abi_version", "rafting_last_error", "rafting_engine_create", "rafting_engine_destroy",
-    "rafting_group_open", "rafting_group_open_bulk", "rafting_group_close", "rafting_lease", "rafting_step",
+    "rafting_group_open", "rafting_group_open_bulk", "rafting_group_close", "rafting_lease", "rafting_lease_ex", "rafting_step",
     "rafting_step_begin", "rafting_step_wait", "rafting_step_device", "rafting_state_export",
     "rafting_state_export_bulk", "rafting_state_digest", "rafting_log_term", "rafting_commit_slice",
     "rafting_comm_init", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_engine_stream",
@@ -69,6 +69,7 @@ def lib():
         L.rafting_group_open_bulk.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.rafting_group_close.argtypes = [C.c_void_p, C.c_uint32]
         L.rafting_lease.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(abi.LeaseC)]
+        L.rafting_lease_ex.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(abi.LeaseC)]
         L.rafting_step.argtypes = [C.c_void_p, C.POINTER(abi.LeaseC)]
         L.rafting_step_begin.argtypes = [C.c_void_p, C.POINTER(abi.LeaseC)]
         L.rafting_step_wait.argtypes = [C.c_void_p, C.POINTER(abi.LeaseC)]
@@ -155,15 +156,17 @@ class Engine:
         _check(lib().rafting_group_close(self._h, gid), "rafting_group_close")
 
     # ---- host path: lease -> fill pinned columns -> step (H2D + kernel + D2H inside) ----------
-    def lease(self, rows: int, n_active: int = 0, ent_count: int = 0) -> "Lease":
+    def lease(self, rows: int, n_active: int = 0, ent_count: int = 0, flags: int = 0) -> "Lease":
         lc = abi.LeaseC()
-        _check(lib().rafting_lease(self._h, rows, n_active, ent_count, C.byref(lc)), "rafting_lease")
-        return Lease(self, lc, rows, n_active if n_active else self.G)
+        _check(lib().rafting_lease_ex(self._h, rows, n_active, ent_count, flags, C.byref(lc)), "rafting_lease_ex")
+        compact = bool(flags & abi.INBOX_COMPACT_GROUPS)
+        return Lease(self, lc, rows, n_active if n_active else self.G, gcols=n_active if compact else self.G)
 
     def step(self, inbox: abi.Inbox, threads: int = 1) -> abi.Outbox:
         """Same call shape as oracle.binding.Oracle.step: numpy inbox in, numpy outbox out."""
         n = inbox.n
-        lease = self.lease(inbox.rows, 0 if inbox.gids is None else len(inbox.gids), inbox.ent_count)
+        lease = self.lease(inbox.rows, 0 if inbox.gids is None else len(inbox.gids), inbox.ent_count,
+                           inbox.flags & abi.INBOX_COMPACT_GROUPS)
         lease.fill_from(inbox)
         lease.run()
         return lease.outbox_copy()
@@ -313,9 +316,9 @@ class Lease:
     IN_OPS = (("op_meta", np.uint64), ("op_nr", abi.I64X2), ("op_ab", abi.I64X2), ("op_cd", abi.I64X2), ("op_e", np.int64))
     IN_EVS = (("ev_meta", np.uint64), ("ev_tn", abi.I64X2), ("ev_el", abi.I64X2))
 
-    def __init__(self, eng: Engine, lc: abi.LeaseC, rows: int, n: int):
+    def __init__(self, eng: Engine, lc: abi.LeaseC, rows: int, n: int, gcols: int | None = None):
         self.eng, self.c, self.rows, self.n = eng, lc, rows, n
-        F, G = eng.F, eng.G
+        F, G = eng.F, (eng.G if gcols is None else gcols)
         i = lc.inbox
         self._orig = {name: getattr(i, name) for name, _ in self.IN_OPS + self.IN_EVS}
         self._orig["row_now"] = i.row_now

@@ -107,6 +107,44 @@ def test_active_list_and_sweep_parity(engine_mod):
     harness.assert_states_equal(o, e, range(G), R - 1, where="sweep")
 
 
+def test_compact_group_columns_parity(engine_mod):
+    """RAFTING_INBOX_COMPACT_GROUPS: per-group outbox columns hold n_active entries indexed by position in
+    gids[]; they must equal the gid-indexed columns of an identical engine at those gids, and the oracle's."""
+    G, R, rows = 768, 3, 3
+    cfg, o, e = _pair(engine_mod, G, R, rows)
+    e2 = engine_mod.Engine(cfg)
+    e2.open_bulk(0, harness.init_array(G, terms=np.arange(G) % 7))
+    w1 = workload.make_wl(11, 1, G, R - 1)
+    harness.elect_all(o, w1), harness.elect_all(e, w1), harness.elect_all(e2, w1)
+    gids = np.arange(5, G, 7, dtype=np.uint32)
+    for step in range(3):
+        ib = abi.Inbox(rows, len(gids), R - 1, gids=gids)
+        for r in range(rows):
+            for i in range(len(gids)):
+                if (i + step) % 2:
+                    ib.submit(r, i, harness.T0 + 10 * step + r, 1 + (i % 3))
+                else:
+                    ib.timeout(r, i, harness.T0 + 10 * step + r, rand=0)
+        wide = e2.step(ib)
+        ib.flags |= abi.INBOX_COMPACT_GROUPS
+        oo, oe = o.step(ib), e.step(ib)
+        assert oe.commit_index.shape == (len(gids),) and oo.commit_index.shape == (len(gids),)
+        harness.assert_outbox_equal(oo, oe, where=f"compact step {step}")
+        for name, _ in abi.Outbox.GROUP_COLS:
+            assert np.array_equal(getattr(oe, name), getattr(wide, name)[gids]), name
+    harness.assert_states_equal(o, e, range(G), R - 1, where="compact")
+    # a lease taken without the flag refuses a step that carries it
+    L = e.lease(1, len(gids))
+    L.gids[:] = gids
+    L.use(ops=True, events=False, flags=abi.INBOX_COMPACT_GROUPS)
+    L.op_meta[:] = 0
+    with pytest.raises(engine_mod.RaftingError):
+        L.begin()
+    L.use(ops=True, events=False, flags=0)
+    L.run()
+    e2.close()
+
+
 def test_closed_group_and_capacity_errors(engine_mod):
     cfg, o, e = _pair(engine_mod, 8, 3, 2)
     o.close_group(3), e.close_group(3)

@@ -113,3 +113,27 @@ def test_mixed_churn_stream_threads_agree_and_covers_paths():
     assert {abi.OP_SUBMIT, abi.OP_TIMEOUT, abi.OP_AE_REQUEST, abi.OP_FLUSH} <= op_kinds
     assert {abi.PLAN_AE, abi.PLAN_IS} <= plan_kinds
     assert any(a.export(g).epoch_index > 0 for g in range(G))
+
+
+def test_oracle_compact_group_columns():
+    """RAFTING_INBOX_COMPACT_GROUPS in the oracle: same step, group columns indexed by position in gids[]."""
+    G, R, rows = 96, 3, 2
+    cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=rows)
+    a, b = binding.Oracle(cfg), binding.Oracle(cfg)
+    init = harness.init_array(G, terms=np.arange(G) % 5)
+    a.open_bulk(0, init), b.open_bulk(0, init)
+    w1 = workload.make_wl(5, 1, G, R - 1)
+    harness.elect_all(a, w1), harness.elect_all(b, w1)
+    gids = np.arange(1, G, 5, dtype=np.uint32)
+    ib = abi.Inbox(rows, len(gids), R - 1, gids=gids)
+    for r in range(rows):
+        for i in range(len(gids)):
+            ib.submit(r, i, harness.T0 + r, 2)
+    wide = a.step(ib)
+    ib.flags |= abi.INBOX_COMPACT_GROUPS
+    tight = b.step(ib)
+    assert tight.commit_index.shape == (len(gids),)
+    assert not wide.equal(tight, gids=slice(0, 0))          # row columns identical
+    for name, _ in abi.Outbox.GROUP_COLS:
+        assert np.array_equal(getattr(tight, name), getattr(wide, name)[gids]), name
+    assert tight.current_term.min() >= 1 and tight.incarnation.min() >= 1

@@ -15,8 +15,42 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rafting_b200 import abi, engine, workload  # noqa: E402
 
 
-def main():
+def caller_owned(e, w, rows, n, F, G, gids, lat):
     import torch
+    # pinned host batch buffers owned by the caller
+    def pinned(shape, dt):
+        t = torch.zeros(int(np.prod(shape)) * np.dtype(dt).itemsize, dtype=torch.uint8).pin_memory()
+        return t, np.frombuffer(t.numpy(), dtype=dt).reshape(shape)
+    ib = abi.Inbox(rows, n, F, gids=gids); ib.flags = abi.INBOX_NO_REQUESTS
+    ob = abi.Outbox(rows, n, F, G)
+    keep = []
+    for obj, names in ((ib, ("op_meta", "op_nr", "op_ab", "ev_meta", "ev_tn", "ev_el")),
+                       (ob, [c[0] for c in abi.Outbox.ROW_COLS] + [c[0] for c in abi.Outbox.GROUP_COLS])):
+        for name in names:
+            a = getattr(obj, name)
+            t, v = pinned(a.shape, a.dtype)
+            keep.append(t); setattr(obj, name, v)
+    ib.op_cd = None; ib.op_e = None
+    prev_out = None
+    for k in range(60):
+        ic = ib.as_c(); ic.op_cd = None; ic.op_e = None
+        workload.leader_step(w, k, None if prev_out is None else prev_out.as_c(), ic)      # the peers (not timed)
+        oc = ob.as_c()
+        t0 = time.perf_counter()
+        e.step_begin_host(0, ic, oc)
+        e.step_wait_slot(0)
+        _ = int(ob.commit_index[0])                                                      # commit column readable
+        dt = time.perf_counter() - t0
+        if k >= 10:
+            lat.append(dt * 1e3)
+        prev_out = ob
+    return int(((ib.ev_meta & np.uint64(0xF)) != 0).sum())
+
+
+LEASE = "--lease" in sys.argv
+
+
+def main():
     G, R = 65536, 3
     F = R - 1
     out = []
@@ -38,36 +72,32 @@ def main():
             workload.election_step(w1, ph, None if prev is None else prev.as_c(), ic)
             ib.op_cd = None; ib.op_e = None
             prev = e.step(ib)
-        # pinned host batch buffers owned by the caller
-        def pinned(shape, dt):
-            t = torch.zeros(int(np.prod(shape)) * np.dtype(dt).itemsize, dtype=torch.uint8).pin_memory()
-            return t, np.frombuffer(t.numpy(), dtype=dt).reshape(shape)
-        ib = abi.Inbox(rows, n, F, gids=gids); ib.flags = abi.INBOX_NO_REQUESTS
-        ob = abi.Outbox(rows, n, F, G)
-        keep = []
-        for obj, names in ((ib, ("op_meta", "op_nr", "op_ab", "ev_meta", "ev_tn", "ev_el")),
-                           (ob, [c[0] for c in abi.Outbox.ROW_COLS] + [c[0] for c in abi.Outbox.GROUP_COLS])):
-            for name in names:
-                a = getattr(obj, name)
-                t, v = pinned(a.shape, a.dtype)
-                keep.append(t); setattr(obj, name, v)
-        ib.op_cd = None; ib.op_e = None
         lat = []
-        prev_out = None
-        for k in range(60):
-            ic = ib.as_c(); ic.op_cd = None; ic.op_e = None
-            workload.leader_step(w, k, None if prev_out is None else prev_out.as_c(), ic)      # the peers (not timed)
-            oc = ob.as_c()
-            t0 = time.perf_counter()
-            e.step_begin_host(0, ic, oc)
-            e.step_wait_slot(0)
-            _ = int(ob.commit_index[0])                                                      # commit column readable
-            dt = time.perf_counter() - t0
-            if k >= 10:
-                lat.append(dt * 1e3)
-            prev_out = ob
-        acks = int(((ib.ev_meta & np.uint64(0xF)) != 0).sum())
-        rec = {"groups_in_step": n, "rows": rows, "acks_per_step": acks, "p50_ms": float(np.percentile(lat, 50)),
+        if LEASE:
+            # engine-owned pinned columns: one contiguous block per direction, so the step is 1 (+1 for an active
+            # list) copy up and 1 copy down; with an active list the group columns are compact (n entries, not G)
+            prev_c = None
+            ev_meta = None
+            for k in range(60):
+                fl = abi.INBOX_NO_REQUESTS | (0 if gids is None else abi.INBOX_COMPACT_GROUPS)
+                L = e.lease(rows, 0 if gids is None else n, 0, fl)
+                if gids is not None:
+                    L.gids[:] = gids
+                L.use(ops=True, events=True, flags=fl)
+                ic = L.c.inbox; ic.op_cd = None; ic.op_e = None
+                workload.leader_step(w, k, prev_c, ic)                                        # the peers (not timed)
+                t0 = time.perf_counter()
+                L.begin(); L.wait()
+                _ = int(L.out.commit_index[0])
+                dt = time.perf_counter() - t0
+                if k >= 10:
+                    lat.append(dt * 1e3)
+                prev_keep = L.outbox_copy(); prev_c = prev_keep.as_c()
+                ev_meta = L.ev_meta
+            acks = int(((ev_meta & np.uint64(0xF)) != 0).sum())
+        else:
+            acks = caller_owned(e, w, rows, n, F, G, gids, lat)
+        rec = {"buffers": "lease" if LEASE else "caller", "groups_in_step": n, "rows": rows, "acks_per_step": acks, "p50_ms": float(np.percentile(lat, 50)),
                "p99_ms": float(np.percentile(lat, 99)), "acks_per_s_at_p50": acks / (np.percentile(lat, 50) * 1e-3)}
         print(json.dumps(rec), flush=True)
         out.append(rec)
