@@ -230,7 +230,9 @@ typedef struct rafting_inbox {
     uint32_t rows;                 /* rows in this step (<= cfg.max_rows)                        */
     uint32_t n_active;             /* 0 = dense over gid 0..G-1, else length of gids[]           */
     const uint32_t* gids;          /* optional compacted active list (strictly increasing)       */
-    const int64_t*  row_now;       /* [rows] optional: != 0 => timer sweep at that time first    */
+    const int64_t*  row_now;       /* [rows] optional: != 0 => SWEEP ROW: the row's group-op slot is the
+                                      implied TIMEOUT of every group whose timer is due at that time
+                                      (op_* of that row are ignored); its lane events still run     */
     /* group ops */
     const uint64_t*        op_meta; /* lo32 RAFTING_OP_MAKE(...), hi32 entry-pool offset          */
     const rafting_i64x2_t* op_nr;   /* (now_ms, election-timeout draw ms)                         */

@@ -1,0 +1,315 @@
+"""A closed-loop Raft cluster made of R independent engines (BASELINE config #1: the reference's 3-node
+file-append cluster, `R/raft1-3.xml` + `T/cluster/TestNode1-3.java`, generalised to G groups).
+
+Every node is one system under test (the CPU oracle or the CUDA engine) with its own `local_slot`; this module
+plays what stays in Java around the engine: the Netty links (FIFO per link, loss, partitions),
+the `Async` time-outs, the payload store behind `RaftLog` and the file-append `RaftMachine`
+(`T/cluster/cmd/FileMachine.java`: apply = append the command to a file).  Nothing here knows Raft: it only turns
+outbox records into the inbox events of the peer they are addressed to, exactly as the tables in
+INTEGRATION.md §3/§4 say.  The reference's stated check for this configuration is "the three files are identical"
+(`README.md:28-33`); `check()` asserts that plus the Raft safety properties that imply it.
+
+Test infrastructure: used by tests/test_cluster_cpu.py (oracle) and tests/test_cluster_gpu.py (engine vs oracle)."""
+from __future__ import annotations
+
+from collections import defaultdict, deque
+
+import numpy as np
+
+from rafting_b200 import abi
+
+T0 = 1_700_000_000_000
+TICK_MS = 10
+RPC_TIMEOUT_TICKS = 12          # Async time-out of an RPC whose request or reply was lost
+ROWS = 4                        # row 0 is the timer-sweep row (its op slot is the implied TIMEOUT), ops use rows 1..3
+
+
+def _splitmix(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+class Node:
+    def __init__(self, sut, slot: int, G: int, R: int):
+        self.sut, self.slot, self.G, self.R, self.F = sut, slot, G, R, R - 1
+        self.queue = [deque() for _ in range(G)]          # per group: events in arrival order
+        self.store = [dict() for _ in range(G)]           # payload store: index -> (term, payload)
+        self.applied = [0] * G
+        self.file = [[] for _ in range(G)]                # the FileMachine's file, one per group
+        self.snap = None                                  # group columns of the previous step
+        self.inc_term = [dict() for _ in range(G)]        # incarnation -> term of that role object
+
+    def lane_of(self, slot: int) -> int:
+        return slot if slot < self.slot else slot - 1
+
+    def slot_of(self, lane: int) -> int:
+        return lane if lane < self.slot else lane + 1
+
+
+class Cluster:
+    def __init__(self, make_sut, G: int = 8, R: int = 3, seed: int = 1, drop_ppm: int = 0, submit_ppm: int = 300_000,
+                 heartbeat_ms: int = 50, election_ms: int = 300):
+        self.G, self.R, self.seed, self.drop_ppm, self.submit_ppm = G, R, seed, drop_ppm, submit_ppm
+        self.nodes = []
+        for k in range(R):
+            cfg = abi.make_cfg(replicas=R, local_slot=k, max_groups=G, max_rows=ROWS, entry_pool_cap=ROWS * G * 64,
+                               heartbeat_ms=heartbeat_ms, election_ms=election_ms, timer_seed=0xC0FFEE + 7919 * k)
+            sut = make_sut(cfg)
+            init = np.zeros(G, dtype=abi.GROUP_INIT_DTYPE)
+            init["ballot"] = -1; init["first_index"] = 1; init["now_ms"] = T0
+            sut.open_bulk(0, init)
+            self.nodes.append(Node(sut, k, G, R))
+        self.tick = 0
+        self.inflight = []                       # (deliver_tick, seq, dst_slot, gid, item)
+        self.link_clock = defaultdict(int)       # FIFO per (src, dst)
+        self.seq = 0
+        self.cut = set()                         # isolated node slots (partition)
+        self.leaders_by_term = [dict() for _ in range(G)]
+        self.submitted = 0
+        self.errors = []                         # per-event error codes seen (besides NotLeader / NotReady)
+        self.counts = defaultdict(int)
+
+    # ---- the network ---------------------------------------------------------------------------
+    def _rand(self, *key) -> int:
+        h = self.seed
+        for k in key:
+            h = _splitmix(h ^ (int(k) & 0xFFFFFFFFFFFFFFFF))
+        return h
+
+    def _lost(self, src, dst, *key) -> bool:
+        if src in self.cut or dst in self.cut:
+            return True
+        return self._rand(0xD409, src, dst, *key) % 1_000_000 < self.drop_ppm
+
+    def _send(self, src, dst, gid, item, extra_delay=0):
+        t = max(self.tick + 1 + extra_delay, self.link_clock[(src, dst)])
+        self.link_clock[(src, dst)] = t
+        self.seq += 1
+        self.inflight.append((t, self.seq, dst, gid, item))
+
+    def _timeout_event(self, node, gid, lane, kind, inc, epoch=0, last=0):
+        """The Async of a lost RPC completes with an error after its time-out (Async.java:239-254)."""
+        self.seq += 1
+        self.inflight.append((self.tick + RPC_TIMEOUT_TICKS, self.seq, node.slot, gid,
+                              ("ev", lane, dict(kind=kind, outcome=abi.OUT_ERROR, success=False, inc=inc, term=0,
+                                                epoch=epoch, last=last))))
+
+    # ---- one tick ------------------------------------------------------------------------------
+    def step(self, submit: bool = True):
+        now = T0 + TICK_MS * (self.tick + 1)
+        due = [m for m in self.inflight if m[0] <= self.tick]
+        self.inflight = [m for m in self.inflight if m[0] > self.tick]
+        for _, _, dst, gid, item in sorted(due, key=lambda m: (m[0], m[1])):
+            self.nodes[dst].queue[gid].append(item)
+        outs = []
+        for nd in self.nodes:
+            outs.append(self._step_node(nd, now, submit))
+        for nd, (ob, placed) in zip(self.nodes, outs):
+            self._dispatch(nd, ob, placed, now)
+        self.tick += 1
+
+    def _step_node(self, nd: Node, now: int, submit: bool):
+        G, F = self.G, nd.F
+        ib = abi.Inbox(ROWS, G, F, ent_cap=ROWS * G * 64, sweep=True)
+        ib.row_now[0] = now                                            # fires every due election / keepAlive timer
+        placed = {}
+        for g in range(G):
+            q = nd.queue[g]
+            # a client command goes to the node that believes it leads the group (RaftStub.submit)
+            if submit and nd.snap is not None and (int(nd.snap.role_word[g]) & 3) == abi.ROLE_LEADER \
+                    and self._rand(0x5B, nd.slot, g, self.tick) % 1_000_000 < self.submit_ppm:
+                q.appendleft(("op", dict(kind=abi.OP_SUBMIT, count=1 + self._rand(0x5C, nd.slot, g, self.tick) % 3)))
+            cursor = 0                                                 # position r*(F+1) + (0 | 1+lane); (0,op) is the sweep
+            while q:
+                it = q[0]
+                if it[0] == "op":
+                    r = cursor // (F + 1) + 1
+                    pos = r * (F + 1)
+                else:
+                    lane = it[1]
+                    r = cursor // (F + 1)
+                    pos = r * (F + 1) + 1 + lane
+                    if pos <= cursor:
+                        r += 1; pos += F + 1
+                if r >= ROWS:
+                    break                                              # stays queued for the next step
+                q.popleft()
+                cursor = pos
+                if it[0] == "op":
+                    self._place_op(nd, ib, r, g, now, it[1])
+                    placed[(r, g)] = it[1]
+                else:
+                    e = it[2]
+                    if e["kind"] in (abi.EV_AE_ACK, abi.EV_IS_ACK):
+                        ib.ack(r, g, lane, now, e["inc"], e["term"], e["success"], e["epoch"], e["last"],
+                               outcome=e["outcome"], snapshot=e["kind"] == abi.EV_IS_ACK)
+                    else:
+                        ib.vote_reply(r, g, lane, now, e["inc"], e["term"], e["success"], outcome=e["outcome"],
+                                      pre=e["kind"] == abi.EV_PV_REPLY)
+        ob = nd.sut.step(ib)
+        return ob, placed
+
+    def _place_op(self, nd, ib, r, g, now, op):
+        k = op["kind"]
+        if k == abi.OP_SUBMIT:
+            ib.submit(r, g, now, count=op["count"])
+        elif k == abi.OP_AE_REQUEST:
+            ib.ae_request(r, g, now, op["src"], op["term"], op["prev_index"], op["prev_term"],
+                          [t for t, _ in op["entries"]], op["leader_commit"])
+        elif k == abi.OP_PREVOTE_REQ:
+            ib.prevote_request(r, g, now, op["src"], op["term"], op["last_index"], op["last_term"])
+        elif k == abi.OP_VOTE_REQ:
+            ib.vote_request(r, g, now, op["src"], op["term"], op["last_index"], op["last_term"])
+        else:
+            raise AssertionError(k)
+
+    # ---- outbox -> messages --------------------------------------------------
+    def _dispatch(self, nd: Node, ob: abi.Outbox, placed, now):
+        G, F = self.G, nd.F
+        prev = nd.snap
+        # role objects and their terms: a role object's term is fixed for its lifetime (RaftMember.java:16-26)
+        for g in range(G):
+            nd.inc_term[g][int(ob.incarnation[g])] = int(ob.current_term[g])
+            if (int(ob.role_word[g]) & 3) == abi.ROLE_LEADER:
+                t = int(ob.current_term[g])
+                who = self.leaders_by_term[g].setdefault(t, nd.slot)
+                assert who == nd.slot, f"two leaders in term {t} of group {g}: {who} and {nd.slot}"   # election safety
+        # row by row, in the serial order of the step: a plan carries the entries the log held when it was made
+        for row in range(ROWS):
+            self._dispatch_row(nd, ob, {k: v for k, v in placed.items() if k[0] == row}, row, prev)
+        # apply committed commands to the file machine (RaftRoutine.commitState -> applyCommand)
+        for g in range(G):
+            c = int(ob.commit_index[g])
+            while nd.applied[g] < c:
+                nd.applied[g] += 1
+                nd.file[g].append(nd.store[g][nd.applied[g]])
+        nd.snap = ob
+
+    def _dispatch_row(self, nd: Node, ob: abi.Outbox, placed, row, prev):
+        F = nd.F
+        # replies to inbound requests, and the outcome of submits
+        for (r, g), op in placed.items():
+            m = int(ob.rep_meta[r, g]); err = (m >> 8) & 0xFF
+            if op["kind"] == abi.OP_SUBMIT:
+                if err == 0:
+                    # the first op of the step: appended right after the log end of the previous snapshot
+                    assert r == 1
+                    last = int(prev.last_entry[g]["x"]); term = int(prev.current_term[g])
+                    for j in range(op["count"]):
+                        self.submitted += 1
+                        nd.store[g][last + 1 + j] = (term, f"g{g}:n{nd.slot}:c{self.submitted}")
+                    self.counts["submit_ok"] += 1
+                elif err not in (24, 25):
+                    self.errors.append(("submit", nd.slot, g, err))
+                else:
+                    self.counts["submit_refused"] += 1
+                continue
+            src = self.nodes[op["src"]]
+            lane = src.lane_of(nd.slot)
+            if err == 3 and op["kind"] == abi.OP_AE_REQUEST:
+                # upstream quirk, mirrored: a follower whose commitIndex is ahead of min(leaderCommit, last.index)
+                # (a new leader that has not yet learnt how far the old one committed) hits "rollback is not
+                # allowed" (RocksLog.java:100-103 via Follower.java:80); the event loop logs it, no reply is sent
+                self.counts["commit_rollback"] += 1
+            elif err:
+                self.errors.append(("request", nd.slot, g, op["kind"], err))
+            valid, success = m & 1, (m >> 1) & 1
+            ekind = {abi.OP_AE_REQUEST: abi.EV_AE_ACK, abi.OP_PREVOTE_REQ: abi.EV_PV_REPLY,
+                     abi.OP_VOTE_REQ: abi.EV_RV_REPLY}[op["kind"]]
+            if op["kind"] == abi.OP_AE_REQUEST and valid and success:
+                self._store_entries(nd, g, op["prev_index"], op["entries"])
+                self.counts["ae_ok"] += 1
+            if not valid or self._lost(nd.slot, src.slot, g, self.tick, 1):
+                self._timeout_event(src, g, lane, ekind, op["inc"], op.get("epoch", 0), op.get("last", 0))
+                continue
+            self._send(nd.slot, src.slot, g, ("ev", lane, dict(kind=ekind, outcome=abi.OUT_OK, success=bool(success),
+                                                               inc=op["inc"], term=int(ob.rep_term[r, g]),
+                                                               epoch=op.get("epoch", 0), last=op.get("last", 0))))
+        # outbound AppendEntries (Leader.replicateLog)
+        pk = (ob.plan_meta[row] & np.uint64(0xF)).astype(np.int64)
+        for g, f in np.argwhere((pk == abi.PLAN_AE) | (pk == abi.PLAN_IS)):
+            r, g, f = row, int(g), int(f)
+            pm = int(ob.plan_meta[r, g, f]); inc = pm >> 32; count = (pm >> 16) & 0xFFFF
+            assert pk[g, f] == abi.PLAN_AE, "no compaction in this simulation, so no InstallSnapshot plan"
+            prev_index, prev_term = int(ob.plan_pp[r, g, f]["x"]), int(ob.plan_pp[r, g, f]["y"])
+            last, commit = int(ob.plan_lc[r, g, f]["x"]), int(ob.plan_lc[r, g, f]["y"])
+            epoch = int(ob.plan_epoch[r, g, f])
+            dst = nd.slot_of(f)
+            term = nd.inc_term[g].get(inc)
+            assert term is not None
+            entries = [nd.store[g][prev_index + 1 + j] for j in range(count)]
+            self.counts["ae_sent"] += 1
+            if self._lost(nd.slot, dst, g, self.tick, 0):
+                self._timeout_event(nd, g, f, abi.EV_AE_ACK, inc, epoch, last)
+                continue
+            self._send(nd.slot, dst, g, ("op", dict(kind=abi.OP_AE_REQUEST, src=nd.slot, term=term, prev_index=prev_index,
+                                                    prev_term=prev_term, entries=entries, leader_commit=commit, inc=inc,
+                                                    epoch=epoch, last=last)))
+        # PreVote / RequestVote broadcasts
+        bk = (ob.ballot_meta[row] & np.uint64(0xF)).astype(np.int64)
+        for (g,) in np.argwhere(bk != 0):
+            r, g = row, int(g)
+            pre = bk[g] == abi.BALLOT_PREVOTE
+            inc = int(ob.ballot_meta[r, g]) >> 32
+            self.counts["prevote" if pre else "vote"] += 1
+            for f in range(F):
+                dst = nd.slot_of(f)
+                if self._lost(nd.slot, dst, g, self.tick, 2 + f):
+                    self._timeout_event(nd, g, f, abi.EV_PV_REPLY if pre else abi.EV_RV_REPLY, inc)
+                    continue
+                self._send(nd.slot, dst, g, ("op", dict(kind=abi.OP_PREVOTE_REQ if pre else abi.OP_VOTE_REQ, src=nd.slot,
+                                                        term=int(ob.ballot_term[r, g]), inc=inc,
+                                                        last_index=int(ob.ballot_last[r, g]["x"]),
+                                                        last_term=int(ob.ballot_last[r, g]["y"]))))
+    @staticmethod
+    def _store_entries(nd, g, prev_index, entries):
+        """Payload side of RocksLog.conflict / truncate / append (RocksLog.java:169-225)."""
+        st = nd.store[g]
+        for j, (term, payload) in enumerate(entries):
+            idx = prev_index + 1 + j
+            have = st.get(idx)
+            if have is not None and have[0] == term:
+                continue
+            if have is not None:
+                for i in [i for i in st if i >= idx]:
+                    del st[i]
+            st[idx] = (term, payload)
+
+    # ---- scenario helpers ------------------------------------------------------------------------
+    def run(self, ticks, submit=True):
+        for _ in range(ticks):
+            self.step(submit)
+
+    def leader_of(self, g):
+        best = None
+        for nd in self.nodes:
+            if nd.snap is not None and (int(nd.snap.role_word[g]) & 3) == abi.ROLE_LEADER:
+                t = int(nd.snap.current_term[g])
+                if best is None or t > best[0]:
+                    best = (t, nd.slot)
+        return None if best is None else best[1]
+
+    # ---- checks ------------------------------------------------------------------------------------
+    def check(self, converged: bool):
+        assert not self.errors, self.errors[:5]
+        for g in range(self.G):
+            files = [nd.file[g] for nd in self.nodes]
+            # state machine safety: every pair of files agrees on its common prefix
+            for a in files:
+                for b in files:
+                    n = min(len(a), len(b))
+                    assert a[:n] == b[:n], f"group {g}: applied logs diverge"
+            for nd in self.nodes:
+                st = nd.sut.export(g)
+                # the engine's term table and the payload store describe the same log
+                lo, hi = st.epoch_index + 1, st.last_index
+                if nd.store[g]:
+                    assert max(nd.store[g]) >= hi
+                for i in range(max(lo, hi - 40), hi + 1):
+                    assert nd.sut.log_term(g, i) == nd.store[g][i][0], (g, nd.slot, i)
+                assert st.commit_index == nd.applied[g]
+            if converged:
+                assert all(f == files[0] for f in files), f"group {g}: the files differ"

@@ -1,0 +1,64 @@
+"""BASELINE config #1 on the GPU: the cluster of tests/cluster_sim.py with every node running BOTH the CUDA engine
+and the CPU oracle in lock-step.  Each step's outbox must be identical (so the two clusters exchange the same
+messages for the whole run), the exported state must match at the end, and the engine cluster must pass the same
+"the files are identical" check."""
+import numpy as np
+import pytest
+
+from oracle import binding
+from tests import harness
+from tests.cluster_sim import Cluster
+
+pytestmark = pytest.mark.gpu
+
+
+class Pair:
+    """Steps the engine and the oracle with the same inbox and insists on identical answers."""
+
+    def __init__(self, engine_mod, cfg):
+        self.e, self.o = engine_mod.Engine(cfg), binding.Oracle(cfg)
+        self.F = cfg.replicas - 1
+        self.steps = 0
+
+    def open_bulk(self, first, init):
+        self.e.open_bulk(first, init), self.o.open_bulk(first, init)
+
+    def step(self, ib):
+        oe, oo = self.e.step(ib), self.o.step(ib)
+        harness.assert_outbox_equal(oo, oe, where=f"cluster step {self.steps}")
+        self.steps += 1
+        return oe
+
+    def export(self, g):
+        se, so = self.e.export(g), self.o.export(g)
+        assert harness.state_bytes(se, self.F) == harness.state_bytes(so, self.F)
+        return se
+
+    def log_term(self, g, i):
+        t = self.e.log_term(g, i)
+        assert t == self.o.log_term(g, i)
+        return t
+
+
+@pytest.fixture(scope="module")
+def engine_mod():
+    from rafting_b200 import engine
+    return engine
+
+
+@pytest.mark.parametrize("R,G,seed", [(3, 24, 5), (5, 8, 6)])
+def test_cluster_engine_matches_oracle_and_files_agree(engine_mod, R, G, seed):
+    c = Cluster(lambda cfg: Pair(engine_mod, cfg), G=G, R=R, seed=seed, drop_ppm=15_000)
+    c.run(140)
+    victim = c.leader_of(0)
+    assert victim is not None
+    c.cut = {victim}
+    c.run(120)
+    c.cut = set()
+    c.run(150)
+    c.drop_ppm = 0
+    c.run(80, submit=False)
+    c.check(converged=True)
+    assert min(len(nd.file[g]) for nd in c.nodes for g in range(G)) > 10
+    for nd in c.nodes:
+        harness.assert_states_equal(nd.sut.o, nd.sut.e, range(G), R - 1, where=f"node {nd.slot}")
