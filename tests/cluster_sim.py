@@ -41,6 +41,8 @@ class Node:
         self.file = [[] for _ in range(G)]                # the FileMachine's file, one per group
         self.snap = None                                  # group columns of the previous step
         self.inc_term = [dict() for _ in range(G)]        # incarnation -> term of that role object
+        self.snapshot = [None] * G                        # SnapshotArchive: (index, term, file prefix) of the last checkpoint
+        self.install = [None] * G                         # pending snapshot installation (download + restore)
 
     def lane_of(self, slot: int) -> int:
         return slot if slot < self.slot else slot - 1
@@ -51,7 +53,8 @@ class Node:
 
 class Cluster:
     def __init__(self, make_sut, G: int = 8, R: int = 3, seed: int = 1, drop_ppm: int = 0, submit_ppm: int = 300_000,
-                 heartbeat_ms: int = 50, election_ms: int = 300):
+                 heartbeat_ms: int = 50, election_ms: int = 300, compact_every: int = 0):
+        self.compact_every = compact_every       # RaftRoutine.compactLog: checkpoint + RaftLog.flush every N applied entries
         self.G, self.R, self.seed, self.drop_ppm, self.submit_ppm = G, R, seed, drop_ppm, submit_ppm
         self.nodes = []
         for k in range(R):
@@ -122,9 +125,20 @@ class Cluster:
             if submit and nd.snap is not None and (int(nd.snap.role_word[g]) & 3) == abi.ROLE_LEADER \
                     and self._rand(0x5B, nd.slot, g, self.tick) % 1_000_000 < self.submit_ppm:
                 q.appendleft(("op", dict(kind=abi.OP_SUBMIT, count=1 + self._rand(0x5C, nd.slot, g, self.tick) % 3)))
+            if self.compact_every and nd.snap is not None and nd.install[g] is None:
+                done = nd.snapshot[g][0] if nd.snapshot[g] else 0
+                if nd.applied[g] - done >= self.compact_every:
+                    idx = nd.applied[g]; term = nd.store[g][idx][0]
+                    nd.snapshot[g] = (idx, term, list(nd.file[g][:idx]))           # RaftMachine.checkpoint
+                    q.appendleft(("op", dict(kind=abi.OP_FLUSH, index=idx, term=term)))
+                    self.counts["compactions"] += 1
             cursor = 0                                                 # position r*(F+1) + (0 | 1+lane); (0,op) is the sweep
             while q:
                 it = q[0]
+                if it[0] == "op" and it[1]["kind"] == abi.OP_IS_REQUEST and "result" not in it[1]:
+                    q.popleft()
+                    q.extendleft(reversed(self._install_snapshot(nd, g, it[1])))
+                    continue
                 if it[0] == "op":
                     r = cursor // (F + 1) + 1
                     pos = r * (F + 1)
@@ -163,8 +177,29 @@ class Cluster:
             ib.prevote_request(r, g, now, op["src"], op["term"], op["last_index"], op["last_term"])
         elif k == abi.OP_VOTE_REQ:
             ib.vote_request(r, g, now, op["src"], op["term"], op["last_index"], op["last_term"])
+        elif k == abi.OP_IS_REQUEST:
+            ib.is_request(r, g, now, op["src"], op["term"], op["index"], op["index_term"], op["result"])
+        elif k == abi.OP_FLUSH:
+            ib.flush(r, g, now, op["index"], op["term"])
         else:
             raise AssertionError(k)
+
+    def _install_snapshot(self, nd, g, op):
+        """Host side of RaftContext.installSnapshot (RaftRoutine.java:408-445): the first request starts the download
+        and answers false; once the machine has been restored from the snapshot the next request corrects the log
+        epoch (accomplishInstallation -> RaftLog.flush(milestone), :451-475) and answers true."""
+        ins = nd.install[g]
+        if ins is None:
+            snap = self.nodes[op["src"]].snapshot[g]
+            nd.install[g] = dict(ready=self.tick + 3, snap=snap)
+            return [("op", dict(op, result=False))]
+        if self.tick < ins["ready"]:
+            return [("op", dict(op, result=False))]
+        idx, term, prefix = ins["snap"]
+        nd.install[g] = None
+        self.counts["snapshots_installed"] += 1
+        ok = idx > op["index"] or (idx == op["index"] and term >= op["index_term"])
+        return [("op", dict(kind=abi.OP_FLUSH, index=idx, term=term, restore=prefix)), ("op", dict(op, result=ok))]
 
     # ---- outbox -> messages (INTEGRATION.md §4) --------------------------------------------------
     def _dispatch(self, nd: Node, ob: abi.Outbox, placed, now):
@@ -195,8 +230,7 @@ class Cluster:
             m = int(ob.rep_meta[r, g]); err = (m >> 8) & 0xFF
             if op["kind"] == abi.OP_SUBMIT:
                 if err == 0:
-                    # the first op of the step: appended right after the log end of the previous snapshot
-                    assert r == 1
+                    # submits (and compaction flushes) lead the step: appended right after the log end of the previous snapshot
                     last = int(prev.last_entry[g]["x"]); term = int(prev.current_term[g])
                     for j in range(op["count"]):
                         self.submitted += 1
@@ -206,6 +240,20 @@ class Cluster:
                     self.errors.append(("submit", nd.slot, g, err))
                 else:
                     self.counts["submit_refused"] += 1
+                continue
+            if op["kind"] == abi.OP_FLUSH:
+                if err:
+                    self.errors.append(("flush", nd.slot, g, err))
+                    continue
+                st = nd.store[g]                                   # RocksLog.flush: deleteRange is end-exclusive
+                if st and op["index"] > max(st):
+                    st.clear()
+                else:
+                    for i in [i for i in st if i < op["index"]]:
+                        del st[i]
+                if "restore" in op:                                # RaftMachine.recover(snapshot)
+                    nd.file[g] = list(op["restore"]); nd.applied[g] = op["index"]
+                    nd.snapshot[g] = (op["index"], op["term"], list(op["restore"]))
                 continue
             src = self.nodes[op["src"]]
             lane = src.lane_of(nd.slot)
@@ -218,7 +266,7 @@ class Cluster:
                 self.errors.append(("request", nd.slot, g, op["kind"], err))
             valid, success = m & 1, (m >> 1) & 1
             ekind = {abi.OP_AE_REQUEST: abi.EV_AE_ACK, abi.OP_PREVOTE_REQ: abi.EV_PV_REPLY,
-                     abi.OP_VOTE_REQ: abi.EV_RV_REPLY}[op["kind"]]
+                     abi.OP_VOTE_REQ: abi.EV_RV_REPLY, abi.OP_IS_REQUEST: abi.EV_IS_ACK}[op["kind"]]
             if op["kind"] == abi.OP_AE_REQUEST and valid and success:
                 self._store_entries(nd, g, op["prev_index"], op["entries"])
                 self.counts["ae_ok"] += 1
@@ -233,13 +281,20 @@ class Cluster:
         for g, f in np.argwhere((pk == abi.PLAN_AE) | (pk == abi.PLAN_IS)):
             r, g, f = row, int(g), int(f)
             pm = int(ob.plan_meta[r, g, f]); inc = pm >> 32; count = (pm >> 16) & 0xFFFF
-            assert pk[g, f] == abi.PLAN_AE, "no compaction in this simulation, so no InstallSnapshot plan"
             prev_index, prev_term = int(ob.plan_pp[r, g, f]["x"]), int(ob.plan_pp[r, g, f]["y"])
             last, commit = int(ob.plan_lc[r, g, f]["x"]), int(ob.plan_lc[r, g, f]["y"])
             epoch = int(ob.plan_epoch[r, g, f])
             dst = nd.slot_of(f)
             term = nd.inc_term[g].get(inc)
             assert term is not None
+            if pk[g, f] == abi.PLAN_IS:                            # (epoch.index, epoch.term) — Leader.java:172
+                self.counts["is_sent"] += 1
+                if self._lost(nd.slot, dst, g, self.tick, 0):
+                    self._timeout_event(nd, g, f, abi.EV_IS_ACK, inc, epoch, last)
+                    continue
+                self._send(nd.slot, dst, g, ("op", dict(kind=abi.OP_IS_REQUEST, src=nd.slot, term=term, index=prev_index,
+                                                        index_term=prev_term, inc=inc, epoch=epoch, last=last)))
+                continue
             entries = [nd.store[g][prev_index + 1 + j] for j in range(count)]
             self.counts["ae_sent"] += 1
             if self._lost(nd.slot, dst, g, self.tick, 0):
@@ -310,6 +365,6 @@ class Cluster:
                     assert max(nd.store[g]) >= hi
                 for i in range(max(lo, hi - 40), hi + 1):
                     assert nd.sut.log_term(g, i) == nd.store[g][i][0], (g, nd.slot, i)
-                assert st.commit_index == nd.applied[g]
+                assert st.commit_index <= nd.applied[g]        # equal unless a snapshot moved the machine ahead of the log
             if converged:
                 assert all(f == files[0] for f in files), f"group {g}: the files differ"

@@ -28,15 +28,17 @@ def state_hash(sut, G, F):
     return h.hexdigest()
 
 
-def run_cluster(sut_factory):
-    """BASELINE config #1 (three real nodes, tests/cluster_sim.py): loss, leader isolation, healing."""
+def run_cluster(sut_factory, snapshots=False):
+    """BASELINE config #1 (three real nodes, tests/cluster_sim.py): loss, leader isolation, healing; with
+    `snapshots` also log compaction and a follower that has to be caught up through InstallSnapshot."""
     from tests.cluster_sim import Cluster
-    c = Cluster(sut_factory, G=6, R=3, seed=0x5EED0001, drop_ppm=10_000)
+    c = Cluster(sut_factory, G=6, R=3, seed=0x5EED0001, drop_ppm=10_000, compact_every=25 if snapshots else 0)
     c.run(120)
-    c.cut = {c.leader_of(0)}
-    c.run(100)
+    lead = c.leader_of(0)
+    c.cut = {(lead + 1) % 3} if snapshots else {lead}
+    c.run(200 if snapshots else 100)
     c.cut = set()
-    c.run(120)
+    c.run(160 if snapshots else 120)
     c.drop_ppm = 0
     c.run(60, submit=False)
     c.check(converged=True)
@@ -49,7 +51,7 @@ def run_cluster(sut_factory):
         for g in range(c.G):
             sh.update(harness.state_bytes(nd.sut.export(g), 2))
     return {
-        "case": "cluster_r3", "groups": c.G, "replicas": 3, "ticks": c.tick, "seed": 0x5EED0001,
+        "case": "cluster_snap_r3" if snapshots else "cluster_r3", "groups": c.G, "replicas": 3, "ticks": c.tick, "seed": 0x5EED0001,
         "file_lengths": [len(c.nodes[0].file[g]) for g in range(c.G)],
         "terms": [int(c.nodes[0].sut.export(g).current_term) for g in range(c.G)],
         "counts": dict(sorted(c.counts.items())),
@@ -61,6 +63,8 @@ def run_case(name, sut_factory=binding.Oracle):
     """Returns the record of one golden case; shared by the generator and by tests/test_golden.py."""
     if name == "cluster_r3":
         return run_cluster(sut_factory)
+    if name == "cluster_snap_r3":
+        return run_cluster(sut_factory, snapshots=True)
     if name == "leader_r3":
         G, R, rows, steps, seed = 512, 3, 4, 12, 0x5EED0002
         cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=rows)
@@ -106,7 +110,7 @@ def run_case(name, sut_factory=binding.Oracle):
     }
 
 
-CASES = ("leader_r3", "votes_r5", "mixed_r3", "cluster_r3")
+CASES = ("leader_r3", "votes_r5", "mixed_r3", "cluster_r3", "cluster_snap_r3")
 
 if __name__ == "__main__":
     recs = {c: run_case(c) for c in CASES}

@@ -56,3 +56,22 @@ def test_five_node_cluster_two_nodes_down():
     c.drop_ppm = 0
     c.run(100, submit=False)
     c.check(converged=True)
+
+
+def test_compaction_and_snapshot_catch_up():
+    """Every node compacts its log every 25 applied commands (RaftRoutine.compactLog -> RaftLog.flush).  A follower
+    that was cut off long enough falls behind the leader's epoch and is caught up through InstallSnapshot
+    (pendingInstallation -> IS RPC answered false until the download has finished -> flush to the milestone ->
+    AppendEntries from there)."""
+    c = Cluster(_oracle, G=4, seed=21, compact_every=25)
+    c.run(120)
+    lead = c.leader_of(0)
+    lagger = (lead + 1) % 3
+    c.cut = {lagger}
+    c.run(220)
+    c.cut = set()
+    c.run(200)
+    c.run(80, submit=False)
+    c.check(converged=True)
+    assert c.counts["compactions"] > 10 and c.counts["is_sent"] > 0 and c.counts["snapshots_installed"] > 0
+    assert all(nd.sut.export(g).epoch_index > 0 for nd in c.nodes for g in range(c.G))

@@ -62,3 +62,18 @@ def test_cluster_engine_matches_oracle_and_files_agree(engine_mod, R, G, seed):
     assert min(len(nd.file[g]) for nd in c.nodes for g in range(G)) > 10
     for nd in c.nodes:
         harness.assert_states_equal(nd.sut.o, nd.sut.e, range(G), R - 1, where=f"node {nd.slot}")
+
+
+def test_cluster_with_compaction_and_snapshot_install(engine_mod):
+    c = Cluster(lambda cfg: Pair(engine_mod, cfg), G=12, R=3, seed=21, compact_every=25, drop_ppm=5_000)
+    c.run(120)
+    c.cut = {(c.leader_of(0) + 1) % 3}
+    c.run(220)
+    c.cut = set()
+    c.run(200)
+    c.drop_ppm = 0
+    c.run(80, submit=False)
+    c.check(converged=True)
+    assert c.counts["snapshots_installed"] > 0 and c.counts["is_sent"] > 0
+    for nd in c.nodes:
+        harness.assert_states_equal(nd.sut.o, nd.sut.e, range(c.G), 2, where=f"node {nd.slot}")
