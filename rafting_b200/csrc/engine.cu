@@ -78,6 +78,8 @@ struct rafting_engine {
     struct rafting::SegLog* seglog = nullptr;   // HBM entry buffer (seglog.cuh), created by rafting_log_config
     cudaEvent_t ev_seg = nullptr;
     uint64_t launches = 0, events = 0;
+    uint32_t* d_perm = nullptr;        // [NCLS * G] class-sorted positions of the step being launched (classify_kernel)
+    uint32_t* d_perm_cnt = nullptr;    // class sizes
     std::vector<void*> dev_allocs;
     std::vector<size_t> dev_bytes;
     std::vector<void*> shadow;         // rafting_checkpoint copies, parallel to dev_allocs
@@ -129,7 +131,7 @@ extern "C" int rafting_engine_create(const rafting_cfg_t* cfg, rafting_engine_t*
         rafting_engine_destroy(e); return rc;
     }
     T.g_commit = e->commit_all;
-    if ((rc = dalloc(e, &e->d_cfg, 1))) { rafting_engine_destroy(e); return rc; }
+    if ((rc = dalloc(e, &e->d_cfg, 1)) || (rc = dalloc(e, &e->d_perm, NCLS * G)) || (rc = dalloc(e, &e->d_perm_cnt, NCLS))) { rafting_engine_destroy(e); return rc; }
     if (cudaMemcpy(e->d_cfg, &e->dcfg, sizeof(CfgD), cudaMemcpyHostToDevice) != cudaSuccess) {
         rafting_engine_destroy(e); return fail(RAFTING_E_CUDA, "cfg upload failed");
     }
@@ -230,11 +232,11 @@ static int launch_t(rafting_engine* e, const InboxD& in, const OutboxD& out, cud
         if (NST > 0) CU(cudaFuncSetAttribute(unrolled::step_kernel<FT, (NST > 0 ? NST : 1), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[e->cfg.device & 63] = true;
     }
-    const uint32_t blocks = (in.n + TPB - 1) / TPB, full = in.n / TPB;
-    if (blocks == 0) return RAFTING_OK;
+    const uint32_t blocks = (in.n + TPB - 1) / TPB + (in.perm ? (uint32_t)NCLS : 0u), full = in.n / TPB;   // + NCLS: every class is padded to a block
+    if (in.n == 0) return RAFTING_OK;
     // TMA bulk staging needs full blocks, F == FT and 16-byte aligned column slices on every row
     auto al16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
-    const bool bulk = NST > 0 && e->F == (uint32_t)FT && full > 0 && (in.n % 2 == 0 || in.rows == 1) &&
+    const bool bulk = NST > 0 && !in.perm && e->F == (uint32_t)FT && full > 0 && (in.n % 2 == 0 || in.rows == 1) &&
                       al16(in.op_meta) && al16(in.op_nr) && al16(in.op_ab) && al16(in.ev_meta) && al16(in.ev_tn) && al16(in.ev_el) &&
                       getenv("RAFTING_BULK_STAGING") != nullptr;   // opt-in: measured slower than per-thread cp.async
     if (bulk) {
@@ -251,10 +253,19 @@ static int launch_looped(rafting_engine* e, const InboxD& in, const OutboxD& out
     looped::step_kernel<32, 0, false><<<blocks, TPB, 64, st>>>(e->T, in, out, e->d_cfg, e->dcfg, 0u);
     return RAFTING_OK;
 }
-static int launch_step(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
+static int launch_step(rafting_engine* e, const InboxD& in0, const OutboxD& out, cudaStream_t st) {
     int rc;
-    if ((uint64_t)in.rows * in.n * e->F >= (1ull << 32)) return fail(RAFTING_E_CAPACITY, "rows * groups * followers must stay below 2^32 per step");
+    if ((uint64_t)in0.rows * in0.n * e->F >= (1ull << 32)) return fail(RAFTING_E_CAPACITY, "rows * groups * followers must stay below 2^32 per step");
     const uint32_t F = e->F;
+    InboxD in = in0; in.perm = nullptr; in.perm_cnt = nullptr;
+    // A step that may hold inbound requests mixes steady-state leaders with groups that need the generic handlers;
+    // one slow lane stalls its whole warp, so such steps are launched class-sorted
+    static const bool sortOff = getenv("RAFTING_NO_CLASS_SORT") != nullptr;
+    if (!(in.flags & RAFTING_INBOX_NO_REQUESTS) && in.op_meta && in.n >= 2048 && F <= 8 && !sortOff) {
+        CU(cudaMemsetAsync(e->d_perm_cnt, 0, NCLS * 4, st));
+        classify_kernel<<<(in.n + 255) / 256, 256, 0, st>>>(e->T, in, e->d_perm, e->d_perm_cnt);
+        in.perm = e->d_perm; in.perm_cnt = e->d_perm_cnt;
+    }
     if (F == 1) rc = launch_t<1, 3>(e, in, out, st);
 #ifndef RAFTING_NST2
 #define RAFTING_NST2 3

@@ -137,6 +137,55 @@ struct __align__(16) Stage {             // one staged input row of this block
 };
 
 
+// Pre-pass of a step that may carry inbound requests: sorts the positions of the batch into NCLS classes so that a
+// warp of the step kernel runs ONE kind of work instead of waiting for its slowest lane:
+//   0 follower, 1 candidate, 2 leader that will need the generic handlers (not prepared / closed, or an op other than
+//   SUBMIT / TIMEOUT in some row)   -> slow_group, the whole step with the generic handlers
+//   3 leader steady state            -> the register-resident fast path
+// perm holds NCLS regions of n positions; cnt the class sizes.  One thread per position; block-level compaction, one
+// atomicAdd per block and class (the order of the blocks' chunks inside a class is irrelevant: groups are independent,
+// and a chunk stays contiguous for coalescing).
+constexpr int NCLS = 4;
+__global__ void __launch_bounds__(256) classify_kernel(Tables T, InboxD in, uint32_t* __restrict__ perm, uint32_t* __restrict__ cnt) {
+    __shared__ uint32_t wcnt[NCLS][8], base[NCLS];
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    const bool valid = i < in.n;
+    int cls = -1;
+    if (valid) {
+        const uint32_t gid = in.gids ? in.gids[i] : i;
+        if (gid >= T.G) cls = 2;
+        else {
+            const uint32_t w = (uint32_t)T.g_meta[gid];
+            const uint32_t role = w & W_ROLE_MASK;
+            if (role == RAFTING_ROLE_FOLLOWER) cls = 0;
+            else if (role == RAFTING_ROLE_CANDIDATE) cls = 1;
+            else {
+                bool slow = !((w & W_ALIVE) && (w & W_PREPARED));
+                if (!slow && in.op_meta)
+                    for (uint32_t r = 0; r < in.rows; r++)
+                        if (!(in.row_now && in.row_now[r] != 0) && RAFTING_OP_KIND((uint32_t)in.op_meta[(size_t)r * in.n + i]) > RAFTING_OP_TIMEOUT) { slow = true; break; }
+                cls = slow ? 2 : 3;
+            }
+        }
+    }
+    const uint32_t lane = threadIdx.x & 31u, wq = threadIdx.x >> 5;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < NCLS; k++) {
+        const uint32_t m = __ballot_sync(0xffffffffu, cls == k);
+        if (lane == 0) wcnt[k][wq] = __popc(m);
+        if (cls == k) mine = m;
+    }
+    __syncthreads();
+    if (threadIdx.x < NCLS) {
+        uint32_t tot = 0;
+        for (int k = 0; k < 8; k++) { const uint32_t c = wcnt[threadIdx.x][k]; wcnt[threadIdx.x][k] = tot; tot += c; }
+        base[threadIdx.x] = tot ? atomicAdd(cnt + threadIdx.x, tot) : 0u;
+    }
+    __syncthreads();
+    if (valid) perm[(size_t)cls * in.n + base[cls] + wcnt[cls][wq] + __popc(mine & ((1u << lane) - 1u))] = i;
+}
+
 #define RAFTING_BODY_NS unrolled
 #define RAFTING_UNROLL _Pragma("unroll")
 #include "step_body.inc"

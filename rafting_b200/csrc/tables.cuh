@@ -72,6 +72,10 @@ struct InboxD {
     const uint64_t* ev_meta;
     const i64x2*    ev_tn;
     const i64x2*    ev_el;
+    // engine-internal (launch_step): positions sorted by class — perm[c * n ..) the positions of class c, perm_cnt[c]
+    // their number (classify_kernel, step_kernel.cuh)
+    const uint32_t* perm;
+    const uint32_t* perm_cnt;
 };
 struct OutboxD {
     uint32_t* rep_meta; int64_t* rep_term;
