@@ -48,6 +48,7 @@ def parse():
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-secondary", action="store_true", help="skip the vote / follower-request rates (configs #3, #5)")
     return p.parse_args()
 
 
@@ -382,6 +383,19 @@ def run_engine(args):
         cpu3 = run_cpu_sample(args, seconds=min(4.0, args.cpu_seconds), threads=3)
         cpu["cores"] = cores; cpu["t3"] = cpu3["value"]
 
+    # vote replies (config #3) and follower-side AppendEntries requests (config #5) are separate rates,
+    # device-resident at full size; reported next to the headline, not part of `value`
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary and not args.no_e2e:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("bench_secondary", os.path.join(ROOT, "tools", "bench_secondary.py"))
+        mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+        secondary = []
+        for r in mod.run_all(quiet=True, steps5=64):
+            secondary.append({"config": r["config"], "groups": r["groups"], "replicas": r["replicas"], "rows_per_step": r["rows_per_step"],
+                              "steps": r["steps"], "kernel_ms_per_step": r["kernel_ms_per_step_median"],
+                              "rates_per_s": r["rates_per_s"], "roofline_frac": r["roofline"]["frac"]})
+
     if rank == 0:
         peak, peak_src = measured_peak()
         acks_per_launch = acks_timed / K
@@ -423,6 +437,8 @@ def run_engine(args):
         if cpu:
             line["cpu_baseline"] = {"value": cpu["value"], "unit": "acks/s", "cores": cpu["cores"], "kind": "port",
                                     "sample": cpu["sample"], "t3_loop_threads_value": cpu["t3"]}
+        if secondary:
+            line["secondary_rates"] = secondary
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -37,7 +37,7 @@ def init_array(G, **cols):
     return a
 
 
-def run(name, G, R, rows, steps, seed, gen, local_slot=0, elect=False, pool=False):
+def run(name, G, R, rows, steps, seed, gen, local_slot=0, elect=False, pool=False, quiet=False):
     import torch
     F = R - 1
     dev = torch.device("cuda:0")
@@ -113,14 +113,20 @@ def run(name, G, R, rows, steps, seed, gen, local_slot=0, elect=False, pool=Fals
                      "bytes_per_unit": {"ack": b_ack, "vote": 64, "request": "160 + 32 n"}},
         "end_state": {"roles": torch.bincount(role.long(), minlength=3).tolist(), "groups_with_error": int(err.sum())},
     }
-    print(json.dumps(rec), flush=True)
+    if not quiet:
+        print(json.dumps(rec), flush=True)
     e.close()
+    return rec
+
+
+def run_all(quiet=False, steps5=64):
+    L = _bind()
+    return [run("config3", 262144, 5, 1, 8, 0x5EED0003, L.rafting_wl_vote_step, local_slot=2, quiet=quiet),
+            run("config5", 524288, 3, 4, steps5, 0x5EED0005, L.rafting_wl_mixed_step, elect=True, pool=True, quiet=quiet)]
 
 
 def main():
-    L = _bind()
-    run("config3", 262144, 5, 1, 8, 0x5EED0003, L.rafting_wl_vote_step, local_slot=2)
-    run("config5", 524288, 3, 4, 64, 0x5EED0005, L.rafting_wl_mixed_step, elect=True, pool=True)
+    run_all()
 
 
 if __name__ == "__main__":
