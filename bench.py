@@ -21,6 +21,9 @@ import argparse
 import ctypes as C
 import json
 import os
+
+# stdout carries exactly one JSON line: NCCL's own banner / debug output ("NCCL version ...") goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import subprocess
 import sys
 import threading
