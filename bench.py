@@ -21,9 +21,6 @@ import argparse
 import ctypes as C
 import json
 import os
-
-# stdout carries exactly one JSON line: NCCL's own banner / debug output ("NCCL version ...") goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 import subprocess
 import sys
 import threading
@@ -166,7 +163,7 @@ def run_reference(args):
         "e2e": {"value": res["value"], "unit": "acks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Java; no JDK in this image -> oracle/ (C port of the reference's EventLoop path) is timed",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -442,13 +439,31 @@ def run_engine(args):
                                     "sample": cpu["sample"], "t3_loop_threads_value": cpu["t3"]}
         if secondary:
             line["secondary_rates"] = secondary
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: anything libraries print on fd 1 while the bench runs (NCCL prints its
+    # version banner there) is diverted to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
