@@ -410,7 +410,10 @@ def run_engine(args):
             "metric": "AppendEntries/sec across Raft groups", "value": value, "unit": "acks/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "groups_per_gpu": G, "replicas": R, "rows_per_step": rows,
+            "config": {"workload": WORKLOAD if world == 1 else
+                       f"{world * G // 1024}K RaftContext groups, 3 replicas, synthetic AppendEntries stream sharded across {world}xB200 "
+                       f"with NCCL commitIndex all-gather (64K groups per GPU, weak scaling of the 1xB200 configuration)",
+                       "groups_per_gpu": G, "replicas": R, "rows_per_step": rows,
                        "acks_per_step_per_gpu": acks_per_launch,
                        "inputs": f"every step reads a distinct pre-generated inbox resident in HBM "
                                  f"({inboxes[0].nbytes() / 1e6:.0f} MB inbox + {outs[0].nbytes() / 1e6:.0f} MB outbox per step, > L2), no L2 flush needed",

@@ -84,6 +84,24 @@ def test_fuzz_parity_all_event_kinds(engine_mod, R, local_slot, pre_vote, seed):
     assert len(errs) > 3
 
 
+@pytest.mark.parametrize("R,seed", [(3, 11), (5, 12)])
+def test_fuzz_parity_class_sorted_launch(engine_mod, R, seed):
+    """The same fuzz over enough groups (>= 2048) that steps with requests take the class-sorted launch: followers,
+    candidates and leaders are separated by classify_kernel and the slow classes run slow_group."""
+    G, rows = 2304, 3
+    cfg, o, e = _pair(engine_mod, G, R, rows, local_slot=1, pre_vote=True, ent=rows * G * 8, terms_mod=3)
+    fz = harness.Fuzzer(cfg, o, seed=seed, rows=rows)
+    out = None
+    roles = set()
+    for k in range(14):
+        ib = fz.make(out)
+        out = o.step(ib, threads=8)
+        harness.assert_outbox_equal(out, e.step(ib), where=f"fuzz step {k}")
+        roles |= set((out.role_word & 3).tolist())
+    harness.assert_states_equal(o, e, range(0, G, 7), R - 1, where="class-sorted fuzz")
+    assert roles == {0, 1, 2}
+
+
 def test_active_list_and_sweep_parity(engine_mod):
     G, R, rows = 512, 3, 2
     cfg, o, e = _pair(engine_mod, G, R, rows)
