@@ -365,6 +365,11 @@ int rafting_group_open     (rafting_engine_t* e, uint32_t gid, const rafting_gro
 int rafting_group_open_bulk(rafting_engine_t* e, uint32_t first_gid, uint32_t count,
                             const rafting_group_init_t* inits /* [count] */);
 int rafting_group_close    (rafting_engine_t* e, uint32_t gid);
+/* Restart with a log that spans several terms (RaftContext.initialize over an existing RocksLog, RaftContext.java:91-113):
+ * after rafting_group_open, hand over the stored log's index->term map as runs, oldest first — runs[k] = (first index of
+ * the run, its term); runs[0].x must be the group's first stored index, the last run's term its last_term.  At most
+ * RAFTING_TERM_RUNS runs (RAFTING_E_CAPACITY beyond: compact the log first). */
+int rafting_group_load_runs(rafting_engine_t* e, uint32_t gid, const rafting_i64x2_t* runs, uint32_t n_runs);
 
 /* host path: fill lease->in (pinned), call step; H2D + kernels + D2H happen inside the call */
 int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_t ent_count,

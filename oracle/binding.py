@@ -39,6 +39,7 @@ def lib():
         L.orc_group_open.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.GroupInit)]
         L.orc_group_open_bulk.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.orc_group_close.argtypes = [C.c_void_p, C.c_uint32]
+        L.orc_group_load_runs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.orc_step.argtypes = [C.c_void_p, C.POINTER(abi.InboxC), C.POINTER(abi.OutboxC), C.c_int]
         L.orc_state_export.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.GroupState)]
         L.orc_log_term.argtypes = [C.c_void_p, C.c_uint32, C.c_int64, C.POINTER(C.c_int64)]
@@ -88,6 +89,12 @@ class Oracle:
         rc = lib().orc_group_open_bulk(self._h, first_gid, len(inits), inits.ctypes.data)
         if rc:
             raise ValueError(f"orc_group_open_bulk rc={rc}")
+
+    def load_runs(self, gid: int, runs):
+        a = np.array(runs, dtype=np.int64).reshape(-1, 2)
+        rc = lib().orc_group_load_runs(self._h, gid, a.ctypes.data, len(a))
+        if rc:
+            raise ValueError(f"orc_group_load_runs rc={rc}")
 
     def close_group(self, gid: int):
         lib().orc_group_close(self._h, gid)

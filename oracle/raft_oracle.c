@@ -841,6 +841,22 @@ int orc_group_open_bulk(orc_engine_t* e, uint32_t first, uint32_t count, const r
     for (uint32_t i = 0; i < count; i++) { int r = orc_group_open(e, first + i, &inits[i]); if (r) return r; }
     return 0;
 }
+/* restart over a stored log spanning several terms: runs[k] = (first index, term), oldest first */
+int orc_group_load_runs(orc_engine_t* e, uint32_t gid, const rafting_i64x2_t* runs, uint32_t n) {
+    if (!e || !runs || gid >= e->cfg.max_groups || n == 0) return RAFTING_E_INVAL;
+    if (n > RAFTING_TERM_RUNS) return RAFTING_E_CAPACITY;
+    olog_t* l = &e->groups[gid].log;
+    if (!e->groups[gid].alive || log_empty(l) || runs[0].x != l->lo) return RAFTING_E_INVAL;
+    int64_t lastT; log_get(l, l->hi, &lastT);
+    if (runs[n - 1].y != lastT) return RAFTING_E_INVAL;
+    for (uint32_t k = 1; k < n; k++)
+        if (runs[k].x <= runs[k - 1].x || runs[k].x > l->hi || runs[k].y == runs[k - 1].y) return RAFTING_E_INVAL;
+    for (uint32_t k = 0; k < n; k++) {
+        int64_t end = (k + 1 < n) ? runs[k + 1].x - 1 : l->hi;
+        for (int64_t i = runs[k].x; i <= end; i++) l->terms[i - l->base] = runs[k].y;
+    }
+    return 0;
+}
 int orc_group_close(orc_engine_t* e, uint32_t gid) {
     if (!e || gid >= e->cfg.max_groups) return RAFTING_E_INVAL;
     e->groups[gid].alive = 0;

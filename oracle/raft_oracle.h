@@ -31,6 +31,7 @@ void          orc_destroy(orc_engine_t* e);
 int           orc_group_open(orc_engine_t* e, uint32_t gid, const rafting_group_init_t* init);
 int           orc_group_open_bulk(orc_engine_t* e, uint32_t first, uint32_t count,
                                   const rafting_group_init_t* inits);
+int           orc_group_load_runs(orc_engine_t* e, uint32_t gid, const rafting_i64x2_t* runs, uint32_t n);
 int           orc_group_close(orc_engine_t* e, uint32_t gid);
 
 /* one batch, canonical serial order, all pointers are host pointers.

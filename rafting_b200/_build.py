@@ -51,5 +51,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+DURABLE_LIB = os.path.join(HERE, "librafting_durable.so")
+
+
+def build_durable(force: bool = False) -> str:
+    """Host-only durability journal (include/rafting_durable.h): plain g++, no CUDA."""
+    src = os.path.join(CSRC, "durable.cpp")
+    hdr = os.path.join(HERE, "..", "include", "rafting_durable.h")
+    if not force and os.path.exists(DURABLE_LIB) and os.path.getmtime(DURABLE_LIB) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return DURABLE_LIB
+    cxx = shutil.which("g++") or "g++"
+    res = subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", src, "-o", DURABLE_LIB],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stderr[-4000:])
+    return DURABLE_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_durable(force=True))

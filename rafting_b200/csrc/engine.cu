@@ -208,6 +208,28 @@ extern "C" int rafting_group_open_bulk(rafting_engine_t* e, uint32_t first, uint
 extern "C" int rafting_group_open(rafting_engine_t* e, uint32_t gid, const rafting_group_init_t* init) {
     return rafting_group_open_bulk(e, gid, 1, init);
 }
+extern "C" int rafting_group_load_runs(rafting_engine_t* e, uint32_t gid, const rafting_i64x2_t* runs, uint32_t n) {
+    if (!e || !runs || gid >= e->G) return fail(RAFTING_E_INVAL, "bad argument");
+    if (n == 0 || n > (uint32_t)KRUNS) return fail(RAFTING_E_CAPACITY, "%u term runs: the engine keeps at most %d per group", n, KRUNS);
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    uint64_t m; int64_t lo, hi; i64x2 newest;
+    CU(cudaMemcpy(&m, e->T.g_meta + gid, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&lo, e->T.g_lo + gid, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&hi, e->T.g_hi + gid, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&newest, e->T.g_runs + gid, 16, cudaMemcpyDeviceToHost));
+    if (!(m & W_ALIVE) || ((uint32_t)(m >> W_NRUNS_SH) & 0xf) != 1 || hi < lo) return fail(RAFTING_E_INVAL, "group %u is not a freshly opened group with a stored log", gid);
+    if (runs[0].x != lo || runs[n - 1].y != newest.y) return fail(RAFTING_E_INVAL, "runs do not match the opened log (first index / last term)");
+    for (uint32_t k = 1; k < n; k++)
+        if (runs[k].x <= runs[k - 1].x || runs[k].x > hi || runs[k].y == runs[k - 1].y) return fail(RAFTING_E_INVAL, "runs must start at increasing indices inside the log and change term");
+    for (uint32_t k = 0; k < n; k++) {                                       // newest run first in the table
+        i64x2 v; v.x = runs[n - 1 - k].x; v.y = runs[n - 1 - k].y;
+        CU(cudaMemcpy(e->T.g_runs + (size_t)k * e->G + gid, &v, 16, cudaMemcpyHostToDevice));
+    }
+    m = (m & ~((uint64_t)0xf << W_NRUNS_SH)) | ((uint64_t)n << W_NRUNS_SH);
+    CU(cudaMemcpy(e->T.g_meta + gid, &m, 8, cudaMemcpyHostToDevice));
+    return RAFTING_OK;
+}
 extern "C" int rafting_group_close(rafting_engine_t* e, uint32_t gid) {
     if (!e || gid >= e->G) return fail(RAFTING_E_INVAL, "bad gid");
     CU(cudaSetDevice(e->cfg.device));

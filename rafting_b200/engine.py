@@ -31,7 +31,7 @@ STATUS = {0: "OK", -1: "E_INVAL", -2: "E_NOMEM", -3: "E_CUDA", -4: "E_CLOSED", -
 
 EXPORTS = [
     "rafting_abi_version", "rafting_last_error", "rafting_engine_create", "rafting_engine_destroy",
-    "rafting_group_open", "rafting_group_open_bulk", "rafting_group_close", "rafting_lease", "rafting_lease_ex", "rafting_step",
+    "rafting_group_open", "rafting_group_open_bulk", "rafting_group_load_runs", "rafting_group_close", "rafting_lease", "rafting_lease_ex", "rafting_step",
     "rafting_step_begin", "rafting_step_wait", "rafting_step_device", "rafting_state_export",
     "rafting_state_export_bulk", "rafting_state_digest", "rafting_log_term", "rafting_commit_slice",
     "rafting_comm_init", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_engine_stream",
@@ -68,6 +68,7 @@ def lib():
         L.rafting_group_open.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.GroupInit)]
         L.rafting_group_open_bulk.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.rafting_group_close.argtypes = [C.c_void_p, C.c_uint32]
+        L.rafting_group_load_runs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.rafting_lease.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(abi.LeaseC)]
         L.rafting_lease_ex.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(abi.LeaseC)]
         L.rafting_step.argtypes = [C.c_void_p, C.POINTER(abi.LeaseC)]
@@ -151,6 +152,11 @@ class Engine:
     def open_bulk(self, first_gid: int, inits: np.ndarray):
         inits = np.ascontiguousarray(inits, dtype=abi.GROUP_INIT_DTYPE)
         _check(lib().rafting_group_open_bulk(self._h, first_gid, len(inits), inits.ctypes.data), "rafting_group_open_bulk")
+
+    def load_runs(self, gid: int, runs):
+        """runs: [(first index of the run, term), ...] oldest first — the stored log's index->term map after a restart."""
+        a = np.array(runs, dtype=np.int64).reshape(-1, 2)
+        _check(lib().rafting_group_load_runs(self._h, gid, a.ctypes.data, len(a)), "rafting_group_load_runs")
 
     def close_group(self, gid: int):
         _check(lib().rafting_group_close(self._h, gid), "rafting_group_close")

@@ -57,9 +57,12 @@ class Cluster:
         self.compact_every = compact_every       # RaftRoutine.compactLog: checkpoint + RaftLog.flush every N applied entries
         self.G, self.R, self.seed, self.drop_ppm, self.submit_ppm = G, R, seed, drop_ppm, submit_ppm
         self.nodes = []
+        self.cfgs = []
+        self.on_outbox = None                    # hook(node, outbox): the pump's durability barrier, before any reply leaves
         for k in range(R):
             cfg = abi.make_cfg(replicas=R, local_slot=k, max_groups=G, max_rows=ROWS, entry_pool_cap=ROWS * G * 64,
                                heartbeat_ms=heartbeat_ms, election_ms=election_ms, timer_seed=0xC0FFEE + 7919 * k)
+            self.cfgs.append(cfg)
             sut = make_sut(cfg)
             init = np.zeros(G, dtype=abi.GROUP_INIT_DTYPE)
             init["ballot"] = -1; init["first_index"] = 1; init["now_ms"] = T0
@@ -111,6 +114,8 @@ class Cluster:
         for nd in self.nodes:
             outs.append(self._step_node(nd, now, submit))
         for nd, (ob, placed) in zip(self.nodes, outs):
+            if self.on_outbox:
+                self.on_outbox(nd, ob)             # persist-before-reply (RaftMember.java:20-26)
             self._dispatch(nd, ob, placed, now)
         self.tick += 1
 
@@ -332,6 +337,39 @@ class Cluster:
                 for i in [i for i in st if i >= idx]:
                     del st[i]
             st[idx] = (term, payload)
+
+    def restart(self, slot, make_sut, restore):
+        """Crash + restart of one node (ContextManager.buildContext, ContextManager.java:57-106): the engine state is
+        gone; what survives is what the reference keeps on disk — the StableLock record (`restore(gid)` -> term, ballot),
+        the payload log (RocksDB: nd.store) and the machine's file + snapshot archive.  commitIndex restarts at 0
+        (RocksLog.java:50, volatile) and is re-learnt from the leader."""
+        nd = self.nodes[slot]
+        sut = make_sut(self.cfgs[slot])
+        now = T0 + TICK_MS * (self.tick + 1)
+        for g in range(self.G):
+            st = restore(g)
+            ms = nd.snapshot[g]
+            keys = sorted(nd.store[g])
+            init = np.zeros(1, dtype=abi.GROUP_INIT_DTYPE)
+            init["term"] = st.term; init["ballot"] = st.ballot; init["now_ms"] = now
+            init["epoch_index"] = ms[0] if ms else 0; init["epoch_term"] = ms[1] if ms else 0
+            init["first_index"] = keys[0] if keys else 1
+            init["last_index"] = keys[-1] if keys else 0
+            init["last_term"] = nd.store[g][keys[-1]][0] if keys else 0
+            sut.open_bulk(g, init)
+            runs = []
+            for i in keys:
+                t = nd.store[g][i][0]
+                if not runs or runs[-1][1] != t:
+                    runs.append((i, t))
+            if len(runs) > 1:
+                sut.load_runs(g, runs)
+            nd.queue[g].clear()
+            nd.install[g] = None
+        nd.sut, nd.snap = sut, None
+        nd.inc_term = [dict() for _ in range(self.G)]
+        self.inflight = [m for m in self.inflight if m[2] != slot]     # nothing addressed to the dead process survives
+        self.counts["restarts"] += 1
 
     # ---- scenario helpers ------------------------------------------------------------------------
     def run(self, ticks, submit=True):

@@ -26,6 +26,15 @@ def test_every_declared_symbol_is_exported():
     assert set(engine.EXPORTS) <= set(names)
 
 
+def test_durable_library_exports_its_header():
+    from rafting_b200 import durable
+    L = durable.lib()
+    names = _declared("rafting_durable.h")
+    assert len(names) >= 9
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/rafting_durable.h but not exported by librafting_durable.so"
+
+
 def test_struct_sizes_match_the_compiled_library():
     out = (C.c_uint32 * 7)()
     assert engine.lib().rafting_abi_sizes(out, 7) == 7

@@ -34,6 +34,9 @@ class Pair:
         assert harness.state_bytes(se, self.F) == harness.state_bytes(so, self.F)
         return se
 
+    def load_runs(self, g, runs):
+        self.e.load_runs(g, runs), self.o.load_runs(g, runs)
+
     def log_term(self, g, i):
         t = self.e.log_term(g, i)
         assert t == self.o.log_term(g, i)
@@ -77,3 +80,30 @@ def test_cluster_with_compaction_and_snapshot_install(engine_mod):
     assert c.counts["snapshots_installed"] > 0 and c.counts["is_sent"] > 0
     for nd in c.nodes:
         harness.assert_states_equal(nd.sut.o, nd.sut.e, range(c.G), 2, where=f"node {nd.slot}")
+
+
+def test_node_crash_and_restart_from_the_journal(engine_mod, tmp_path):
+    """Durability journal + rafting_group_open + rafting_group_load_runs: a killed node comes back from what the
+    reference keeps on disk; engine and oracle stay identical through the restart and the files converge."""
+    from rafting_b200 import durable
+    G = 8
+    journals = [durable.Journal(str(tmp_path / f"n{k}"), G) for k in range(3)]
+    c = Cluster(lambda cfg: Pair(engine_mod, cfg), G=G, seed=31, drop_ppm=10_000)
+    c.on_outbox = lambda nd, ob: journals[nd.slot].commit_step(ob.role_word, ob.current_term)
+    c.run(150)
+    victim = c.leader_of(0)
+    c.cut = {victim}
+    c.run(2)
+    journals[victim].close()
+    journals[victim] = durable.Journal(str(tmp_path / f"n{victim}"), G)
+    c.restart(victim, lambda cfg: Pair(engine_mod, cfg), lambda g: journals[victim].restore(g))
+    c.run(60)
+    c.cut = set()
+    c.run(250)
+    c.drop_ppm = 0
+    c.run(80, submit=False)
+    c.check(converged=True)
+    for nd in c.nodes:
+        harness.assert_states_equal(nd.sut.o, nd.sut.e, range(G), 2, where=f"node {nd.slot}")
+    for j in journals:
+        j.close()

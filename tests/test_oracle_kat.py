@@ -588,6 +588,29 @@ def test_install_snapshot_request():
     assert rep(out) == (1, 0, 0, t)
 
 
+def test_restart_over_a_log_with_several_terms():
+    """RaftContext.initialize over an existing RocksLog (RaftContext.java:91-113): the index->term map of the stored log
+    comes back as runs; AppendEntries consistency checks must then see the right term at every index."""
+    g = One(term=5, first_index=1, last_index=10, last_term=3)
+    g.o.load_runs(0, [(1, 1), (4, 2), (8, 3)])
+    assert [g.o.log_term(0, i) for i in (1, 3, 4, 7, 8, 10)] == [1, 1, 2, 2, 3, 3]
+    # prev (7, 2) matches, (7, 3) does not (Follower.logContains, Follower.java:177-191)
+    ib = g.inbox(); ib.ae_request(0, 0, g.now, 1, 5, 7, 3, [], leader_commit=0); out = g.run(ib)
+    assert rep(out)[:2] == (1, 0)
+    ib = g.inbox(); ib.ae_request(0, 0, g.now, 1, 5, 7, 2, [3, 3, 3, 5], leader_commit=9); out = g.run(ib)
+    assert rep(out)[:2] == (1, 1)
+    st = g.st
+    assert (st.last_index, st.last_term, st.commit_index) == (11, 5, 9)
+    assert g.o.log_term(0, 11) == 5 and g.o.log_term(0, 6) == 2
+    # a conflicting suffix is cut at the first index whose stored term differs (RocksLog.conflict, RocksLog.java:199-216)
+    ib = g.inbox(); ib.ae_request(0, 0, g.now, 1, 5, 9, 3, [4, 4], leader_commit=9); out = g.run(ib)
+    assert rep(out)[:2] == (1, 1) and g.st.last_index == 11 and g.o.log_term(0, 10) == 4 and g.o.log_term(0, 9) == 3
+    for bad in ([(2, 1), (8, 3)], [(1, 1), (4, 1), (8, 3)], [(1, 1), (4, 2)], [(1, 1), (12, 3)]):
+        h = One(term=5, first_index=1, last_index=10, last_term=3)
+        with pytest.raises(Exception):
+            h.o.load_runs(0, bad)
+
+
 # --------------------------------------------------------------------------------------------
 # timers
 # --------------------------------------------------------------------------------------------
