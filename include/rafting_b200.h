@@ -424,8 +424,12 @@ int rafting_log_read  (rafting_engine_t* e, uint32_t gid, int64_t first_index, u
 int rafting_log_gather(rafting_engine_t* e, uint32_t n_ranges, const uint32_t* gids, const int64_t* firsts,
                        const uint32_t* counts, rafting_entry_ref_t* refs_out, uint32_t refs_cap,
                        void* blob_out, size_t blob_cap, uint32_t* n_out, size_t* bytes_out);
+/* garbage collection behind RaftLog.flush (RocksLog.java:228-242): drops the index entries below each group's lowest
+   stored key and frees cold (pinned host) segments that hold no live record any more */
+int rafting_log_trim  (rafting_engine_t* e, uint32_t first_gid, uint32_t count, uint64_t* dropped_entries, uint64_t* freed_cold_bytes);
 int rafting_log_stats (rafting_engine_t* e, uint64_t* out /* appended, head, spilled_bytes, hbm_hits, cold_hits, indexed,
-                                                              last gather kernels ns, last gather bytes */, uint32_t n);
+                                                              last gather kernels ns, last gather bytes, trimmed entries,
+                                                              cold bytes freed, spills skipped (dead segments) */, uint32_t n);
 
 /* multi-GPU summary: device pointer of this shard's commitIndex[G_local] (int64), and the
    NCCL all-gather of it into a [world * G_local] device buffer owned by the engine */

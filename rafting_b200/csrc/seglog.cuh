@@ -10,9 +10,9 @@
 //   RocksLog.newEntry / append  (put)          -> rafting_log_append  (batch: one H2D + one index kernel)
 //   RocksLog.get / batch        (multiGet)     -> rafting_log_read    (one group), rafting_log_gather
 //                                                 (many (gid, first, count) ranges = the AE plans of a step)
-//   RocksLog.truncate / flush   (deleteRange)  -> nothing to do here: visibility of a record is decided by
-//                                                 the group's stored key range [g_lo, g_hi] in the tables,
-//                                                 and a re-appended index overwrites its ring slot
+//   RocksLog.truncate / flush   (deleteRange)  -> visibility of a record is decided by the group's stored key range
+//                                                 [g_lo, g_hi] in the tables, and a re-appended index overwrites
+//                                                 its ring slot; rafting_log_trim reclaims what a flush left behind
 //
 // Record layout inside a segment: 24-byte header {gid u32, len u32, index i64, term i64} + payload padded
 // to 8 bytes.  Records never straddle segments.  A logical byte offset (segment number * seg_bytes + offset)
@@ -45,6 +45,8 @@ struct SegLog {
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     cudaStream_t s_spill = nullptr;
     uint64_t appended = 0, spilled_bytes = 0, hbm_hits = 0, cold_hits = 0, indexed = 0;
+    std::vector<uint32_t> seg_live;           // live (indexed, not overwritten, not trimmed) records per logical segment
+    uint64_t trimmed = 0, cold_freed_bytes = 0, spills_skipped = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;    // device time of the last gather's kernel
     float last_gather_kernel_ms = 0; uint64_t last_gather_bytes = 0;
 };
@@ -158,6 +160,10 @@ static inline void seglog_put(SegLog* L, uint32_t gid, int64_t index, const Host
     if (index >= gi.base + (int64_t)gi.v.size()) gi.v.resize((size_t)(index - gi.base) + 1, none);
     HostLoc& slot = gi.v[(size_t)(index - gi.base)];
     if (slot.len == 0xffffffffu) L->indexed++;
+    else L->seg_live[slot.off / L->seg_bytes]--;                   // the overwritten record is dead
+    const uint64_t seg = hl.off / L->seg_bytes;
+    if (L->seg_live.size() <= seg) L->seg_live.resize(seg + 1, 0);
+    L->seg_live[seg]++;
     slot = hl;                                                     // RocksDB put: the latest value wins
 }
 
@@ -167,6 +173,10 @@ static int seglog_spill_for(rafting_engine* e, SegLog* L, uint64_t new_head) {
     while (last_seg >= L->nseg && L->spilled_upto <= last_seg - L->nseg) {
         const uint64_t s = L->spilled_upto;
         if (L->cold.size() <= s) { L->cold.resize(s + 1, nullptr); L->cold_ready.resize(s + 1, nullptr); }
+        if (s < L->seg_live.size() && L->seg_live[s] == 0) {       // nothing live in it (compacted / overwritten): no cold copy
+            L->spilled_upto = s + 1; L->spills_skipped++;
+            continue;
+        }
         CU(cudaHostAlloc((void**)&L->cold[s], L->seg_bytes, cudaHostAllocDefault));
         CU(cudaEventCreateWithFlags(&L->cold_ready[s], cudaEventDisableTiming));
         CU(cudaEventRecord(e->ev_seg, e->stream));                 // the spill sees every append already enqueued
@@ -369,11 +379,59 @@ extern "C" int rafting_log_gather(rafting_engine_t* e, uint32_t n_ranges, const 
     return RAFTING_OK;
 }
 
+// Garbage collection behind RaftLog.flush (RocksLog.java:228-242: deleteRange below the new epoch): index entries below
+// a group's lowest stored key are dropped, and a cold (pinned host) segment whose last live record went away is freed.
+// A segment with no live record is also never spilled in the first place (seglog_spill_for).
+extern "C" int rafting_log_trim(rafting_engine_t* e, uint32_t first_gid, uint32_t count, uint64_t* dropped_entries, uint64_t* freed_cold_bytes) {
+    if (!e || !e->seglog) return fail(RAFTING_E_INVAL, "entry buffer not configured (rafting_log_config)");
+    if ((uint64_t)first_gid + count > e->G) return fail(RAFTING_E_CAPACITY, "gid range beyond max_groups");
+    SegLog* L = e->seglog;
+    CU(cudaSetDevice(e->cfg.device));
+    std::vector<uint64_t> meta(count); std::vector<int64_t> lo(count), hi(count);
+    if (count) {
+        CU(cudaMemcpyAsync(meta.data(), e->T.g_meta + first_gid, (size_t)count * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(lo.data(), e->T.g_lo + first_gid, (size_t)count * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(hi.data(), e->T.g_hi + first_gid, (size_t)count * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    uint64_t dropped = 0, freed = 0;
+    for (uint32_t k = 0; k < count; k++) {
+        rafting::GroupIdx& gi = L->index[first_gid + k];
+        if (gi.v.empty()) continue;
+        const bool empty = (((uint32_t)meta[k] >> rafting::W_NRUNS_SH) & 0xf) == 0;
+        // entries below the lowest stored key are gone for good (an empty store after a flush beyond its end: everything
+        // up to the old end); a truncated suffix is NOT dropped here — re-appends overwrite it
+        const int64_t keep_from = empty ? hi[k] + 1 : lo[k];
+        int64_t cut = keep_from - gi.base;
+        if (cut <= 0) continue;
+        if (cut > (int64_t)gi.v.size()) cut = (int64_t)gi.v.size();
+        for (int64_t i = 0; i < cut; i++) {
+            const HostLoc& h = gi.v[(size_t)i];
+            if (h.len == 0xffffffffu) continue;
+            L->seg_live[h.off / L->seg_bytes]--; L->indexed--; dropped++;
+        }
+        gi.v.erase(gi.v.begin(), gi.v.begin() + cut);
+        gi.base += cut;
+    }
+    for (size_t s = 0; s < L->cold.size(); s++) {
+        if (!L->cold[s] || (s < L->seg_live.size() && L->seg_live[s] != 0)) continue;
+        CU(cudaEventSynchronize(L->cold_ready[s]));
+        cudaFreeHost(L->cold[s]); L->cold[s] = nullptr;
+        cudaEventDestroy(L->cold_ready[s]); L->cold_ready[s] = nullptr;
+        freed += L->seg_bytes;
+    }
+    L->trimmed += dropped; L->cold_freed_bytes += freed;
+    if (dropped_entries) *dropped_entries = dropped;
+    if (freed_cold_bytes) *freed_cold_bytes = freed;
+    return RAFTING_OK;
+}
+
 extern "C" int rafting_log_stats(rafting_engine_t* e, uint64_t* out, uint32_t n) {
     if (!e || !e->seglog || !out) return fail(RAFTING_E_INVAL, "entry buffer not configured");
     SegLog* L = e->seglog;
     const uint64_t v[] = {L->appended, L->head, L->spilled_bytes, L->hbm_hits, L->cold_hits, L->indexed,
-                          (uint64_t)(L->last_gather_kernel_ms * 1e6), L->last_gather_bytes};
-    for (uint32_t i = 0; i < n && i < 8; i++) out[i] = v[i];
-    return 8;
+                          (uint64_t)(L->last_gather_kernel_ms * 1e6), L->last_gather_bytes,
+                          L->trimmed, L->cold_freed_bytes, L->spills_skipped};
+    for (uint32_t i = 0; i < n && i < 11; i++) out[i] = v[i];
+    return 11;
 }

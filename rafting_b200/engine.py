@@ -37,7 +37,7 @@ EXPORTS = [
     "rafting_comm_init", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_engine_stream",
     "rafting_engine_counters", "rafting_abi_sizes", "rafting_checkpoint", "rafting_restore",
     "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_backoff_step", "rafting_allgather_join",
-    "rafting_log_config", "rafting_log_append", "rafting_log_read", "rafting_log_gather", "rafting_log_stats",
+    "rafting_log_config", "rafting_log_append", "rafting_log_read", "rafting_log_gather", "rafting_log_trim", "rafting_log_stats",
 ]
 
 
@@ -91,6 +91,7 @@ def lib():
         L.rafting_log_gather.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]
         L.rafting_log_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.rafting_log_trim.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.rafting_engine_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.rafting_engine_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.rafting_abi_sizes.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
@@ -307,10 +308,17 @@ class Engine:
         return out
 
     def log_stats(self) -> dict:
-        v = np.zeros(8, dtype=np.uint64)
-        lib().rafting_log_stats(self._h, v.ctypes.data, 8)
+        v = np.zeros(11, dtype=np.uint64)
+        lib().rafting_log_stats(self._h, v.ctypes.data, 11)
         return dict(zip(("appended", "head", "spilled_bytes", "hbm_hits", "cold_hits", "indexed", "gather_kernel_ns",
-                         "gather_bytes"), v.tolist()))
+                         "gather_bytes", "trimmed", "cold_freed_bytes", "spills_skipped"), v.tolist()))
+
+    def log_trim(self, first_gid: int = 0, count: int | None = None) -> tuple[int, int]:
+        """GC behind RaftLog.flush: (index entries dropped, cold bytes freed)."""
+        d, f = C.c_uint64(), C.c_uint64()
+        _check(lib().rafting_log_trim(self._h, first_gid, self.G - first_gid if count is None else count, C.byref(d), C.byref(f)),
+               "rafting_log_trim")
+        return d.value, f.value
 
     def allgather_join(self):
         _check(lib().rafting_allgather_join(self._h), "rafting_allgather_join")

@@ -73,3 +73,67 @@ def test_append_read_gather_truncate_and_spill():
     models[5].put(101, 2, p101), models[5].put(102, 2, p102)
     assert e.log_read(5, 95, 20) == models[5].batch(95, 20)
     assert e.log_read(5, 103, 5) == []
+
+
+def test_trim_after_compaction_frees_index_and_cold_tier():
+    """RaftLog.flush moves the epoch (RocksLog.java:228-242); rafting_log_trim then drops the index entries below every
+    group's lowest stored key and frees cold segments without a live record; later segments that hold only dead
+    records are never spilled at all.  Reads of the surviving range stay byte-exact."""
+    from rafting_b200 import engine
+    G, R = 16, 3
+    cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=1, entry_pool_cap=8)
+    e = engine.Engine(cfg)
+    init = harness.init_array(G, terms=1)
+    init["last_index"] = 400
+    init["last_term"] = 1
+    e.open_bulk(0, init)
+    e.log_config(segment_bytes=8192, hbm_segments=4, ring_slots=16)
+    rng = np.random.default_rng(9)
+    models = [PayloadLog() for _ in range(G)]
+    for lo in range(1, 201, 40):
+        batch = []
+        for gid in range(G):
+            for index in range(lo, lo + 40):
+                p = _payload(rng, gid, index, 1)
+                batch.append((gid, index, 1, p)); models[gid].put(index, 1, p)
+        e.log_append(batch)
+    before = e.log_stats()
+    assert before["spilled_bytes"] > 0 and before["indexed"] == G * 200
+    # compaction: every group flushes to index 150 (the entry AT the index survives: deleteRange is end-exclusive)
+    ib = abi.Inbox(1, G, R - 1)
+    for gid in range(G):
+        ib.flush(0, gid, harness.T0, 150, 1)
+    e.step(ib)
+    for m in models:
+        m.flush(0, 150)
+    assert e.export(3).epoch_index == 150
+    dropped, freed = e.log_trim()
+    assert dropped == G * 149 and freed > 0
+    st = e.log_stats()
+    assert st["indexed"] == G * 51 and st["trimmed"] == dropped and st["cold_freed_bytes"] == freed
+    for gid in (0, 9, 15):
+        assert e.log_read(gid, 150, 60) == models[gid].batch(150, 60)
+        assert e.log_read(gid, 149, 5) == []
+    got = e.log_gather([(2, 150, 51), (7, 190, 11)])
+    assert [(g, i, t, p) for g, i, t, p in got] == [(2, i, 1, models[2].kv[i][1]) for i in range(150, 201)] + \
+        [(7, i, 1, models[7].kv[i][1]) for i in range(190, 201)]
+    # keep appending: the arena wraps over segments whose records were all trimmed -> no spill for those
+    for lo in range(201, 401, 40):
+        batch = []
+        for gid in range(G):
+            for index in range(lo, lo + 40):
+                p = _payload(rng, gid, index, 1)
+                batch.append((gid, index, 1, p)); models[gid].put(index, 1, p)
+        e.log_append(batch)
+        ib = abi.Inbox(1, G, R - 1)
+        for gid in range(G):
+            ib.flush(0, gid, harness.T0, lo + 30, 1)
+        e.step(ib)
+        for m in models:
+            m.flush(0, lo + 30)
+        e.log_trim()
+    st2 = e.log_stats()
+    assert st2["spills_skipped"] > 0
+    for gid in (1, 14):
+        assert e.log_read(gid, 391, 20) == models[gid].batch(391, 20)
+    assert e.log_read(1, 300, 5) == []
