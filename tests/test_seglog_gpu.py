@@ -117,23 +117,24 @@ def test_trim_after_compaction_frees_index_and_cold_tier():
     got = e.log_gather([(2, 150, 51), (7, 190, 11)])
     assert [(g, i, t, p) for g, i, t, p in got] == [(2, i, 1, models[2].kv[i][1]) for i in range(150, 201)] + \
         [(7, i, 1, models[7].kv[i][1]) for i in range(190, 201)]
-    # keep appending: the arena wraps over segments whose records were all trimmed -> no spill for those
-    for lo in range(201, 401, 40):
+    # keep appending in rounds smaller than the arena, compacting after each: by the time a segment is recycled every
+    # record in it has been trimmed -> it is not spilled at all
+    for lo in range(201, 401, 10):
         batch = []
         for gid in range(G):
-            for index in range(lo, lo + 40):
+            for index in range(lo, lo + 10):
                 p = _payload(rng, gid, index, 1)
                 batch.append((gid, index, 1, p)); models[gid].put(index, 1, p)
         e.log_append(batch)
         ib = abi.Inbox(1, G, R - 1)
         for gid in range(G):
-            ib.flush(0, gid, harness.T0, lo + 30, 1)
+            ib.flush(0, gid, harness.T0, lo + 9, 1)
         e.step(ib)
         for m in models:
-            m.flush(0, lo + 30)
+            m.flush(0, lo + 9)
         e.log_trim()
     st2 = e.log_stats()
     assert st2["spills_skipped"] > 0
     for gid in (1, 14):
-        assert e.log_read(gid, 391, 20) == models[gid].batch(391, 20)
-    assert e.log_read(1, 300, 5) == []
+        assert e.log_read(gid, 400, 20) == models[gid].batch(400, 20) and len(models[gid].batch(400, 20)) == 1
+    assert e.log_read(1, 300, 5) == [] and e.log_stats()["indexed"] == G
