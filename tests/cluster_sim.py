@@ -53,7 +53,10 @@ class Node:
 
 class Cluster:
     def __init__(self, make_sut, G: int = 8, R: int = 3, seed: int = 1, drop_ppm: int = 0, submit_ppm: int = 300_000,
-                 heartbeat_ms: int = 50, election_ms: int = 300, compact_every: int = 0):
+                 heartbeat_ms: int = 50, election_ms: int = 300, compact_every: int = 0, pre_vote: bool = True,
+                 guard_candidate_votes: bool = False):
+        # see _vote_request_is_unsafe: the reference's Candidate grants votes without the log check
+        self.guard_candidate_votes = guard_candidate_votes
         self.compact_every = compact_every       # RaftRoutine.compactLog: checkpoint + RaftLog.flush every N applied entries
         self.G, self.R, self.seed, self.drop_ppm, self.submit_ppm = G, R, seed, drop_ppm, submit_ppm
         self.nodes = []
@@ -61,7 +64,8 @@ class Cluster:
         self.on_outbox = None                    # hook(node, outbox): the pump's durability barrier, before any reply leaves
         for k in range(R):
             cfg = abi.make_cfg(replicas=R, local_slot=k, max_groups=G, max_rows=ROWS, entry_pool_cap=ROWS * G * 64,
-                               heartbeat_ms=heartbeat_ms, election_ms=election_ms, timer_seed=0xC0FFEE + 7919 * k)
+                               heartbeat_ms=heartbeat_ms, election_ms=election_ms, timer_seed=0xC0FFEE + 7919 * k,
+                               pre_vote=pre_vote)
             self.cfgs.append(cfg)
             sut = make_sut(cfg)
             init = np.zeros(G, dtype=abi.GROUP_INIT_DTYPE)
@@ -156,6 +160,12 @@ class Cluster:
                 if r >= ROWS:
                     break                                              # stays queued for the next step
                 q.popleft()
+                if it[0] == "op" and self.guard_candidate_votes and self._vote_request_is_unsafe(nd, g, it[1]):
+                    src = self.nodes[it[1]["src"]]                     # dropped on the wire: the asker sees a time-out
+                    self._timeout_event(src, g, src.lane_of(nd.slot),
+                                        abi.EV_PV_REPLY if it[1]["kind"] == abi.OP_PREVOTE_REQ else abi.EV_RV_REPLY, it[1]["inc"])
+                    self.counts["unsafe_vote_requests_dropped"] += 1
+                    continue
                 cursor = pos
                 if it[0] == "op":
                     self._place_op(nd, ib, r, g, now, it[1])
@@ -170,6 +180,23 @@ class Cluster:
                                       pre=e["kind"] == abi.EV_PV_REPLY)
         ob = nd.sut.step(ib)
         return ob, placed
+
+    @staticmethod
+    def _vote_request_is_unsafe(nd, g, op):
+        """UPSTREAM FLAW, mirrored faithfully by oracle and engine: `Candidate.requestVote` (Candidate.java:49-72, and
+        `Candidate.preVote`, which delegates to it, :44-46) answers a request of a higher term with
+        `switchTo(Follower, term, candidateId)` — it votes for the asker WITHOUT `logUpToDate`, which only
+        `Follower.requestVote` checks (Follower.java:108-127).  A node that is itself mid-election can thereby elect a peer
+        whose log misses committed entries (leader completeness breaks, the state machines diverge; reproduced by
+        tests/test_cluster_cpu.py::test_upstream_candidate_votes_without_log_check).  With this guard the SIMULATED NETWORK
+        drops exactly those requests — asker's log behind the receiver's, receiver not a leader — to show that nothing
+        else stands between the restated protocol and Raft's safety properties."""
+        if op["kind"] not in (abi.OP_VOTE_REQ, abi.OP_PREVOTE_REQ) or nd.snap is None:
+            return False
+        if (int(nd.snap.role_word[g]) & 3) == abi.ROLE_LEADER:
+            return False
+        mi, mt = int(nd.snap.last_entry[g]["x"]), int(nd.snap.last_entry[g]["y"])
+        return not (op["last_term"] > mt or (op["last_term"] == mt and op["last_index"] >= mi))
 
     def _place_op(self, nd, ib, r, g, now, op):
         k = op["kind"]
@@ -272,9 +299,15 @@ class Cluster:
             valid, success = m & 1, (m >> 1) & 1
             ekind = {abi.OP_AE_REQUEST: abi.EV_AE_ACK, abi.OP_PREVOTE_REQ: abi.EV_PV_REPLY,
                      abi.OP_VOTE_REQ: abi.EV_RV_REPLY, abi.OP_IS_REQUEST: abi.EV_IS_ACK}[op["kind"]]
-            if op["kind"] == abi.OP_AE_REQUEST and valid and success:
+            # payload side of the append: on success — and on the one throw site that comes AFTER RaftLog.append inside
+            # Follower.appendEntries, the commit rollback assertion (Follower.java:68-80): the entries are in the log
+            # although no reply leaves
+            if op["kind"] == abi.OP_AE_REQUEST and ((valid and success) or err == 3):
                 self._store_entries(nd, g, op["prev_index"], op["entries"])
                 self.counts["ae_ok"] += 1
+            if op["kind"] in (abi.OP_VOTE_REQ, abi.OP_PREVOTE_REQ) and valid and success and prev is not None and \
+                    self._vote_request_is_unsafe(nd, g, op):
+                self.counts["votes_granted_to_a_stale_log"] += 1       # the upstream flaw at work (see _vote_request_is_unsafe)
             if not valid or self._lost(nd.slot, src.slot, g, self.tick, 1):
                 self._timeout_event(src, g, lane, ekind, op["inc"], op.get("epoch", 0), op.get("last", 0))
                 continue

@@ -75,3 +75,59 @@ def test_compaction_and_snapshot_catch_up():
     c.check(converged=True)
     assert c.counts["compactions"] > 10 and c.counts["is_sent"] > 0 and c.counts["snapshots_installed"] > 0
     assert all(nd.sut.export(g).epoch_index > 0 for nd in c.nodes for g in range(c.G))
+
+
+@pytest.mark.parametrize("R,pre_vote,seed", [(3, True, 101), (3, False, 102), (5, True, 103), (5, False, 104), (2, True, 105),
+                                             (3, False, 106), (5, False, 107), (3, True, 108)])
+def test_random_partitions_keep_raft_safe(R, pre_vote, seed):
+    """Jepsen-style: every 40 ticks a random minority (possibly the leader) is cut off, 3 % of the messages are lost,
+    logs are compacted every 30 commands.  Election safety is asserted on every step inside the simulator, prefix
+    agreement of the applied files after every phase, identical files after healing.  The simulated network drops the
+    vote requests the reference's Candidate would wrongly grant (cluster_sim._vote_request_is_unsafe)."""
+    c = _jepsen(R, pre_vote, seed, guard=True)
+    assert c.counts["votes_granted_to_a_stale_log"] == 0
+    assert min(len(nd.file[g]) for nd in c.nodes for g in range(c.G)) > (5 if R == 2 else 30)
+
+
+def _jepsen(R, pre_vote, seed, guard, keep=None):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    c = Cluster(_oracle, G=4, R=R, seed=seed, drop_ppm=30_000, compact_every=30, pre_vote=pre_vote, guard_candidate_votes=guard)
+    if keep is not None:
+        keep.append(c)
+    c.run(80)
+    for phase in range(10):
+        k = int(rng.integers(0, (R - 1) // 2 + 1))
+        c.cut = set(int(x) for x in rng.choice(R, size=k, replace=False))
+        c.run(40)
+        c.check(converged=False)
+    c.cut = set()
+    c.run(250)
+    c.drop_ppm = 0
+    c.run(120, submit=False)
+    c.check(converged=True)
+    return c
+
+
+def test_upstream_candidate_votes_without_log_check():
+    """The flaw itself, first as a known answer: a Candidate of term 3 whose log ends at (124, 1) receives
+    RequestVote(term 4) from a peer whose log ends at (84, 1) and GRANTS it (Candidate.java:68-71 — switchTo(Follower,
+    term, candidateId) with no logUpToDate), where a Follower in the same position refuses (Follower.java:118-122).
+    Then end to end: the unguarded run of seed 102 elects that peer and the applied files diverge."""
+    from rafting_b200 import abi
+    from tests import harness
+    for role_first, want in (("candidate", 1), ("follower", 0)):
+        cfg = abi.make_cfg(replicas=3, local_slot=2, max_groups=1, max_rows=1, pre_vote=False, election_ms=900)
+        o = binding.Oracle(cfg)
+        o.open_group(0, term=2, first_index=1, last_index=124, last_term=1, now_ms=harness.T0, rand_ms=1000)
+        if role_first == "candidate":
+            ib = abi.Inbox(1, 1, 2); ib.timeout(0, 0, harness.T0 + 1000, rand=1000); o.step(ib)      # election timeout -> Candidate, term 3
+            assert o.export(0).role == abi.ROLE_CANDIDATE and o.export(0).current_term == 3
+        ib = abi.Inbox(1, 1, 2); ib.vote_request(0, 0, harness.T0 + 1100, 1, 4, 84, 1)
+        out = o.step(ib)
+        m = int(out.rep_meta[0, 0])
+        assert (m & 1, (m >> 1) & 1) == (1, want), role_first
+    keep = []
+    with pytest.raises(AssertionError):
+        _jepsen(3, False, 102, guard=False, keep=keep)
+    assert keep[0].counts["votes_granted_to_a_stale_log"] > 0
