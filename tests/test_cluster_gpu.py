@@ -107,3 +107,23 @@ def test_node_crash_and_restart_from_the_journal(engine_mod, tmp_path):
         harness.assert_states_equal(nd.sut.o, nd.sut.e, range(G), 2, where=f"node {nd.slot}")
     for j in journals:
         j.close()
+
+
+@pytest.mark.parametrize("R,pre_vote,seed", [(3, False, 106), (5, True, 103)])
+def test_random_partitions_engine_in_lock_step(engine_mod, R, pre_vote, seed):
+    """The Jepsen-style run of tests/test_cluster_cpu.py with every node stepping engine and oracle together."""
+    rng = np.random.default_rng(seed)
+    c = Cluster(lambda cfg: Pair(engine_mod, cfg), G=4, R=R, seed=seed, drop_ppm=30_000, compact_every=30, pre_vote=pre_vote,
+                guard_candidate_votes=True)
+    c.run(80)
+    for phase in range(10):
+        k = int(rng.integers(0, (R - 1) // 2 + 1))
+        c.cut = set(int(x) for x in rng.choice(R, size=k, replace=False))
+        c.run(40)
+    c.cut = set()
+    c.run(250)
+    c.drop_ppm = 0
+    c.run(120, submit=False)
+    c.check(converged=True)
+    for nd in c.nodes:
+        harness.assert_states_equal(nd.sut.o, nd.sut.e, range(c.G), R - 1, where=f"node {nd.slot}")
