@@ -562,6 +562,7 @@ extern "C" int rafting_step_begin_host(rafting_engine_t* e, uint32_t slot, const
     if (!e || !in_host || !out_host || slot >= RAFTING_HOST_SLOTS) return fail(RAFTING_E_INVAL, "bad argument");
     CU(cudaSetDevice(e->cfg.device));
     int rc = hostpath_init(e); if (rc) return rc;
+    if (hp(e)->slot[slot].leased) return fail(RAFTING_E_BUSY, "slot %u is held by an outstanding lease", slot);
     return step_enqueue(e, slot, in_host, out_host);
 }
 extern "C" int rafting_step_wait_slot(rafting_engine_t* e, uint32_t slot) {
