@@ -221,6 +221,8 @@ class Cluster:
         and answers false; once the machine has been restored from the snapshot the next request corrects the log
         epoch (accomplishInstallation -> RaftLog.flush(milestone), :451-475) and answers true."""
         ins = nd.install[g]
+        if ins is None and nd.applied[g] >= op["index"]:
+            return [("op", dict(op, result=True))]              # the machine is already past that snapshot: nothing to install
         if ins is None:
             snap = self.nodes[op["src"]].snapshot[g]
             nd.install[g] = dict(ready=self.tick + 3, snap=snap)

@@ -131,3 +131,34 @@ def test_upstream_candidate_votes_without_log_check():
     with pytest.raises(AssertionError):
         _jepsen(3, False, 102, guard=False, keep=keep)
     assert keep[0].counts["votes_granted_to_a_stale_log"] > 0
+
+
+def test_upstream_commit_rollback_can_stall_a_group():
+    """Second upstream finding, a LIVENESS one, mirrored faithfully: commitIndex is neither persisted nor carried by votes,
+    so a freshly elected leader may know a lower commitIndex than a majority of its followers.  Every AppendEntries it
+    sends then makes those followers throw "rollback is not allowed" (RocksLog.java:100-103 via Follower.java:76-84) —
+    AFTER resetting their election timers in the `finally` — so no ack ever reaches the leader, its commitIndex never
+    moves, and nobody times out: the group is stuck for good.  Seed 1030 of the Jepsen run ends in exactly that state."""
+    import numpy as np
+    R, seed = 5, 1030
+    rng = np.random.default_rng(seed)
+    c = Cluster(_oracle, G=4, R=R, seed=seed, drop_ppm=30_000, compact_every=30, pre_vote=True, guard_candidate_votes=True)
+    c.run(80)
+    for phase in range(10):
+        k = int(rng.integers(0, (R - 1) // 2 + 1))
+        c.cut = set(int(x) for x in rng.choice(R, size=k, replace=False))
+        c.run(40)
+        c.check(converged=False)                      # safety holds throughout
+    c.cut = set()
+    c.run(250)
+    c.drop_ppm = 0
+    c.run(200, submit=False)
+    before = c.counts["commit_rollback"]
+    c.run(200, submit=False)                          # a perfect network, and still ...
+    g = 1
+    lead = c.leader_of(g)
+    commits = [nd.sut.export(g).commit_index for nd in c.nodes]
+    assert lead is not None and sum(x > commits[lead] for x in commits) >= R // 2 + 1 - 1   # a blocking set is ahead of the leader
+    assert c.counts["commit_rollback"] - before > 50                                          # ... every heartbeat is thrown away
+    assert len({len(nd.file[g]) for nd in c.nodes}) > 1                                       # ... and the group never converges
+    c.check(converged=False)                                                                  # (what was applied still agrees)
