@@ -162,3 +162,15 @@ def test_upstream_commit_rollback_can_stall_a_group():
     assert c.counts["commit_rollback"] - before > 50                                          # ... every heartbeat is thrown away
     assert len({len(nd.file[g]) for nd in c.nodes}) > 1                                       # ... and the group never converges
     c.check(converged=False)                                                                  # (what was applied still agrees)
+
+
+def test_gpu_scenarios_converge_on_the_oracle(tmp_path):
+    """tests/test_cluster_gpu.py runs these scenarios with engine and oracle in lock-step; the trajectory is the oracle's,
+    so their convergence can (and must) be checked here without a GPU."""
+    from tests import cluster_scenarios as scenarios
+    for R, G, seed in scenarios.GPU_ISOLATION:
+        scenarios.isolation(_oracle, R, G, seed)
+    scenarios.compaction(_oracle)
+    scenarios.restart(_oracle, tmp_path)
+    for R, pre_vote, seed in scenarios.GPU_JEPSEN:
+        scenarios.jepsen(_oracle, R, pre_vote, seed)

@@ -7,7 +7,7 @@ import pytest
 
 from oracle import binding
 from tests import harness
-from tests.cluster_sim import Cluster
+from tests import cluster_scenarios as scenarios
 
 pytestmark = pytest.mark.gpu
 
@@ -49,81 +49,28 @@ def engine_mod():
     return engine
 
 
-@pytest.mark.parametrize("R,G,seed", [(3, 24, 5), (5, 8, 6)])
+@pytest.mark.parametrize("R,G,seed", scenarios.GPU_ISOLATION)
 def test_cluster_engine_matches_oracle_and_files_agree(engine_mod, R, G, seed):
-    c = Cluster(lambda cfg: Pair(engine_mod, cfg), G=G, R=R, seed=seed, drop_ppm=15_000)
-    c.run(140)
-    victim = c.leader_of(0)
-    assert victim is not None
-    c.cut = {victim}
-    c.run(120)
-    c.cut = set()
-    c.run(150)
-    c.drop_ppm = 0
-    c.run(80, submit=False)
-    c.check(converged=True)
-    assert min(len(nd.file[g]) for nd in c.nodes for g in range(G)) > 10
-    for nd in c.nodes:
-        harness.assert_states_equal(nd.sut.o, nd.sut.e, range(G), R - 1, where=f"node {nd.slot}")
+    c = scenarios.isolation(lambda cfg: Pair(engine_mod, cfg), R, G, seed)
+    _states_equal(c, R)
 
 
 def test_cluster_with_compaction_and_snapshot_install(engine_mod):
-    c = Cluster(lambda cfg: Pair(engine_mod, cfg), G=12, R=3, seed=21, compact_every=25, drop_ppm=5_000)
-    c.run(120)
-    c.cut = {(c.leader_of(0) + 1) % 3}
-    c.run(220)
-    c.cut = set()
-    c.run(200)
-    c.drop_ppm = 0
-    c.run(80, submit=False)
-    c.check(converged=True)
-    assert c.counts["snapshots_installed"] > 0 and c.counts["is_sent"] > 0
-    for nd in c.nodes:
-        harness.assert_states_equal(nd.sut.o, nd.sut.e, range(c.G), 2, where=f"node {nd.slot}")
+    _states_equal(scenarios.compaction(lambda cfg: Pair(engine_mod, cfg)), 3)
 
 
 def test_node_crash_and_restart_from_the_journal(engine_mod, tmp_path):
     """Durability journal + rafting_group_open + rafting_group_load_runs: a killed node comes back from what the
     reference keeps on disk; engine and oracle stay identical through the restart and the files converge."""
-    from rafting_b200 import durable
-    G = 8
-    journals = [durable.Journal(str(tmp_path / f"n{k}"), G) for k in range(3)]
-    c = Cluster(lambda cfg: Pair(engine_mod, cfg), G=G, seed=31, drop_ppm=10_000)
-    c.on_outbox = lambda nd, ob: journals[nd.slot].commit_step(ob.role_word, ob.current_term)
-    c.run(150)
-    victim = c.leader_of(0)
-    c.cut = {victim}
-    c.run(2)
-    journals[victim].close()
-    journals[victim] = durable.Journal(str(tmp_path / f"n{victim}"), G)
-    c.restart(victim, lambda cfg: Pair(engine_mod, cfg), lambda g: journals[victim].restore(g))
-    c.run(60)
-    c.cut = set()
-    c.run(250)
-    c.drop_ppm = 0
-    c.run(80, submit=False)
-    c.check(converged=True)
-    for nd in c.nodes:
-        harness.assert_states_equal(nd.sut.o, nd.sut.e, range(G), 2, where=f"node {nd.slot}")
-    for j in journals:
-        j.close()
+    _states_equal(scenarios.restart(lambda cfg: Pair(engine_mod, cfg), tmp_path), 3)
 
 
-@pytest.mark.parametrize("R,pre_vote,seed", [(3, False, 106), (5, True, 103)])
+@pytest.mark.parametrize("R,pre_vote,seed", scenarios.GPU_JEPSEN)
 def test_random_partitions_engine_in_lock_step(engine_mod, R, pre_vote, seed):
     """The Jepsen-style run of tests/test_cluster_cpu.py with every node stepping engine and oracle together."""
-    rng = np.random.default_rng(seed)
-    c = Cluster(lambda cfg: Pair(engine_mod, cfg), G=4, R=R, seed=seed, drop_ppm=30_000, compact_every=30, pre_vote=pre_vote,
-                guard_candidate_votes=True)
-    c.run(80)
-    for phase in range(10):
-        k = int(rng.integers(0, (R - 1) // 2 + 1))
-        c.cut = set(int(x) for x in rng.choice(R, size=k, replace=False))
-        c.run(40)
-    c.cut = set()
-    c.run(250)
-    c.drop_ppm = 0
-    c.run(120, submit=False)
-    c.check(converged=True)
+    _states_equal(scenarios.jepsen(lambda cfg: Pair(engine_mod, cfg), R, pre_vote, seed), R)
+
+
+def _states_equal(c, R):
     for nd in c.nodes:
         harness.assert_states_equal(nd.sut.o, nd.sut.e, range(c.G), R - 1, where=f"node {nd.slot}")
