@@ -129,8 +129,12 @@ typedef struct rafting_cfg {
     int64_t  election_ms;           /* E = round(election*tick); timeouts are drawn in [E, 2E]  */
     uint64_t timer_seed;            /* seed of the counter-based draw used when an event carries none */
     int32_t  device;                /* CUDA ordinal                                            */
-    uint32_t flags;                 /* reserved, 0                                             */
+    uint32_t flags;                 /* RAFTING_CFG_* ; 0 = bit-identical to the reference      */
 } rafting_cfg_t;
+/* Opt-in departures from the reference that close the two flaws DESIGN.md §2 documents.  Specified and tested in the
+   oracle (tests/test_cluster_cpu.py); the CUDA engine of this version REJECTS a non-zero cfg.flags (RAFTING_E_INVAL). */
+#define RAFTING_CFG_STRICT_CANDIDATE_VOTE   1u   /* a Candidate applies logUpToDate before it votes (Candidate.java:68-71 does not) */
+#define RAFTING_CFG_LENIENT_FOLLOWER_COMMIT 2u   /* leaderCommit below the follower's commitIndex is ignored instead of asserted */
 
 /*
  * Election-timeout draws.  The reference draws ThreadLocalRandom.nextInt(E, 2E+1) at every

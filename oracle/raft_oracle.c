@@ -602,7 +602,11 @@ static int follower_append(octx_t* c, int peer, int64_t term, int64_t prevIndex,
     if (leaderCommit > l->epochIndex) {                                      /* Follower.java:76-82 */
         int64_t li, lt;
         if (log_last(l, &li, &lt)) {
-            err = commit_log(g, leaderCommit < li ? leaderCommit : li);
+            int64_t ci = leaderCommit < li ? leaderCommit : li;
+            /* RAFTING_CFG_LENIENT_FOLLOWER_COMMIT (opt-in, NOT the reference): a leader that knows less than this
+               follower about what is committed is simply ignored, as in the Raft paper (commitIndex = max(...)) */
+            if ((c->e->cfg.flags & RAFTING_CFG_LENIENT_FOLLOWER_COMMIT) && ci < g->log.commitIndex) ci = g->log.commitIndex;
+            err = commit_log(g, ci);
             if (err) goto finally;
         }
     }
@@ -689,7 +693,12 @@ static int op_request_vote(octx_t* c, int peer, int64_t term, int64_t lastIndex,
             if (peer != g->ballot) { *rep = reply(g->term, 0); return 0; }
             else if (g->ballot != (int)c->e->cfg.local_slot) return RAFTING_ERR_CANDIDATE_VOTE_SELF;
         }
-        err = switch_to(c, RAFTING_ROLE_FOLLOWER, term, peer);
+        /* RAFTING_CFG_STRICT_CANDIDATE_VOTE (opt-in, NOT the reference): step down at the own term first, like the Leader
+           does (Leader.java:106-108), so that Follower.requestVote applies logUpToDate to the higher-term request */
+        if ((c->e->cfg.flags & RAFTING_CFG_STRICT_CANDIDATE_VOTE) && term > g->term)
+            err = switch_to(c, RAFTING_ROLE_FOLLOWER, g->term, g->ballot);
+        else
+            err = switch_to(c, RAFTING_ROLE_FOLLOWER, term, peer);
         if (err) return err;
         return follower_request_vote(c, peer, term, lastIndex, lastTerm, rep);
     default:

