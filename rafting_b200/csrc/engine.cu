@@ -105,7 +105,9 @@ extern "C" const char* rafting_last_error(void) { return g_err; }
 extern "C" int rafting_engine_create(const rafting_cfg_t* cfg, rafting_engine_t** out) {
     if (!cfg || !out) return fail(RAFTING_E_INVAL, "null argument");
     if (cfg->struct_size != sizeof(rafting_cfg_t)) return fail(RAFTING_E_INVAL, "cfg.struct_size %u != %zu", cfg->struct_size, sizeof(rafting_cfg_t));
+#ifndef RAFTING_ENABLE_CFG_FLAGS
     if (cfg->flags != 0) return fail(RAFTING_E_INVAL, "cfg.flags 0x%x: the opt-in protocol fixes exist in the oracle only in this version", cfg->flags);
+#endif
     if (cfg->replicas < 2 || cfg->replicas > RAFTING_MAX_REPLICAS || cfg->local_slot >= cfg->replicas || cfg->max_groups == 0)
         return fail(RAFTING_E_INVAL, "bad replicas/local_slot/max_groups");
     int ndev = 0;
@@ -121,6 +123,9 @@ extern "C" int rafting_engine_create(const rafting_cfg_t* cfg, rafting_engine_t*
     e->dcfg.pre_vote = cfg->pre_vote; e->dcfg.avail_critical_point = cfg->avail_critical_point;
     e->dcfg.recovery_cool_down_ms = cfg->recovery_cool_down_ms; e->dcfg.heartbeat_ms = cfg->heartbeat_ms;
     e->dcfg.election_ms = cfg->election_ms; e->dcfg.timer_seed = cfg->timer_seed;
+#ifdef RAFTING_ENABLE_CFG_FLAGS
+    e->dcfg.flags = cfg->flags; e->dcfg._pad = 0;
+#endif
     int rc = 0;
     Tables& T = e->T; const size_t G = e->G, F = e->F;
     T.G = e->G; T.F = e->F;

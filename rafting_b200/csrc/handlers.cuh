@@ -335,8 +335,13 @@ __device__ __noinline__ int follower_append(GS& g, const Ctx& c, RowOut& ro, int
                     }
             }
         }
-        if (!err && leaderCommit > g.epochIndex && nruns_of(g) > 0)         // Follower.java:76-82
-            err = commit_log(g, leaderCommit < g.hi ? leaderCommit : g.hi);
+        if (!err && leaderCommit > g.epochIndex && nruns_of(g) > 0) {       // Follower.java:76-82
+            int64_t ci = leaderCommit < g.hi ? leaderCommit : g.hi;
+#ifdef RAFTING_ENABLE_CFG_FLAGS
+            if ((c.cfg->flags & RAFTING_CFG_LENIENT_FOLLOWER_COMMIT) && ci < g.commit) ci = g.commit;   // ignored, not asserted
+#endif
+            err = commit_log(g, ci);
+        }
     }
     reset_timer(g, c, false, false);                                         // finally :83-85
     if (!err && !rep.valid) { rep.valid = 1; rep.success = 1; rep.term = term; }
@@ -405,7 +410,15 @@ __device__ __forceinline__ int op_request_vote(GS& g, const Ctx& c, RowOut& ro, 
             if (peer != ballot_of(g)) { rep.valid = 1; rep.success = 0; rep.term = g.term; return 0; }
             else if (ballot_of(g) != self) return RAFTING_ERR_CANDIDATE_VOTE_SELF;
         }
+#ifdef RAFTING_ENABLE_CFG_FLAGS
+        // RAFTING_CFG_STRICT_CANDIDATE_VOTE: step down at the own term first (as Leader.java:106-108 does), so that
+        // Follower.requestVote applies logUpToDate to the higher-term request — same rule as oracle/raft_oracle.c
+        const bool strict = (c.cfg->flags & RAFTING_CFG_STRICT_CANDIDATE_VOTE) && term > g.term;
+        int err = strict ? switch_to(g, c, ro, RAFTING_ROLE_FOLLOWER, g.term, ballot_of(g))
+                         : switch_to(g, c, ro, RAFTING_ROLE_FOLLOWER, term, peer);
+#else
         int err = switch_to(g, c, ro, RAFTING_ROLE_FOLLOWER, term, peer);
+#endif
         if (err) return err;
     }
     return follower_request_vote(g, c, ro, peer, term, lastIndex, lastTerm, rep);

@@ -90,6 +90,9 @@ struct CfgD {
     int32_t  pre_vote, avail_critical_point;
     int64_t  recovery_cool_down_ms, heartbeat_ms, election_ms;
     uint64_t timer_seed;
+#ifdef RAFTING_ENABLE_CFG_FLAGS      // round-2 build switch: the opt-in protocol fixes on the device
+    uint32_t flags, _pad;
+#endif
 };
 
 }  // namespace rafting
