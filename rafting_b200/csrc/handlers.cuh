@@ -412,7 +412,7 @@ __device__ __forceinline__ int op_request_vote(GS& g, const Ctx& c, RowOut& ro, 
         }
 #ifdef RAFTING_ENABLE_CFG_FLAGS
         // RAFTING_CFG_STRICT_CANDIDATE_VOTE: step down at the own term first (as Leader.java:106-108 does), so that
-        // Follower.requestVote applies logUpToDate to the higher-term request — same rule as oracle/raft_oracle.c
+        // Follower.requestVote applies logUpToDate to the higher-term request
         const bool strict = (c.cfg->flags & RAFTING_CFG_STRICT_CANDIDATE_VOTE) && term > g.term;
         int err = strict ? switch_to(g, c, ro, RAFTING_ROLE_FOLLOWER, g.term, ballot_of(g))
                          : switch_to(g, c, ro, RAFTING_ROLE_FOLLOWER, term, peer);
