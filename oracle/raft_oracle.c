@@ -74,11 +74,13 @@ typedef struct {
     int      persistDirty, commitDirty, readyBit;
 } ogroup_t;
 
+struct orc_pool;
 struct orc_engine {
     rafting_cfg_t cfg;
     uint32_t F;
     ogroup_t* groups;
     uint64_t events;
+    struct orc_pool* pool;   /* the loop threads (ContextLoop-k, ContextManager.java:46), created on first use */
 };
 
 /* per-event context: where outputs of the running event go */
@@ -817,8 +819,10 @@ orc_engine_t* orc_create(const rafting_cfg_t* cfg) {
     e->groups = (ogroup_t*)calloc(cfg->max_groups, sizeof(ogroup_t));
     return e;
 }
+static void pool_destroy(struct orc_pool* p);
 void orc_destroy(orc_engine_t* e) {
     if (!e) return;
+    pool_destroy(e->pool);
     for (uint32_t i = 0; i < e->cfg.max_groups; i++) free(e->groups[i].log.terms);
     free(e->groups); free(e);
 }
@@ -984,19 +988,63 @@ static void step_group(orc_engine_t* e, const rafting_inbox_t* in, const rafting
     if (out->last_entry)   last_or_epoch(&g->log, &out->last_entry[go].x, &out->last_entry[go].y);
 }
 
-typedef struct { orc_engine_t* e; const rafting_inbox_t* in; const rafting_outbox_t* out;
-                 uint32_t n, t, T; uint64_t events; } worker_t;
-static void* worker_main(void* p) {
-    worker_t* w = (worker_t*)p;
+/* The loop threads live as long as the engine (the reference's ContextLoop-k threads do, too): a step hands every
+   thread its share and waits for all of them — no thread creation inside the timed region of the CPU baseline. */
+typedef struct orc_pool {
+    pthread_t th[256]; int T;
+    pthread_mutex_t mu; pthread_cond_t go, done;
+    uint64_t gen; int pending, quit;
+    orc_engine_t* e; const rafting_inbox_t* in; const rafting_outbox_t* out; uint32_t n;
+    uint64_t events[256];
+    int ids[256];
+    struct orc_pool* self[256];
+} orc_pool_t;
+typedef struct { orc_pool_t* p; int t; } pool_arg_t;
+
+static void run_share(orc_pool_t* p, int t) {
     /* groups are bound to loops round-robin (EventLoopGroup.next(), EventLoopGroup.java:77-80) — here in chunks of 64
        consecutive groups, so that two loop threads never write the same cache line of a batch column (in the JVM every
        context is its own heap object; strict per-group round-robin over SoA columns would charge the CPU baseline for
        false sharing the reference does not have).  Results do not depend on the binding. */
-    for (uint32_t c0 = w->t * 64u; c0 < w->n; c0 += w->T * 64u) {
-        const uint32_t c1 = c0 + 64u < w->n ? c0 + 64u : w->n;
-        for (uint32_t i = c0; i < c1; i++) step_group(w->e, w->in, w->out, i, w->n, &w->events);
+    uint64_t ev = 0;
+    for (uint32_t c0 = (uint32_t)t * 64u; c0 < p->n; c0 += (uint32_t)p->T * 64u) {
+        const uint32_t c1 = c0 + 64u < p->n ? c0 + 64u : p->n;
+        for (uint32_t i = c0; i < c1; i++) step_group(p->e, p->in, p->out, i, p->n, &ev);
     }
-    return NULL;
+    p->events[t] = ev;
+}
+static void* pool_main(void* a) {
+    pool_arg_t* pa = (pool_arg_t*)a; orc_pool_t* p = pa->p; const int t = pa->t; free(pa);
+    uint64_t seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&p->mu);
+        while (p->gen == seen && !p->quit) pthread_cond_wait(&p->go, &p->mu);
+        if (p->quit) { pthread_mutex_unlock(&p->mu); return NULL; }
+        seen = p->gen;
+        pthread_mutex_unlock(&p->mu);
+        run_share(p, t);
+        pthread_mutex_lock(&p->mu);
+        if (--p->pending == 0) pthread_cond_signal(&p->done);
+        pthread_mutex_unlock(&p->mu);
+    }
+}
+static orc_pool_t* pool_create(int T) {
+    orc_pool_t* p = (orc_pool_t*)calloc(1, sizeof(*p));
+    if (!p) return NULL;
+    p->T = T;
+    pthread_mutex_init(&p->mu, NULL); pthread_cond_init(&p->go, NULL); pthread_cond_init(&p->done, NULL);
+    for (int t = 0; t < T; t++) {
+        pool_arg_t* a = (pool_arg_t*)malloc(sizeof(*a)); a->p = p; a->t = t;
+        pthread_create(&p->th[t], NULL, pool_main, a);
+    }
+    return p;
+}
+static void pool_destroy(struct orc_pool* p) {
+    if (!p) return;
+    pthread_mutex_lock(&p->mu); p->quit = 1; pthread_cond_broadcast(&p->go); pthread_mutex_unlock(&p->mu);
+    for (int t = 0; t < p->T; t++) pthread_join(p->th[t], NULL);
+    pthread_mutex_destroy(&p->mu); pthread_cond_destroy(&p->go); pthread_cond_destroy(&p->done);
+    free(p);
 }
 int orc_step(orc_engine_t* e, const rafting_inbox_t* in, const rafting_outbox_t* out, int threads) {
     if (!e || !in || !out) return RAFTING_E_INVAL;
@@ -1008,12 +1056,15 @@ int orc_step(orc_engine_t* e, const rafting_inbox_t* in, const rafting_outbox_t*
         return 0;
     }
     if (threads > 256) threads = 256;
-    pthread_t th[256]; worker_t w[256];
-    for (int t = 0; t < threads; t++) {
-        w[t].e = e; w[t].in = in; w[t].out = out; w[t].n = n; w[t].t = (uint32_t)t; w[t].T = (uint32_t)threads; w[t].events = 0;
-        pthread_create(&th[t], NULL, worker_main, &w[t]);
-    }
-    for (int t = 0; t < threads; t++) { pthread_join(th[t], NULL); e->events += w[t].events; }
+    if (e->pool && e->pool->T != threads) { pool_destroy(e->pool); e->pool = NULL; }
+    if (!e->pool) { e->pool = pool_create(threads); if (!e->pool) return RAFTING_E_NOMEM; }
+    orc_pool_t* p = e->pool;
+    pthread_mutex_lock(&p->mu);
+    p->e = e; p->in = in; p->out = out; p->n = n; p->pending = threads; p->gen++;
+    pthread_cond_broadcast(&p->go);
+    while (p->pending) pthread_cond_wait(&p->done, &p->mu);
+    pthread_mutex_unlock(&p->mu);
+    for (int t = 0; t < threads; t++) e->events += p->events[t];
     return 0;
 }
 uint64_t orc_events_processed(orc_engine_t* e) { return e ? e->events : 0; }
