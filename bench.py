@@ -1,19 +1,27 @@
 #!/usr/bin/env python
 """bench.py — AppendEntries/sec across Raft groups on B200 (BASELINE.json metric).
 
-A "step" is one rafting_step over one batch: ROWS ticks x G groups, each tick carrying one group op
-(SUBMIT / heartbeat) and one AppendEntries ack per follower lane.  Unit of work = one AE ack
-consumed by the leader path (ack -> Leadership.State update -> quorum index -> commitIndex).
+Unit of work = one AppendEntries ack consumed by the leader path (ack -> Leadership.State update -> quorum index ->
+commitIndex).  One engine LAUNCH drains one batch: ROWS ticks x G groups, each tick one group op (SUBMIT / heartbeat) and
+one ack per follower lane.  One bench STEP = one pass over a recorded WINDOW of L consecutive batches of the synthetic
+stream (L x ROWS ticks: at N=1, 128 x 16 = 2 048 ticks, twice the 1 024 timed ticks SURVEY.md §8(d) names for config #2), so
+that K = 20 steps give a timed region of >= 100 ms.  The window is generated closed-loop on the device (the peers are workload.cu), recorded in HBM
+and replayed bit-exactly; each replay starts by rolling the tables back to the window's start (a 22 MB device copy
+enqueued on the step stream, inside the timed region, < 0.5 % of it).
 
-  value     device-resident: inboxes already in HBM (a different, freshly generated >L2 batch each
-            step), timed with CUDA events on the engine's stream, max over ranks.
-  e2e       the same stream through the C-ABI host path (rafting_lease + rafting_step): pinned host
-            inbox -> H2D -> kernel -> D2H of the outbox, every step inside the timed region.
-  roofline  algorithmic bytes per ack (192 B at R=3) x acks per launch / mean kernel
-            time, against MEASURED_PEAKS.json's HBM copy bandwidth.
+  N == 1   BASELINE config #2: 64K groups, 3 replicas, one B200.
+  N  > 1   BASELINE config #4: 1 M groups (same total at N = 2, 4, 8: strong scaling), contiguous gid blocks per rank, one
+           ncclAllGather of commitIndex[G/N] after EVERY launch; the last gathered vector of the timed region is
+           checked against the ranks' own commit columns (config.gather_verified).
+
+  value     device-resident inputs, CUDA events on the engine's stream, max over ranks.
+  e2e       the same stream through the C-ABI host path (rafting_step_begin_host / rafting_step_wait_slot): pinned host
+            inbox -> H2D -> kernel -> D2H of the outbox, every launch inside the timed region.
+  roofline  algorithmic bytes per ack (192 B at R=3) x acks per launch / mean kernel time, against
+            MEASURED_PEAKS.json's HBM copy bandwidth.
   cpu_baseline / --impl reference
-            the CPU restatement of the reference's EventLoop path (oracle/, "port": the reference is
-            Java and there is no JDK in this image) on the host cores, on a bounded sample.
+            the CPU restatement of the reference's EventLoop path (oracle/, "port": the reference is Java and neither
+            this image nor the GPU box has a JDK) on every host core, on a bounded sample of the same stream.
 """
 from __future__ import annotations
 
@@ -31,8 +39,11 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-SEED = 0x5EED0002
-WORKLOAD = "64K RaftContext groups, 3 replicas, synthetic AppendEntries stream on 1xB200"
+SEED2, SEED4 = 0x5EED0002, 0x5EED0004
+WORKLOAD2 = "64K RaftContext groups, 3 replicas, synthetic AppendEntries stream on 1xB200"
+WORKLOAD4 = "1M groups, 3 replicas, sharded across {n}xB200 with NCCL commitIndex all-gather"
+G_CONFIG2, G_CONFIG4 = 65536, 1 << 20
+METRIC = "AppendEntries/sec across Raft groups"
 
 
 def parse():
@@ -41,14 +52,17 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--groups", type=int, default=65536, help="groups per GPU")
+    p.add_argument("--groups", type=int, default=0, help="groups per GPU (default: 65536 at N=1, 1M/N at N>1)")
     p.add_argument("--replicas", type=int, default=3)
-    p.add_argument("--rows", type=int, default=16, help="ticks per step")
-    p.add_argument("--cpu-groups", type=int, default=65536, help="groups in the CPU baseline sample")
-    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--rows", type=int, default=16, help="ticks per launch")
+    p.add_argument("--launches", type=int, default=0, help="launches per step = length of the recorded window (default: sized to ~7 GB of inboxes)")
+    p.add_argument("--cpu-groups", type=int, default=65536, help="groups in the CPU sample")
+    p.add_argument("--cpu-launches", type=int, default=4, help="oracle passes (rows ticks each) per CPU step")
+    p.add_argument("--cpu-steps", type=int, default=12, help="timed steps of the in-line cpu_baseline leg")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-secondary", action="store_true", help="skip the vote / follower-request rates (configs #3, #5)")
+    p.add_argument("--no-bind", action="store_true", help="do not bind the process to the GPU's NUMA node")
     return p.parse_args()
 
 
@@ -76,24 +90,47 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def inbox_bytes_per_launch(G, rows, F):
+    """op_meta 8 + op_nr 16 per (row, group); ev_meta 8 + ev_tn 16 + ev_el 16 per (row, group, lane)."""
+    return rows * G * (24 + 40 * F)
+
+
+def window_launches(args, G):
+    """launches per step = length of the recorded window: up to ~14 GB of distinct inboxes in HBM, 4..128 launches."""
+    return args.launches or int(max(4, min(128, 14.0e9 // inbox_bytes_per_launch(G, args.rows, args.replicas - 1))))
+
+
+def workload_config(args, world, G):
+    """The `config` object: the workload definition, identical in the engine arm and in the reference arm."""
+    if world == 1:
+        name, total, seed = WORKLOAD2, G, SEED2
+    else:
+        name, total, seed = WORKLOAD4.format(n=world), G * world, SEED4
+    L = window_launches(args, G)
+    return {"workload": name, "groups_total": total, "groups_per_gpu": G, "replicas": args.replicas, "rows_per_launch": args.rows,
+            "launches_per_step": L, "ticks_per_step": L * args.rows, "seed": hex(seed),
+            "step": "one pass over a window of consecutive batches of the stream (ticks per step = launches x rows); the CPU arm "
+                    "times a bounded sample of it (cpu_baseline.sample)"}
+
+
 class ClockSampler(threading.Thread):
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.armed = index, [], False, False
 
     def run(self):
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
+                if out and self.armed:
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def summary(self):
         sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
@@ -109,9 +146,43 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (port of the reference's EventLoop path) on a bounded sample
+# host placement: a rank runs on the CPUs of the NUMA node its GPU hangs off, so that its pinned staging buffers are
+# first-touched there and every H2D / D2H copy stays off the socket interconnect
 # ------------------------------------------------------------------------------------------------
-def run_cpu_sample(args, seconds, threads, steps=None, warmup=1):
+def parse_cpulist(txt):
+    cpus = set()
+    for part in txt.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(local_rank):
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        path = f"/sys/bus/pci/devices/{bus}/local_cpulist"
+        cpus = parse_cpulist(open(path).read()) & os.sched_getaffinity(0)
+        node = open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip()
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": int(node), "cpus": len(cpus), "pci": bus}
+    except Exception as ex:            # no sysfs entry (container without the topology): stay unbound
+        return {"numa_node": None, "error": str(ex)[:80]}
+    return {"numa_node": None}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference's EventLoop path) on a bounded sample of the same stream
+# ------------------------------------------------------------------------------------------------
+def run_cpu_sample(args, threads, steps, warmup, launches, seed):
+    """steps x (launches oracle passes of rows ticks over cpu_groups groups).  Only orc_step is inside the clock: the
+    stream generator (the simulated peers) runs between passes, untimed; outboxes are preallocated and touched once so
+    no page fault of a fresh buffer lands in the timed region."""
     from oracle import binding
     from rafting_b200 import abi, workload
     G, R, rows = args.cpu_groups, args.replicas, args.rows
@@ -121,47 +192,66 @@ def run_cpu_sample(args, seconds, threads, steps=None, warmup=1):
     init["ballot"] = -1; init["first_index"] = 1; init["now_ms"] = workload.T0_MS - 2000
     init["term"] = np.arange(G) % 7
     o.open_bulk(0, init)
-    w1 = workload.make_wl(SEED, 1, G, R - 1)
-    w = workload.make_wl(SEED, rows, G, R - 1)
+    w1 = workload.make_wl(seed, 1, G, R - 1)
+    w = workload.make_wl(seed, rows, G, R - 1)
     out = None
     for ph in (0, 1, 2):
         out = o.step(workload.election_inbox_host(w1, ph, out), threads=threads)
-    prev, acks, spent, k, times = None, 0, 0.0, 0, []
-    while True:
-        ib = workload.leader_inbox_host(w, k, prev)
-        n_acks = int(((ib.ev_meta & np.uint64(0xF)) != 0).sum())
-        t0 = time.perf_counter()
-        prev = o.step(ib, threads=threads)
-        dt = time.perf_counter() - t0
-        if k >= warmup:
-            acks += n_acks; spent += dt; times.append(dt)
-        k += 1
-        if steps is not None:
-            if k >= warmup + steps:
-                break
-        elif spent >= seconds:
-            break
-    return {"value": acks / spent if spent > 0 else 0.0, "acks": acks, "seconds": spent, "steps": len(times),
-            "ms_per_step": 1e3 * spent / max(1, len(times)),
-            "sample": f"{G} groups x {rows} ticks/step x {len(times)} steps of the same keyed stream (first {G} group ids), "
-                      f"in-memory log, {threads} loop threads (groups round-robined like EventLoopGroup)"}
+    outs = [abi.Outbox(rows, G, R - 1, G) for _ in range(2)]
+    for ob in outs:                                         # touch every page once, outside the clock
+        for name, _, _ in abi.Outbox.ROW_COLS:
+            getattr(ob, name)[...] = 0
+        for name, _ in abi.Outbox.GROUP_COLS:
+            getattr(ob, name)[...] = 0
+    L = binding.lib()
+    prev, k = None, 0
+    step_s, step_acks = [], []
+    for s in range(warmup + steps):
+        spent, acks = 0.0, 0
+        for _ in range(launches):
+            ib = workload.leader_inbox_host(w, k, prev)
+            acks += int(((ib.ev_meta & np.uint64(0xF)) != 0).sum())
+            ob = outs[k % 2]
+            ic, oc = ib.as_c(), ob.as_c()
+            t0 = time.perf_counter()
+            rc = L.orc_step(o._h, C.byref(ic), C.byref(oc), threads)
+            spent += time.perf_counter() - t0
+            if rc:
+                raise RuntimeError(f"orc_step rc={rc}")
+            prev = ob
+            k += 1
+        if s >= warmup:
+            step_s.append(spent); step_acks.append(acks)
+    total_s, total_acks = float(np.sum(step_s)), int(np.sum(step_acks))
+    rates = np.array(step_acks) / np.array(step_s)
+    return {"value": total_acks / total_s, "acks": total_acks, "seconds": total_s, "steps": len(step_s),
+            "ms_per_step": 1e3 * total_s / len(step_s),
+            "median_rate": float(np.median(rates)), "min_rate": float(rates.min()), "max_rate": float(rates.max()),
+            "sample": f"{G} groups x {rows} ticks x {launches} passes per step x {len(step_s)} steps of the same keyed stream "
+                      f"(first {G} group ids, {total_acks} acks, {total_s:.1f} s of CPU wall time), in-memory log, {threads} pinned loop "
+                      f"threads taking 64-group chunks from a shared queue; only orc_step is timed (generator and buffers outside)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    # bound the per-step sample so K steps finish in a few minutes
-    res = run_cpu_sample(args, seconds=0, threads=cores, steps=args.steps, warmup=args.warmup)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cores = len(os.sched_getaffinity(0))
+    seed = SEED2 if world == 1 else SEED4
+    G = args.groups or (G_CONFIG2 if world == 1 else G_CONFIG4 // world)
+    res = run_cpu_sample(args, threads=cores, steps=args.steps, warmup=max(args.warmup, 1), launches=args.cpu_launches, seed=seed)
+    cfg = workload_config(args, world, G)
     line = {
-        "impl": "reference", "metric": "AppendEntries/sec across Raft groups", "value": res["value"], "unit": "acks/s",
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "acks/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "replicas": args.replicas, "rows_per_step": args.rows},
-        "cpu_baseline": {"value": res["value"], "unit": "acks/s", "cores": cores, "kind": "port", "sample": res["sample"]},
+        "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": res["value"], "unit": "acks/s", "cores": cores, "kind": "port", "sample": res["sample"],
+                         "median_step_rate": res["median_rate"], "min_step_rate": res["min_rate"], "max_step_rate": res["max_rate"]},
         "e2e": {"value": res["value"], "unit": "acks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is Java; no JDK in this image -> oracle/ (C port of the reference's EventLoop path) is timed",
+        "note": "reference is Java; no JDK in this image or on the GPU box -> oracle/ (C port of the reference's EventLoop path) is timed; "
+                "this process loads liboracle.so and the stream generator librafting_workload.so, not the product library",
     }
     emit(line)
 
@@ -170,12 +260,17 @@ def run_reference(args):
 # B200 arm
 # ------------------------------------------------------------------------------------------------
 def run_engine(args):
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    all_cpus = os.sched_getaffinity(0)
+    placement = {"numa_node": None, "bound": False}
+    if not args.no_bind:
+        placement = bind_to_gpu_numa(local)
+        placement["bound"] = placement.get("numa_node") is not None
     import torch
     import torch.distributed as dist
     from rafting_b200 import abi, devbatch, engine, workload
 
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
     torch.cuda.set_device(local)
@@ -187,7 +282,9 @@ def run_engine(args):
         if world > 1:
             dist.barrier()
 
-    G, R, rows = args.groups, args.replicas, args.rows
+    R, rows = args.replicas, args.rows
+    G = args.groups or (G_CONFIG2 if world == 1 else G_CONFIG4 // world)
+    seed = SEED2 if world == 1 else SEED4
     F = R - 1
     K, W = args.steps, max(args.warmup, 3)
     cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=rows, device=local)
@@ -207,8 +304,8 @@ def run_engine(args):
     ext = torch.cuda.ExternalStream(stream_ptr, device=dev)
 
     # ---- election warm-up + settle, all on the device ------------------------------------------
-    w1 = workload.make_wl(SEED, 1, G, F, gid_base=gid_base)
-    w = workload.make_wl(SEED, rows, G, F, gid_base=gid_base)
+    w1 = workload.make_wl(seed, 1, G, F, gid_base=gid_base)
+    w = workload.make_wl(seed, rows, G, F, gid_base=gid_base)
     in1, out1 = devbatch.DevInbox(1, G, F, dev), devbatch.DevOutbox(1, G, F, G, dev)
     prev_c = None
     for ph in (0, 1, 2):
@@ -218,10 +315,13 @@ def run_engine(args):
         e.step_device(ic, oc, stream_ptr)
         prev_c = oc
     outs = [devbatch.DevOutbox(rows, G, F, G, dev) for _ in range(2)]
-    n_rec = W + K
     # the leader stream never marks a follower unavailable: the op_ab column (its only field used by SUBMIT / TIMEOUT)
     # is omitted from the batch, as a shim would do
-    inboxes = [devbatch.DevInbox(rows, G, F, dev, unavail=False) for _ in range(n_rec)]
+    probe = devbatch.DevInbox(rows, G, F, dev, unavail=False)
+    inbox_bytes, outbox_bytes = probe.nbytes(), outs[0].nbytes()
+    L = window_launches(args, G)
+    assert inbox_bytes == inbox_bytes_per_launch(G, rows, F)
+    inboxes = [probe] + [devbatch.DevInbox(rows, G, F, dev, unavail=False) for _ in range(L - 1)]
     settle = devbatch.DevInbox(rows, G, F, dev, unavail=False)
     SETTLE = 3
     prev_out = None
@@ -231,87 +331,99 @@ def run_engine(args):
         prev_out = outs[k % 2]
         e.step_device(ic, prev_out.as_c(), stream_ptr)
     torch.cuda.synchronize()
-    # keep the outbox the recorded stream starts from, then checkpoint the tables
+    # keep the outbox the recorded window starts from, then checkpoint the tables
     start_out = devbatch.DevOutbox(rows, G, F, G, dev)
     for name in start_out.t:
         start_out.t[name].copy_(prev_out.t[name])
     torch.cuda.synchronize()
     e.checkpoint()
 
-    # ---- phase A: generate + record the stream closed-loop (untimed) ------------------------------
+    # ---- phase A: generate + record the window closed-loop (untimed) ------------------------------
     prev_out = start_out
-    acks_per_step = []
-    for k in range(n_rec):
+    for k in range(L):
         ic = inboxes[k].as_c()
         workload.leader_step(w, SETTLE + k, prev_out.as_c(), ic, on_device=True, stream=stream_ptr)
         prev_out = outs[k % 2]
         e.step_device(ic, prev_out.as_c(), stream_ptr)
     torch.cuda.synchronize()
-    for k in range(n_rec):
-        m = inboxes[k].t["ev_meta"].view(torch.int64)
-        acks_per_step.append(int(((m & 0xF) != 0).sum().item()))
+    acks_per_launch = [int(((inboxes[k].t["ev_meta"].view(torch.int64) & 0xF) != 0).sum().item()) for k in range(L)]
+    acks_window = sum(acks_per_launch)
     digest_a = e.digest(0, G)
+    del start_out
 
     # ---- phase B: timed replay, inputs resident in HBM ---------------------------------------------
-    e.restore()
-    sampler = ClockSampler(local); sampler.start()
-    out_b = outs[0]
-    ics = [ib.as_c() for ib in inboxes]
-    ocs = [outs[k % 2].as_c() for k in range(n_rec)]
+    ics = (abi.InboxC * L)(*[ib.as_c() for ib in inboxes])
+    ocs = (abi.OutboxC * L)(*[outs[k % 2].as_c() for k in range(L)])
+    gather = world > 1
+
+    def window():
+        e.restore(sync=False)
+        e.step_device_seq(ics, ocs, L, gather=gather, stream=0)
+
     def warm():
-        for k in range(W):
-            e.step_device(ics[k], ocs[k], stream_ptr)
-            if world > 1:
-                e.allgather_commit(to_host=False)
-        if world > 1:
-            e.allgather_join()
+        for _ in range(W):
+            window()
+        e.allgather_join()
         torch.cuda.synchronize(); barrier()
 
-    # pass 1 — the metric: K steps back to back, two events around the whole region
+    sampler = ClockSampler(local); sampler.start()
     warm()
+    sampler.armed = True
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(ext)
-    for j in range(K):
-        e.step_device(ics[W + j], ocs[W + j], stream_ptr)
-        if world > 1:
-            e.allgather_commit(to_host=False)
-    if world > 1:
-        e.allgather_join()                      # the timed region ends when the last summary has been gathered
+    for _ in range(K):
+        window()
+    e.allgather_join()                      # the timed region ends when the last summary has been gathered
     ev1.record(ext)
     torch.cuda.synchronize(); barrier()
+    sampler.armed = False                   # clocks are sampled only while the GPU is under the timed load
     total_ms = ev0.elapsed_time(ev1)
     digest_b = e.digest(0, G)
-    # pass 2 — the same K steps again with an event pair around every kernel (roofline of the dominant kernel)
-    e.restore()
+    replay_ok = bool((digest_a == digest_b).all())
+
+    # ---- the gathered vector of the timed region's LAST launch against the ranks' own commit columns ----
+    gather_ok = None
+    if world > 1:
+        got = torch.from_numpy(e.allgather_last()).to(dev)
+        mine = outs[(L - 1) % 2].t["commit_index"].view(torch.int64).clone()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)                       # torch.distributed's own all-gather of the same column
+        table = torch.from_numpy(np.array([s.commit_index for s in e.export_bulk(0, min(G, 4096))], dtype=np.int64)).to(dev)
+        ok = bool(torch.equal(got, torch.cat(parts))) and bool(torch.equal(mine[:table.numel()], table)) and int(got.max().item()) > 0
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(flag.item())
+
+    # pass 2 — one window with an event pair around every kernel (roofline of the dominant kernel)
     warm()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K)]
-    for j in range(K):
+    sampler.armed = True
+    NK = min(L, 32)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * NK)]
+    e.restore(sync=False)
+    for j in range(NK):
         evs[2 * j].record(ext)
-        e.step_device(ics[W + j], ocs[W + j], stream_ptr)
+        e.step_device(ics[j], ocs[j], stream_ptr)
         evs[2 * j + 1].record(ext)
     torch.cuda.synchronize(); barrier()
-    kern_ms = [evs[2 * j].elapsed_time(evs[2 * j + 1]) for j in range(K)]
-
-    replay_ok = bool((digest_a == digest_b).all())
-    acks_timed = sum(acks_per_step[W:])
-    launches0, _ = e.counters()
+    kern_ms = [evs[2 * j].elapsed_time(evs[2 * j + 1]) for j in range(NK)]
+    sampler.armed = False
 
     # ---- e2e: the same stream through the C-ABI host path, HOST buffers in, HOST buffers out ---------
     e2e = None
     lat_ms = []
     if not args.no_e2e:
-        # the transport's pinned receive buffers: one pinned inbox per timed step (filled before the clock
-        # starts, as Netty would have decoded them), two pinned outboxes (one per slot)
-        K2 = min(K, 24)                                   # pinned host memory is bounded: at most 24 timed e2e steps
+        # the transport's pinned receive buffers: one pinned inbox per launch of the (prefix of the) window, filled before
+        # the clock starts as the transport would have decoded them; three pinned outboxes (one per slot in flight)
+        K2 = int(max(3, min(L, 24, 3.0e9 // inbox_bytes)))
         host_in = []
-        for k in range(W, W + K2):
+        for k in range(K2):
             cols = {name: t.cpu().pin_memory() for name, t in inboxes[k].t.items()}
             ic = abi.InboxC()
             ic.rows, ic.n_active, ic.flags = rows, 0, abi.INBOX_NO_REQUESTS
             for name, t in cols.items():
                 setattr(ic, name, t.data_ptr())
             host_in.append((cols, ic))
-        NSL = 3                                           # steps in flight on the host path
+        NSL = 3                                           # launches in flight on the host path
         host_out = []
         for sl in range(NSL):
             cols = {name: torch.zeros(t.numel(), dtype=torch.uint8).pin_memory() for name, t in outs[0].t.items()}
@@ -320,56 +432,51 @@ def run_engine(args):
                 setattr(oc, name, t.data_ptr())
             host_out.append((cols, oc))
         h2d = sum(t.numel() for t in host_in[0][0].values())
-        sparse = ("rep_term", "ballot_term", "ballot_last")        # copied down only when a step produced replies / ballots
+        sparse = ("rep_term", "ballot_term", "ballot_last")        # copied down only when a launch produced replies / ballots
         d2h = sum(t.numel() for name, t in host_out[0][0].items() if name not in sparse) + 16
+        acks_pass = sum(acks_per_launch[:K2])
 
-        def rewind():
-            e.restore()
-            for k in range(W):
-                e.step_device(ics[k], ocs[k], stream_ptr)
-            torch.cuda.synchronize()
+        def host_pass():
+            for j in range(K2):
+                sl = j % NSL
+                if j >= NSL:
+                    e.step_wait_slot(sl)                  # outbox of launch j-NSL is readable on the host
+                e.step_begin_host(sl, host_in[j][1], host_out[sl][1])
+            for sl in range(NSL):
+                e.step_wait_slot(sl)
 
-        # untimed: touch both slots once so their device staging exists before the clock starts
-        rewind()
-        for sl in range(NSL):
-            e.step_begin_host(sl, host_in[sl % len(host_in)][1], host_out[sl][1])
-        for sl in range(NSL):
-            e.step_wait_slot(sl)
-        # (1) throughput: two slots in flight — H2D of step j+1, kernel of step j and D2H of step j-1 overlap
-        rewind(); barrier()
+        # untimed: one pass so that every slot's device staging exists before the clock starts
+        e.restore(); host_pass()
+        est = 1.4e-3 * (G / 65536) * K2
+        reps = int(max(2, min(40, 0.12 / est + 1)))
+        barrier()
+        sampler.armed = True
         t0 = time.perf_counter()
-        for j in range(K2):
-            sl = j % NSL
-            if j >= NSL:
-                e.step_wait_slot(sl)                      # outbox of step j-NSL is readable on the host
-            e.step_begin_host(sl, host_in[j][1], host_out[sl][1])
-        for sl in range(NSL):
-            e.step_wait_slot(sl)
+        for _ in range(reps):
+            e.restore(sync=False)
+            host_pass()
         spent = time.perf_counter() - t0
-        acks_e2e = sum(acks_per_step[W:W + K2])
-        e2e_ok = None                                     # verified only when the e2e pass replays all K steps
-        if K2 == K:
-            digest_c = e.digest(0, G)
-            e2e_ok = bool((digest_a == digest_c).all())
-        # (2) latency: one step at a time, host ack in -> commit record readable out
-        rewind()
+        sampler.armed = False
+        # (2) latency: one launch at a time, host ack in -> commit record readable out
+        e.restore()
         for j in range(min(K2, 12)):
             t1 = time.perf_counter()
             e.step_begin_host(0, host_in[j][1], host_out[0][1])
             e.step_wait_slot(0)
             lat_ms.append((time.perf_counter() - t1) * 1e3)
         t = torch.tensor([spent], dtype=torch.float64, device=dev)
+        ae = torch.tensor([float(acks_pass * reps)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ae = torch.tensor([acks_e2e], dtype=torch.float64, device=dev)
-        if world > 1:
             dist.all_reduce(ae, op=dist.ReduceOp.SUM)
-        e2e = {"spent": float(t.item()), "h2d": int(h2d), "d2h": int(d2h), "ok": e2e_ok, "acks": float(ae.item()), "steps": K2}
+        e2e = {"spent": float(t.item()), "h2d": int(h2d), "d2h": int(d2h), "acks": float(ae.item()), "launches": K2 * reps,
+               "launches_per_pass": K2, "passes": reps}
+        del host_in, host_out
     sampler.stop_flag = True
 
     # ---- reduce over ranks ------------------------------------------------------------------------
     tt = torch.tensor([total_ms, float(np.mean(kern_ms))], dtype=torch.float64, device=dev)
-    aa = torch.tensor([acks_timed], dtype=torch.float64, device=dev)
+    aa = torch.tensor([float(acks_window * K)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(aa, op=dist.ReduceOp.SUM)
@@ -378,15 +485,18 @@ def run_engine(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        cpu = run_cpu_sample(args, seconds=args.cpu_seconds, threads=cores)
-        cpu3 = run_cpu_sample(args, seconds=min(4.0, args.cpu_seconds), threads=3)
+        os.sched_setaffinity(0, all_cpus)                   # the CPU leg may use every host core, not just the GPU's node
+        cores = len(all_cpus)
+        cpu = run_cpu_sample(args, threads=cores, steps=args.cpu_steps, warmup=1, launches=args.cpu_launches, seed=seed)
+        cpu3 = run_cpu_sample(args, threads=3, steps=2, warmup=1, launches=2, seed=seed)
         cpu["cores"] = cores; cpu["t3"] = cpu3["value"]
 
     # vote replies (config #3) and follower-side AppendEntries requests (config #5) are separate rates,
     # device-resident at full size; reported next to the headline, not part of `value`
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary and not args.no_e2e:
+        del inboxes, ics
+        torch.cuda.empty_cache()
         import importlib.util
         spec = importlib.util.spec_from_file_location("bench_secondary", os.path.join(ROOT, "tools", "bench_secondary.py"))
         mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
@@ -398,48 +508,54 @@ def run_engine(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        acks_per_launch = acks_timed / K
-        # dominant kernel's launch duration: at N=1 the timed region holds nothing but the K step kernels, so the
-        # region's own CUDA-event time / K is the unperturbed figure; with N>1 the region also holds the gathers, so
-        # the per-kernel event pairs of pass 2 are used (they include ~2 us of event overhead per launch)
-        k_ms = total_ms / K if world == 1 else float(np.mean(kern_ms))
-        achieved = acks_per_launch * b_ack(R) / (k_ms * 1e-3) / 1e9
+        launches = K * L
+        acks_launch = acks_window / L
+        # dominant kernel's launch duration: at N=1 the timed region holds the K*L step kernels and K table roll-backs
+        # (22 MB device copies), so region time / launches is the (slightly pessimistic) unperturbed figure; with N>1 the
+        # region also holds the gathers, so the per-kernel event pairs of pass 2 are used
+        k_ms = total_ms / launches if world == 1 else float(np.mean(kern_ms))
+        achieved = acks_launch * b_ack(R) / (k_ms * 1e-3) / 1e9
         traffic, traffic_src = measured_traffic(G, R, rows)
         value = acks_all / (total_ms_max * 1e-3)
+        cfgd = workload_config(args, world, G)
+        run = {
+            "acks_per_launch_per_gpu": acks_launch,
+            "inputs": f"each launch reads its own pre-generated inbox resident in HBM ({inbox_bytes / 1e6:.0f} MB inbox + "
+                      f"{outbox_bytes / 1e6:.0f} MB outbox per launch, window {L * inbox_bytes / 1e9:.1f} GB >> L2), no L2 flush needed",
+            "collective": ("ncclAllGather of commitIndex[G/N] after every launch, source = the launch's outbox commit column, on its "
+                           "own stream; the step stream waits for the gather issued one launch earlier") if world > 1 else "none (1 GPU)",
+            "bit_exact_replay": replay_ok, "host_placement": placement}
+        if world > 1:
+            cfgd["gather_verified"] = gather_ok            # SURVEY §8(d) #4's pass criterion, checked on every rank
         line = {
-            "metric": "AppendEntries/sec across Raft groups", "value": value, "unit": "acks/s",
+            "metric": METRIC, "value": value, "unit": "acks/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": WORKLOAD if world == 1 else
-                       f"{world * G // 1024}K RaftContext groups, 3 replicas, synthetic AppendEntries stream sharded across {world}xB200 "
-                       f"with NCCL commitIndex all-gather (64K groups per GPU, weak scaling of the 1xB200 configuration)",
-                       "groups_per_gpu": G, "replicas": R, "rows_per_step": rows,
-                       "acks_per_step_per_gpu": acks_per_launch,
-                       "inputs": f"every step reads a distinct pre-generated inbox resident in HBM "
-                                 f"({inboxes[0].nbytes() / 1e6:.0f} MB inbox + {outs[0].nbytes() / 1e6:.0f} MB outbox per step, > L2), no L2 flush needed",
-                       "collective": "ncclAllGather of commitIndex[G] after every step, on its own stream behind the producing kernel" if world > 1 else "none (1 GPU)",
-                       "bit_exact_replay": replay_ok},
-            "gpu_launches": K,
+            "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": cfgd, "run": run,
+            "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "bytes_per_ack": b_ack(R), "algorithmic_bytes_per_launch": acks_per_launch * b_ack(R),
+                         "bytes_per_ack": b_ack(R), "algorithmic_bytes_per_launch": acks_launch * b_ack(R),
                          "kernel_ms": k_ms, "kernel_ms_event_pair_per_launch": float(np.mean(kern_ms)),
                          "kernel": "rafting::unrolled::step_kernel<FT=R-1,NST=3>"},
             "clocks": sampler.summary(),
+            "timed_region_ms": total_ms_max,
         }
         if e2e:
             ev = e2e["acks"] / e2e["spent"]
-            line["e2e"] = {"value": ev, "unit": "acks/s", "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                           "bit_exact_replay": e2e["ok"], "steps": e2e["steps"],
-                           "note": "wall clock around K x rafting_step_begin_host/rafting_step_wait_slot with caller-owned pinned "
-                                   "buffers, three slots in flight (H2D / kernel / D2H of successive steps overlap); every step's inbox "
-                                   "crosses PCIe up and its outbox crosses PCIe down inside the timed region (the payload columns of "
-                                   "replies / ballots only when the step produced any)"}
+            line["e2e"] = {"value": ev, "unit": "acks/s", "h2d_bytes_per_step": e2e["h2d"] * L, "d2h_bytes_per_step": e2e["d2h"] * L,
+                           "h2d_bytes_per_launch": e2e["h2d"], "d2h_bytes_per_launch": e2e["d2h"],
+                           "launches": e2e["launches"], "timed_region_ms": e2e["spent"] * 1e3,
+                           "note": "wall clock around rafting_step_begin_host/rafting_step_wait_slot with caller-owned pinned buffers, three "
+                                   "launches in flight (H2D / kernel / D2H of successive launches overlap); every launch's inbox crosses PCIe up "
+                                   "and its outbox crosses PCIe down inside the timed region (the payload columns of replies / ballots only "
+                                   "when the launch produced any); bytes_per_step = per launch x the launches of one step"}
             line["commit_latency_ms"] = {"p50": float(np.percentile(lat_ms, 50)), "p99": float(np.percentile(lat_ms, 99)),
-                                         "what": "one synchronous step: host ack in pinned inbox -> commit record readable in pinned outbox"}
+                                         "what": "one synchronous launch: host ack in pinned inbox -> commit record readable in pinned outbox"}
         if cpu:
             line["cpu_baseline"] = {"value": cpu["value"], "unit": "acks/s", "cores": cpu["cores"], "kind": "port",
-                                    "sample": cpu["sample"], "t3_loop_threads_value": cpu["t3"]}
+                                    "sample": cpu["sample"], "median_step_rate": cpu["median_rate"], "min_step_rate": cpu["min_rate"],
+                                    "max_step_rate": cpu["max_rate"], "t3_loop_threads_value": cpu["t3"]}
         if secondary:
             line["secondary_rates"] = secondary
         emit(line)

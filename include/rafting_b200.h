@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define RAFTING_ABI_VERSION 1u
+#define RAFTING_ABI_VERSION 2u
 
 /* ------------------------------------------------------------------------------------------ */
 /* status codes (call level)                                                                  */
@@ -353,6 +353,9 @@ typedef struct rafting_engine rafting_engine_t;
 typedef struct rafting_lease {
     rafting_inbox_t  in;    /* const-cast to fill; pointers are into pinned host memory */
     rafting_outbox_t out;   /* filled by rafting_step */
+    uint32_t generation;    /* set by rafting_lease: a stale copy of an ended lease is rejected, even if a later lease
+                               was carved at the same addresses */
+    uint32_t _pad;
 } rafting_lease_t;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -369,6 +372,9 @@ int rafting_group_open     (rafting_engine_t* e, uint32_t gid, const rafting_gro
 int rafting_group_open_bulk(rafting_engine_t* e, uint32_t first_gid, uint32_t count,
                             const rafting_group_init_t* inits /* [count] */);
 int rafting_group_close    (rafting_engine_t* e, uint32_t gid);
+/* group_open / group_open_bulk / group_close / group_load_runs edit the tables from the host: they drain the engine's step
+   stream first and return RAFTING_E_BUSY while a host-path step (step_begin / step_begin_host) has not been waited for.
+   Steps enqueued on a CALLER's stream through rafting_step_device must be synchronised by the caller. */
 /* Restart with a log that spans several terms (RaftContext.initialize over an existing RocksLog, RaftContext.java:91-113):
  * after rafting_group_open, hand over the stored log's index->term map as runs, oldest first — runs[k] = (first index of
  * the run, its term); runs[0].x must be the group's first stored index, the last run's term its last_term.  At most
@@ -385,7 +391,8 @@ int rafting_lease_ex(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint
                      rafting_lease_t* out);
 int rafting_step (rafting_engine_t* e, rafting_lease_t* lease);          /* synchronous         */
 int rafting_step_begin(rafting_engine_t* e, rafting_lease_t* lease);     /* async: enqueue      */
-int rafting_step_wait (rafting_engine_t* e, rafting_lease_t* lease);     /* async: outbox ready; ends the lease */
+int rafting_step_wait (rafting_engine_t* e, rafting_lease_t* lease);     /* async: outbox ready; ends the lease (on error the lease stays) */
+int rafting_lease_release(rafting_engine_t* e, rafting_lease_t* lease);  /* give back a lease that will not be stepped */
 /* Up to RAFTING_HOST_SLOTS (4) leases may be outstanding: begin(A); fill B; begin(B); wait(A); ... overlaps
    the H2D of one step, the kernel of another and the D2H of a third.
    Caller-owned buffers (e.g. the transport's pinned receive pool, north_star "Netty feeds pinned
@@ -410,6 +417,7 @@ int rafting_log_term    (rafting_engine_t* e, uint32_t gid, int64_t index, int64
    the whole shard is snapshotted / rolled back at once).  One shadow copy per engine. */
 int rafting_checkpoint(rafting_engine_t* e);
 int rafting_restore   (rafting_engine_t* e);
+int rafting_restore_async(rafting_engine_t* e);   /* the same, enqueued on the step stream without a host synchronisation */
 
 /* ---- HBM-resident segmented entry buffer with async pinned-host spill (rafting_b200/csrc/seglog.cuh) ----
    Payload side of RaftLog (M/command/RaftLog.java:72-132; RocksLog.java:82-242): newEntry/append ->
@@ -435,14 +443,35 @@ int rafting_log_stats (rafting_engine_t* e, uint64_t* out /* appended, head, spi
                                                               last gather kernels ns, last gather bytes, trimmed entries,
                                                               cold bytes freed, spills skipped (dead segments) */, uint32_t n);
 
-/* multi-GPU summary: device pointer of this shard's commitIndex[G_local] (int64), and the
-   NCCL all-gather of it into a [world * G_local] device buffer owned by the engine */
+/* multi-GPU summary (BASELINE config #4): groups shard by contiguous gid blocks, rank r owns global groups
+   [r*G, (r+1)*G); the ONLY exchange is one ncclAllGather of commitIndex[G] (int64) per step into a [world * G] device
+   buffer every rank keeps (two, alternating).  The gather runs on its own stream behind the kernel that produced the column.
+     rafting_comm_init          one process per GPU: every rank passes the same 128-byte NCCL unique id (world == 1: no NCCL)
+     rafting_comm_init_all      ONE process owning n shards on n devices (the reference's host is a single JVM,
+                                ContextManager.java:46): engines[r] becomes rank r; the n ncclCommInitRank calls are grouped
+     rafting_allgather_commit_from   source = a device column the caller names, normally the step's outbox commit_index
+                                column (an end-of-step snapshot): the gathered vector is exactly the state after that step
+                                on every rank, and the next step kernel does not wait for the gather (the step stream waits
+                                for the gather issued one call EARLIER, so rotate at least two outboxes)
+     rafting_allgather_commit   source = the live table column; the next step kernel waits for the gather
+     rafting_allgather_commit_all    the same for every shard of a rafting_comm_init_all communicator, issued as one NCCL group
+   host_out != NULL: the call synchronises and copies the [world * G] vector to the host. */
 int rafting_commit_slice(rafting_engine_t* e, void** dev_ptr, uint32_t* count);
 int rafting_comm_init   (rafting_engine_t* e, int rank, int world, const void* nccl_unique_id, size_t id_len);
+int rafting_comm_init_all(rafting_engine_t** engines, int n);
 int rafting_comm_unique_id(void* out, size_t* len);
-int rafting_allgather_commit(rafting_engine_t* e, int64_t* host_out /* [world*G], may be NULL */,
-                             void** dev_out);       /* asynchronous on its own stream unless host_out != NULL */
+int rafting_allgather_commit(rafting_engine_t* e, int64_t* host_out /* [world*G], may be NULL */, void** dev_out);
+int rafting_allgather_commit_from(rafting_engine_t* e, const int64_t* dev_src /* [G] device, NULL = table column */,
+                                  int64_t* host_out, void** dev_out);
+int rafting_allgather_commit_all(rafting_engine_t** engines, int n, const int64_t* const* dev_srcs /* may be NULL */,
+                                 int64_t* const* host_outs /* may be NULL */, void** dev_outs /* [n], may be NULL */);
 int rafting_allgather_join  (rafting_engine_t* e);  /* the step stream waits for the gathers enqueued so far */
+int rafting_allgather_last  (rafting_engine_t* e, int64_t* host_out /* [world*G] */);  /* the most recently gathered vector */
+/* n device-resident steps enqueued by one call (ins[k] -> outs[k], in order): what a pump thread with a queue of decoded
+   batches does, without n trips through the binding.  gather != 0: each step is followed by
+   rafting_allgather_commit_from(outs[k].commit_index). */
+int rafting_step_device_seq(rafting_engine_t* e, const rafting_inbox_t* ins_dev, const rafting_outbox_t* outs_dev, uint32_t n,
+                            int gather, void* stream);
 
 /* introspection used by bench/tests */
 int rafting_engine_stream(rafting_engine_t* e, void** cuda_stream);

@@ -44,7 +44,11 @@ int rafting_journal_close(rafting_journal_t* j);
 
 /* One step's persist records + ONE fdatasync.  gids == NULL: position i is group i (dense step); with an active list,
  * role_word / current_term are indexed by gid unless `compact` != 0 (RAFTING_INBOX_COMPACT_GROUPS), then by position.
- * votedFor is taken from role_word bits 8..15 (slot + 1).  *n_records (optional) = records written (0 = no sync issued). */
+ * votedFor is taken from role_word bits 8..15 (slot + 1).  *n_records (optional) = records written (0 = no sync issued).
+ * Failure contract: a batch is durable as a whole or absent.  If the write or the fdatasync fails (ENOSPC, EIO, ...) the file
+ * is cut back to the pre-batch offset, the batch sequence number is not consumed and RAFTING_E_IO (-3) is returned: the step's
+ * replies must NOT be released, the same step may be committed again.  If the cut-back fails too the journal is sticky-failed:
+ * every later commit / milestone / checkpoint returns -3 until the journal is reopened (recovery then cuts the torn tail). */
 int rafting_journal_commit_step(rafting_journal_t* j, const uint32_t* gids, uint32_t n, int compact,
                                 const uint32_t* role_word, const int64_t* current_term, uint64_t* n_records);
 /* StableLock.persist(Snapshot): durable before it returns */

@@ -20,6 +20,7 @@
 
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -994,6 +995,7 @@ typedef struct orc_pool {
     pthread_t th[256]; int T;
     pthread_mutex_t mu; pthread_cond_t go, done;
     uint64_t gen; int pending, quit;
+    uint32_t next_chunk;     /* work queue of the step in flight: chunks of 64 consecutive groups, taken with an atomic add */
     orc_engine_t* e; const rafting_inbox_t* in; const rafting_outbox_t* out; uint32_t n;
     uint64_t events[256];
     int ids[256];
@@ -1006,9 +1008,15 @@ static void run_share(orc_pool_t* p, int t) {
        consecutive groups, so that two loop threads never write the same cache line of a batch column (in the JVM every
        context is its own heap object; strict per-group round-robin over SoA columns would charge the CPU baseline for
        false sharing the reference does not have).  Results do not depend on the binding. */
+    /* round 2: the chunks are handed out dynamically (one atomic add per 64 groups) instead of by a fixed stride, so a loop
+       thread that lost its core for a while (hyper-thread sibling, remote NUMA node, another tenant) no longer sets the
+       step time: a faster and steadier CPU baseline than the reference's fixed binding would give. */
     uint64_t ev = 0;
-    for (uint32_t c0 = (uint32_t)t * 64u; c0 < p->n; c0 += (uint32_t)p->T * 64u) {
-        const uint32_t c1 = c0 + 64u < p->n ? c0 + 64u : p->n;
+    const uint32_t nchunks = (p->n + 63u) / 64u;
+    for (;;) {
+        const uint32_t c = __atomic_fetch_add(&p->next_chunk, 1u, __ATOMIC_RELAXED);
+        if (c >= nchunks) break;
+        const uint32_t c0 = c * 64u, c1 = c0 + 64u < p->n ? c0 + 64u : p->n;
         for (uint32_t i = c0; i < c1; i++) step_group(p->e, p->in, p->out, i, p->n, &ev);
     }
     p->events[t] = ev;
@@ -1033,9 +1041,17 @@ static orc_pool_t* pool_create(int T) {
     if (!p) return NULL;
     p->T = T;
     pthread_mutex_init(&p->mu, NULL); pthread_cond_init(&p->go, NULL); pthread_cond_init(&p->done, NULL);
+    /* loop thread t is pinned to the t-th CPU this process may run on (wrapping): no migrations inside the timed region */
+    cpu_set_t allowed; int ncpu = 0, cpus[1024];
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+        for (int c = 0; c < CPU_SETSIZE && ncpu < 1024; c++) if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
     for (int t = 0; t < T; t++) {
         pool_arg_t* a = (pool_arg_t*)malloc(sizeof(*a)); a->p = p; a->t = t;
         pthread_create(&p->th[t], NULL, pool_main, a);
+        if (ncpu > 0 && !getenv("ORACLE_NO_PIN")) {
+            cpu_set_t one; CPU_ZERO(&one); CPU_SET(cpus[t % ncpu], &one);
+            pthread_setaffinity_np(p->th[t], sizeof(one), &one);
+        }
     }
     return p;
 }
@@ -1060,7 +1076,7 @@ int orc_step(orc_engine_t* e, const rafting_inbox_t* in, const rafting_outbox_t*
     if (!e->pool) { e->pool = pool_create(threads); if (!e->pool) return RAFTING_E_NOMEM; }
     orc_pool_t* p = e->pool;
     pthread_mutex_lock(&p->mu);
-    p->e = e; p->in = in; p->out = out; p->n = n; p->pending = threads; p->gen++;
+    p->e = e; p->in = in; p->out = out; p->n = n; p->pending = threads; p->next_chunk = 0; p->gen++;
     pthread_cond_broadcast(&p->go);
     while (p->pending) pthread_cond_wait(&p->done, &p->mu);
     pthread_mutex_unlock(&p->mu);

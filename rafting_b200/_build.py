@@ -11,9 +11,11 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librafting_b200.so")
-SOURCES = ["engine.cu", "workload.cu"]
-HEADERS = ["step_kernel.cuh", "step_body.inc", "seglog.cuh", "handlers.cuh", "tables.cuh", os.path.join("..", "..", "include", "rafting_b200.h"),
-           os.path.join("..", "..", "include", "rafting_workload.h")]
+SOURCES = ["engine.cu"]
+HEADERS = ["step_kernel.cuh", "step_body.inc", "seglog.cuh", "handlers.cuh", "tables.cuh", os.path.join("..", "..", "include", "rafting_b200.h")]
+# the synthetic-stream generator (the simulated peers) is NOT part of the product library: tests, bench and the CPU
+# reference arm load it on its own, so a process that times the CPU port never maps librafting_b200.so
+WORKLOAD_LIB = os.path.join(HERE, "librafting_workload.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-Wno-deprecated-gpu-targets",
@@ -51,6 +53,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_workload(force: bool = False) -> str:
+    src = os.path.join(CSRC, "workload.cu")
+    deps = [src, os.path.join(HERE, "..", "include", "rafting_workload.h"), os.path.join(HERE, "..", "include", "rafting_b200.h")]
+    if not force and os.path.exists(WORKLOAD_LIB) and os.path.getmtime(WORKLOAD_LIB) > max(os.path.getmtime(d) for d in deps):
+        return WORKLOAD_LIB
+    res = subprocess.run([nvcc()] + NVCC_FLAGS + [src, "-o", WORKLOAD_LIB], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc (workload) failed:\n" + (res.stdout + res.stderr)[-4000:])
+    return WORKLOAD_LIB
+
+
 DURABLE_LIB = os.path.join(HERE, "librafting_durable.so")
 
 
@@ -70,4 +83,5 @@ def build_durable(force: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_workload(force=True))
     print(build_durable(force=True))

@@ -14,7 +14,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 INBOX_NO_REQUESTS = 1
 INBOX_COMPACT_GROUPS = 2
 CFG_STRICT_CANDIDATE_VOTE = 1
@@ -98,7 +98,7 @@ class OutboxC(C.Structure):
 
 
 class LeaseC(C.Structure):
-    _fields_ = [("inbox", InboxC), ("outbox", OutboxC)]
+    _fields_ = [("inbox", InboxC), ("outbox", OutboxC), ("generation", C.c_uint32), ("_pad", C.c_uint32)]
 
 
 class GroupInit(C.Structure):

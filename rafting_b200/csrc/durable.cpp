@@ -71,6 +71,7 @@ struct rafting_journal {
     std::vector<Row> rows;          // the recovered + applied state (what restore() answers from)
     std::vector<uint8_t> buf;       // batch under construction
     uint64_t seq = 0, batches = 0, records = 0, syncs = 0, wal_bytes = 0;
+    bool failed = false;            // sticky: a batch could not be written AND could not be rolled back
 };
 
 static void apply(rafting_journal* j, const Rec& r) {
@@ -79,12 +80,24 @@ static void apply(rafting_journal* j, const Rec& r) {
     else if (r.kind == KIND_MILESTONE) { w.ms_index = r.a; w.ms_term = r.b; }
 }
 
+// A batch is either durable as a whole or absent: when the write or the barrier fails, the file is cut back to the
+// pre-batch offset and the sequence number is not consumed, so a later batch can never be appended behind torn bytes
+// (recovery stops at the first torn batch and would silently drop everything after it — acknowledged votes included).
+// If the cut-back itself fails the journal turns sticky-failed: every later commit answers E_IO until it is reopened.
 static int commit_buf(rafting_journal* j, uint32_t n) {
+    if (j->failed) return fail(E_IO, "journal is failed (an earlier batch could not be rolled back): reopen it");
     Hdr* h = (Hdr*)j->buf.data();
-    h->magic = MAGIC; h->n = n; h->seq = ++j->seq; h->_pad = 0;
+    h->magic = MAGIC; h->n = n; h->seq = j->seq + 1; h->_pad = 0;
     h->crc = crc32c(j->buf.data() + sizeof(Hdr), (size_t)n * sizeof(Rec), crc32c(&h->seq, 8));
-    if (!write_all(j->fd_wal, j->buf.data(), j->buf.size())) return fail(E_IO, "journal write failed: %s", strerror(errno));
-    if (fdatasync(j->fd_wal) != 0) return fail(E_IO, "fdatasync failed: %s", strerror(errno));
+    const char* what = nullptr; int err = 0;
+    if (!write_all(j->fd_wal, j->buf.data(), j->buf.size())) { what = "journal write"; err = errno; }
+    else if (fdatasync(j->fd_wal) != 0) { what = "fdatasync"; err = errno; }
+    if (what) {
+        const off_t back = (off_t)j->wal_bytes;
+        if (ftruncate(j->fd_wal, back) != 0 || lseek(j->fd_wal, back, SEEK_SET) < 0 || fdatasync(j->fd_wal) != 0) j->failed = true;
+        return fail(E_IO, "%s failed: %s%s", what, strerror(err), j->failed ? " (and the batch could not be rolled back: journal failed)" : " (batch rolled back)");
+    }
+    j->seq = h->seq;
     j->syncs++; j->batches++; j->records += n; j->wal_bytes += j->buf.size();
     const Rec* r = (const Rec*)(j->buf.data() + sizeof(Hdr));
     for (uint32_t k = 0; k < n; k++) apply(j, r[k]);
@@ -103,6 +116,16 @@ extern "C" int rafting_journal_open(const char* dir, uint32_t max_groups, raftin
     j->fd_tbl = open(tbl.c_str(), O_RDWR | O_CREAT, 0644);
     j->fd_wal = open(wal.c_str(), O_RDWR | O_CREAT, 0644);
     if (j->fd_tbl < 0 || j->fd_wal < 0) { int rc = fail(E_IO, "open journal files in %s: %s", dir, strerror(errno)); rafting_journal_close(j); return rc; }
+    // the directory entries of the two files must survive a crash too: one fsync of the directory after creating them
+    {
+        const int dfd = open(dir, O_RDONLY | O_DIRECTORY);
+        if (dfd < 0 || fsync(dfd) != 0) {
+            int rc = fail(E_IO, "fsync of directory %s: %s", dir, strerror(errno));
+            if (dfd >= 0) close(dfd);
+            rafting_journal_close(j); return rc;
+        }
+        close(dfd);
+    }
     // table: as many complete rows as the file holds (a fresh file holds none)
     struct stat sb;
     if (fstat(j->fd_tbl, &sb) == 0 && sb.st_size > 0) {
@@ -187,6 +210,7 @@ extern "C" int rafting_journal_restore(rafting_journal_t* j, uint32_t gid, rafti
 
 extern "C" int rafting_journal_checkpoint(rafting_journal_t* j) {
     if (!j) return fail(E_INVAL, "null argument");
+    if (j->failed) return fail(E_IO, "journal is failed: reopen it");
     // 1. the table becomes durable first; only then may the journal that produced it disappear
     if (pwrite(j->fd_tbl, j->rows.data(), j->rows.size() * sizeof(Row), 0) != (ssize_t)(j->rows.size() * sizeof(Row)))
         return fail(E_IO, "table write failed: %s", strerror(errno));

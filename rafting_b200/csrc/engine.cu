@@ -42,6 +42,8 @@ struct NcclApi {
     int (*CommInitRank)(nccl_comm_t*, int, nccl_uid_t, int) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
@@ -55,6 +57,8 @@ static int nccl_load() {
     *(void**)&g_nccl.AllGather = dlsym(g_nccl.h, "ncclAllGather");
     *(void**)&g_nccl.CommDestroy = dlsym(g_nccl.h, "ncclCommDestroy");
     *(void**)&g_nccl.GetErrorString = dlsym(g_nccl.h, "ncclGetErrorString");
+    *(void**)&g_nccl.GroupStart = dlsym(g_nccl.h, "ncclGroupStart");
+    *(void**)&g_nccl.GroupEnd = dlsym(g_nccl.h, "ncclGroupEnd");
     if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather)
         return fail(RAFTING_E_NCCL, "libnccl lacks required symbols");
     return 0;
@@ -69,20 +73,23 @@ struct rafting_engine {
     Tables T;
     uint32_t G, F;
     cudaStream_t stream = nullptr;
-    int64_t* commit_all = nullptr;     // [world * G]; T.g_commit points at this rank's slice
+    int64_t* gather[2] = {nullptr, nullptr};   // [world * G] x 2: cross-shard commitIndex summaries, alternating
+    uint64_t gather_seq = 0;
     int rank = 0, world = 1;
     nccl_comm_t comm = nullptr;
     cudaStream_t s_comm = nullptr;     // the summary all-gather runs here, off the kernels' critical path
-    cudaEvent_t ev_step = nullptr, ev_comm = nullptr;
+    cudaEvent_t ev_step = nullptr, ev_gather[2] = {nullptr, nullptr};
     struct HostPath* host = nullptr;  // slots, copy streams (created on first use)
     struct rafting::SegLog* seglog = nullptr;   // HBM entry buffer (seglog.cuh), created by rafting_log_config
     cudaEvent_t ev_seg = nullptr;
     uint64_t launches = 0, events = 0;
+    uint32_t lease_counter = 0;
     uint32_t* d_perm = nullptr;        // [NCLS * G] class-sorted positions of the step being launched (classify_kernel)
     uint32_t* d_perm_cnt = nullptr;    // class sizes
     std::vector<void*> dev_allocs;
     std::vector<size_t> dev_bytes;
-    std::vector<void*> shadow;         // rafting_checkpoint copies, parallel to dev_allocs
+    std::vector<void*> shadow;         // rafting_checkpoint copies of the first n_state_allocs entries of dev_allocs
+    size_t n_state_allocs = 0;         // the tables (allocated by engine_create); later allocations are scratch
 };
 
 template <typename T>
@@ -99,6 +106,7 @@ static int dalloc(rafting_engine* e, T** p, size_t count) {
 
 static void rafting_hostpath_release(rafting_engine* e);
 static void seglog_release(rafting_engine* e);
+static int quiesce_for_table_edit(rafting_engine* e, const char* who);
 extern "C" uint32_t rafting_abi_version(void) { return RAFTING_ABI_VERSION; }
 extern "C" const char* rafting_last_error(void) { return g_err; }
 
@@ -129,14 +137,14 @@ extern "C" int rafting_engine_create(const rafting_cfg_t* cfg, rafting_engine_t*
     int rc = 0;
     Tables& T = e->T; const size_t G = e->G, F = e->F;
     T.G = e->G; T.F = e->F;
-    if ((rc = dalloc(e, &T.g_meta, G)) || (rc = dalloc(e, &T.g_term, G)) || (rc = dalloc(e, &e->commit_all, G)) ||
+    if ((rc = dalloc(e, &T.g_meta, G)) || (rc = dalloc(e, &T.g_term, G)) || (rc = dalloc(e, &T.g_commit, G)) ||
         (rc = dalloc(e, &T.g_lo, G)) || (rc = dalloc(e, &T.g_hi, G)) || (rc = dalloc(e, &T.g_timer, G)) ||
         (rc = dalloc(e, &T.g_epoch, G)) || (rc = dalloc(e, &T.g_elect, G)) || (rc = dalloc(e, &T.g_err, G)) ||
         (rc = dalloc(e, &T.g_runs, G * KRUNS)) || (rc = dalloc(e, &T.l_nm, G * F)) || (rc = dalloc(e, &T.l_es, G * F)) ||
         (rc = dalloc(e, &T.l_fr, G * F)) || (rc = dalloc(e, &T.l_cnt, G * F))) {
         rafting_engine_destroy(e); return rc;
     }
-    T.g_commit = e->commit_all;
+    e->n_state_allocs = e->dev_allocs.size();
     if ((rc = dalloc(e, &e->d_cfg, 1)) || (rc = dalloc(e, &e->d_perm, NCLS * G)) || (rc = dalloc(e, &e->d_perm_cnt, NCLS))) { rafting_engine_destroy(e); return rc; }
     if (cudaMemcpy(e->d_cfg, &e->dcfg, sizeof(CfgD), cudaMemcpyHostToDevice) != cudaSuccess) {
         rafting_engine_destroy(e); return fail(RAFTING_E_CUDA, "cfg upload failed");
@@ -152,7 +160,10 @@ extern "C" int rafting_engine_destroy(rafting_engine_t* e) {
     if (!e) return RAFTING_OK;
     cudaSetDevice(e->cfg.device);
     if (e->stream) { cudaStreamSynchronize(e->stream); }
-    if (e->s_comm) { cudaStreamSynchronize(e->s_comm); cudaStreamDestroy(e->s_comm); cudaEventDestroy(e->ev_step); cudaEventDestroy(e->ev_comm); }
+    if (e->s_comm) {
+        cudaStreamSynchronize(e->s_comm); cudaStreamDestroy(e->s_comm); cudaEventDestroy(e->ev_step);
+        for (int p = 0; p < 2; p++) if (e->ev_gather[p]) cudaEventDestroy(e->ev_gather[p]);
+    }
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void* p : e->dev_allocs) cudaFree(p);
     for (void* p : e->shadow) cudaFree(p);
@@ -173,6 +184,10 @@ extern "C" int rafting_group_open_bulk(rafting_engine_t* e, uint32_t first, uint
     if ((uint64_t)first + count > e->G) return fail(RAFTING_E_CAPACITY, "gid range beyond max_groups");
     if (count == 0) return RAFTING_OK;
     CU(cudaSetDevice(e->cfg.device));
+    // e->stream is non-blocking: the legacy-stream copies below are NOT ordered against queued step kernels, and a dense
+    // step loads and writes back the hot columns of every gid.  Opening is rare (ContextManager.buildContext is
+    // synchronized): drain the step stream first, and refuse while a host-path step is still in flight.
+    if (int rc = quiesce_for_table_edit(e, "rafting_group_open")) return rc;
     const size_t F = e->F;
     std::vector<uint64_t> meta(count); std::vector<int64_t> term(count), commit(count), lo(count), hi(count), timer(count);
     std::vector<i64x2> epoch(count), elect(count), run0(count); std::vector<uint32_t> err(count, 0);
@@ -239,6 +254,7 @@ extern "C" int rafting_group_load_runs(rafting_engine_t* e, uint32_t gid, const 
 extern "C" int rafting_group_close(rafting_engine_t* e, uint32_t gid) {
     if (!e || gid >= e->G) return fail(RAFTING_E_INVAL, "bad gid");
     CU(cudaSetDevice(e->cfg.device));
+    if (int rc = quiesce_for_table_edit(e, "rafting_group_close")) return rc;   // host read-modify-write of g_meta
     uint64_t m;
     CU(cudaMemcpy(&m, e->T.g_meta + gid, 8, cudaMemcpyDeviceToHost));
     m &= ~(uint64_t)W_ALIVE;
@@ -329,6 +345,18 @@ extern "C" int rafting_step_device(rafting_engine_t* e, const rafting_inbox_t* i
     return launch_step(e, di, dout, stream ? (cudaStream_t)stream : e->stream);
 }
 
+extern "C" int rafting_allgather_commit_from(rafting_engine_t* e, const int64_t* dev_src, int64_t* host_out, void** dev_out);
+extern "C" int rafting_step_device_seq(rafting_engine_t* e, const rafting_inbox_t* ins, const rafting_outbox_t* outs, uint32_t n,
+                                       int gather, void* stream) {
+    if (!e || !ins || !outs) return fail(RAFTING_E_INVAL, "null argument");
+    if (gather && stream && (cudaStream_t)stream != e->stream) return fail(RAFTING_E_INVAL, "gathers follow the engine's own stream");
+    for (uint32_t k = 0; k < n; k++) {
+        int rc = rafting_step_device(e, &ins[k], &outs[k], stream); if (rc) return rc;
+        if (gather) { rc = rafting_allgather_commit_from(e, outs[k].commit_index, nullptr, nullptr); if (rc) return rc; }
+    }
+    return RAFTING_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host path.  Two SLOTS, each with its own device staging (and, for leases, engine-owned pinned
 // buffers), and three streams: H2D copies, the step kernel, D2H copies.  A step in slot s is
@@ -405,7 +433,8 @@ struct Slot {
     cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
     bool leased = false, inflight = false;
     uint32_t rows = 0, n = 0, ent = 0; bool list = false, compact = false;
-    void* lease_key = nullptr;                // the lease's commit_index pointer identifies it
+    void* lease_key = nullptr;                // the lease's commit_index pointer + its generation identify it
+    uint32_t lease_gen = 0;
     // of the step in flight (for the sparse columns fetched at wait time)
     rafting_outbox_t host_out; rafting_outbox_t dev_out; size_t rows_ = 0, n_ = 0; const uint32_t* flags_host = nullptr;
 };
@@ -415,6 +444,16 @@ struct HostPath {
     bool ready = false;
 };
 static HostPath* hp(rafting_engine* e) { if (!e->host) e->host = new HostPath(); return e->host; }
+
+// Host-side edits of the tables (group open / close / load_runs) must not interleave with step kernels: RAFTING_E_BUSY
+// while a host-path step has been begun and not waited for, then the step stream is drained.
+static int quiesce_for_table_edit(rafting_engine* e, const char* who) {
+    if (e->host)
+        for (int k = 0; k < RAFTING_HOST_SLOTS; k++)
+            if (e->host->slot[k].inflight) return fail(RAFTING_E_BUSY, "%s: slot %d has a step in flight (wait for it first)", who, k);
+    CU(cudaStreamSynchronize(e->stream));
+    return RAFTING_OK;
+}
 
 static int hostpath_init(rafting_engine* e) {
     HostPath* H = hp(e);
@@ -522,7 +561,8 @@ static int step_enqueue(rafting_engine* e, uint32_t slot, const rafting_inbox_t*
     InboxD di; OutboxD dov;
     to_dev_views(&din, &dout, e->G, di, dov);
     dov.flags = d_flags;
-    rc = launch_step(e, di, dov, e->stream); if (rc) return rc;
+    rc = launch_step(e, di, dov, e->stream);
+    if (rc) { cudaStreamSynchronize(H->s_h2d); return rc; }                  // no copy of this step may outlive the failed call
     CU(cudaEventRecord(S.ev_kernel, e->stream));
     // ---- D2H: dense columns always; the payload of the SPARSE families (rep_term, ballot_term, ballot_last —
     //      meaningful only where a reply / ballot exists, i.e. never in leader steady state) only if the kernel
@@ -606,6 +646,8 @@ extern "C" int rafting_lease_ex(rafting_engine_t* e, uint32_t rows, uint32_t n_a
     S.compact = compact;
     S.leased = true; S.rows = rows; S.n = (uint32_t)n; S.ent = ent_count; S.list = n_active != 0;
     S.lease_key = out->out.commit_index;
+    S.lease_gen = ++e->lease_counter; if (S.lease_gen == 0) S.lease_gen = ++e->lease_counter;
+    out->generation = S.lease_gen;
     return RAFTING_OK;
 }
 extern "C" int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_active, uint32_t ent_count, rafting_lease_t* out) {
@@ -614,8 +656,20 @@ extern "C" int rafting_lease(rafting_engine_t* e, uint32_t rows, uint32_t n_acti
 static int lease_slot(rafting_engine* e, const rafting_lease_t* L) {
     HostPath* H = hp(e);
     for (int k = 0; k < RAFTING_HOST_SLOTS; k++)
-        if (H->slot[k].leased && L->out.commit_index == (int64_t*)H->slot[k].lease_key) return k;
+        if (H->slot[k].leased && L->out.commit_index == (int64_t*)H->slot[k].lease_key && L->generation == H->slot[k].lease_gen) return k;
     return -1;
+}
+// give back a lease that will not be stepped (or whose step has been waited for already: then it is a no-op error)
+extern "C" int rafting_lease_release(rafting_engine_t* e, rafting_lease_t* L) {
+    if (!e || !L) return fail(RAFTING_E_INVAL, "null argument");
+    if (!e->host) return fail(RAFTING_E_INVAL, "not an outstanding lease");
+    CU(cudaSetDevice(e->cfg.device));
+    const int sl = lease_slot(e, L);
+    if (sl < 0) return fail(RAFTING_E_INVAL, "not an outstanding lease");
+    Slot& S = hp(e)->slot[sl];
+    if (S.inflight) { int rc = slot_wait(e, (uint32_t)sl); if (rc) return rc; }   // begun but never waited for: finish it
+    S.leased = false; S.lease_key = nullptr; L->generation = 0;
+    return RAFTING_OK;
 }
 extern "C" int rafting_step_begin(rafting_engine_t* e, rafting_lease_t* L) {
     if (!e || !L) return fail(RAFTING_E_INVAL, "null argument");
@@ -635,7 +689,9 @@ extern "C" int rafting_step_wait(rafting_engine_t* e, rafting_lease_t* L) {
     const int sl = lease_slot(e, L);
     if (sl < 0) return fail(RAFTING_E_INVAL, "not an outstanding lease");
     int rc = slot_wait(e, (uint32_t)sl);
-    hp(e)->slot[sl].leased = false;                                          // the lease ends with its step
+    if (rc) return rc;                                                       // the lease stays valid: wait again or release it
+    hp(e)->slot[sl].leased = false; hp(e)->slot[sl].lease_key = nullptr;     // the lease ends with its step
+    L->generation = 0;
     return rc;
 }
 extern "C" int rafting_step(rafting_engine_t* e, rafting_lease_t* L) {
@@ -751,29 +807,49 @@ extern "C" int rafting_log_term(rafting_engine_t* e, uint32_t gid, int64_t index
 extern "C" int rafting_checkpoint(rafting_engine_t* e) {
     if (!e) return fail(RAFTING_E_INVAL, "null argument");
     CU(cudaSetDevice(e->cfg.device));
-    while (e->shadow.size() < e->dev_allocs.size()) {
+    while (e->shadow.size() < e->n_state_allocs) {
         void* q = nullptr;
         CU(cudaMalloc(&q, e->dev_bytes[e->shadow.size()]));
         e->shadow.push_back(q);
     }
-    for (size_t i = 0; i < e->dev_allocs.size(); i++)
+    for (size_t i = 0; i < e->shadow.size(); i++)
         CU(cudaMemcpyAsync(e->shadow[i], e->dev_allocs[i], e->dev_bytes[i], cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     return RAFTING_OK;
 }
+// The checkpoint covers the allocations that existed when it was taken (the tables); buffers created later (the
+// gather buffers of rafting_comm_init) are not state and are left alone.
+static int restore_enqueue(rafting_engine* e) {
+    if (e->shadow.empty() || e->shadow.size() > e->dev_allocs.size()) return fail(RAFTING_E_INVAL, "no checkpoint taken");
+    CU(cudaSetDevice(e->cfg.device));
+    for (size_t i = 0; i < e->shadow.size(); i++)
+        CU(cudaMemcpyAsync(e->dev_allocs[i], e->shadow[i], e->dev_bytes[i], cudaMemcpyDeviceToDevice, e->stream));
+    return RAFTING_OK;
+}
 extern "C" int rafting_restore(rafting_engine_t* e) {
     if (!e) return fail(RAFTING_E_INVAL, "null argument");
-    if (e->shadow.size() != e->dev_allocs.size()) return fail(RAFTING_E_INVAL, "no checkpoint taken (or tables re-homed since)");
-    CU(cudaSetDevice(e->cfg.device));
-    for (size_t i = 0; i < e->dev_allocs.size(); i++)
-        CU(cudaMemcpyAsync(e->dev_allocs[i], e->shadow[i], e->dev_bytes[i], cudaMemcpyDeviceToDevice, e->stream));
+    int rc = restore_enqueue(e); if (rc) return rc;
     CU(cudaStreamSynchronize(e->stream));
     return RAFTING_OK;
+}
+extern "C" int rafting_restore_async(rafting_engine_t* e) {          // enqueued on the step stream, no host synchronisation
+    if (!e) return fail(RAFTING_E_INVAL, "null argument");
+    return restore_enqueue(e);
 }
 
 // ---------------------------------------------------------------------------------------------
 // multi-GPU commitIndex summary
 // ---------------------------------------------------------------------------------------------
+// Shards are contiguous gid blocks: rank r owns global groups [r*G, (r+1)*G).  The only exchange between shards is one
+// ncclAllGather of commitIndex[G] per step into a [world * G] buffer kept on every rank (two of them, alternating, so the
+// consumer of step k's summary is not overwritten by step k+1's gather).
+//   * the gather runs on its own stream (s_comm) behind the kernel that produced the column;
+//   * SOURCE = a device column the caller names (normally the step's outbox commit_index column: an end-of-step
+//     snapshot no later kernel writes, so the gathered vector is EXACTLY the state after that step on every rank), or the
+//     live table column, in which case the step stream is made to wait for the gather before the next kernel may change it;
+//   * after enqueuing gather k the step stream waits for gather k-1: a caller that rotates two (or more) outboxes
+//     therefore never overwrites a column a gather is still reading, and the next step kernel never waits for the
+//     gather of the step right before it.
 extern "C" int rafting_commit_slice(rafting_engine_t* e, void** dev_ptr, uint32_t* count) {
     if (!e || !dev_ptr || !count) return fail(RAFTING_E_INVAL, "null argument");
     *dev_ptr = e->T.g_commit; *count = e->G;
@@ -788,20 +864,22 @@ extern "C" int rafting_comm_unique_id(void* out, size_t* len) {
     memcpy(out, &id, sizeof(id)); *len = sizeof(id);
     return RAFTING_OK;
 }
-// Shards are contiguous gid blocks: rank r owns global groups [r*G, (r+1)*G).  The commit column is
-// re-homed INSIDE the gather buffer so the step kernel writes its slice straight into the
-// all-gather send position (in-place ncclAllGather, no staging copy).
+static int comm_prepare(rafting_engine* e, int rank, int world) {
+    if (e->gather[0]) return fail(RAFTING_E_INVAL, "communicator already initialised");
+    CU(cudaSetDevice(e->cfg.device));
+    for (int p = 0; p < 2; p++) { int rc = dalloc(e, &e->gather[p], (size_t)world * e->G); if (rc) return rc; }
+    CU(cudaStreamCreateWithFlags(&e->s_comm, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
+    for (int p = 0; p < 2; p++) CU(cudaEventCreateWithFlags(&e->ev_gather[p], cudaEventDisableTiming));
+    e->rank = rank; e->world = world; e->gather_seq = 0;
+    return RAFTING_OK;
+}
+// one process per GPU (torchrun shape): every rank calls this with the same unique id
 extern "C" int rafting_comm_init(rafting_engine_t* e, int rank, int world, const void* uid, size_t id_len) {
     if (!e || world < 1 || rank < 0 || rank >= world) return fail(RAFTING_E_INVAL, "bad rank/world");
-    CU(cudaSetDevice(e->cfg.device));
-    CU(cudaStreamSynchronize(e->stream));
-    int64_t* buf = nullptr;
-    int rc = dalloc(e, &buf, (size_t)world * e->G); if (rc) return rc;
-    CU(cudaMemcpy(buf + (size_t)rank * e->G, e->T.g_commit, (size_t)e->G * 8, cudaMemcpyDeviceToDevice));
-    e->commit_all = buf; e->T.g_commit = buf + (size_t)rank * e->G;
-    e->rank = rank; e->world = world;
+    if (world > 1 && (!uid || id_len != sizeof(nccl_uid_t))) return fail(RAFTING_E_INVAL, "unique id must be 128 bytes");
+    int rc = comm_prepare(e, rank, world); if (rc) return rc;
     if (world > 1) {
-        if (!uid || id_len != sizeof(nccl_uid_t)) return fail(RAFTING_E_INVAL, "unique id must be 128 bytes");
         rc = nccl_load(); if (rc) return rc;
         nccl_uid_t id; memcpy(&id, uid, sizeof(id));
         int nr = g_nccl.CommInitRank(&e->comm, world, id, rank);
@@ -809,39 +887,109 @@ extern "C" int rafting_comm_init(rafting_engine_t* e, int rank, int world, const
     }
     return RAFTING_OK;
 }
-// The all-gather is enqueued on its own stream behind the kernel that produced the slice, so the NEXT
-// step kernel does not wait for it (the gathered vector is a monotone summary: each entry is the group's
-// commitIndex at or after the step the gather was issued for).  With host_out the call synchronises and
-// the vector is exactly the state after the last enqueued step.
-extern "C" int rafting_allgather_commit(rafting_engine_t* e, int64_t* host_out, void** dev_out) {
-    if (!e) return fail(RAFTING_E_INVAL, "null argument");
-    CU(cudaSetDevice(e->cfg.device));
-    if (!e->s_comm) {
-        CU(cudaStreamCreateWithFlags(&e->s_comm, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&e->ev_comm, cudaEventDisableTiming));
+// ONE process that owns several shards (the reference's host is one JVM: ContextManager.java:46 — one pump thread per
+// shard): engines[r] becomes rank r of an n-rank communicator.  ncclCommInitRank blocks until every rank has joined, so
+// the n calls are issued inside one ncclGroupStart / ncclGroupEnd from this single thread.
+extern "C" int rafting_comm_init_all(rafting_engine_t** engines, int n) {
+    if (!engines || n < 1) return fail(RAFTING_E_INVAL, "bad argument");
+    for (int r = 0; r < n; r++) {
+        if (!engines[r]) return fail(RAFTING_E_INVAL, "null engine");
+        if (engines[r]->G != engines[0]->G) return fail(RAFTING_E_INVAL, "every shard must have the same max_groups");
+        for (int q = 0; q < r; q++) if (engines[q]->cfg.device == engines[r]->cfg.device) return fail(RAFTING_E_INVAL, "two shards on device %d", engines[r]->cfg.device);
     }
+    int rc;
+    for (int r = 0; r < n; r++) if ((rc = comm_prepare(engines[r], r, n))) return rc;
+    if (n == 1) return RAFTING_OK;
+    rc = nccl_load(); if (rc) return rc;
+    if (!g_nccl.GroupStart || !g_nccl.GroupEnd) return fail(RAFTING_E_NCCL, "libnccl lacks ncclGroupStart/End");
+    nccl_uid_t id;
+    int nr = g_nccl.GetUniqueId(&id);
+    if (nr) return fail(RAFTING_E_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+    g_nccl.GroupStart();
+    for (int r = 0; r < n && !nr; r++) {
+        cudaSetDevice(engines[r]->cfg.device);
+        nr = g_nccl.CommInitRank(&engines[r]->comm, n, id, r);
+    }
+    const int ne = g_nccl.GroupEnd();
+    if (nr || ne) return fail(RAFTING_E_NCCL, "ncclCommInitRank (grouped): %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr ? nr : ne) : "?");
+    return RAFTING_OK;
+}
+// enqueue half of one shard's gather (no host synchronisation)
+static int gather_enqueue(rafting_engine* e, const int64_t* dev_src, int64_t** recv_out) {
+    if (!e->gather[0]) return fail(RAFTING_E_NCCL, "communicator not initialised (rafting_comm_init)");
+    CU(cudaSetDevice(e->cfg.device));
+    const int p = (int)(e->gather_seq & 1);
+    const int64_t* src = dev_src ? dev_src : e->T.g_commit;
+    int64_t* recv = e->gather[p];
     CU(cudaEventRecord(e->ev_step, e->stream));
     CU(cudaStreamWaitEvent(e->s_comm, e->ev_step, 0));
     if (e->world > 1) {
         if (!e->comm) return fail(RAFTING_E_NCCL, "communicator not initialised");
-        int nr = g_nccl.AllGather(e->T.g_commit, e->commit_all, e->G, /*ncclInt64*/ 4, e->comm, e->s_comm);
+        int nr = g_nccl.AllGather(src, recv, e->G, /*ncclInt64*/ 4, e->comm, e->s_comm);
         if (nr) return fail(RAFTING_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nr) : "?");
+    } else {
+        CU(cudaMemcpyAsync(recv, src, (size_t)e->G * 8, cudaMemcpyDeviceToDevice, e->s_comm));
     }
-    if (dev_out) *dev_out = e->commit_all;
+    CU(cudaEventRecord(e->ev_gather[p], e->s_comm));
+    // the live table column may change with the next kernel: that kernel waits for THIS gather; a snapshot column only
+    // has to survive until the caller's rotation comes back to it: the step stream waits for the PREVIOUS gather
+    if (!dev_src) CU(cudaStreamWaitEvent(e->stream, e->ev_gather[p], 0));
+    else if (e->gather_seq > 0) CU(cudaStreamWaitEvent(e->stream, e->ev_gather[p ^ 1], 0));
+    e->gather_seq++;
+    *recv_out = recv;
+    return RAFTING_OK;
+}
+static int gather_finish(rafting_engine* e, int64_t* recv, int64_t* host_out, void** dev_out) {
+    if (dev_out) *dev_out = recv;
     if (host_out) {
-        CU(cudaMemcpyAsync(host_out, e->commit_all, (size_t)e->world * e->G * 8, cudaMemcpyDeviceToHost, e->s_comm));
+        CU(cudaSetDevice(e->cfg.device));
+        CU(cudaMemcpyAsync(host_out, recv, (size_t)e->world * e->G * 8, cudaMemcpyDeviceToHost, e->s_comm));
         CU(cudaStreamSynchronize(e->s_comm));
     }
+    return RAFTING_OK;
+}
+extern "C" int rafting_allgather_commit_from(rafting_engine_t* e, const int64_t* dev_src, int64_t* host_out, void** dev_out) {
+    if (!e) return fail(RAFTING_E_INVAL, "null argument");
+    int64_t* recv = nullptr;
+    int rc = gather_enqueue(e, dev_src, &recv); if (rc) return rc;
+    return gather_finish(e, recv, host_out, dev_out);
+}
+extern "C" int rafting_allgather_commit(rafting_engine_t* e, int64_t* host_out, void** dev_out) {
+    return rafting_allgather_commit_from(e, nullptr, host_out, dev_out);
+}
+// the same for every shard of a single-process communicator (rafting_comm_init_all): the n ncclAllGather calls are
+// issued as one group; dev_srcs / host_outs / dev_outs may be NULL or hold NULL entries
+extern "C" int rafting_allgather_commit_all(rafting_engine_t** engines, int n, const int64_t* const* dev_srcs,
+                                            int64_t* const* host_outs, void** dev_outs) {
+    if (!engines || n < 1) return fail(RAFTING_E_INVAL, "bad argument");
+    for (int r = 0; r < n; r++) if (!engines[r] || engines[r]->world != n || engines[r]->rank != r) return fail(RAFTING_E_INVAL, "engines[%d] is not rank %d of an %d-shard communicator", r, r, n);
+    std::vector<int64_t*> recv((size_t)n, nullptr);
+    int rc = RAFTING_OK;
+    if (n > 1) g_nccl.GroupStart();
+    for (int r = 0; r < n && !rc; r++) rc = gather_enqueue(engines[r], dev_srcs ? dev_srcs[r] : nullptr, &recv[r]);
+    if (n > 1) { const int ne = g_nccl.GroupEnd(); if (!rc && ne) rc = fail(RAFTING_E_NCCL, "ncclGroupEnd: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(ne) : "?"); }
+    if (rc) return rc;
+    for (int r = 0; r < n; r++) {
+        rc = gather_finish(engines[r], recv[r], host_outs ? host_outs[r] : nullptr, dev_outs ? &dev_outs[r] : nullptr);
+        if (rc) return rc;
+    }
+    return RAFTING_OK;
+}
+// the most recently gathered vector, copied to the host (synchronises the gather stream)
+extern "C" int rafting_allgather_last(rafting_engine_t* e, int64_t* host_out) {
+    if (!e || !host_out) return fail(RAFTING_E_INVAL, "null argument");
+    if (!e->s_comm || e->gather_seq == 0) return fail(RAFTING_E_INVAL, "no gather has been issued");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaMemcpyAsync(host_out, e->gather[(e->gather_seq - 1) & 1], (size_t)e->world * e->G * 8, cudaMemcpyDeviceToHost, e->s_comm));
+    CU(cudaStreamSynchronize(e->s_comm));
     return RAFTING_OK;
 }
 // makes the step stream wait for every all-gather enqueued so far (e.g. before a timing event or a restore)
 extern "C" int rafting_allgather_join(rafting_engine_t* e) {
     if (!e) return fail(RAFTING_E_INVAL, "null argument");
-    if (!e->s_comm) return RAFTING_OK;
+    if (!e->s_comm || e->gather_seq == 0) return RAFTING_OK;
     CU(cudaSetDevice(e->cfg.device));
-    CU(cudaEventRecord(e->ev_comm, e->s_comm));
-    CU(cudaStreamWaitEvent(e->stream, e->ev_comm, 0));
+    CU(cudaStreamWaitEvent(e->stream, e->ev_gather[(e->gather_seq - 1) & 1], 0));
     return RAFTING_OK;
 }
 

@@ -29,6 +29,20 @@ class DevInbox:
             self.t[name] = torch.zeros(cnt * sz, dtype=torch.uint8, device=device)
         self.flags = 0 if requests else abi.INBOX_NO_REQUESTS
 
+    @classmethod
+    def from_host(cls, ib: abi.Inbox, device) -> "DevInbox":
+        """Device-resident copy of a dense host inbox (columns absent on the host stay absent)."""
+        import numpy as np
+        self = cls.__new__(cls)
+        self.rows, self.n, self.F = ib.rows, ib.n, ib.F
+        self.t = {}
+        for name, _, _ in _IN_COLS:
+            col = getattr(ib, name)
+            if col is not None:
+                self.t[name] = torch.from_numpy(np.ascontiguousarray(col).view(np.uint8).reshape(-1)).to(device)
+        self.flags = ib.flags
+        return self
+
     def nbytes(self):
         return sum(t.numel() for t in self.t.values())
 

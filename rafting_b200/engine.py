@@ -31,10 +31,11 @@ STATUS = {0: "OK", -1: "E_INVAL", -2: "E_NOMEM", -3: "E_CUDA", -4: "E_CLOSED", -
 
 EXPORTS = [
     "rafting_abi_version", "rafting_last_error", "rafting_engine_create", "rafting_engine_destroy",
-    "rafting_group_open", "rafting_group_open_bulk", "rafting_group_load_runs", "rafting_group_close", "rafting_lease", "rafting_lease_ex", "rafting_step",
+    "rafting_group_open", "rafting_group_open_bulk", "rafting_group_load_runs", "rafting_group_close", "rafting_lease", "rafting_lease_ex", "rafting_lease_release", "rafting_step",
     "rafting_step_begin", "rafting_step_wait", "rafting_step_device", "rafting_state_export",
     "rafting_state_export_bulk", "rafting_state_digest", "rafting_log_term", "rafting_commit_slice",
-    "rafting_comm_init", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_engine_stream",
+    "rafting_comm_init", "rafting_comm_init_all", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_allgather_commit_from",
+    "rafting_allgather_commit_all", "rafting_allgather_last", "rafting_restore_async", "rafting_step_device_seq", "rafting_engine_stream",
     "rafting_engine_counters", "rafting_abi_sizes", "rafting_checkpoint", "rafting_restore",
     "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_backoff_step", "rafting_allgather_join",
     "rafting_log_config", "rafting_log_append", "rafting_log_read", "rafting_log_gather", "rafting_log_trim", "rafting_log_stats",
@@ -71,6 +72,7 @@ def lib():
         L.rafting_group_load_runs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.rafting_lease.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(abi.LeaseC)]
         L.rafting_lease_ex.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(abi.LeaseC)]
+        L.rafting_lease_release.argtypes = [C.c_void_p, C.POINTER(abi.LeaseC)]
         L.rafting_step.argtypes = [C.c_void_p, C.POINTER(abi.LeaseC)]
         L.rafting_step_begin.argtypes = [C.c_void_p, C.POINTER(abi.LeaseC)]
         L.rafting_step_wait.argtypes = [C.c_void_p, C.POINTER(abi.LeaseC)]
@@ -84,6 +86,11 @@ def lib():
         L.rafting_comm_unique_id.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
         L.rafting_allgather_commit.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.rafting_allgather_join.argtypes = [C.c_void_p]
+        L.rafting_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.rafting_allgather_commit_from.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.rafting_allgather_commit_all.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                   C.POINTER(C.c_void_p)]
+        L.rafting_step_device_seq.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
         L.rafting_log_config.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         L.rafting_log_append.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
         L.rafting_log_read.argtypes = [C.c_void_p, C.c_uint32, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t,
@@ -99,6 +106,8 @@ def lib():
         L.rafting_step_wait_slot.argtypes = [C.c_void_p, C.c_uint32]
         L.rafting_checkpoint.argtypes = [C.c_void_p]
         L.rafting_restore.argtypes = [C.c_void_p]
+        L.rafting_restore_async.argtypes = [C.c_void_p]
+        L.rafting_allgather_last.argtypes = [C.c_void_p, C.c_void_p]
         if L.rafting_abi_version() != abi.ABI_VERSION:
             raise RuntimeError("librafting_b200.so ABI version mismatch")
         _LIB = L
@@ -214,8 +223,16 @@ class Engine:
     def checkpoint(self):
         _check(lib().rafting_checkpoint(self._h), "rafting_checkpoint")
 
-    def restore(self):
-        _check(lib().rafting_restore(self._h), "rafting_restore")
+    def restore(self, sync: bool = True):
+        if sync:
+            _check(lib().rafting_restore(self._h), "rafting_restore")
+        else:
+            _check(lib().rafting_restore_async(self._h), "rafting_restore_async")
+
+    def allgather_last(self) -> np.ndarray:
+        out = np.zeros(getattr(self, "world", 1) * self.G, dtype=np.int64)
+        _check(lib().rafting_allgather_last(self._h, out.ctypes.data), "rafting_allgather_last")
+        return out
 
     def stream(self) -> int:
         s = C.c_void_p()
@@ -248,15 +265,40 @@ class Engine:
             _check(lib().rafting_comm_init(self._h, rank, world, b, len(uid)), "rafting_comm_init")
         self.rank, self.world = rank, world
 
-    def allgather_commit(self, to_host: bool = True):
+    def allgather_commit(self, to_host: bool = True, src: int | None = None):
+        """Cross-shard commitIndex summary.  src = device pointer of the column to gather (normally the step's outbox
+        commit_index column); None = the live table column."""
         world = getattr(self, "world", 1)
         dev = C.c_void_p()
         if to_host:
             out = np.zeros(world * self.G, dtype=np.int64)
-            _check(lib().rafting_allgather_commit(self._h, out.ctypes.data, C.byref(dev)), "rafting_allgather_commit")
+            _check(lib().rafting_allgather_commit_from(self._h, src, out.ctypes.data, C.byref(dev)), "rafting_allgather_commit_from")
             return out
-        _check(lib().rafting_allgather_commit(self._h, None, C.byref(dev)), "rafting_allgather_commit")
+        _check(lib().rafting_allgather_commit_from(self._h, src, None, C.byref(dev)), "rafting_allgather_commit_from")
         return dev.value
+
+    @staticmethod
+    def comm_init_all(engines: list["Engine"]):
+        """ONE process owning len(engines) shards: engines[r] becomes rank r (grouped ncclCommInitRank)."""
+        arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+        _check(lib().rafting_comm_init_all(arr, len(engines)), "rafting_comm_init_all")
+        for r, e in enumerate(engines):
+            e.rank, e.world = r, len(engines)
+
+    @staticmethod
+    def allgather_commit_all(engines: list["Engine"], srcs: list[int] | None = None) -> list[np.ndarray]:
+        n = len(engines)
+        arr = (C.c_void_p * n)(*[e._h for e in engines])
+        outs = [np.zeros(n * e.G, dtype=np.int64) for e in engines]
+        ho = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        sr = None if srcs is None else (C.c_void_p * n)(*srcs)
+        _check(lib().rafting_allgather_commit_all(arr, n, sr, ho, None), "rafting_allgather_commit_all")
+        return outs
+
+    def step_device_seq(self, ins, outs, n: int, gather: bool = False, stream: int = 0):
+        """ins / outs: ctypes arrays of abi.InboxC / abi.OutboxC with device pointers; n steps enqueued by one call."""
+        _check(lib().rafting_step_device_seq(self._h, C.cast(ins, C.c_void_p), C.cast(outs, C.c_void_p), n, 1 if gather else 0,
+                                             C.c_void_p(stream)), "rafting_step_device_seq")
 
 
     # ---- HBM segmented entry buffer (payload side of RaftLog) ------------------------------------
@@ -393,6 +435,10 @@ class Lease:
 
     def wait(self):
         _check(lib().rafting_step_wait(self.eng._h, C.byref(self.c)), "rafting_step_wait")
+
+    def release(self):
+        """Give back a lease that will not be stepped."""
+        _check(lib().rafting_lease_release(self.eng._h, C.byref(self.c)), "rafting_lease_release")
 
     def outbox_copy(self) -> abi.Outbox:
         o = abi.Outbox.__new__(abi.Outbox)

@@ -1,4 +1,5 @@
-"""Synthetic replication streams (ctypes over rafting_wl_* in librafting_b200.so).
+"""Synthetic replication streams (ctypes over rafting_wl_* in librafting_workload.so — a library of its own: the
+simulated peers are test / bench infrastructure, not part of the product library).
 
 Concretises BASELINE.json's one-line configs; see rafting_b200/csrc/workload.cu.  The host entry
 points run on the CPU (no CUDA call is made), the device ones launch a generator kernel so the
@@ -8,8 +9,9 @@ from __future__ import annotations
 
 import ctypes as C
 
-from . import abi
-from .engine import lib
+from . import _build, abi
+
+_WL = None
 
 T0_MS = 1_700_000_000_000
 
@@ -33,7 +35,10 @@ def make_wl(seed, rows, n, F, gid_base=0, max_submit=4, p_reject_ppm=20_000, p_e
 
 
 def _bind():
-    L = lib()
+    global _WL
+    if _WL is None:
+        _WL = C.CDLL(_build.build_workload())
+    L = _WL
     if not getattr(L, "_wl_bound", False):
         L.rafting_wl_leader_step.argtypes = [C.POINTER(WlCfg), C.c_uint64, C.POINTER(abi.OutboxC), C.POINTER(abi.InboxC),
                                              C.c_int, C.c_void_p]

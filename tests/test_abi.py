@@ -19,11 +19,16 @@ def _declared(header):
 
 def test_every_declared_symbol_is_exported():
     L = engine.lib()
-    names = _declared("rafting_b200.h") + _declared("rafting_workload.h")
+    names = _declared("rafting_b200.h")
     assert len(names) >= 25
     for n in names:
-        assert hasattr(L, n), f"{n} declared in include/ but not exported by librafting_b200.so"
+        assert hasattr(L, n), f"{n} declared in include/rafting_b200.h but not exported by librafting_b200.so"
     assert set(engine.EXPORTS) <= set(names)
+    from rafting_b200 import workload
+    W = workload._bind()
+    for n in _declared("rafting_workload.h"):
+        assert hasattr(W, n), f"{n} declared in include/rafting_workload.h but not exported by librafting_workload.so"
+        assert not hasattr(L, n), f"{n}: the stream generator must not live in the product library"
 
 
 def test_durable_library_exports_its_header():

@@ -110,3 +110,42 @@ def test_node_crash_and_restart_in_the_cluster(tmp_path):
     assert all(j.stats()["syncs"] <= j.stats()["batches"] for j in journals)   # one barrier per step, never per group
     for j in journals:
         j.close()
+
+
+def _fsize_limited_commit(d, limit):
+    """Child process: commits batches against an RLIMIT_FSIZE so that a real write(2) fails in the middle of a batch."""
+    import resource
+    import signal
+    signal.signal(signal.SIGXFSZ, signal.SIG_IGN)
+    j = durable.Journal(d, 64)
+    term = np.arange(64, dtype=np.int64) + 100
+    rw = np.array([_role_word(0, 1, True)] * 64, dtype=np.uint32)
+    assert j.commit_step(rw[:2], term[:2]) == 2                                # batch 1: 24 + 48 bytes
+    resource.setrlimit(resource.RLIMIT_FSIZE, (limit, resource.getrlimit(resource.RLIMIT_FSIZE)[1]))
+    failed = False
+    try:
+        j.commit_step(rw, term * 2)                                            # batch 2 would need 24 + 64*24 bytes: torn by EFBIG
+    except RuntimeError as ex:
+        failed = "rolled back" in str(ex)
+    assert failed
+    size_after_failure = os.path.getsize(os.path.join(d, "stable.wal"))
+    assert size_after_failure == 72, size_after_failure                        # cut back to the pre-batch offset
+    assert j.restore(5).term == 0                                              # nothing of the failed batch was applied
+    # a smaller batch fits under the limit: it is appended right behind batch 1 with the NEXT sequence number
+    assert j.commit_step(rw[:3], term[:3] * 3) == 3
+    j.close()
+
+
+def test_failed_batch_is_rolled_back_and_later_batches_survive_recovery(tmp_path):
+    """a partial write used to leave torn bytes + a consumed sequence number, so batches committed after the
+    failure were dropped by recovery (acknowledged votes lost).  Now the batch is cut back and the journal stays consistent."""
+    import multiprocessing as mp
+    d = str(tmp_path / "j")
+    ctx = mp.get_context("fork")
+    p = ctx.Process(target=_fsize_limited_commit, args=(d, 400))
+    p.start(); p.join()
+    assert p.exitcode == 0
+    j = durable.Journal(d, 64)                                                 # recovery sees batch 1 and batch 3, both complete
+    assert [j.restore(g).term for g in (0, 1, 2, 5)] == [300, 303, 306, 0]
+    assert j.stats()["journal_bytes"] == 72 + 24 + 72
+    j.close()
