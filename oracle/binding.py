@@ -46,6 +46,7 @@ def lib():
         L.orc_events_processed.restype = C.c_uint64
         L.orc_events_processed.argtypes = [C.c_void_p]
         L.orc_major_indices.argtypes = [C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int64)]
+        L.orc_state_apply.argtypes = [C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.orc_backoff_step.restype = C.c_int64
         L.orc_backoff_step.argtypes = [C.c_int32]
         L.orc_is_better.restype = C.c_int

@@ -194,10 +194,12 @@ static void stat_failure(ostate_t* s, int64_t now, int unreachable, int reject) 
     if (reject) s->recentRejection = (int32_t)((uint32_t)s->recentRejection + 1u);
 }
 /* isUnhealthy / isReady — Leadership.java:44-51 */
+static int state_unhealthy(const ostate_t* s, int32_t crit, int64_t cool, int64_t now) {
+    return (crit > 0 && (uint32_t)s->recentFailure > (uint32_t)crit) ||
+           (cool > 0 && (int64_t)((uint64_t)now - (uint64_t)s->requestFailure) < cool);
+}
 static int state_ready(const ostate_t* s, int32_t crit, int64_t cool, int64_t now) {
-    int unhealthy = (crit > 0 && (uint32_t)s->recentFailure > (uint32_t)crit) ||
-                    (cool > 0 && (int64_t)((uint64_t)now - (uint64_t)s->requestFailure) < cool);
-    return s->requestSuccess != 0 && !(s->pendingInstallation || unhealthy);
+    return s->requestSuccess != 0 && !(s->pendingInstallation || state_unhealthy(s, crit, cool, now));
 }
 /* round(ln(e + r)) — Leadership.java:105, double arithmetic exactly as the JVM does it */
 int64_t orc_backoff_step(int32_t r) {
@@ -236,6 +238,27 @@ static int update_index(ostate_t* s, int64_t epoch, int64_t index, int success, 
     }
     if (s->nextIndex <= epoch && !s->pendingInstallation) s->pendingInstallation = 1;  /* :111-113 */
     return 0;
+}
+/* Test hook for the upstream golden vectors (oracle/java/GoldenGen.java): one Leadership.State method applied to a flat
+   state vector [lastRequest, requestSuccess, requestFailure, requestInFlight, recentRejection, recentFailure, lastEpoch,
+   nextIndex, matchIndex, pendingInstallation].  op: 0 statSuccess(now, reject)  1 statFailure(now, unreachable, reject)
+   2 isReady(criticalPoint, coolDown, now) -> ret = {isReady, isUnhealthy}  3 updateIndex(epoch, index, success, snapshot).
+   Returns the per-event error code (RAFTING_ERR_MATCH_ROLLBACK for the AbstractMethodError). */
+int orc_state_apply(int64_t st[10], int op, const int64_t* a, int64_t ret[2]) {
+    ostate_t s; memset(&s, 0, sizeof(s));
+    s.lastRequest = st[0]; s.requestSuccess = st[1]; s.requestFailure = st[2]; s.requestInFlight = (int32_t)st[3];
+    s.recentRejection = (int32_t)st[4]; s.recentFailure = (int32_t)st[5]; s.lastEpoch = st[6]; s.nextIndex = st[7];
+    s.matchIndex = st[8]; s.pendingInstallation = (int)st[9];
+    int err = 0;
+    if (op == 0) stat_success(&s, a[0], (int)a[1]);
+    else if (op == 1) stat_failure(&s, a[0], (int)a[1], (int)a[2]);
+    else if (op == 2) { ret[0] = state_ready(&s, (int32_t)a[0], a[1], a[2]); ret[1] = state_unhealthy(&s, (int32_t)a[0], a[1], a[2]); }
+    else if (op == 3) err = update_index(&s, a[0], a[1], (int)a[2], (int)a[3]);
+    else return -1;
+    st[0] = s.lastRequest; st[1] = s.requestSuccess; st[2] = s.requestFailure; st[3] = s.requestInFlight;
+    st[4] = s.recentRejection; st[5] = s.recentFailure; st[6] = s.lastEpoch; st[7] = s.nextIndex; st[8] = s.matchIndex;
+    st[9] = s.pendingInstallation;
+    return err;
 }
 /* majorIndices — Leadership.java:116-130 */
 static int cmp_i64(const void* a, const void* b) {

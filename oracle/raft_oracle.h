@@ -45,6 +45,7 @@ int           orc_log_term(orc_engine_t* e, uint32_t gid, int64_t index, int64_t
 uint64_t      orc_events_processed(orc_engine_t* e);
 
 /* stand-alone pieces exposed for known-answer tests */
+int           orc_state_apply(int64_t st[10], int op, const int64_t* args, int64_t ret[2]);   /* Leadership.State methods, test hook */
 void          orc_major_indices(const int64_t* match, int n, int64_t out[2]); /* Leadership.java:116-130 */
 int64_t       orc_backoff_step(int32_t recent_rejection);  /* round(ln(e + r)), Leadership.java:105 (libm) */
 int           orc_is_better(int new_role, int64_t new_term, int new_ballot,

@@ -291,6 +291,31 @@ static int launch_t(rafting_engine* e, const InboxD& in, const OutboxD& out, cud
     }
     return RAFTING_OK;
 }
+// R = 3: the steady-leader class (or, without a class sort, every position) runs one thread per (group, follower)
+// (pair_kernel.cuh, v7); RAFTING_NO_PAIR=1 keeps the thread-per-group kernel (v6) for A/B runs
+static int launch_pair(rafting_engine* e, const InboxD& in0, const OutboxD& out, cudaStream_t st) {
+    constexpr int NSTP = 3;
+    const size_t smem = (size_t)NSTP * sizeof(pair::PStage);
+    static bool configured[64] = {false};
+    if (!configured[e->cfg.device & 63]) {
+        CU(cudaFuncSetAttribute(pair::pair_kernel<NSTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[e->cfg.device & 63] = true;
+    }
+    if (in0.n == 0) return RAFTING_OK;
+    const uint32_t blocks = (in0.n + TPB - 1) / TPB;
+    if (in0.perm) {                              // slow classes first (they take longest), then the steady leaders
+        InboxD in = in0; in.flags |= INBOX_INTERNAL_FAST_ELSEWHERE;
+        const size_t smem2 = (size_t)3 * sizeof(Stage<2>) + (size_t)3 * (TPB / 32) * 8 + 16;
+        static bool conf2[64] = {false};
+        if (!conf2[e->cfg.device & 63]) {
+            CU(cudaFuncSetAttribute(unrolled::step_kernel<2, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            conf2[e->cfg.device & 63] = true;
+        }
+        unrolled::step_kernel<2, 3, false><<<blocks + (uint32_t)NCLS, TPB, smem2, st>>>(e->T, in, out, e->d_cfg, e->dcfg, 0u);
+    }
+    pair::pair_kernel<NSTP><<<blocks, pair::PTPB, smem, st>>>(e->T, in0, out, e->d_cfg, e->dcfg);
+    return RAFTING_OK;
+}
 static int launch_looped(rafting_engine* e, const InboxD& in, const OutboxD& out, cudaStream_t st) {
     const uint32_t blocks = (in.n + TPB - 1) / TPB;
     if (blocks == 0) return RAFTING_OK;
@@ -314,7 +339,10 @@ static int launch_step(rafting_engine* e, const InboxD& in0, const OutboxD& out,
 #ifndef RAFTING_NST2
 #define RAFTING_NST2 3
 #endif
-    else if (F == 2) rc = launch_t<2, RAFTING_NST2>(e, in, out, st);
+    else if (F == 2) {
+        static const bool pairOff = getenv("RAFTING_NO_PAIR") != nullptr;
+        rc = pairOff ? launch_t<2, RAFTING_NST2>(e, in, out, st) : launch_pair(e, in, out, st);
+    }
     else if (F <= 4) rc = launch_t<4, 3>(e, in, out, st);
     else if (F <= 8) rc = launch_t<8, 2>(e, in, out, st);
     else rc = launch_looped(e, in, out, st);

@@ -146,6 +146,7 @@ struct __align__(16) Stage {             // one staged input row of this block
 // atomicAdd per block and class (the order of the blocks' chunks inside a class is irrelevant: groups are independent,
 // and a chunk stays contiguous for coalescing).
 constexpr int NCLS = 4;
+constexpr uint32_t INBOX_INTERNAL_FAST_ELSEWHERE = 1u << 31;   // InboxD.flags: the steady-leader class runs in pair_kernel
 __global__ void __launch_bounds__(256) classify_kernel(Tables T, InboxD in, uint32_t* __restrict__ perm, uint32_t* __restrict__ cnt) {
     __shared__ uint32_t wcnt[NCLS][8], base[NCLS];
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
@@ -198,3 +199,8 @@ __global__ void __launch_bounds__(256) classify_kernel(Tables T, InboxD in, uint
 #undef RAFTING_UNROLL
 
 }  // namespace rafting
+
+#ifndef RAFTING_PAIR_MINBLOCKS
+#define RAFTING_PAIR_MINBLOCKS 7     // 7 x 128 threads per SM: 64 K groups x 2 lanes fit in one wave (<= 72 registers)
+#endif
+#include "pair_kernel.cuh"

@@ -5,6 +5,7 @@ comment table at M/context/member/Leadership.java:120-126, checked first.  Every
 hand-derived from the cited reference lines (M/ = src/main/java/io/lubricant/consensus/raft/).
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -631,3 +632,66 @@ def test_reset_timer_monotonic_guard_and_sweep():
     assert (s.incarnation, s.timeout_detected) == (inc + 1, 1)
     draw = binding.lib().orc_draw(g.cfg.timer_seed, 0, inc + 1, g.cfg.election_ms)
     assert 900 <= draw <= 1800 and s.timer == g.now + 100 + draw
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# upstream golden vectors (oracle/java/GoldenGen.java drives the reference's own, unmodified Leadership.State and
+# Membership classes).  No JDK exists in the build image or on the GPU box (probed in rounds 1 and 2), so the vector file is
+# produced by a maintainer with `make -C oracle/java`; until it is committed the replay test skips and parity stays
+# "unpinned by upstream" (DESIGN.md §2).  The replay code itself is exercised on the one upstream table that exists in
+# source form: the majority-position comment table, Leadership.java:120-126.
+# ---------------------------------------------------------------------------------------------------------------------
+UPSTREAM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "upstream_leadership.json")
+_OPS = {"statSuccess": 0, "statFailure": 1, "isReady": 2, "updateIndex": 3}
+
+
+def replay_upstream(doc):
+    """Replays a GoldenGen document through the oracle; returns the number of checks made."""
+    import ctypes as C
+    L = binding.lib()
+    checks = 0
+    for seq in doc.get("state", []):
+        st = (C.c_int64 * 10)(*seq["init"])
+        for call in seq["calls"]:
+            name, args = call["c"][0], list(call["c"][1:])
+            if name == "updateIndex":
+                st[4] = args.pop()                     # recentRejection as the generator set it before the call
+            a = (C.c_int64 * 4)(*(args + [0] * (4 - len(args))))
+            ret = (C.c_int64 * 2)(0, 0)
+            err = L.orc_state_apply(st, _OPS[name], a, ret)
+            assert (err != 0) == (call["err"] != 0), (name, args, err)
+            assert list(st) == call["s"], (name, args, list(st), call["s"])
+            if call["r"] is not None:
+                assert [ret[0], ret[1]] == call["r"], (name, args)
+            checks += 1
+    for m in doc.get("major", []):
+        assert binding.major_indices(m["match"]) == (m["full"], m["major"]), m
+        checks += 1
+    for nr, nt, nb, cr, cb, want in doc.get("better", []):
+        got = L.orc_is_better(nr, nt, nb, cr, 10, cb, 0)
+        assert ("T" if got > 0 else "F" if got == 0 else "E") == want, (nr, nt, nb, cr, cb, got, want)
+        checks += 1
+    return checks
+
+
+def test_upstream_replay_plumbing_on_the_source_comment_table():
+    # Leadership.java:120-126: N = 2..7 nodes, position of the majority element among the N-1 sorted follower indices
+    rows = []
+    for n_nodes, major_pos in ((2, 0), (3, 1), (4, 1), (5, 2), (6, 2), (7, 3)):
+        match = list(range(10, 10 + n_nodes - 1))
+        rows.append({"match": match[::-1], "full": match[0], "major": match[major_pos]})
+    doc = {"state": [{"init": [0, 0, 0, 0, 0, 0, 0, 8, 0, 0],
+                      "calls": [{"c": ["statSuccess", 5, 0], "r": None, "err": 0, "s": [0, 5, 0, 0, 0, 0, 0, 8, 0, 0]},
+                                {"c": ["updateIndex", 0, 7, 1, 0, 0], "r": None, "err": 0, "s": [0, 5, 0, 0, 0, 0, 0, 8, 7, 0]},
+                                {"c": ["updateIndex", 0, 3, 1, 0, 0], "r": None, "err": 1, "s": [0, 5, 0, 0, 0, 0, 0, 8, 7, 0]},
+                                {"c": ["isReady", 0, 0, 9], "r": [1, 0], "err": 0, "s": [0, 5, 0, 0, 0, 0, 0, 8, 7, 0]}]}],
+           "major": rows, "better": [[2, 10, 0, 1, 0, "T"], [2, 10, 0, 0, 0, "E"], [1, 10, 0, 1, 1, "E"], [0, 9, 0, 0, 0, "F"]]}
+    assert replay_upstream(doc) == 4 + 6 + 4
+
+
+@pytest.mark.skipif(not os.path.exists(UPSTREAM), reason="tests/golden/upstream_leadership.json absent: no JDK here (make -C oracle/java)")
+def test_upstream_golden_vectors():
+    import json
+    with open(UPSTREAM) as f:
+        doc = json.load(f)
+    assert replay_upstream(doc) > 6000
