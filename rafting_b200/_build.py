@@ -81,7 +81,25 @@ def build_durable(force: bool = False) -> str:
     return DURABLE_LIB
 
 
+INGEST_LIB = os.path.join(HERE, "librafting_ingest.so")
+
+
+def build_ingest(force: bool = False) -> str:
+    """Host-only transport framing (include/rafting_ingest.h): plain g++, no CUDA."""
+    src = os.path.join(CSRC, "ingest.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "rafting_ingest.h"), os.path.join(HERE, "..", "include", "rafting_b200.h")]
+    if not force and os.path.exists(INGEST_LIB) and os.path.getmtime(INGEST_LIB) > max(os.path.getmtime(d) for d in deps):
+        return INGEST_LIB
+    cxx = shutil.which("g++") or "g++"
+    res = subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", src, "-o", INGEST_LIB],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + res.stderr[-4000:])
+    return INGEST_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
     print(build_workload(force=True))
     print(build_durable(force=True))
+    print(build_ingest(force=True))

@@ -1,0 +1,134 @@
+// ingest.cpp — the reference's wire framing, restated for the pump thread (include/rafting_ingest.h).  Host only (g++).
+#include "../../include/rafting_ingest.h"
+
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+
+namespace {
+constexpr uint8_t SOH = 0x01, STX = 0x02, ETX = 0x03, EOT = 0x04;          // EventCodec.java:29-32
+inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+inline void put_be32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v; }
+}  // namespace
+
+// FrameDecoder.decode (EventCodec.java:281-334) as a scan over a contiguous buffer: a frame is reported only when all of
+// it is present; the decoder's incremental states collapse into "not enough bytes yet -> stop".
+extern "C" int rafting_frame_scan(const uint8_t* buf, size_t len, rafting_frame_t* out, uint32_t cap, uint32_t* n,
+                                  size_t* consumed, int* transparent) {
+    if (!buf || !out || !n || !consumed) return RAFTING_E_INVAL;
+    uint32_t cnt = 0; size_t pos = 0;
+    if (transparent) *transparent = 0;
+    *n = 0; *consumed = 0;
+    while (pos < len && cnt < cap) {
+        size_t p = pos;
+        const uint8_t first = buf[p++];
+        if (first == EOT) { if (transparent) *transparent = 1; pos = p; break; }      // verify(buf, SOH, EOT) :299-301
+        if (first != SOH) { *n = cnt; *consumed = pos; return RAFTING_E_INVAL; }
+        rafting_frame_t f; memset(&f, 0, sizeof(f));
+        if (p >= len) break;
+        f.type = buf[p++];                                                             // readType :237-242
+        f.has_sequence = (f.type == RAFTING_FRAME_ENQ || f.type == RAFTING_FRAME_ACK) ? 1 : 0;
+        if (f.has_sequence) {
+            if (len - p < 4) break;
+            f.sequence = (int32_t)be32(buf + p); p += 4;                               // readSequence :244-247
+        }
+        if (len - p < 5) break;
+        if (buf[p++] != STX) { *n = cnt; *consumed = pos; return RAFTING_E_INVAL; }     // readHeadLen :249-256
+        const uint32_t hl = be32(buf + p); p += 4;
+        if ((int32_t)hl < 0 || hl > RAFTING_FRAME_MAX_HEAD) { *n = cnt; *consumed = pos; return RAFTING_E_INVAL; }
+        if (len - p < (size_t)hl + 4) break;
+        f.head_off = (uint32_t)p; f.head_len = hl; p += hl;
+        const uint32_t bl = be32(buf + p); p += 4;                                     // readBodyLen :258-266
+        if ((int32_t)bl < 0 || bl > RAFTING_FRAME_MAX_BODY) { *n = cnt; *consumed = pos; return RAFTING_E_INVAL; }
+        if (len - p < (size_t)bl + 1) break;
+        f.body_off = (uint32_t)p; f.body_len = bl; p += bl;
+        if (buf[p++] != ETX) { *n = cnt; *consumed = pos; return RAFTING_E_INVAL; }     // readBody :268-278
+        // an Event.Ending frame is followed by EOT (FrameEncoder :193-195): the next "frame start" is the EOT that makes the
+        // channel transparent; it is reported with the frame it ends so that the caller sees both at once
+        if (p < len && buf[p] == EOT) { f.ending = 1; out[cnt++] = f; pos = p + 1; if (transparent) *transparent = 1; break; }
+        out[cnt++] = f; pos = p;
+    }
+    *n = cnt; *consumed = pos;
+    return RAFTING_OK;
+}
+
+// FrameEncoder.encode — EventCodec.java:171-201
+extern "C" size_t rafting_frame_encode(uint8_t* dst, size_t cap, uint8_t type, int has_sequence, int32_t sequence,
+                                       const char* head, uint32_t head_len, const void* body, uint32_t body_len, int ending) {
+    if (!dst || head_len > RAFTING_FRAME_MAX_HEAD || body_len > RAFTING_FRAME_MAX_BODY || (head_len && !head) || (body_len && !body)) return 0;
+    const size_t need = 2 + (has_sequence ? 4 : 0) + 1 + 4 + head_len + 4 + body_len + 1 + (ending ? 1 : 0);
+    if (need > cap) return 0;
+    uint8_t* p = dst;
+    *p++ = SOH; *p++ = type;
+    if (has_sequence) { put_be32(p, (uint32_t)sequence); p += 4; }
+    *p++ = STX;
+    put_be32(p, head_len); p += 4;
+    if (head_len) { memcpy(p, head, head_len); p += head_len; }
+    put_be32(p, body_len); p += 4;
+    if (body_len) { memcpy(p, body, body_len); p += body_len; }
+    *p++ = ETX;
+    if (ending) *p++ = EOT;
+    return (size_t)(p - dst);
+}
+
+// NettyNode.parseContextId / prepareLocalInvocation dispatch — NettyNode.java:92-107,109-158
+extern "C" int rafting_scope_parse(const char* head, uint32_t head_len, uint32_t* op_kind, uint32_t* ctx_off) {
+    if (!head || !op_kind || !ctx_off) return RAFTING_E_INVAL;
+    static const struct { const char* name; uint32_t kind; } M[] = {
+        {"appendEntries", RAFTING_OP_AE_REQUEST}, {"preVote", RAFTING_OP_PREVOTE_REQ},
+        {"requestVote", RAFTING_OP_VOTE_REQ}, {"installSnapshot", RAFTING_OP_IS_REQUEST}};
+    for (const auto& m : M) {
+        const size_t k = strlen(m.name);
+        // startsWith(method name), then the context id begins one character further (the ':')
+        if (head_len >= k && memcmp(head, m.name, k) == 0) {
+            if (head_len < k + 1) return RAFTING_E_INVAL;          // substring(k + 1) of a shorter string throws
+            *op_kind = m.kind; *ctx_off = (uint32_t)k + 1;
+            return RAFTING_OK;
+        }
+    }
+    return RAFTING_E_INVAL;
+}
+
+struct rafting_ctxmap { std::unordered_map<std::string, uint32_t> m; };
+extern "C" int rafting_ctxmap_create(rafting_ctxmap_t** out) {
+    if (!out) return RAFTING_E_INVAL;
+    try { *out = new rafting_ctxmap(); } catch (...) { return RAFTING_E_NOMEM; }
+    return RAFTING_OK;
+}
+extern "C" int rafting_ctxmap_destroy(rafting_ctxmap_t* m) { delete m; return RAFTING_OK; }
+extern "C" int rafting_ctxmap_put(rafting_ctxmap_t* m, const char* ctx, uint32_t len, uint32_t gid) {
+    if (!m || (!ctx && len)) return RAFTING_E_INVAL;
+    try { m->m[std::string(ctx ? ctx : "", len)] = gid; } catch (...) { return RAFTING_E_NOMEM; }
+    return RAFTING_OK;
+}
+extern "C" int rafting_ctxmap_get(const rafting_ctxmap_t* m, const char* ctx, uint32_t len, uint32_t* gid) {
+    if (!m || !gid || (!ctx && len)) return RAFTING_E_INVAL;
+    try {
+        auto it = m->m.find(std::string(ctx ? ctx : "", len));
+        if (it == m->m.end()) return RAFTING_E_INVAL;
+        *gid = it->second;
+    } catch (...) { return RAFTING_E_NOMEM; }
+    return RAFTING_OK;
+}
+
+extern "C" int rafting_batch_to_inbox(const rafting_batch_rec_t* recs, uint32_t n, int64_t now_ms, const rafting_inbox_t* in,
+                                      uint32_t n_groups, uint32_t F, uint32_t* n_done) {
+    if (!recs || !in || !n_done || !in->ev_meta || !in->ev_tn || in->gids) return RAFTING_E_INVAL;
+    uint64_t* em = const_cast<uint64_t*>(in->ev_meta);
+    rafting_i64x2_t* tn = const_cast<rafting_i64x2_t*>(in->ev_tn);
+    rafting_i64x2_t* el = const_cast<rafting_i64x2_t*>(in->ev_el);
+    *n_done = 0;
+    for (uint32_t k = 0; k < n; k++) {
+        const rafting_batch_rec_t& r = recs[k];
+        if (r.gid >= n_groups || r.lane >= F || r.row >= in->rows || r.kind == RAFTING_EV_NONE || r.kind > RAFTING_EV_RV_REPLY)
+            return RAFTING_E_INVAL;
+        const size_t li = ((size_t)r.row * n_groups + r.gid) * F + r.lane;
+        if (RAFTING_EVM_KIND(em[li]) != RAFTING_EV_NONE) return RAFTING_E_INVAL;       // one event per (row, group, lane)
+        em[li] = RAFTING_EVM_MAKE(r.kind, r.flags & 3u, (r.flags >> 2) & 1u, r.incarnation);
+        tn[li].x = r.term; tn[li].y = now_ms;
+        if (el) { el[li].x = r.epoch_at_send; el[li].y = r.last_at_send; }
+        *n_done = k + 1;
+    }
+    return RAFTING_OK;
+}

@@ -40,6 +40,15 @@ def test_durable_library_exports_its_header():
         assert hasattr(L, n), f"{n} declared in include/rafting_durable.h but not exported by librafting_durable.so"
 
 
+def test_ingest_library_exports_its_header():
+    from rafting_b200 import ingest
+    L = ingest.lib()
+    names = _declared("rafting_ingest.h")
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/rafting_ingest.h but not exported by librafting_ingest.so"
+
+
 def test_struct_sizes_match_the_compiled_library():
     out = (C.c_uint32 * 7)()
     assert engine.lib().rafting_abi_sizes(out, 7) == 7

@@ -1,0 +1,111 @@
+"""Transport framing (include/rafting_ingest.h): the reference's EventCodec frame layout
+(transport/EventCodec.java:169-201 encoder, :222-334 decoder) restated in C.  The expected bytes below are written out by
+hand from the layout constants of EventCodec.java:25-41, not produced by the code under test."""
+import struct
+
+import numpy as np
+import pytest
+
+from rafting_b200 import abi, ingest
+
+SOH, STX, ETX, EOT = b"\x01", b"\x02", b"\x03", b"\x04"
+
+
+def hand_frame(ftype, head, body, seq=None, ending=False):
+    """|SOH|TYPE|{SEQUENCE}|STX|HEAD_LEN|HEAD|BODY_LEN|{BODY}|ETX[|EOT] — EventCodec.java:297, big-endian ints (ByteBuf.writeInt)"""
+    out = SOH + bytes([ftype])
+    if seq is not None:
+        out += struct.pack(">i", seq)
+    out += STX + struct.pack(">i", len(head)) + head + struct.pack(">i", len(body)) + body + ETX
+    return out + (EOT if ending else b"")
+
+
+def test_encoder_is_byte_exact_against_the_hand_written_layout():
+    cases = [(ingest.ENQ, b"appendEntries:ctx-7", b"\x01\x00kryo-bytes", 42, False),
+             (ingest.ACK, b"requestVote:group/with:colon", b"", -5, False),          # sequence is a signed int, body may be empty
+             (ingest.SYN, b"node-1:8080", b"", None, False),
+             (ingest.PM, b"snap@ctx", b"", None, True)]                              # Event.Ending -> trailing EOT
+    for ftype, head, body, seq, ending in cases:
+        assert ingest.encode(ftype, head, body, seq, ending) == hand_frame(ftype, head, body, seq, ending)
+    # the single-frame overhead FrameEncoder.allocateBuffer budgets for (12 + head + body, :206) holds for StrEvents
+    assert len(ingest.encode(ingest.SYN, b"abc")) == 12 + 3
+
+
+def test_scan_round_trip_and_partial_input():
+    frames = [hand_frame(ingest.ENQ, b"appendEntries:g%d" % k, bytes([k]) * (k * 3), seq=1000 + k) for k in range(5)]
+    frames.append(hand_frame(ingest.SYN, b"hello", b""))
+    stream = b"".join(frames)
+    rc, fr, used, tr = ingest.scan(stream)
+    assert rc == 0 and used == len(stream) and not tr and len(fr) == 6
+    for k in range(5):
+        f = fr[k]
+        assert f["type"] == ingest.ENQ and f["has_sequence"] == 1 and f["sequence"] == 1000 + k
+        assert stream[f["head_off"]:f["head_off"] + f["head_len"]] == b"appendEntries:g%d" % k
+        assert stream[f["body_off"]:f["body_off"] + f["body_len"]] == bytes([k]) * (k * 3)
+    assert fr[5]["type"] == ingest.SYN and fr[5]["has_sequence"] == 0
+    # every prefix: only complete frames are consumed, the rest stays for the next read (ByteToMessageDecoder cumulation)
+    bounds = np.cumsum([len(f) for f in frames])
+    for cut in range(len(stream) + 1):
+        rc, fr, used, tr = ingest.scan(stream[:cut])
+        assert rc == 0 and not tr
+        assert used == ([0] + list(bounds[bounds <= cut]))[-1] and len(fr) == int((bounds <= cut).sum())
+    # re-encoding what was scanned gives the same bytes back
+    rc, fr, used, _ = ingest.scan(stream)
+    again = b"".join(ingest.encode(int(f["type"]), stream[f["head_off"]:f["head_off"] + f["head_len"]],
+                                   stream[f["body_off"]:f["body_off"] + f["body_len"]],
+                                   int(f["sequence"]) if f["has_sequence"] else None) for f in fr)
+    assert again == stream
+
+
+def test_eot_switches_to_transparent_and_malformed_input_is_refused():
+    a = hand_frame(ingest.PM, b"snap", b"", ending=True)
+    rc, fr, used, tr = ingest.scan(a + b"raw snapshot bytes")
+    assert rc == 0 and len(fr) == 1 and fr[0]["ending"] == 1 and tr and used == len(a)
+    rc, fr, used, tr = ingest.scan(EOT + b"xyz")                          # EOT at a frame start (verify(buf, SOH, EOT), :299)
+    assert rc == 0 and len(fr) == 0 and tr and used == 1
+    good = hand_frame(ingest.ACK, b"preVote:c", b"\x07", seq=3)
+    for bad in (b"\x09" + good,                                                        # neither SOH nor EOT
+                good[:6] + b"\x09" + good[7:],                                         # STX missing after the sequence
+                good[:-1] + b"\x09",                                                   # ETX missing
+                SOH + bytes([ingest.SYN]) + STX + struct.pack(">i", 129) + b"x" * 140,  # head longer than MAX_HEAD_SIZE = 128
+                SOH + bytes([ingest.SYN]) + STX + struct.pack(">i", -1) + b"x" * 8,
+                SOH + bytes([ingest.SYN]) + STX + struct.pack(">i", 1) + b"h" + struct.pack(">i", (1 << 26) + 1) + b"y" * 8):
+        rc, fr, used, tr = ingest.scan(good + bad)
+        assert rc == -1 and len(fr) == 1 and used == len(good)             # the frame before the error is still delivered
+    with pytest.raises(ValueError):
+        ingest.encode(ingest.SYN, b"h" * 129)
+
+
+def test_scope_and_context_registry():
+    assert ingest.scope_parse(b"appendEntries:ctx-1") == (abi.OP_AE_REQUEST, b"ctx-1")
+    assert ingest.scope_parse(b"preVote:a:b") == (abi.OP_PREVOTE_REQ, b"a:b")
+    assert ingest.scope_parse(b"requestVote:") == (abi.OP_VOTE_REQ, b"")
+    assert ingest.scope_parse(b"installSnapshot:@raft") == (abi.OP_IS_REQUEST, b"@raft")
+    for bad in (b"obtainSnapshot:x", b"appendEntries", b""):
+        with pytest.raises(ValueError):
+            ingest.scope_parse(bad)
+    m = ingest.CtxMap()
+    for k in range(1000):
+        m.put(b"ctx-%d" % k, 5000 + k)
+    assert m.get(b"ctx-0") == 5000 and m.get(b"ctx-999") == 5999 and m.get(b"ctx-1000") is None
+
+
+def test_batch_records_land_in_the_inbox_columns():
+    rows, n, F = 3, 16, 2
+    ib = abi.Inbox(rows, n, F)
+    recs = np.zeros(5, dtype=ingest.BATCH_REC)
+    recs[0] = (3, abi.EV_AE_ACK, 1, abi.OUT_OK | 4, 0, 77, 0, 9, 100, 140)
+    recs[1] = (3, abi.EV_AE_ACK, 0, abi.OUT_OK, 0, 77, 0, 9, 100, 141)               # success = false
+    recs[2] = (15, abi.EV_RV_REPLY, 1, abi.OUT_ERROR, 2, 5, 0, 0, 0, 0)
+    recs[3] = (3, abi.EV_AE_ACK, 1, abi.OUT_OK | 4, 0, 77, 0, 9, 100, 150)           # slot (0, 3, 1) is taken: stops here
+    recs[4] = (4, abi.EV_IS_ACK, 0, abi.OUT_OK | 4, 1, 1, 0, 2, 30, 30)
+    rc, done = ingest.batch_to_inbox(recs, 1234, ib)
+    assert rc == -1 and done == 3
+    assert ib.ev_meta[0, 3, 1] == abi.evm_make(abi.EV_AE_ACK, abi.OUT_OK, True, 77)
+    assert ib.ev_meta[0, 3, 0] == abi.evm_make(abi.EV_AE_ACK, abi.OUT_OK, False, 77)
+    assert tuple(ib.ev_tn[0, 3, 1]) == (9, 1234) and tuple(ib.ev_el[0, 3, 1]) == (100, 140)
+    assert ib.ev_meta[2, 15, 1] == abi.evm_make(abi.EV_RV_REPLY, abi.OUT_ERROR, False, 5)
+    rc, done = ingest.batch_to_inbox(recs[4:], 1300, ib)
+    assert rc == 0 and done == 1 and tuple(ib.ev_el[1, 4, 0]) == (30, 30)
+    bad = recs[:1].copy(); bad["gid"] = 16
+    assert ingest.batch_to_inbox(bad, 0, ib)[0] == -1
