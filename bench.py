@@ -179,57 +179,95 @@ def bind_to_gpu_numa(local_rank):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of the reference's EventLoop path) on a bounded sample of the same stream
 # ------------------------------------------------------------------------------------------------
+def interleave_host_memory():
+    """MPOL_INTERLEAVE over every NUMA node for this thread's future allocations (the recorded inboxes of the CPU arm): the loop
+    threads of both sockets then stream their inputs at the same bandwidth.  Best effort (raw syscall, no libnuma here)."""
+    try:
+        nodes = [int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if len(nodes) < 2:
+            return False
+        mask = C.c_ulong(sum(1 << n for n in nodes))
+        libc = C.CDLL(None, use_errno=True)
+        return libc.syscall(238, 3, C.byref(mask), C.c_ulong(max(nodes) + 2)) == 0        # set_mempolicy(MPOL_INTERLEAVE)
+    except Exception:
+        return False
+
+
 def run_cpu_sample(args, threads, steps, warmup, launches, seed):
-    """steps x (launches oracle passes of rows ticks over cpu_groups groups).  Only orc_step is inside the clock: the
-    stream generator (the simulated peers) runs between passes, untimed; outboxes are preallocated and touched once so
-    no page fault of a fresh buffer lands in the timed region."""
+    """steps x (launches oracle passes of rows ticks over cpu_groups groups), RECORD then REPLAY like the GPU arm: a first
+    oracle instance runs the closed loop (oracle pass -> simulated peers -> next inbox) untimed and keeps every inbox; a
+    second, fresh instance then replays the recorded inboxes back to back with nothing between the passes, so the loop
+    threads never park on the single-threaded generator.  Only orc_step of the replay is inside the clock; outboxes are
+    preallocated and touched once; the two instances must end with identical commit columns."""
     from oracle import binding
     from rafting_b200 import abi, workload
     G, R, rows = args.cpu_groups, args.replicas, args.rows
     cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=rows)
-    o = binding.Oracle(cfg)
+    interleaved = interleave_host_memory()
     init = np.zeros(G, dtype=abi.GROUP_INIT_DTYPE)
     init["ballot"] = -1; init["first_index"] = 1; init["now_ms"] = workload.T0_MS - 2000
     init["term"] = np.arange(G) % 7
-    o.open_bulk(0, init)
     w1 = workload.make_wl(seed, 1, G, R - 1)
     w = workload.make_wl(seed, rows, G, R - 1)
-    out = None
-    for ph in (0, 1, 2):
-        out = o.step(workload.election_inbox_host(w1, ph, out), threads=threads)
+    L = binding.lib()
     outs = [abi.Outbox(rows, G, R - 1, G) for _ in range(2)]
     for ob in outs:                                         # touch every page once, outside the clock
         for name, _, _ in abi.Outbox.ROW_COLS:
             getattr(ob, name)[...] = 0
         for name, _ in abi.Outbox.GROUP_COLS:
             getattr(ob, name)[...] = 0
-    L = binding.lib()
-    prev, k = None, 0
+    n_pass = (warmup + steps) * launches
+
+    def fresh():
+        o = binding.Oracle(cfg)
+        o.open_bulk(0, init)
+        out, elect = None, []
+        for ph in (0, 1, 2):
+            ib = workload.election_inbox_host(w1, ph, out)
+            out = o.step(ib, threads=threads)
+            elect.append(ib)
+        return o
+
+    # ---- record (untimed) ----
+    o = fresh()
+    inboxes, acks, prev = [], [], None
+    for k in range(n_pass):
+        ib = workload.leader_inbox_host(w, k, prev)
+        acks.append(int(((ib.ev_meta & np.uint64(0xF)) != 0).sum()))
+        ob = outs[k % 2]
+        ic, oc = ib.as_c(), ob.as_c()
+        if L.orc_step(o._h, C.byref(ic), C.byref(oc), threads):
+            raise RuntimeError("orc_step failed")
+        inboxes.append(ib); prev = ob
+    commit_a = prev.commit_index.copy()
+    o.close()
+    # ---- replay (timed) ----
+    o = fresh()
+    ics = [ib.as_c() for ib in inboxes]
+    ocs = [outs[k % 2].as_c() for k in range(n_pass)]
     step_s, step_acks = [], []
+    k = 0
     for s in range(warmup + steps):
-        spent, acks = 0.0, 0
+        t0 = time.perf_counter()
         for _ in range(launches):
-            ib = workload.leader_inbox_host(w, k, prev)
-            acks += int(((ib.ev_meta & np.uint64(0xF)) != 0).sum())
-            ob = outs[k % 2]
-            ic, oc = ib.as_c(), ob.as_c()
-            t0 = time.perf_counter()
-            rc = L.orc_step(o._h, C.byref(ic), C.byref(oc), threads)
-            spent += time.perf_counter() - t0
-            if rc:
-                raise RuntimeError(f"orc_step rc={rc}")
-            prev = ob
+            if L.orc_step(o._h, C.byref(ics[k]), C.byref(ocs[k]), threads):
+                raise RuntimeError("orc_step failed")
             k += 1
+        dt = time.perf_counter() - t0
         if s >= warmup:
-            step_s.append(spent); step_acks.append(acks)
+            step_s.append(dt); step_acks.append(sum(acks[k - launches:k]))
+    replay_ok = bool(np.array_equal(commit_a, outs[(n_pass - 1) % 2].commit_index))
+    o.close()
     total_s, total_acks = float(np.sum(step_s)), int(np.sum(step_acks))
     rates = np.array(step_acks) / np.array(step_s)
     return {"value": total_acks / total_s, "acks": total_acks, "seconds": total_s, "steps": len(step_s),
-            "ms_per_step": 1e3 * total_s / len(step_s),
+            "ms_per_step": 1e3 * total_s / len(step_s), "replay_ok": replay_ok,
             "median_rate": float(np.median(rates)), "min_rate": float(rates.min()), "max_rate": float(rates.max()),
             "sample": f"{G} groups x {rows} ticks x {launches} passes per step x {len(step_s)} steps of the same keyed stream "
                       f"(first {G} group ids, {total_acks} acks, {total_s:.1f} s of CPU wall time), in-memory log, {threads} pinned loop "
-                      f"threads taking 64-group chunks from a shared queue; only orc_step is timed (generator and buffers outside)"}
+                      f"threads taking 64-group chunks from a shared queue; recorded closed-loop by one oracle instance, replayed back "
+                      f"to back by a fresh one (only orc_step is timed; inbox pages interleaved over NUMA nodes: {interleaved}; "
+                      f"replay == record: {replay_ok})"}
 
 
 def run_reference(args):

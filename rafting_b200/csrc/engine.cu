@@ -292,7 +292,7 @@ static int launch_t(rafting_engine* e, const InboxD& in, const OutboxD& out, cud
     return RAFTING_OK;
 }
 // R = 3: the steady-leader class (or, without a class sort, every position) runs one thread per (group, follower)
-// (pair_kernel.cuh, v7); RAFTING_NO_PAIR=1 keeps the thread-per-group kernel (v6) for A/B runs
+// (pair_kernel.cuh, v7) when RAFTING_PAIR=1 is set; the default is the thread-per-group kernel (v6), which measured faster
 static int launch_pair(rafting_engine* e, const InboxD& in0, const OutboxD& out, cudaStream_t st) {
     constexpr int NSTP = 3;
     const size_t smem = (size_t)NSTP * sizeof(pair::PStage);
@@ -340,8 +340,10 @@ static int launch_step(rafting_engine* e, const InboxD& in0, const OutboxD& out,
 #define RAFTING_NST2 3
 #endif
     else if (F == 2) {
-        static const bool pairOff = getenv("RAFTING_NO_PAIR") != nullptr;
-        rc = pairOff ? launch_t<2, RAFTING_NST2>(e, in, out, st) : launch_pair(e, in, out, st);
+        // v7 (pair_kernel.cuh) measured SLOWER than v6 on the headline stream (0.0796 vs 0.0584 ms per launch, same box, same
+        // run: profiles/r2_ab_pair_vs_v6.txt): opt-in only
+        static const bool pairOn = getenv("RAFTING_PAIR") != nullptr;
+        rc = pairOn ? launch_pair(e, in, out, st) : launch_t<2, RAFTING_NST2>(e, in, out, st);
     }
     else if (F <= 4) rc = launch_t<4, 3>(e, in, out, st);
     else if (F <= 8) rc = launch_t<8, 2>(e, in, out, st);

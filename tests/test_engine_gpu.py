@@ -25,7 +25,8 @@ def _scenarios():
 
 
 SINGLE_GROUP = [n for n in _scenarios() if n not in (
-    "test_major_position_table", "test_major_indices_random", "test_backoff_step_matches_double_math", "test_is_better")]
+    "test_major_position_table", "test_major_indices_random", "test_backoff_step_matches_double_math", "test_is_better",
+    "test_upstream_golden_vectors", "test_upstream_replay_plumbing_on_the_source_comment_table")]
 
 
 @pytest.mark.parametrize("name", SINGLE_GROUP)
