@@ -114,35 +114,65 @@ def workload_config(args, world, G):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons sampled while `armed` (NVML in-process every ~2 ms; nvidia-smi subprocess as a fallback)."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag, self.armed = index, [], False, False
+        self.index, self.stop_flag, self.armed = index, False, False
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
+        except Exception:
+            self.nv = None
+
+    def sample_nvml(self):
+        nv, h = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+        except Exception:
+            pass
+        self.sm.append(float(sm)); self.mx.append(float(mx))
+        for bit, name in self.REASONS.items():
+            if bits & bit:
+                self.reasons.add(name)
+
+    def sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [x.strip() for x in out.split(",")]
+        if len(r) > 8 and r[1].replace(".", "").isdigit():
+            self.sm.append(float(r[1])); self.mx.append(float(r[2]))
+            for k, nm in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                if r[5 + k].lower().startswith("active"):
+                    self.reasons.add(nm)
 
     def run(self):
         while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out and self.armed:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.02)
+            if self.armed:
+                try:
+                    self.sample_nvml() if self.nv else self.sample_smi()
+                except Exception:
+                    pass
+                time.sleep(0.002)
+            else:
+                time.sleep(0.0005)
 
     def summary(self):
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None,
+                "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -448,68 +478,139 @@ def run_engine(args):
 
     # ---- e2e: the same stream through the C-ABI host path, HOST buffers in, HOST buffers out ---------
     e2e = None
+    e2e_dense = None
     lat_ms = []
     if not args.no_e2e:
-        # the transport's pinned receive buffers: one pinned inbox per launch of the (prefix of the) window, filled before
-        # the clock starts as the transport would have decoded them; three pinned outboxes (one per slot in flight)
-        K2 = int(max(3, min(L, 24, 3.0e9 // inbox_bytes)))
-        host_in = []
-        for k in range(K2):
-            cols = {name: t.cpu().pin_memory() for name, t in inboxes[k].t.items()}
-            ic = abi.InboxC()
-            ic.rows, ic.n_active, ic.flags = rows, 0, abi.INBOX_NO_REQUESTS
-            for name, t in cols.items():
-                setattr(ic, name, t.data_ptr())
-            host_in.append((cols, ic))
+        from rafting_b200 import compact
         NSL = 3                                           # launches in flight on the host path
-        host_out = []
-        for sl in range(NSL):
-            cols = {name: torch.zeros(t.numel(), dtype=torch.uint8).pin_memory() for name, t in outs[0].t.items()}
-            oc = abi.OutboxC()
-            for name, t in cols.items():
-                setattr(oc, name, t.data_ptr())
-            host_out.append((cols, oc))
-        h2d = sum(t.numel() for t in host_in[0][0].values())
-        sparse = ("rep_term", "ballot_term", "ballot_last")        # copied down only when a launch produced replies / ballots
-        d2h = sum(t.numel() for name, t in host_out[0][0].items() if name not in sparse) + 16
-        acks_pass = sum(acks_per_launch[:K2])
 
-        def host_pass():
-            for j in range(K2):
+        def pinned_like(a):
+            t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
+            v = t.numpy().view(a.dtype).reshape(a.shape)
+            v[...] = a
+            return t, v
+
+        def host_inbox(k):                                # numpy views of launch k's recorded dense inbox
+            ib = abi.Inbox(rows, G, F, with_ops=False, with_events=False)
+            for name, dt, lane in (("op_meta", np.uint64, 0), ("op_nr", abi.I64X2, 0), ("ev_meta", np.uint64, 1), ("ev_tn", abi.I64X2, 1), ("ev_el", abi.I64X2, 1)):
+                setattr(ib, name, inboxes[k].t[name].cpu().numpy().view(dt).reshape((rows, G, F) if lane else (rows, G)))
+            ib.flags = abi.INBOX_NO_REQUESTS
+            return ib
+
+        # (A) the COMPACT host path (include/rafting_b200.h): narrow wire columns, the (epochAtSend, lastIndexAtSend) echo kept in HBM.
+        # The transport's pinned receive buffers are filled before the clock starts, as the transport would have decoded
+        # them.  Launch 0 of the window answers RPCs that were planned on the device path (no tags): it runs untimed,
+        # every one of its acks an escape record, and the state right after it is the starting point of every timed pass.
+        K2 = int(max(4, min(L, 25)))
+        e.restore(); e.checkpoint()                       # (the in-flight table, created by the first compact call, joins the checkpoint)
+        cout0 = compact.CompactOutbox(rows, G, F, esc_cap=1 << 16)
+        e.step_compact(compact.encode_inbox(host_inbox(0), None, None), cout0)
+        e.checkpoint()
+        tags, sent_term = cout0.tags(), cout0.current_term.copy()
+        cins, keep = [], []
+        couts = []
+        for sl in range(NSL):
+            co = compact.CompactOutbox(rows, G, F, esc_cap=1 << 16)
+            for name in co.COLS + ("esc", "counts"):
+                t, v = pinned_like(getattr(co, name)); keep.append(t); setattr(co, name, v)
+            couts.append(co)
+        for k in range(1, K2):                            # record pass (untimed): the tags the engine hands out are replayed below
+            ci = compact.encode_inbox(host_inbox(k), tags, sent_term)
+            for name in ("row_base", "op_c", "ev_c", "esc"):
+                if len(getattr(ci, name)):
+                    t, v = pinned_like(getattr(ci, name)); keep.append(t); setattr(ci, name, v)
+            e.step_compact(ci, couts[0])
+            assert int(couts[0].counts[0]) <= couts[0].esc_cap
+            tags, sent_term = couts[0].tags(), couts[0].current_term.copy()
+            cins.append(ci)
+        digest_c = e.digest(0, G)
+        cin_c = [ci.as_c() for ci in cins]
+        cout_c = [co.as_c() for co in couts]
+        h2d = int(np.mean([ci.nbytes() for ci in cins])); d2h = couts[0].nbytes()
+        esc_in = int(np.mean([len(ci.esc) for ci in cins]))
+        acks_pass = sum(acks_per_launch[1:K2])
+        n_pass_launch = K2 - 1
+
+        def compact_pass():
+            for j in range(n_pass_launch):
                 sl = j % NSL
                 if j >= NSL:
-                    e.step_wait_slot(sl)                  # outbox of launch j-NSL is readable on the host
-                e.step_begin_host(sl, host_in[j][1], host_out[sl][1])
+                    e.step_wait_compact(sl)               # outbox of launch j-NSL is readable on the host
+                e.step_begin_compact(sl, cin_c[j], cout_c[sl])
             for sl in range(NSL):
-                e.step_wait_slot(sl)
+                e.step_wait_compact(sl)
 
-        # untimed: one pass so that every slot's device staging exists before the clock starts
-        e.restore(); host_pass()
-        est = 1.4e-3 * (G / 65536) * K2
-        reps = int(max(2, min(40, 0.12 / est + 1)))
+        e.restore(); compact_pass()                       # untimed: every slot's device staging exists before the clock starts
+        e2e_exact = bool((e.digest(0, G) == digest_c).all())
+        reps = int(max(2, min(40, 0.15 / (0.8e-3 * (G / 65536) * n_pass_launch) + 1)))
         barrier()
         sampler.armed = True
         t0 = time.perf_counter()
         for _ in range(reps):
             e.restore(sync=False)
-            host_pass()
+            compact_pass()
         spent = time.perf_counter() - t0
         sampler.armed = False
-        # (2) latency: one launch at a time, host ack in -> commit record readable out
+        # latency: one launch at a time, host ack in -> commit record readable out
         e.restore()
-        for j in range(min(K2, 12)):
+        for j in range(min(n_pass_launch, 12)):
             t1 = time.perf_counter()
-            e.step_begin_host(0, host_in[j][1], host_out[0][1])
-            e.step_wait_slot(0)
+            e.step_begin_compact(0, cin_c[j], cout_c[0])
+            e.step_wait_compact(0)
             lat_ms.append((time.perf_counter() - t1) * 1e3)
+        # the device path over the same launches ends in the same state
+        e.restore()
+        e.step_device_seq((abi.InboxC * n_pass_launch)(*[inboxes[k].as_c() for k in range(1, K2)]),
+                          (abi.OutboxC * n_pass_launch)(*[outs[k % 2].as_c() for k in range(1, K2)]), n_pass_launch, gather=False, stream=0)
+        torch.cuda.synchronize()
+        e2e_exact = e2e_exact and bool((e.digest(0, G) == digest_c).all())
         t = torch.tensor([spent], dtype=torch.float64, device=dev)
         ae = torch.tensor([float(acks_pass * reps)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(ae, op=dist.ReduceOp.SUM)
-        e2e = {"spent": float(t.item()), "h2d": int(h2d), "d2h": int(d2h), "acks": float(ae.item()), "launches": K2 * reps,
-               "launches_per_pass": K2, "passes": reps}
-        del host_in, host_out
+        e2e = {"spent": float(t.item()), "h2d": h2d, "d2h": d2h, "acks": float(ae.item()), "launches": n_pass_launch * reps,
+               "launches_per_pass": n_pass_launch, "passes": reps, "exact": e2e_exact, "esc_in": esc_in}
+        del cins, keep, couts
+
+        # (B) the DENSE host path of round 1 on a few launches of the same window, for the before / after of the byte cut
+        if world == 1:
+            K3 = int(max(3, min(L, 6)))
+            host_in = []
+            for k in range(K3):
+                cols = {name: t.cpu().pin_memory() for name, t in inboxes[k].t.items()}
+                ic = abi.InboxC()
+                ic.rows, ic.n_active, ic.flags = rows, 0, abi.INBOX_NO_REQUESTS
+                for name, t in cols.items():
+                    setattr(ic, name, t.data_ptr())
+                host_in.append((cols, ic))
+            host_out = []
+            for sl in range(NSL):
+                cols = {name: torch.zeros(t.numel(), dtype=torch.uint8).pin_memory() for name, t in outs[0].t.items()}
+                oc = abi.OutboxC()
+                for name, t in cols.items():
+                    setattr(oc, name, t.data_ptr())
+                host_out.append((cols, oc))
+            sparse = ("rep_term", "ballot_term", "ballot_last")
+            dh2d = sum(t.numel() for t in host_in[0][0].values())
+            dd2h = sum(t.numel() for name, t in host_out[0][0].items() if name not in sparse) + 16
+
+            def dense_pass():
+                for j in range(K3):
+                    sl = j % NSL
+                    if j >= NSL:
+                        e.step_wait_slot(sl)
+                    e.step_begin_host(sl, host_in[j][1], host_out[sl][1])
+                for sl in range(NSL):
+                    e.step_wait_slot(sl)
+            e.restore(); dense_pass()
+            t0 = time.perf_counter()
+            for _ in range(6):
+                e.restore(sync=False); dense_pass()
+            dspent = time.perf_counter() - t0
+            e2e_dense = {"value": sum(acks_per_launch[:K3]) * 6 / dspent, "unit": "acks/s", "h2d_bytes_per_launch": int(dh2d),
+                         "d2h_bytes_per_launch": int(dd2h), "launches": 6 * K3}
+            del host_in, host_out
     sampler.stop_flag = True
 
     # ---- reduce over ranks ------------------------------------------------------------------------
@@ -583,11 +684,16 @@ def run_engine(args):
             ev = e2e["acks"] / e2e["spent"]
             line["e2e"] = {"value": ev, "unit": "acks/s", "h2d_bytes_per_step": e2e["h2d"] * L, "d2h_bytes_per_step": e2e["d2h"] * L,
                            "h2d_bytes_per_launch": e2e["h2d"], "d2h_bytes_per_launch": e2e["d2h"],
-                           "launches": e2e["launches"], "timed_region_ms": e2e["spent"] * 1e3,
-                           "note": "wall clock around rafting_step_begin_host/rafting_step_wait_slot with caller-owned pinned buffers, three "
-                                   "launches in flight (H2D / kernel / D2H of successive launches overlap); every launch's inbox crosses PCIe up "
-                                   "and its outbox crosses PCIe down inside the timed region (the payload columns of replies / ballots only "
-                                   "when the launch produced any); bytes_per_step = per launch x the launches of one step"}
+                           "h2d_bytes_per_ack": e2e["h2d"] / acks_launch, "d2h_bytes_per_ack": e2e["d2h"] / acks_launch,
+                           "launches": e2e["launches"], "timed_region_ms": e2e["spent"] * 1e3, "same_end_state_as_device_path": e2e["exact"],
+                           "escape_records_per_launch_up": e2e["esc_in"],
+                           "path": "compact (rafting_step_begin_compact / rafting_step_wait_compact)",
+                           "note": "wall clock around the compact host path with caller-owned pinned buffers, three launches in flight (H2D / "
+                                   "unpack + step + pack kernels / D2H of successive launches overlap); every launch's wire columns cross PCIe up "
+                                   "and down inside the timed region; lossless: the end state equals the device path's, bit for bit; "
+                                   "bytes_per_step = per launch x the launches of one step"}
+            if e2e_dense:
+                line["e2e_dense_path"] = e2e_dense
             line["commit_latency_ms"] = {"p50": float(np.percentile(lat_ms, 50)), "p99": float(np.percentile(lat_ms, 99)),
                                          "what": "one synchronous launch: host ack in pinned inbox -> commit record readable in pinned outbox"}
         if cpu:

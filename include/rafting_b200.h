@@ -401,6 +401,80 @@ int rafting_step_begin_host(rafting_engine_t* e, uint32_t slot /* 0..3 */, const
                             const rafting_outbox_t* out_host);
 int rafting_step_wait_slot (rafting_engine_t* e, uint32_t slot);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * COMPACT host path (round 2): the same step, a third of the PCIe bytes.
+ *
+ * The dense host path moves 65 B up and 69 B down per AppendEntries ack and is PCIe-bound.  Most of those bytes are
+ * redundant in leader steady state: every time of a row lies within 65 s of the row's base time; a reply's term is the
+ * term its request was sent with; (epochAtSend, lastIndexAtSend) — which the reference keeps in the callback closure of
+ * Leader.replicateLog (Leader.java:216-237) — only travel down to be sent up again; a plan's prevLogIndex / leaderCommit
+ * lie close to the group's end-of-step snapshot.  The compact format drops them LOSSLESSLY: whatever does not fit its rules
+ * travels in full through an escape list, and two device kernels (unpack before, pack after the step kernel) convert
+ * between the compact wire columns and the dense SoA batch the step kernel works on.
+ *   * the (epochAtSend, lastIndexAtSend) echo stays in an HBM in-flight table: pack gives every AE / IS plan a TAG (a free
+ *     slot 0..31 of its (group, follower) lane), the reply echoes the tag, unpack looks the pair up and frees the slot.
+ *     No free slot (more than 32 RPCs of one lane outstanding): tag 255, and the reply must come back as an escape record.
+ *   * dense steps only (no active list), no inbound-request ops (RAFTING_INBOX_NO_REQUESTS is implied): SUBMIT / TIMEOUT
+ *     ops, AE / IS acks; vote replies and anything irregular use the escape list.
+ * ------------------------------------------------------------------------------------------------------------------- */
+/* ev_c : bits 0..3 kind (RAFTING_EV_NONE / _AE_ACK / _IS_ACK, or 15 = "see the escape list") | 4..5 outcome | 6 success |
+ *        7 term-as-sent (RaftResponse.term() == the term the request carried; required for outcome OK, else escape) |
+ *        8..15 tag echoed from plan_c | 16..31 now - row_base[row] (ms, unsigned) | 32..63 incarnation
+ * op_c : bits 0..31 RAFTING_OP_MAKE(kind, peer, count) with kind NONE / SUBMIT / TIMEOUT | 32..47 now - row_base[row] |
+ *        48..63 unavailable-follower mask (lanes 0..15; clusters with more lanes use the dense path)                       */
+#define RAFTING_CEV_ESCAPED 15u
+#define RAFTING_CEV_MAKE(kind, outcome, success, term_as_sent, tag, dt, incarnation)                                   \
+    ((uint64_t)(kind) | ((uint64_t)(outcome) << 4) | ((uint64_t)((success) ? 1 : 0) << 6) |                            \
+     ((uint64_t)((term_as_sent) ? 1 : 0) << 7) | ((uint64_t)((tag) & 0xffu) << 8) | ((uint64_t)((dt) & 0xffffu) << 16) | \
+     ((uint64_t)(uint32_t)(incarnation) << 32))
+#define RAFTING_COP_MAKE(op_make, dt, unavail) ((uint64_t)(uint32_t)(op_make) | ((uint64_t)((dt) & 0xffffu) << 32) | ((uint64_t)((unavail) & 0xffffu) << 48))
+#define RAFTING_CTAG_NONE 255u
+typedef struct rafting_cesc_in {     /* a lane event in full: overwrites slot (row * G + gid) * F + lane after unpacking */
+    uint32_t slot, _pad;
+    uint64_t ev_meta;                /* RAFTING_EVM_MAKE(...) */
+    int64_t  term, now_ms, epoch_at_send, last_at_send;
+} rafting_cesc_in_t;
+#define RAFTING_CINBOX_HAS_UNAVAIL 1u   /* some op_c carries a non-zero unavailable-follower mask (else the masks are not read) */
+typedef struct rafting_cinbox {
+    uint32_t rows, n_esc;
+    uint32_t flags, _pad;
+    const int64_t*           row_base;   /* [rows] */
+    const uint64_t*          op_c;       /* [rows][G], may be NULL (no group ops) */
+    const uint64_t*          ev_c;       /* [rows][G][F], may be NULL (no lane events) */
+    const rafting_cesc_in_t* esc;        /* [n_esc] */
+} rafting_cinbox_t;
+/* plan_c : plan_meta (kind | hb << 4 | count << 16 | incarnation << 32) | bit 6 escaped | bits 8..15 tag.  Not escaped means:
+ *          AE  prevLogIndex = last_entry[g].x - (plan_d & 0xffff), prevLogTerm = current_term[g], lastIndex = prevLogIndex + count,
+ *              leaderCommit = commit_index[g] - (plan_d >> 16), epochAtSend = epoch[g].x, incarnation == incarnation[g]
+ *          IS  (epoch.index, epoch.term) = epoch[g], leaderCommit as above
+ *          SKIP_INFLIGHT / UNAVAILABLE: no payload
+ * rep_c  : per-event error code of the row's group op (rafting_outbox_t.rep_meta bits 8..15); a row whose op produced a
+ *          REPLY (inbound requests are not part of compact steps, but the generic handler may answer) is escaped         */
+enum { RAFTING_CESC_PLAN = 1, RAFTING_CESC_BALLOT = 2, RAFTING_CESC_REPLY = 3 };
+typedef struct rafting_cesc_out {
+    uint32_t kind, slot;             /* PLAN: lane slot; BALLOT / REPLY: row * G + gid */
+    uint64_t meta;                   /* plan_meta (| tag << 8) / ballot_meta / rep_meta */
+    int64_t  a, b, c, d, e;          /* PLAN: plan_pp.x, .y, plan_lc.x, .y, plan_epoch; BALLOT: term, last.x, last.y; REPLY: rep_term */
+} rafting_cesc_out_t;
+typedef struct rafting_coutbox {
+    uint64_t* plan_c;                /* [rows][G][F] */
+    uint32_t* plan_d;                /* [rows][G][F] */
+    uint8_t*  rep_c;                 /* [rows][G]    */
+    int64_t*  commit_index; int64_t* current_term; uint32_t* role_word; uint32_t* incarnation; uint32_t* err_word;
+    rafting_i64x2_t* last_entry;     /* [G] each, as in rafting_outbox_t */
+    rafting_i64x2_t* epoch;          /* [G] RaftLog.epoch() at the end of the step */
+    rafting_cesc_out_t* esc;         /* [esc_cap] */
+    uint32_t  esc_cap, _pad;
+    uint32_t* counts;                /* [4] escape records produced (may exceed esc_cap: then use rafting_step_fetch_dense),
+                                        ballots, valid replies, reserved */
+} rafting_coutbox_t;
+int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot /* 0..3 */, const rafting_cinbox_t* in_host,
+                               const rafting_coutbox_t* out_host);
+int rafting_step_wait_compact (rafting_engine_t* e, uint32_t slot);
+/* the dense outbox of the compact step last waited for in `slot` (every column that is non-NULL in out_host): the lossless
+   fallback when the escape list overflowed */
+int rafting_step_fetch_dense  (rafting_engine_t* e, uint32_t slot, const rafting_outbox_t* out_host);
+
 /* device path: inbox/outbox columns already resident in HBM (pointers are device pointers).
    `stream` is a cudaStream_t (0 = engine's stream). No host copies, no sync. */
 int rafting_step_device(rafting_engine_t* e, const rafting_inbox_t* in_dev,

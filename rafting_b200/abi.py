@@ -328,3 +328,25 @@ def voted_for_of(role_word: int) -> int:
 
 def leader_of(role_word: int) -> int:
     return ((role_word >> 16) & 0xFF) - 1
+
+
+# ---- compact host path (include/rafting_b200.h "COMPACT host path") --------------------------------------------------
+CEV_ESCAPED, CTAG_NONE = 15, 255
+CINBOX_HAS_UNAVAIL = 1
+CESC_PLAN, CESC_BALLOT, CESC_REPLY = 1, 2, 3
+CESC_IN = np.dtype([("slot", "<u4"), ("_pad", "<u4"), ("ev_meta", "<u8"), ("term", "<i8"), ("now_ms", "<i8"),
+                    ("epoch_at_send", "<i8"), ("last_at_send", "<i8")])
+CESC_OUT = np.dtype([("kind", "<u4"), ("slot", "<u4"), ("meta", "<u8"), ("a", "<i8"), ("b", "<i8"), ("c", "<i8"), ("d", "<i8"), ("e", "<i8")])
+assert CESC_IN.itemsize == 48 and CESC_OUT.itemsize == 56
+
+
+class CInboxC(C.Structure):
+    _fields_ = [("rows", C.c_uint32), ("n_esc", C.c_uint32), ("flags", C.c_uint32), ("_pad", C.c_uint32),
+                ("row_base", C.c_void_p), ("op_c", C.c_void_p), ("ev_c", C.c_void_p), ("esc", C.c_void_p)]
+
+
+class COutboxC(C.Structure):
+    _fields_ = [("plan_c", C.c_void_p), ("plan_d", C.c_void_p), ("rep_c", C.c_void_p),
+                ("commit_index", C.c_void_p), ("current_term", C.c_void_p), ("role_word", C.c_void_p), ("incarnation", C.c_void_p),
+                ("err_word", C.c_void_p), ("last_entry", C.c_void_p), ("epoch", C.c_void_p), ("esc", C.c_void_p),
+                ("esc_cap", C.c_uint32), ("_pad", C.c_uint32), ("counts", C.c_void_p)]

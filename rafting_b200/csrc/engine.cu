@@ -88,8 +88,10 @@ struct rafting_engine {
     uint32_t* d_perm_cnt = nullptr;    // class sizes
     std::vector<void*> dev_allocs;
     std::vector<size_t> dev_bytes;
-    std::vector<void*> shadow;         // rafting_checkpoint copies of the first n_state_allocs entries of dev_allocs
-    size_t n_state_allocs = 0;         // the tables (allocated by engine_create); later allocations are scratch
+    std::vector<char>  dev_is_state;   // parallel to dev_allocs: 1 = protocol state (tables, in-flight table), 0 = scratch
+    std::vector<void*> shadow;         // rafting_checkpoint copies, parallel to dev_allocs (null for scratch)
+    bool alloc_state = true;           // what dalloc marks new allocations as
+    struct CompactState* compact = nullptr;   // in-flight table of the compact host path (compact.cuh), created on first use
 };
 
 template <typename T>
@@ -100,12 +102,14 @@ static int dalloc(rafting_engine* e, T** p, size_t count) {
     CU(cudaMemset(q, 0, bytes));
     e->dev_allocs.push_back(q);
     e->dev_bytes.push_back(bytes);
+    e->dev_is_state.push_back(e->alloc_state ? 1 : 0);
     *p = (T*)q;
     return 0;
 }
 
 static void rafting_hostpath_release(rafting_engine* e);
 static void seglog_release(rafting_engine* e);
+static void compact_release(rafting_engine* e);
 static int quiesce_for_table_edit(rafting_engine* e, const char* who);
 extern "C" uint32_t rafting_abi_version(void) { return RAFTING_ABI_VERSION; }
 extern "C" const char* rafting_last_error(void) { return g_err; }
@@ -144,7 +148,7 @@ extern "C" int rafting_engine_create(const rafting_cfg_t* cfg, rafting_engine_t*
         (rc = dalloc(e, &T.l_fr, G * F)) || (rc = dalloc(e, &T.l_cnt, G * F))) {
         rafting_engine_destroy(e); return rc;
     }
-    e->n_state_allocs = e->dev_allocs.size();
+    e->alloc_state = false;
     if ((rc = dalloc(e, &e->d_cfg, 1)) || (rc = dalloc(e, &e->d_perm, NCLS * G)) || (rc = dalloc(e, &e->d_perm_cnt, NCLS))) { rafting_engine_destroy(e); return rc; }
     if (cudaMemcpy(e->d_cfg, &e->dcfg, sizeof(CfgD), cudaMemcpyHostToDevice) != cudaSuccess) {
         rafting_engine_destroy(e); return fail(RAFTING_E_CUDA, "cfg upload failed");
@@ -166,7 +170,8 @@ extern "C" int rafting_engine_destroy(rafting_engine_t* e) {
     }
     if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
     for (void* p : e->dev_allocs) cudaFree(p);
-    for (void* p : e->shadow) cudaFree(p);
+    for (void* p : e->shadow) if (p) cudaFree(p);
+    compact_release(e);
     rafting_hostpath_release(e);
     seglog_release(e);
     if (e->ev_seg) cudaEventDestroy(e->ev_seg);
@@ -458,6 +463,9 @@ static int blk_reserve(Blk& b, size_t bytes, bool pinned) {
 
 struct Slot {
     Blk din, dout;                            // device staging (both paths)
+    Blk cin, cout, chin, chout;               // compact path: device wire blocks + pinned landing block of the small items
+    bool compact_step = false;                // the step in flight came through rafting_step_begin_compact
+    rafting_coutbox_t c_host; size_t c_esc_off = 0; uint32_t* c_counts_pinned = nullptr; void* c_esc_dev = nullptr;
     Blk hin, hout;                            // pinned host staging (leases only), same layout as din / dout
     uint32_t* h_flags = nullptr;              // pinned landing place of the flag words on the caller-owned path
     cudaEvent_t ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
@@ -506,6 +514,10 @@ static void hostpath_free(rafting_engine* e) {
         if (s.dout.p) cudaFree(s.dout.p);
         if (s.hin.p) cudaFreeHost(s.hin.p);
         if (s.hout.p) cudaFreeHost(s.hout.p);
+        if (s.cin.p) cudaFree(s.cin.p);
+        if (s.cout.p) cudaFree(s.cout.p);
+        if (s.chin.p) cudaFreeHost(s.chin.p);
+        if (s.chout.p) cudaFreeHost(s.chout.p);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
@@ -613,12 +625,14 @@ static int step_enqueue(rafting_engine* e, uint32_t slot, const rafting_inbox_t*
     if ((rc = issue_copies(down, false, H->s_d2h, S.hout))) return rc;
     CU(cudaEventRecord(S.ev_done, H->s_d2h));
     S.host_out = *out; S.dev_out = dout; S.rows_ = rows; S.n_ = n; S.flags_host = hf;
+    S.compact_step = false;
     S.inflight = true;
     return RAFTING_OK;
 }
 static int slot_wait(rafting_engine* e, uint32_t slot) {
     HostPath* H = hp(e); Slot& S = H->slot[slot];
     if (!S.inflight) return RAFTING_OK;
+    if (S.compact_step) return fail(RAFTING_E_INVAL, "slot %u holds a compact step (use rafting_step_wait_compact)", slot);
     CU(cudaEventSynchronize(S.ev_done));
     S.inflight = false;
     // sparse families: fetch their payload columns only when the step produced ballots / valid replies
@@ -837,23 +851,22 @@ extern "C" int rafting_log_term(rafting_engine_t* e, uint32_t gid, int64_t index
 extern "C" int rafting_checkpoint(rafting_engine_t* e) {
     if (!e) return fail(RAFTING_E_INVAL, "null argument");
     CU(cudaSetDevice(e->cfg.device));
-    while (e->shadow.size() < e->n_state_allocs) {
-        void* q = nullptr;
-        CU(cudaMalloc(&q, e->dev_bytes[e->shadow.size()]));
-        e->shadow.push_back(q);
-    }
-    for (size_t i = 0; i < e->shadow.size(); i++)
+    e->shadow.resize(e->dev_allocs.size(), nullptr);
+    for (size_t i = 0; i < e->dev_allocs.size(); i++) {
+        if (!e->dev_is_state[i]) continue;
+        if (!e->shadow[i]) CU(cudaMalloc(&e->shadow[i], e->dev_bytes[i]));
         CU(cudaMemcpyAsync(e->shadow[i], e->dev_allocs[i], e->dev_bytes[i], cudaMemcpyDeviceToDevice, e->stream));
+    }
     CU(cudaStreamSynchronize(e->stream));
     return RAFTING_OK;
 }
 // The checkpoint covers the allocations that existed when it was taken (the tables); buffers created later (the
 // gather buffers of rafting_comm_init) are not state and are left alone.
 static int restore_enqueue(rafting_engine* e) {
-    if (e->shadow.empty() || e->shadow.size() > e->dev_allocs.size()) return fail(RAFTING_E_INVAL, "no checkpoint taken");
+    if (e->shadow.empty()) return fail(RAFTING_E_INVAL, "no checkpoint taken");
     CU(cudaSetDevice(e->cfg.device));
     for (size_t i = 0; i < e->shadow.size(); i++)
-        CU(cudaMemcpyAsync(e->dev_allocs[i], e->shadow[i], e->dev_bytes[i], cudaMemcpyDeviceToDevice, e->stream));
+        if (e->shadow[i]) CU(cudaMemcpyAsync(e->dev_allocs[i], e->shadow[i], e->dev_bytes[i], cudaMemcpyDeviceToDevice, e->stream));
     return RAFTING_OK;
 }
 extern "C" int rafting_restore(rafting_engine_t* e) {
@@ -1044,4 +1057,5 @@ extern "C" int rafting_abi_sizes(uint32_t* out, uint32_t n) {
     return 7;
 }
 
+#include "compact.cuh"
 #include "seglog.cuh"

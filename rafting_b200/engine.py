@@ -37,7 +37,7 @@ EXPORTS = [
     "rafting_comm_init", "rafting_comm_init_all", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_allgather_commit_from",
     "rafting_allgather_commit_all", "rafting_allgather_last", "rafting_restore_async", "rafting_step_device_seq", "rafting_engine_stream",
     "rafting_engine_counters", "rafting_abi_sizes", "rafting_checkpoint", "rafting_restore",
-    "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_backoff_step", "rafting_allgather_join",
+    "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_step_begin_compact", "rafting_step_wait_compact", "rafting_step_fetch_dense", "rafting_backoff_step", "rafting_allgather_join",
     "rafting_log_config", "rafting_log_append", "rafting_log_read", "rafting_log_gather", "rafting_log_trim", "rafting_log_stats",
 ]
 
@@ -104,6 +104,9 @@ def lib():
         L.rafting_abi_sizes.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
         L.rafting_step_begin_host.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.InboxC), C.POINTER(abi.OutboxC)]
         L.rafting_step_wait_slot.argtypes = [C.c_void_p, C.c_uint32]
+        L.rafting_step_begin_compact.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.CInboxC), C.POINTER(abi.COutboxC)]
+        L.rafting_step_wait_compact.argtypes = [C.c_void_p, C.c_uint32]
+        L.rafting_step_fetch_dense.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.OutboxC)]
         L.rafting_checkpoint.argtypes = [C.c_void_p]
         L.rafting_restore.argtypes = [C.c_void_p]
         L.rafting_restore_async.argtypes = [C.c_void_p]
@@ -193,6 +196,22 @@ class Engine:
 
     def step_wait_slot(self, slot: int):
         _check(lib().rafting_step_wait_slot(self._h, slot), "rafting_step_wait_slot")
+
+    # ---- compact host path: a third of the PCIe bytes (include/rafting_b200.h, rafting_b200/compact.py) ----------------
+    def step_begin_compact(self, slot: int, cin_c: abi.CInboxC, cout_c: abi.COutboxC):
+        _check(lib().rafting_step_begin_compact(self._h, slot, C.byref(cin_c), C.byref(cout_c)), "rafting_step_begin_compact")
+
+    def step_wait_compact(self, slot: int):
+        _check(lib().rafting_step_wait_compact(self._h, slot), "rafting_step_wait_compact")
+
+    def step_fetch_dense(self, slot: int, outbox_c: abi.OutboxC):
+        _check(lib().rafting_step_fetch_dense(self._h, slot, C.byref(outbox_c)), "rafting_step_fetch_dense")
+
+    def step_compact(self, cin, cout, slot: int = 0):
+        """Synchronous compact step: cin / cout are rafting_b200.compact.CompactInbox / CompactOutbox."""
+        self.step_begin_compact(slot, cin.as_c(), cout.as_c())
+        self.step_wait_compact(slot)
+        return cout
 
     # ---- device path -------------------------------------------------------------------------
     def step_device(self, inbox_c: abi.InboxC, outbox_c: abi.OutboxC, stream: int = 0):
