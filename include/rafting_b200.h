@@ -517,6 +517,27 @@ int rafting_log_stats (rafting_engine_t* e, uint64_t* out /* appended, head, spi
                                                               last gather kernels ns, last gather bytes, trimmed entries,
                                                               cold bytes freed, spills skipped (dead segments) */, uint32_t n);
 
+/* Durable tier of the entry buffer (what flushWal(true) gives RocksLog, RocksLog.java:87,195).  With an
+   entry file open every rafting_log_append is framed into it first (write-ahead) and rafting_log_sync is the ONE durability
+   barrier per step (fdatasync) — issue it before the step's replies are released.  The stored key range is metadata of the
+   step kernel, so the pump logs truncations / compactions with rafting_log_mark; rafting_log_store_open replays the file
+   (torn tail cut) and rafting_log_recovered summarises a group for rafting_group_open + rafting_group_load_runs.  The file
+   is also the coldest read tier, which bounds the pinned-host pool to cold_max_segments (0 = unbounded).
+   rafting_log_append / gather / read run on the entry buffer's own stream: the step kernel's stream never waits for them.
+   Visibility of gathered entries is the CALLER's: pass ranges taken from this step's plans (rafting_log_read checks the
+   group's stored key range itself). */
+int rafting_log_store_open(rafting_engine_t* e, const char* path, uint32_t cold_max_segments, uint64_t* recovered_records);
+int rafting_log_sync      (rafting_engine_t* e);
+int rafting_log_mark      (rafting_engine_t* e, uint32_t gid, int64_t lowest_key, int64_t highest_key /* lo > hi: empty */,
+                           int64_t epoch_index, int64_t epoch_term);
+int rafting_log_recovered (rafting_engine_t* e, uint32_t gid, rafting_group_init_t* init /* epoch, key range, last term */,
+                           rafting_i64x2_t* runs /* [cap] (first index, term), oldest first */, uint32_t cap, uint32_t* n_runs);
+/* one stored entry in the reference's RocksDB layout (RocksLog.java:82-89,259-280): key = 8-byte BE index,
+   value = 8-byte BE term || payload — what the reference's LogChecker iterates over */
+int rafting_log_export_kv (rafting_engine_t* e, uint32_t gid, int64_t index, uint8_t key_out[8], void* val_out, size_t val_cap,
+                           size_t* val_len);
+int rafting_log_store_stats(rafting_engine_t* e, uint64_t out[6] /* file bytes, synced bytes, fdatasync calls, file-tier reads,
+                                                                    cold segments evicted, cold segments resident */);
 /* multi-GPU summary (BASELINE config #4): groups shard by contiguous gid blocks, rank r owns global groups
    [r*G, (r+1)*G); the ONLY exchange is one ncclAllGather of commitIndex[G] (int64) per step into a [world * G] device
    buffer every rank keeps (two, alternating).  The gather runs on its own stream behind the kernel that produced the column.

@@ -906,103 +906,100 @@ static uint32_t role_word(const ogroup_t* g) {
            ((uint32_t)(g->persistDirty ? 1 : 0) << 30) | ((uint32_t)(g->commitDirty ? 1 : 0) << 31);
 }
 
-static void step_group(orc_engine_t* e, const rafting_inbox_t* in, const rafting_outbox_t* out,
-                       uint32_t i, uint32_t n, uint64_t* events) {
+/* one row of one group: [sweep?] op(r); ev(r,0); ...; ev(r,F-1) — the canonical serial order */
+static void step_row(orc_engine_t* e, const rafting_inbox_t* in, const rafting_outbox_t* out,
+                     uint32_t i, uint32_t n, uint32_t gid, ogroup_t* g, uint32_t r, uint64_t* events) {
     const uint32_t F = e->F;
-    uint32_t gid = in->gids ? in->gids[i] : i;
-    if (gid >= e->cfg.max_groups) return;
-    ogroup_t* g = &e->groups[gid];
-    g->persistDirty = 0; g->commitDirty = 0;
-    for (uint32_t r = 0; r < in->rows; r++) {
-        size_t gi = (size_t)r * n + i;
-        octx_t c; memset(&c, 0, sizeof(c));
-        c.e = e; c.g = g; c.gid = gid;
-        if (out->plan_meta) {
-            c.plan_meta = out->plan_meta + gi * F; c.plan_pp = out->plan_pp + gi * F;
-            c.plan_lc = out->plan_lc + gi * F; c.plan_epoch = out->plan_epoch + gi * F;
-            for (uint32_t f = 0; f < F; f++) c.plan_meta[f] = 0;
+    size_t gi = (size_t)r * n + i;
+    octx_t c; memset(&c, 0, sizeof(c));
+    c.e = e; c.g = g; c.gid = gid;
+    if (out->plan_meta) {
+        c.plan_meta = out->plan_meta + gi * F; c.plan_pp = out->plan_pp + gi * F;
+        c.plan_lc = out->plan_lc + gi * F; c.plan_epoch = out->plan_epoch + gi * F;
+        for (uint32_t f = 0; f < F; f++) c.plan_meta[f] = 0;
+    }
+    if (out->ballot_meta) {
+        c.ballot_meta = out->ballot_meta + gi; c.ballot_term = out->ballot_term + gi; c.ballot_last = out->ballot_last + gi;
+        *c.ballot_meta = 0;
+    }
+    if (out->rep_meta) { out->rep_meta[gi] = 0; }
+    /* ---- group op (or sweep) ---- */
+    int64_t sweep = in->row_now ? in->row_now[r] : 0;
+    uint32_t kind = RAFTING_OP_NONE, meta = 0, entoff = 0;
+    if (sweep != 0) {
+        /* timer sweep row: implied TIMEOUT for groups whose timer is due (RaftRoutine.java:53-77) */
+        if (g->alive) {
+            int due = (g->role == RAFTING_ROLE_LEADER) ? (g->hbDue <= sweep)
+                      : (g->deadline > 0 && g->deadline != I64_MAX && g->deadline <= sweep);
+            if (due) { kind = RAFTING_OP_TIMEOUT; c.now = sweep; c.draw = 0; }
         }
-        if (out->ballot_meta) {
-            c.ballot_meta = out->ballot_meta + gi; c.ballot_term = out->ballot_term + gi; c.ballot_last = out->ballot_last + gi;
-            *c.ballot_meta = 0;
+    } else if (in->op_meta) {
+        uint64_t m = in->op_meta[gi];
+        meta = (uint32_t)m; entoff = (uint32_t)(m >> 32);
+        kind = RAFTING_OP_KIND(meta);
+        if (kind != RAFTING_OP_NONE) { c.now = in->op_nr[gi].x; c.draw = in->op_nr[gi].y; }
+    }
+    if (kind != RAFTING_OP_NONE) {
+        (*events)++;
+        int err = 0; oreply_t rep = {0, 0, 0};
+        int64_t a = 0, b = 0, cc = 0, d = 0;
+        if (sweep == 0) {
+            if (in->op_ab) { a = in->op_ab[gi].x; b = in->op_ab[gi].y; }
+            if (in->op_cd) { cc = in->op_cd[gi].x; d = in->op_cd[gi].y; }
         }
-        if (out->rep_meta) { out->rep_meta[gi] = 0; }
-        /* ---- group op (or sweep) ---- */
-        int64_t sweep = in->row_now ? in->row_now[r] : 0;
-        uint32_t kind = RAFTING_OP_NONE, meta = 0, entoff = 0;
-        if (sweep != 0) {
-            /* timer sweep row: implied TIMEOUT for groups whose timer is due (RaftRoutine.java:53-77) */
-            if (g->alive) {
-                int due = (g->role == RAFTING_ROLE_LEADER) ? (g->hbDue <= sweep)
-                          : (g->deadline > 0 && g->deadline != I64_MAX && g->deadline <= sweep);
-                if (due) { kind = RAFTING_OP_TIMEOUT; c.now = sweep; c.draw = 0; }
-            }
-        } else if (in->op_meta) {
-            uint64_t m = in->op_meta[gi];
-            meta = (uint32_t)m; entoff = (uint32_t)(m >> 32);
-            kind = RAFTING_OP_KIND(meta);
-            if (kind != RAFTING_OP_NONE) { c.now = in->op_nr[gi].x; c.draw = in->op_nr[gi].y; }
+        int peer = (int)RAFTING_OP_PEER(meta); uint32_t count = RAFTING_OP_COUNT(meta);
+        if (!g->alive) err = RAFTING_ERR_CLOSED_GROUP;
+        else switch (kind) {
+        case RAFTING_OP_SUBMIT:  err = op_submit(&c, count, (uint64_t)a); break;
+        case RAFTING_OP_TIMEOUT: err = op_timeout(&c, (uint64_t)a); break;
+        case RAFTING_OP_AE_REQUEST: {
+            int64_t first = in->op_e ? in->op_e[gi] : (int64_t)((uint64_t)b + 1u);
+            const int64_t* terms = in->ent_terms ? in->ent_terms + entoff : NULL;
+            if (count > 0 && (!terms || (uint64_t)entoff + count > in->ent_count)) { err = RAFTING_ERR_BAD_EVENT; break; }
+            err = op_append_entries(&c, peer, a, b, cc, first, count, terms, d, &rep);
+            break;
         }
-        if (kind != RAFTING_OP_NONE) {
-            (*events)++;
-            int err = 0; oreply_t rep = {0, 0, 0};
-            int64_t a = 0, b = 0, cc = 0, d = 0;
-            if (sweep == 0) {
-                if (in->op_ab) { a = in->op_ab[gi].x; b = in->op_ab[gi].y; }
-                if (in->op_cd) { cc = in->op_cd[gi].x; d = in->op_cd[gi].y; }
-            }
-            int peer = (int)RAFTING_OP_PEER(meta); uint32_t count = RAFTING_OP_COUNT(meta);
-            if (!g->alive) err = RAFTING_ERR_CLOSED_GROUP;
-            else switch (kind) {
-            case RAFTING_OP_SUBMIT:  err = op_submit(&c, count, (uint64_t)a); break;
-            case RAFTING_OP_TIMEOUT: err = op_timeout(&c, (uint64_t)a); break;
-            case RAFTING_OP_AE_REQUEST: {
-                int64_t first = in->op_e ? in->op_e[gi] : (int64_t)((uint64_t)b + 1u);
-                const int64_t* terms = in->ent_terms ? in->ent_terms + entoff : NULL;
-                if (count > 0 && (!terms || (uint64_t)entoff + count > in->ent_count)) { err = RAFTING_ERR_BAD_EVENT; break; }
-                err = op_append_entries(&c, peer, a, b, cc, first, count, terms, d, &rep);
-                break;
-            }
-            case RAFTING_OP_PREVOTE_REQ: err = op_pre_vote(&c, peer, a, b, cc, &rep); break;
-            case RAFTING_OP_VOTE_REQ:    err = op_request_vote(&c, peer, a, b, cc, &rep); break;
-            case RAFTING_OP_IS_REQUEST:  err = op_install_snapshot(&c, peer, a, d != 0, &rep); break;
-            case RAFTING_OP_FLUSH:       err = log_flush(&g->log, b, cc); break;
-            default: err = RAFTING_ERR_BAD_EVENT;
-            }
-            if (err) { if (g->alive) flag_err(g, err); rep.valid = 0; }
-            if (out->rep_meta) {
-                out->rep_meta[gi] = (uint32_t)(rep.valid ? 1 : 0) | ((uint32_t)(rep.success ? 1 : 0) << 1) | ((uint32_t)err << 8);
-                out->rep_term[gi] = rep.valid ? rep.term : 0;
-            }
+        case RAFTING_OP_PREVOTE_REQ: err = op_pre_vote(&c, peer, a, b, cc, &rep); break;
+        case RAFTING_OP_VOTE_REQ:    err = op_request_vote(&c, peer, a, b, cc, &rep); break;
+        case RAFTING_OP_IS_REQUEST:  err = op_install_snapshot(&c, peer, a, d != 0, &rep); break;
+        case RAFTING_OP_FLUSH:       err = log_flush(&g->log, b, cc); break;
+        default: err = RAFTING_ERR_BAD_EVENT;
         }
-        /* ---- lane events f = 0..F-1 ---- */
-        if (in->ev_meta) {
-            for (uint32_t f = 0; f < F; f++) {
-                size_t li = gi * F + f;
-                uint64_t m = in->ev_meta[li];
-                uint32_t ek = RAFTING_EVM_KIND(m);
-                if (ek == RAFTING_EV_NONE) continue;
-                (*events)++;
-                if (!g->alive) continue;
-                c.now = in->ev_tn[li].y; c.draw = 0;
-                int64_t respTerm = in->ev_tn[li].x;
-                int outcome = (int)RAFTING_EVM_OUTCOME(m), success = (int)RAFTING_EVM_SUCCESS(m);
-                uint32_t inc = RAFTING_EVM_INC(m);
-                int err = 0;
-                switch (ek) {
-                case RAFTING_EV_AE_ACK: case RAFTING_EV_IS_ACK:
-                    err = ev_ack(&c, f, (int)ek, outcome, success, respTerm,
-                                 in->ev_el ? in->ev_el[li].x : 0, in->ev_el ? in->ev_el[li].y : 0, inc);
-                    break;
-                case RAFTING_EV_PV_REPLY: err = ev_prevote_reply(&c, f, outcome, success, respTerm, inc); break;
-                case RAFTING_EV_RV_REPLY: err = ev_vote_reply(&c, f, outcome, success, respTerm, inc); break;
-                default: err = RAFTING_ERR_BAD_EVENT;
-                }
-                if (err) flag_err(g, err);
-            }
+        if (err) { if (g->alive) flag_err(g, err); rep.valid = 0; }
+        if (out->rep_meta) {
+            out->rep_meta[gi] = (uint32_t)(rep.valid ? 1 : 0) | ((uint32_t)(rep.success ? 1 : 0) << 1) | ((uint32_t)err << 8);
+            out->rep_term[gi] = rep.valid ? rep.term : 0;
         }
     }
-    /* end-of-step snapshot columns: by gid, or by position in the active list (RAFTING_INBOX_COMPACT_GROUPS) */
+    /* ---- lane events f = 0..F-1 ---- */
+    if (in->ev_meta) {
+        for (uint32_t f = 0; f < F; f++) {
+            size_t li = gi * F + f;
+            uint64_t m = in->ev_meta[li];
+            uint32_t ek = RAFTING_EVM_KIND(m);
+            if (ek == RAFTING_EV_NONE) continue;
+            (*events)++;
+            if (!g->alive) continue;
+            c.now = in->ev_tn[li].y; c.draw = 0;
+            int64_t respTerm = in->ev_tn[li].x;
+            int outcome = (int)RAFTING_EVM_OUTCOME(m), success = (int)RAFTING_EVM_SUCCESS(m);
+            uint32_t inc = RAFTING_EVM_INC(m);
+            int err = 0;
+            switch (ek) {
+            case RAFTING_EV_AE_ACK: case RAFTING_EV_IS_ACK:
+                err = ev_ack(&c, f, (int)ek, outcome, success, respTerm,
+                             in->ev_el ? in->ev_el[li].x : 0, in->ev_el ? in->ev_el[li].y : 0, inc);
+                break;
+            case RAFTING_EV_PV_REPLY: err = ev_prevote_reply(&c, f, outcome, success, respTerm, inc); break;
+            case RAFTING_EV_RV_REPLY: err = ev_vote_reply(&c, f, outcome, success, respTerm, inc); break;
+            default: err = RAFTING_ERR_BAD_EVENT;
+            }
+            if (err) flag_err(g, err);
+        }
+    }
+}
+/* end-of-step snapshot columns: by gid, or by position in the active list (RAFTING_INBOX_COMPACT_GROUPS) */
+static void step_end(const rafting_inbox_t* in, const rafting_outbox_t* out, uint32_t i, uint32_t gid, ogroup_t* g) {
     const uint32_t go = (in->gids && (in->flags & RAFTING_INBOX_COMPACT_GROUPS)) ? i : gid;
     if (out->commit_index) out->commit_index[go] = g->log.commitIndex;
     if (out->current_term) out->current_term[go] = g->term;
@@ -1010,6 +1007,25 @@ static void step_group(orc_engine_t* e, const rafting_inbox_t* in, const rafting
     if (out->incarnation)  out->incarnation[go] = g->incarnation;
     if (out->err_word)     out->err_word[go] = g->errWord;
     if (out->last_entry)   last_or_epoch(&g->log, &out->last_entry[go].x, &out->last_entry[go].y);
+}
+/* A chunk of consecutive positions, ROW-major: every column of the batch is [row][group], so walking a row across the
+   chunk streams contiguous memory, while one group's rows lie rows * n * 8 bytes apart (a different page per access).  The
+   per-group order of rows — the only order the semantics fix — is unchanged; the 64 contexts of a chunk stay in L1/L2. */
+static void step_chunk(orc_engine_t* e, const rafting_inbox_t* in, const rafting_outbox_t* out,
+                       uint32_t c0, uint32_t c1, uint32_t n, uint64_t* events) {
+    for (uint32_t i = c0; i < c1; i++) {
+        uint32_t gid = in->gids ? in->gids[i] : i;
+        if (gid < e->cfg.max_groups) { e->groups[gid].persistDirty = 0; e->groups[gid].commitDirty = 0; }
+    }
+    for (uint32_t r = 0; r < in->rows; r++)
+        for (uint32_t i = c0; i < c1; i++) {
+            uint32_t gid = in->gids ? in->gids[i] : i;
+            if (gid < e->cfg.max_groups) step_row(e, in, out, i, n, gid, &e->groups[gid], r, events);
+        }
+    for (uint32_t i = c0; i < c1; i++) {
+        uint32_t gid = in->gids ? in->gids[i] : i;
+        if (gid < e->cfg.max_groups) step_end(in, out, i, gid, &e->groups[gid]);
+    }
 }
 
 /* The loop threads live as long as the engine (the reference's ContextLoop-k threads do, too): a step hands every
@@ -1040,7 +1056,7 @@ static void run_share(orc_pool_t* p, int t) {
         const uint32_t c = __atomic_fetch_add(&p->next_chunk, 1u, __ATOMIC_RELAXED);
         if (c >= nchunks) break;
         const uint32_t c0 = c * 64u, c1 = c0 + 64u < p->n ? c0 + 64u : p->n;
-        for (uint32_t i = c0; i < c1; i++) step_group(p->e, p->in, p->out, i, p->n, &ev);
+        step_chunk(p->e, p->in, p->out, c0, c1, p->n, &ev);
     }
     p->events[t] = ev;
 }
@@ -1090,7 +1106,7 @@ int orc_step(orc_engine_t* e, const rafting_inbox_t* in, const rafting_outbox_t*
     uint32_t n = in->gids ? in->n_active : e->cfg.max_groups;
     if (threads <= 1) {
         uint64_t ev = 0;
-        for (uint32_t i = 0; i < n; i++) step_group(e, in, out, i, n, &ev);
+        for (uint32_t c0 = 0; c0 < n; c0 += 64u) step_chunk(e, in, out, c0, c0 + 64u < n ? c0 + 64u : n, n, &ev);
         e->events += ev;
         return 0;
     }

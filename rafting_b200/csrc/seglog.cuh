@@ -21,14 +21,19 @@
 //
 // Included at the end of engine.cu (same translation unit: it uses rafting_engine, fail(), CU()).
 #pragma once
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace rafting {
 
 struct alignas(16) SegHdr { uint32_t gid, len; int64_t index, term; uint64_t seq; };
 static_assert(sizeof(SegHdr) == 32, "segment record header");
 
-struct HostLoc { uint64_t off; uint32_t len; int64_t term; };      // len == 0xffffffff: absent
-struct GroupIdx { int64_t base = 0; std::vector<HostLoc> v; };     // host index of one group: v[i] <-> index base + i
+struct HostLoc { uint64_t off; uint32_t len; int64_t term; uint64_t file_off; };      // len == 0xffffffff: absent; file_off: payload offset in the durable file (~0 = none)
+constexpr uint64_t NO_FILE = ~0ull, NO_ARENA = ~0ull;                                  // off == NO_ARENA: recovered from the file, never resident
+struct GroupIdx { int64_t base = 0; std::vector<HostLoc> v; int64_t epoch_index = 0, epoch_term = 0; };     // host index of one group: v[i] <-> index base + i
 
 struct SegLog {
     uint32_t seg_bytes = 0, nseg = 0, K = 0;
@@ -44,6 +49,16 @@ struct SegLog {
     uint8_t* d_blob = nullptr; size_t d_blob_cap = 0;      // staged payload blob of the append in flight
     uint8_t* d_out = nullptr; size_t d_out_cap = 0;
     cudaStream_t s_spill = nullptr;
+    cudaStream_t s_log = nullptr;             // every append / gather / read of the entry buffer runs here: the step kernel's stream
+                                              // never waits for payload traffic (only the other way round, for the stored key ranges)
+    cudaEvent_t ev_tables = nullptr, ev_log = nullptr;
+    // durable tier (rafting_log_store_open): every appended record is also framed into an append-only file; fdatasync is one
+    // call per step (rafting_log_sync).  The file doubles as the coldest tier, which is what lets the pinned pool be bounded.
+    int wal_fd = -1; uint64_t wal_bytes = 0, wal_synced = 0, wal_syncs = 0; bool wal_failed = false;
+    std::vector<uint8_t> wal_buf;
+    uint32_t cold_max = 0;                    // pinned cold segments kept at most (0 = unbounded; needs the file tier)
+    std::vector<uint64_t> cold_lru;           // spilled segments in spill order
+    uint64_t cold_evicted = 0, file_hits = 0;
     uint64_t appended = 0, spilled_bytes = 0, hbm_hits = 0, cold_hits = 0, indexed = 0;
     std::vector<uint32_t> seg_live;           // live (indexed, not overwritten, not trimmed) records per logical segment
     uint64_t trimmed = 0, cold_freed_bytes = 0, spills_skipped = 0;
@@ -114,7 +129,11 @@ using rafting::SegLog; using rafting::SegHdr; using rafting::HostLoc; using raft
 
 static void seglog_release(rafting_engine* e) {
     SegLog* L = e->seglog; if (!L) return;
+    if (L->s_log) { cudaStreamSynchronize(L->s_log); cudaStreamDestroy(L->s_log); }
     if (L->s_spill) { cudaStreamSynchronize(L->s_spill); cudaStreamDestroy(L->s_spill); }
+    if (L->ev_tables) cudaEventDestroy(L->ev_tables);
+    if (L->ev_log) cudaEventDestroy(L->ev_log);
+    if (L->wal_fd >= 0) close(L->wal_fd);
     for (auto ev : L->cold_ready) if (ev) cudaEventDestroy(ev);
     for (auto p : L->cold) if (p) cudaFreeHost(p);
     if (L->arena) cudaFree(L->arena);
@@ -142,6 +161,9 @@ extern "C" int rafting_log_config(rafting_engine_t* e, uint32_t segment_bytes, u
     CU(cudaMalloc(&L->ring, ring * 8));
     CU(cudaMemset(L->ring, 0, ring * 8));                          // 0 = empty slot
     CU(cudaStreamCreateWithFlags(&L->s_spill, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&L->s_log, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&L->ev_tables, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&L->ev_log, cudaEventDisableTiming));
     if (!e->ev_seg) CU(cudaEventCreateWithFlags(&e->ev_seg, cudaEventDisableTiming));
     return RAFTING_OK;
 }
@@ -152,18 +174,37 @@ static inline const HostLoc* seglog_find(const SegLog* L, uint32_t gid, int64_t 
     const HostLoc& h = gi.v[(size_t)(index - gi.base)];
     return h.len == 0xffffffffu ? nullptr : &h;
 }
+constexpr int64_t SEGLOG_INDEX_WINDOW = 1 << 22;      // indices one group's host index spans at most (4 M entries, 128 MB of index)
+static inline void seglog_drop(SegLog* L, const HostLoc& h) {
+    if (h.len == 0xffffffffu) return;
+    if (h.off != rafting::NO_ARENA) L->seg_live[h.off / L->seg_bytes]--;
+    L->indexed--;
+}
 static inline void seglog_put(SegLog* L, uint32_t gid, int64_t index, const HostLoc& hl) {
     rafting::GroupIdx& gi = L->index[gid];
-    const HostLoc none = {0, 0xffffffffu, 0};
+    const HostLoc none = {0, 0xffffffffu, 0, rafting::NO_FILE};
     if (gi.v.empty()) gi.base = index;
+    // An index far from everything stored (an InstallSnapshot moved the follower's log, RaftRoutine.java:408-445) starts a
+    // new window instead of materialising the gap: what lay on the other side of it is no longer reachable by any plan.
+    if (index < gi.base - SEGLOG_INDEX_WINDOW || index >= gi.base + (int64_t)gi.v.size() + SEGLOG_INDEX_WINDOW) {
+        for (const HostLoc& h : gi.v) seglog_drop(L, h);
+        gi.v.clear(); gi.base = index;
+    }
     if (index < gi.base) { gi.v.insert(gi.v.begin(), (size_t)(gi.base - index), none); gi.base = index; }
     if (index >= gi.base + (int64_t)gi.v.size()) gi.v.resize((size_t)(index - gi.base) + 1, none);
+    if (gi.v.size() > (size_t)SEGLOG_INDEX_WINDOW) {                // keep the newest window
+        const size_t cut = gi.v.size() - (size_t)SEGLOG_INDEX_WINDOW;
+        for (size_t k = 0; k < cut; k++) seglog_drop(L, gi.v[k]);
+        gi.v.erase(gi.v.begin(), gi.v.begin() + (ptrdiff_t)cut); gi.base += (int64_t)cut;
+    }
     HostLoc& slot = gi.v[(size_t)(index - gi.base)];
     if (slot.len == 0xffffffffu) L->indexed++;
-    else L->seg_live[slot.off / L->seg_bytes]--;                   // the overwritten record is dead
-    const uint64_t seg = hl.off / L->seg_bytes;
-    if (L->seg_live.size() <= seg) L->seg_live.resize(seg + 1, 0);
-    L->seg_live[seg]++;
+    else if (slot.off != rafting::NO_ARENA) L->seg_live[slot.off / L->seg_bytes]--;   // the overwritten record is dead
+    if (hl.off != rafting::NO_ARENA) {
+        const uint64_t seg = hl.off / L->seg_bytes;
+        if (L->seg_live.size() <= seg) L->seg_live.resize(seg + 1, 0);
+        L->seg_live[seg]++;
+    }
     slot = hl;                                                     // RocksDB put: the latest value wins
 }
 
@@ -179,31 +220,57 @@ static int seglog_spill_for(rafting_engine* e, SegLog* L, uint64_t new_head) {
         }
         CU(cudaHostAlloc((void**)&L->cold[s], L->seg_bytes, cudaHostAllocDefault));
         CU(cudaEventCreateWithFlags(&L->cold_ready[s], cudaEventDisableTiming));
-        CU(cudaEventRecord(e->ev_seg, e->stream));                 // the spill sees every append already enqueued
+        CU(cudaEventRecord(e->ev_seg, L->s_log));                  // the spill sees every append already enqueued
         CU(cudaStreamWaitEvent(L->s_spill, e->ev_seg, 0));
         CU(cudaMemcpyAsync(L->cold[s], L->arena + (s % L->nseg) * (uint64_t)L->seg_bytes, L->seg_bytes, cudaMemcpyDeviceToHost, L->s_spill));
         CU(cudaEventRecord(L->cold_ready[s], L->s_spill));
-        CU(cudaStreamWaitEvent(e->stream, L->cold_ready[s], 0));   // later appends into that arena slot wait for it
+        CU(cudaStreamWaitEvent(L->s_log, L->cold_ready[s], 0));    // later appends into that arena slot wait for it
         L->spilled_upto = s + 1; L->spilled_bytes += L->seg_bytes;
+        L->cold_lru.push_back(s);
+        // bounded pinned pool: the oldest cold copies go once the file tier holds the same bytes durably
+        while (L->cold_max && L->wal_fd >= 0 && L->cold_lru.size() > L->cold_max) {
+            const uint64_t v = L->cold_lru.front();
+            if (L->cold[v]) {
+                if ((v + 1) * (uint64_t)L->seg_bytes > L->head) break;
+                CU(cudaEventSynchronize(L->cold_ready[v]));
+                cudaFreeHost(L->cold[v]); L->cold[v] = nullptr;
+                cudaEventDestroy(L->cold_ready[v]); L->cold_ready[v] = nullptr;
+                L->cold_evicted++;
+            }
+            L->cold_lru.erase(L->cold_lru.begin());
+        }
     }
     return RAFTING_OK;
 }
 
-extern "C" int rafting_log_append(rafting_engine_t* e, const rafting_entry_ref_t* refs, uint32_t n, const void* blob, size_t blob_bytes) {
+static int seglog_wal_put(SegLog* L, const rafting_entry_ref_t* refs, uint32_t n, const uint8_t* blob, std::vector<uint64_t>& file_offs);
+static int log_append_impl(rafting_engine_t* e, const rafting_entry_ref_t* refs, uint32_t n, const void* blob, size_t blob_bytes) {
     if (!e || !e->seglog) return fail(RAFTING_E_INVAL, "entry buffer not configured (rafting_log_config)");
     if (n == 0) return RAFTING_OK;
     if (!refs || (!blob && blob_bytes)) return fail(RAFTING_E_INVAL, "null argument");
     SegLog* L = e->seglog;
     CU(cudaSetDevice(e->cfg.device));
+    // every ref is checked before anything changes: a bad one must not leave earlier entries of the batch indexed at arena
+    // offsets that were never written
+    for (uint32_t i = 0; i < n; i++) {
+        if (refs[i].gid >= e->G) return fail(RAFTING_E_INVAL, "ref %u: gid out of range", i);
+        if (refs[i].index <= 0) return fail(RAFTING_E_INVAL, "ref %u: log indices start at 1", i);
+        if (refs[i].blob_off > blob_bytes || (uint64_t)refs[i].len > blob_bytes - refs[i].blob_off) return fail(RAFTING_E_INVAL, "ref %u: payload beyond the blob", i);
+        if (sizeof(SegHdr) + (((uint64_t)refs[i].len + 15) & ~15ull) > L->seg_bytes) return fail(RAFTING_E_CAPACITY, "ref %u: record larger than a segment", i);
+    }
+    if ((uint64_t)L->seg_bytes * (L->nseg - 1) < sizeof(SegHdr) + 16) return fail(RAFTING_E_CAPACITY, "arena too small for a single record");
+    // durable tier first (write-ahead): the records are framed into the file buffer; rafting_log_sync makes them durable
+    std::vector<uint64_t> file_offs;
+    if (L->wal_fd >= 0) { int rc = seglog_wal_put(L, refs, n, (const uint8_t*)blob, file_offs); if (rc) return rc; }
     // the payload blob travels to the device once and stays there while the sub-batches below are scattered
     // (pin it on the host for a truly asynchronous copy)
-    CU(cudaStreamSynchronize(e->stream));                          // previous append done with d_blob / staging
+    CU(cudaStreamSynchronize(L->s_log));                          // previous append done with d_blob / staging
     if (blob_bytes > L->d_blob_cap) {
         if (L->d_blob) cudaFree(L->d_blob);
         L->d_blob_cap = blob_bytes + blob_bytes / 2 + 256;
         CU(cudaMalloc((void**)&L->d_blob, L->d_blob_cap));
     }
-    if (blob_bytes) CU(cudaMemcpyAsync(L->d_blob, blob, blob_bytes, cudaMemcpyHostToDevice, e->stream));
+    if (blob_bytes) CU(cudaMemcpyAsync(L->d_blob, blob, blob_bytes, cudaMemcpyHostToDevice, L->s_log));
     const uint64_t room = (uint64_t)L->seg_bytes * (L->nseg - 1), arena_bytes = (uint64_t)L->seg_bytes * L->nseg;
     uint32_t done = 0;
     while (done < n) {
@@ -211,24 +278,22 @@ extern "C" int rafting_log_append(rafting_engine_t* e, const rafting_entry_ref_t
         // minus one segment, would be exceeded
         const size_t need = (size_t)(n - done) * sizeof(AppendRec);
         if (need > L->stage_cap) {
-            CU(cudaStreamSynchronize(e->stream));
+            CU(cudaStreamSynchronize(L->s_log));
             if (L->stage) cudaFreeHost(L->stage);
             L->stage_cap = need + need / 2;
             CU(cudaHostAlloc((void**)&L->stage, L->stage_cap, cudaHostAllocDefault));
-        } else if (done) CU(cudaStreamSynchronize(e->stream));     // the previous sub-batch has left the staging buffer
+        } else if (done) CU(cudaStreamSynchronize(L->s_log));     // the previous sub-batch has left the staging buffer
         AppendRec* recs = (AppendRec*)L->stage;
         uint64_t head = L->head; uint32_t m = 0;
         for (uint32_t i = done; i < n; i++) {
-            if (refs[i].gid >= e->G) return fail(RAFTING_E_INVAL, "ref %u: gid out of range", i);
-            if ((uint64_t)refs[i].blob_off + refs[i].len > blob_bytes) return fail(RAFTING_E_INVAL, "ref %u: payload beyond the blob", i);
             const uint64_t rec = sizeof(SegHdr) + (((uint64_t)refs[i].len + 15) & ~15ull);
-            if (rec > L->seg_bytes) return fail(RAFTING_E_CAPACITY, "ref %u: record larger than a segment", i);
             uint64_t h2 = head;
             if (h2 / L->seg_bytes != (h2 + rec - 1) / L->seg_bytes) h2 = (h2 / L->seg_bytes + 1) * L->seg_bytes;   // skip the tail
             if (h2 + rec - L->head > room) break;
             AppendRec& r = recs[m];
             r.gid = refs[i].gid; r.len = refs[i].len; r.index = refs[i].index; r.term = refs[i].term; r.loc = h2; r.src = refs[i].blob_off;
             HostLoc hl; hl.off = h2; hl.len = refs[i].len; hl.term = refs[i].term;
+            hl.file_off = file_offs.empty() ? rafting::NO_FILE : file_offs[i];
             seglog_put(L, refs[i].gid, refs[i].index, hl);
             head = h2 + rec; m++;
         }
@@ -236,13 +301,13 @@ extern "C" int rafting_log_append(rafting_engine_t* e, const rafting_entry_ref_t
         int rc = seglog_spill_for(e, L, head); if (rc) return rc;
         const size_t rec_bytes = (size_t)m * sizeof(AppendRec);
         if (rec_bytes > L->d_req_cap) {
-            CU(cudaStreamSynchronize(e->stream));
+            CU(cudaStreamSynchronize(L->s_log));
             if (L->d_req) cudaFree(L->d_req);
             L->d_req_cap = rec_bytes * 2;
             CU(cudaMalloc(&L->d_req, L->d_req_cap));
         }
-        CU(cudaMemcpyAsync(L->d_req, recs, rec_bytes, cudaMemcpyHostToDevice, e->stream));
-        rafting::seglog_scatter_kernel<<<(uint32_t)(((uint64_t)m * 8 + 255) / 256), 256, 0, e->stream>>>(
+        CU(cudaMemcpyAsync(L->d_req, recs, rec_bytes, cudaMemcpyHostToDevice, L->s_log));
+        rafting::seglog_scatter_kernel<<<(uint32_t)(((uint64_t)m * 8 + 255) / 256), 256, 0, L->s_log>>>(
             (const AppendRec*)L->d_req, m, L->appended, L->d_blob, L->arena, arena_bytes, L->ring, L->K);
         CU(cudaGetLastError());
         L->head = head; L->appended += m; done += m;
@@ -250,13 +315,29 @@ extern "C" int rafting_log_append(rafting_engine_t* e, const rafting_entry_ref_t
     return RAFTING_OK;
 }
 
+// no C++ exception may cross the C ABI (a host index that cannot grow is RAFTING_E_NOMEM, not std::terminate)
+extern "C" int rafting_log_append(rafting_engine_t* e, const rafting_entry_ref_t* refs, uint32_t n, const void* blob, size_t blob_bytes) {
+    try { return log_append_impl(e, refs, n, blob, blob_bytes); }
+    catch (const std::bad_alloc&) { return fail(RAFTING_E_NOMEM, "rafting_log_append: out of host memory"); }
+    catch (const std::exception& ex) { return fail(RAFTING_E_NOMEM, "rafting_log_append: %s", ex.what()); }
+}
+
 // stored key range of a group straight from the tables (RocksLog visibility: epoch / truncate are metadata)
+// the tables are written by the step kernels: a read of the stored key ranges is ordered behind every step enqueued so
+// far (event on the step stream, waited for by the log stream) — the step stream itself never waits for the entry buffer
+static int seglog_after_tables(rafting_engine* e, SegLog* L) {
+    CU(cudaEventRecord(L->ev_tables, e->stream));
+    CU(cudaStreamWaitEvent(L->s_log, L->ev_tables, 0));
+    return RAFTING_OK;
+}
 static int seglog_range(rafting_engine* e, uint32_t gid, int64_t* lo, int64_t* hi) {
+    SegLog* L = e->seglog;
+    int rc0 = seglog_after_tables(e, L); if (rc0) return rc0;
     uint64_t meta;
-    CU(cudaMemcpyAsync(&meta, e->T.g_meta + gid, 8, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(lo, e->T.g_lo + gid, 8, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaMemcpyAsync(hi, e->T.g_hi + gid, 8, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpyAsync(&meta, e->T.g_meta + gid, 8, cudaMemcpyDeviceToHost, L->s_log));
+    CU(cudaMemcpyAsync(lo, e->T.g_lo + gid, 8, cudaMemcpyDeviceToHost, L->s_log));
+    CU(cudaMemcpyAsync(hi, e->T.g_hi + gid, 8, cudaMemcpyDeviceToHost, L->s_log));
+    CU(cudaStreamSynchronize(L->s_log));
     if ((((uint32_t)meta >> rafting::W_NRUNS_SH) & 0xf) == 0) { *lo = 1; *hi = 0; }
     return RAFTING_OK;
 }
@@ -265,18 +346,37 @@ static inline bool seglog_resident(const SegLog* L, uint64_t off) {
     return off / L->seg_bytes + L->nseg > newest;
 }
 static int seglog_fetch(rafting_engine* e, SegLog* L, const HostLoc& hl, void* dst) {
+    (void)e;
     const uint64_t arena_bytes = (uint64_t)L->seg_bytes * L->nseg;
-    const uint64_t seg = hl.off / L->seg_bytes;
-    if (seglog_resident(L, hl.off)) {                              // still in HBM
-        CU(cudaMemcpyAsync(dst, L->arena + (hl.off % arena_bytes) + sizeof(SegHdr), hl.len, cudaMemcpyDeviceToHost, e->stream));
+    if (hl.off != rafting::NO_ARENA && seglog_resident(L, hl.off)) {                            // still in HBM
+        CU(cudaMemcpyAsync(dst, L->arena + (hl.off % arena_bytes) + sizeof(SegHdr), hl.len, cudaMemcpyDeviceToHost, L->s_log));
         L->hbm_hits++;
-    } else {                                                       // cold tier
-        if (seg >= L->cold.size() || !L->cold[seg]) return fail(RAFTING_E_INVAL, "segment %llu neither resident nor spilled", (unsigned long long)seg);
+        return RAFTING_OK;
+    }
+    const uint64_t seg = hl.off == rafting::NO_ARENA ? ~0ull : hl.off / L->seg_bytes;
+    if (seg < L->cold.size() && L->cold[seg]) {                                                 // pinned cold tier
         CU(cudaEventSynchronize(L->cold_ready[seg]));
         memcpy(dst, L->cold[seg] + (hl.off % L->seg_bytes) + sizeof(SegHdr), hl.len);
         L->cold_hits++;
+        return RAFTING_OK;
     }
-    return RAFTING_OK;
+    if (hl.file_off != rafting::NO_FILE && L->wal_fd >= 0) {                                    // durable file tier
+        if (hl.file_off + hl.len > L->wal_bytes - L->wal_buf.size()) {                          // still in the write buffer
+            const uint64_t flushed = L->wal_bytes - L->wal_buf.size();
+            if (hl.file_off >= flushed) { memcpy(dst, L->wal_buf.data() + (hl.file_off - flushed), hl.len); L->file_hits++; return RAFTING_OK; }
+            return fail(RAFTING_E_INVAL, "record straddles the file buffer");
+        }
+        size_t got = 0;
+        while (got < hl.len) {
+            const ssize_t r = pread(L->wal_fd, (uint8_t*)dst + got, hl.len - got, (off_t)(hl.file_off + got));
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) return fail(RAFTING_E_CUDA, "pread of the entry file failed: %s", r < 0 ? strerror(errno) : "short file");
+            got += (size_t)r;
+        }
+        L->file_hits++;
+        return RAFTING_OK;
+    }
+    return fail(RAFTING_E_INVAL, "segment %llu neither resident, nor in the pinned pool, nor on file", (unsigned long long)seg);
 }
 
 extern "C" int rafting_log_read(rafting_engine_t* e, uint32_t gid, int64_t first_index, uint32_t max_n,
@@ -296,7 +396,7 @@ extern "C" int rafting_log_read(rafting_engine_t* e, uint32_t gid, int64_t first
         refs_out[n].gid = gid; refs_out[n].len = hl->len; refs_out[n].index = idx; refs_out[n].term = hl->term; refs_out[n].blob_off = used;
         used += ((size_t)hl->len + 15) & ~(size_t)15; n++;
     }
-    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(L->s_log));
     *n_out = n;
     return RAFTING_OK;
 }
@@ -324,7 +424,7 @@ extern "C" int rafting_log_gather(rafting_engine_t* e, uint32_t n_ranges, const 
             if (hl) {
                 if (used + hl->len > blob_cap) return fail(RAFTING_E_CAPACITY, "blob_out too small");
                 o.len = hl->len; o.term = hl->term;
-                if (seglog_resident(L, hl->off)) { GatherReq q; q.gid = gids[r]; q.slot = m; q.index = idx; q.out_off = used; req.push_back(q); }
+                if (hl->off != rafting::NO_ARENA && seglog_resident(L, hl->off)) { GatherReq q; q.gid = gids[r]; q.slot = m; q.index = idx; q.out_off = used; req.push_back(q); }
                 else if (hl->len) cold.push_back(m);
                 used += ((size_t)hl->len + 15) & ~(size_t)15;
             }
@@ -334,7 +434,7 @@ extern "C" int rafting_log_gather(rafting_engine_t* e, uint32_t n_ranges, const 
     const uint32_t nq = (uint32_t)req.size();
     if (nq) {
         const size_t req_bytes = (size_t)nq * sizeof(GatherReq), len_bytes = (size_t)nq * 4;
-        if (req_bytes + len_bytes > L->d_req_cap || used > L->d_out_cap) CU(cudaStreamSynchronize(e->stream));
+        if (req_bytes + len_bytes > L->d_req_cap || used > L->d_out_cap) CU(cudaStreamSynchronize(L->s_log));
         if (req_bytes + len_bytes > L->d_req_cap) {
             if (L->d_req) cudaFree(L->d_req);
             L->d_req_cap = (req_bytes + len_bytes) * 2;
@@ -346,19 +446,19 @@ extern "C" int rafting_log_gather(rafting_engine_t* e, uint32_t n_ranges, const 
             CU(cudaMalloc((void**)&L->d_out, L->d_out_cap));
         }
         uint32_t* d_lens = (uint32_t*)((uint8_t*)L->d_req + req_bytes);
-        CU(cudaMemcpyAsync(L->d_req, req.data(), req_bytes, cudaMemcpyHostToDevice, e->stream));
+        CU(cudaMemcpyAsync(L->d_req, req.data(), req_bytes, cudaMemcpyHostToDevice, L->s_log));
         if (!L->t0) { CU(cudaEventCreate(&L->t0)); CU(cudaEventCreate(&L->t1)); }
         const uint64_t newest = L->head ? (L->head - 1) / L->seg_bytes : 0;
         const uint64_t oldest = newest + 1 >= L->nseg ? (newest + 1 - L->nseg) * (uint64_t)L->seg_bytes : 0;
-        CU(cudaEventRecord(L->t0, e->stream));
-        rafting::seglog_gather_kernel<<<(uint32_t)(((uint64_t)nq * 8 + 255) / 256), 256, 0, e->stream>>>(
+        CU(cudaEventRecord(L->t0, L->s_log));
+        rafting::seglog_gather_kernel<<<(uint32_t)(((uint64_t)nq * 8 + 255) / 256), 256, 0, L->s_log>>>(
             (const GatherReq*)L->d_req, nq, L->ring, L->K, L->arena, (uint64_t)L->seg_bytes * L->nseg, oldest, d_lens, L->d_out);
         CU(cudaGetLastError());
-        CU(cudaEventRecord(L->t1, e->stream));
+        CU(cudaEventRecord(L->t1, L->s_log));
         std::vector<uint32_t> lens(nq);
-        CU(cudaMemcpyAsync(lens.data(), d_lens, len_bytes, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaMemcpyAsync(blob_out, L->d_out, used, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpyAsync(lens.data(), d_lens, len_bytes, cudaMemcpyDeviceToHost, L->s_log));
+        CU(cudaMemcpyAsync(blob_out, L->d_out, used, cudaMemcpyDeviceToHost, L->s_log));
+        CU(cudaStreamSynchronize(L->s_log));
         CU(cudaEventElapsedTime(&L->last_gather_kernel_ms, L->t0, L->t1));
         L->last_gather_bytes = used;
         // ring misses (the slot now caches a newer index of the same group): direct copy through the host index
@@ -373,7 +473,7 @@ extern "C" int rafting_log_gather(rafting_engine_t* e, uint32_t n_ranges, const 
         const rafting_entry_ref_t& o = refs_out[k];
         int rc = seglog_fetch(e, L, *seglog_find(L, o.gid, o.index), (uint8_t*)blob_out + o.blob_off); if (rc) return rc;
     }
-    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamSynchronize(L->s_log));
     *n_out = m;
     if (bytes_out) *bytes_out = used;
     return RAFTING_OK;
@@ -388,11 +488,12 @@ extern "C" int rafting_log_trim(rafting_engine_t* e, uint32_t first_gid, uint32_
     SegLog* L = e->seglog;
     CU(cudaSetDevice(e->cfg.device));
     std::vector<uint64_t> meta(count); std::vector<int64_t> lo(count), hi(count);
+    { int rc0 = seglog_after_tables(e, L); if (rc0) return rc0; }
     if (count) {
-        CU(cudaMemcpyAsync(meta.data(), e->T.g_meta + first_gid, (size_t)count * 8, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaMemcpyAsync(lo.data(), e->T.g_lo + first_gid, (size_t)count * 8, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaMemcpyAsync(hi.data(), e->T.g_hi + first_gid, (size_t)count * 8, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpyAsync(meta.data(), e->T.g_meta + first_gid, (size_t)count * 8, cudaMemcpyDeviceToHost, L->s_log));
+        CU(cudaMemcpyAsync(lo.data(), e->T.g_lo + first_gid, (size_t)count * 8, cudaMemcpyDeviceToHost, L->s_log));
+        CU(cudaMemcpyAsync(hi.data(), e->T.g_hi + first_gid, (size_t)count * 8, cudaMemcpyDeviceToHost, L->s_log));
+        CU(cudaStreamSynchronize(L->s_log));
     }
     uint64_t dropped = 0, freed = 0;
     for (uint32_t k = 0; k < count; k++) {
@@ -408,7 +509,7 @@ extern "C" int rafting_log_trim(rafting_engine_t* e, uint32_t first_gid, uint32_
         for (int64_t i = 0; i < cut; i++) {
             const HostLoc& h = gi.v[(size_t)i];
             if (h.len == 0xffffffffu) continue;
-            L->seg_live[h.off / L->seg_bytes]--; L->indexed--; dropped++;
+            seglog_drop(L, h); dropped++;
         }
         gi.v.erase(gi.v.begin(), gi.v.begin() + cut);
         gi.base += cut;
@@ -434,4 +535,176 @@ extern "C" int rafting_log_stats(rafting_engine_t* e, uint64_t* out, uint32_t n)
                           L->trimmed, L->cold_freed_bytes, L->spills_skipped};
     for (uint32_t i = 0; i < n && i < 11; i++) out[i] = v[i];
     return 11;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Durable tier ("crash-durable spill file replacing flushWal(true)", RocksLog.java:87,195).  Every appended
+// record is framed into an append-only file BEFORE it is scattered into HBM (write-ahead); rafting_log_sync is the one
+// durability barrier per step (fdatasync) the pump issues before it releases the step's replies.  Truncations and
+// compactions — which in the engine are pure metadata (the stored key range lives in the step kernel's tables) — are
+// logged as RANGE / EPOCH marks by the pump, so that recovery does not resurrect a truncated suffix.  Little-endian frames:
+//     { magic 'RLE1', kind, gid, len, a, b, crc32c(header[0..32) ++ payload), pad }  + payload padded to 8 bytes
+//     PUT a = index, b = term | RANGE a = lowest stored key, b = highest (a > b: empty) | EPOCH a = epoch.index, b = epoch.term
+// The file is also the coldest read tier (pread), which is what allows the pinned pool to be bounded.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr uint32_t WAL_MAGIC = 0x31454C52u;   // "RLE1"
+enum { WAL_PUT = 1, WAL_RANGE = 2, WAL_EPOCH = 3 };
+struct WalHdr { uint32_t magic, kind, gid, len; int64_t a, b; uint32_t crc, pad; };
+static_assert(sizeof(WalHdr) == 40, "entry file frame header");
+uint32_t wal_crc_table[256]; bool wal_crc_ready = false;
+uint32_t wal_crc32c(const void* p, size_t n, uint32_t c) {
+    if (!wal_crc_ready) {
+        for (uint32_t i = 0; i < 256; i++) { uint32_t v = i; for (int k = 0; k < 8; k++) v = (v & 1) ? (v >> 1) ^ 0x82F63B78u : v >> 1; wal_crc_table[i] = v; }
+        wal_crc_ready = true;
+    }
+    const uint8_t* b = (const uint8_t*)p; c = ~c;
+    for (size_t i = 0; i < n; i++) c = wal_crc_table[(c ^ b[i]) & 0xff] ^ (c >> 8);
+    return ~c;
+}
+void wal_frame(std::vector<uint8_t>& buf, uint32_t kind, uint32_t gid, uint32_t len, int64_t a, int64_t b, const uint8_t* payload) {
+    WalHdr h; h.magic = WAL_MAGIC; h.kind = kind; h.gid = gid; h.len = len; h.a = a; h.b = b; h.pad = 0;
+    h.crc = wal_crc32c(payload, len, wal_crc32c(&h, 32, 0));
+    const size_t at = buf.size(), padded = ((size_t)len + 7) & ~(size_t)7;
+    buf.resize(at + sizeof(h) + padded, 0);
+    memcpy(buf.data() + at, &h, sizeof(h));
+    if (len) memcpy(buf.data() + at + sizeof(h), payload, len);
+}
+bool wal_write_all(int fd, const uint8_t* p, size_t n) {
+    while (n) { const ssize_t w = write(fd, p, n); if (w < 0) { if (errno == EINTR) continue; return false; } p += w; n -= (size_t)w; }
+    return true;
+}
+}  // namespace
+
+static int seglog_wal_flush(SegLog* L) {
+    if (L->wal_buf.empty()) return RAFTING_OK;
+    if (L->wal_failed) return fail(RAFTING_E_CUDA, "entry file is failed (an earlier write error): reopen the store");
+    if (!wal_write_all(L->wal_fd, L->wal_buf.data(), L->wal_buf.size())) {
+        // the index already points into the unwritten tail: no later record may be acknowledged as durable
+        L->wal_failed = true;
+        return fail(RAFTING_E_CUDA, "entry file write failed: %s", strerror(errno));
+    }
+    L->wal_buf.clear();
+    return RAFTING_OK;
+}
+static int seglog_wal_put(SegLog* L, const rafting_entry_ref_t* refs, uint32_t n, const uint8_t* blob, std::vector<uint64_t>& file_offs) {
+    if (L->wal_failed) return fail(RAFTING_E_CUDA, "entry file is failed (an earlier write error): reopen the store");
+    file_offs.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        file_offs[i] = L->wal_bytes + sizeof(WalHdr);
+        wal_frame(L->wal_buf, WAL_PUT, refs[i].gid, refs[i].len, refs[i].index, refs[i].term, blob + refs[i].blob_off);
+        L->wal_bytes += sizeof(WalHdr) + (((uint64_t)refs[i].len + 7) & ~7ull);
+    }
+    if (L->wal_buf.size() > (8u << 20)) return seglog_wal_flush(L);
+    return RAFTING_OK;
+}
+
+// opens (creates) the entry file and replays what it holds into the host index: the HBM arena starts empty, recovered
+// records are served from the file.  cold_max_segments bounds the pinned-host pool (0 = unbounded).
+extern "C" int rafting_log_store_open(rafting_engine_t* e, const char* path, uint32_t cold_max_segments, uint64_t* recovered_records) {
+    if (!e || !e->seglog || !path) return fail(RAFTING_E_INVAL, "entry buffer not configured (rafting_log_config)");
+    SegLog* L = e->seglog;
+    if (L->wal_fd >= 0) return fail(RAFTING_E_INVAL, "entry file already open");
+    if (L->appended) return fail(RAFTING_E_INVAL, "open the entry file before the first append");
+    try {
+        const int fd = open(path, O_RDWR | O_CREAT, 0644);
+        if (fd < 0) return fail(RAFTING_E_CUDA, "open %s: %s", path, strerror(errno));
+        uint64_t pos = 0, recs = 0;
+        std::vector<uint8_t> pay;
+        for (;;) {
+            WalHdr h;
+            if (pread(fd, &h, sizeof(h), (off_t)pos) != (ssize_t)sizeof(h)) break;
+            if (h.magic != WAL_MAGIC || h.kind < WAL_PUT || h.kind > WAL_EPOCH || h.gid >= e->G || h.len > L->seg_bytes) break;
+            const size_t padded = ((size_t)h.len + 7) & ~(size_t)7;
+            pay.resize(padded);
+            if (padded && pread(fd, pay.data(), padded, (off_t)(pos + sizeof(h))) != (ssize_t)padded) break;
+            if (wal_crc32c(pay.data(), h.len, wal_crc32c(&h, 32, 0)) != h.crc) break;
+            rafting::GroupIdx& gi = L->index[h.gid];
+            if (h.kind == WAL_PUT) {
+                if (h.a <= 0) break;
+                HostLoc hl; hl.off = rafting::NO_ARENA; hl.len = h.len; hl.term = h.b; hl.file_off = pos + sizeof(h);
+                seglog_put(L, h.gid, h.a, hl);
+            } else if (h.kind == WAL_RANGE) {
+                for (size_t k = 0; k < gi.v.size(); k++) {
+                    const int64_t idx = gi.base + (int64_t)k;
+                    if ((idx < h.a || idx > h.b) && gi.v[k].len != 0xffffffffu) { seglog_drop(L, gi.v[k]); gi.v[k].len = 0xffffffffu; }
+                }
+            } else { gi.epoch_index = h.a; gi.epoch_term = h.b; }
+            pos += sizeof(h) + padded; recs++;
+        }
+        if (ftruncate(fd, (off_t)pos) != 0 || lseek(fd, (off_t)pos, SEEK_SET) < 0) { close(fd); return fail(RAFTING_E_CUDA, "cannot position the entry file: %s", strerror(errno)); }
+        L->wal_fd = fd; L->wal_bytes = pos; L->wal_synced = pos; L->cold_max = cold_max_segments;
+        if (recovered_records) *recovered_records = recs;
+    } catch (const std::exception& ex) { return fail(RAFTING_E_NOMEM, "rafting_log_store_open: %s", ex.what()); }
+    return RAFTING_OK;
+}
+// the durability barrier of a step: everything appended / marked so far is on stable storage when this returns 0
+extern "C" int rafting_log_sync(rafting_engine_t* e) {
+    if (!e || !e->seglog) return fail(RAFTING_E_INVAL, "entry buffer not configured");
+    SegLog* L = e->seglog;
+    if (L->wal_fd < 0) return fail(RAFTING_E_INVAL, "no entry file (rafting_log_store_open)");
+    int rc = seglog_wal_flush(L); if (rc) return rc;
+    if (L->wal_synced == L->wal_bytes) return RAFTING_OK;
+    if (fdatasync(L->wal_fd) != 0) { L->wal_failed = true; return fail(RAFTING_E_CUDA, "fdatasync of the entry file failed: %s", strerror(errno)); }
+    L->wal_synced = L->wal_bytes; L->wal_syncs++;
+    return RAFTING_OK;
+}
+// RocksLog.truncate / flush are deleteRange calls (RocksLog.java:219-242): the pump logs the group's new stored key range
+// (and epoch) so that recovery agrees with the tables.  lo > hi: the store is empty.
+extern "C" int rafting_log_mark(rafting_engine_t* e, uint32_t gid, int64_t lo, int64_t hi, int64_t epoch_index, int64_t epoch_term) {
+    if (!e || !e->seglog || gid >= e->G) return fail(RAFTING_E_INVAL, "bad argument");
+    SegLog* L = e->seglog;
+    if (L->wal_fd < 0) return fail(RAFTING_E_INVAL, "no entry file (rafting_log_store_open)");
+    if (L->wal_failed) return fail(RAFTING_E_CUDA, "entry file is failed: reopen the store");
+    try {
+        wal_frame(L->wal_buf, WAL_RANGE, gid, 0, lo, hi, nullptr); L->wal_bytes += sizeof(WalHdr);
+        wal_frame(L->wal_buf, WAL_EPOCH, gid, 0, epoch_index, epoch_term, nullptr); L->wal_bytes += sizeof(WalHdr);
+        L->index[gid].epoch_index = epoch_index; L->index[gid].epoch_term = epoch_term;
+    } catch (const std::exception& ex) { return fail(RAFTING_E_NOMEM, "rafting_log_mark: %s", ex.what()); }
+    return RAFTING_OK;
+}
+// what RaftContext.initialize needs from a recovered log (RaftContext.java:91-113): epoch, stored key range, last term and
+// the index->term runs (oldest first) for rafting_group_open + rafting_group_load_runs.  *n_runs > cap: RAFTING_E_CAPACITY.
+extern "C" int rafting_log_recovered(rafting_engine_t* e, uint32_t gid, rafting_group_init_t* init, rafting_i64x2_t* runs, uint32_t cap, uint32_t* n_runs) {
+    if (!e || !e->seglog || gid >= e->G || !init || !n_runs) return fail(RAFTING_E_INVAL, "bad argument");
+    const rafting::GroupIdx& gi = e->seglog->index[gid];
+    memset(init, 0, sizeof(*init));
+    init->ballot = -1; init->epoch_index = gi.epoch_index; init->epoch_term = gi.epoch_term; init->first_index = 1; init->last_index = 0;
+    *n_runs = 0;
+    // the stored range is the CONTIGUOUS run of records that ends at the highest one (RocksLog keeps its keys contiguous)
+    int64_t hi = -1;
+    for (size_t k = gi.v.size(); k-- > 0;) if (gi.v[k].len != 0xffffffffu) { hi = gi.base + (int64_t)k; break; }
+    if (hi < 0) return RAFTING_OK;
+    int64_t lo = hi;
+    while (lo - 1 >= gi.base && gi.v[(size_t)(lo - 1 - gi.base)].len != 0xffffffffu) lo--;
+    init->first_index = lo; init->last_index = hi; init->last_term = gi.v[(size_t)(hi - gi.base)].term;
+    uint32_t nr = 0; int64_t t = 0;
+    for (int64_t i = lo; i <= hi; i++) {
+        const int64_t ti = gi.v[(size_t)(i - gi.base)].term;
+        if (i == lo || ti != t) { if (runs && nr < cap) { runs[nr].x = i; runs[nr].y = ti; } nr++; t = ti; }
+    }
+    *n_runs = nr;
+    return nr > cap && runs ? fail(RAFTING_E_CAPACITY, "%u term runs, room for %u", nr, cap) : RAFTING_OK;
+}
+// one stored entry in the reference's RocksDB layout (RocksLog.java:82-89,259-280): key = 8-byte big-endian index,
+// value = 8-byte big-endian term || payload — what src/test/java/.../cluster/LogChecker.java iterates over
+extern "C" int rafting_log_export_kv(rafting_engine_t* e, uint32_t gid, int64_t index, uint8_t key_out[8], void* val_out, size_t val_cap, size_t* val_len) {
+    if (!e || !e->seglog || gid >= e->G || !key_out || !val_out || !val_len) return fail(RAFTING_E_INVAL, "bad argument");
+    SegLog* L = e->seglog;
+    CU(cudaSetDevice(e->cfg.device));
+    const HostLoc* hl = seglog_find(L, gid, index);
+    if (!hl) return fail(RAFTING_E_INVAL, "no such entry");
+    if (val_cap < 8 + (size_t)hl->len) return fail(RAFTING_E_CAPACITY, "value needs %zu bytes", 8 + (size_t)hl->len);
+    for (int i = 0; i < 8; i++) { key_out[i] = (uint8_t)((uint64_t)index >> (56 - 8 * i)); ((uint8_t*)val_out)[i] = (uint8_t)((uint64_t)hl->term >> (56 - 8 * i)); }
+    if (hl->len) { int rc = seglog_fetch(e, L, *hl, (uint8_t*)val_out + 8); if (rc) return rc; CU(cudaStreamSynchronize(L->s_log)); }
+    *val_len = 8 + hl->len;
+    return RAFTING_OK;
+}
+extern "C" int rafting_log_store_stats(rafting_engine_t* e, uint64_t out[6]) {
+    if (!e || !e->seglog || !out) return fail(RAFTING_E_INVAL, "entry buffer not configured");
+    SegLog* L = e->seglog;
+    out[0] = L->wal_bytes; out[1] = L->wal_synced; out[2] = L->wal_syncs; out[3] = L->file_hits; out[4] = L->cold_evicted;
+    uint64_t live = 0; for (auto p : L->cold) if (p) live++;
+    out[5] = live;
+    return RAFTING_OK;
 }

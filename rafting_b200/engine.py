@@ -39,6 +39,7 @@ EXPORTS = [
     "rafting_engine_counters", "rafting_abi_sizes", "rafting_checkpoint", "rafting_restore",
     "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_step_begin_compact", "rafting_step_wait_compact", "rafting_step_fetch_dense", "rafting_backoff_step", "rafting_allgather_join",
     "rafting_log_config", "rafting_log_append", "rafting_log_read", "rafting_log_gather", "rafting_log_trim", "rafting_log_stats",
+    "rafting_log_store_open", "rafting_log_sync", "rafting_log_mark", "rafting_log_recovered", "rafting_log_export_kv", "rafting_log_store_stats",
 ]
 
 
@@ -99,6 +100,12 @@ def lib():
                                          C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]
         L.rafting_log_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.rafting_log_trim.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.rafting_log_store_open.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.rafting_log_sync.argtypes = [C.c_void_p]
+        L.rafting_log_mark.argtypes = [C.c_void_p, C.c_uint32, C.c_int64, C.c_int64, C.c_int64, C.c_int64]
+        L.rafting_log_recovered.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.GroupInit), C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.rafting_log_export_kv.argtypes = [C.c_void_p, C.c_uint32, C.c_int64, C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.rafting_log_store_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 6)]
         L.rafting_engine_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.rafting_engine_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.rafting_abi_sizes.argtypes = [C.POINTER(C.c_uint32), C.c_uint32]
@@ -380,6 +387,37 @@ class Engine:
         _check(lib().rafting_log_trim(self._h, first_gid, self.G - first_gid if count is None else count, C.byref(d), C.byref(f)),
                "rafting_log_trim")
         return d.value, f.value
+
+    # ---- durable tier of the entry buffer (what flushWal(true) gives RocksLog) -------------------------------------------
+    def log_store_open(self, path: str, cold_max_segments: int = 0) -> int:
+        """Opens (creates) the entry file and replays it; returns the number of records recovered."""
+        n = C.c_uint64()
+        _check(lib().rafting_log_store_open(self._h, path.encode(), cold_max_segments, C.byref(n)), "rafting_log_store_open")
+        return n.value
+
+    def log_sync(self):
+        _check(lib().rafting_log_sync(self._h), "rafting_log_sync")
+
+    def log_mark(self, gid: int, lo: int, hi: int, epoch_index: int, epoch_term: int):
+        _check(lib().rafting_log_mark(self._h, gid, lo, hi, epoch_index, epoch_term), "rafting_log_mark")
+
+    def log_recovered(self, gid: int):
+        """-> (abi.GroupInit with epoch / key range / last term, [(first index, term), ...] runs oldest first)"""
+        gi = abi.GroupInit()
+        runs = np.zeros((64, 2), dtype=np.int64)
+        n = C.c_uint32()
+        _check(lib().rafting_log_recovered(self._h, gid, C.byref(gi), runs.ctypes.data, 64, C.byref(n)), "rafting_log_recovered")
+        return gi, [tuple(int(x) for x in r) for r in runs[:n.value]]
+
+    def log_export_kv(self, gid: int, index: int, cap: int = 1 << 16) -> tuple[bytes, bytes]:
+        key, val, n = C.create_string_buffer(8), C.create_string_buffer(cap), C.c_size_t()
+        _check(lib().rafting_log_export_kv(self._h, gid, index, key, val, cap, C.byref(n)), "rafting_log_export_kv")
+        return key.raw, val.raw[:n.value]
+
+    def log_store_stats(self) -> dict:
+        a = (C.c_uint64 * 6)()
+        _check(lib().rafting_log_store_stats(self._h, C.byref(a)), "rafting_log_store_stats")
+        return dict(zip(("file_bytes", "synced_bytes", "syncs", "file_hits", "cold_evicted", "cold_resident"), list(a)))
 
     def allgather_join(self):
         _check(lib().rafting_allgather_join(self._h), "rafting_allgather_join")

