@@ -391,7 +391,7 @@ def run_engine(args):
     assert inbox_bytes == inbox_bytes_per_launch(G, rows, F)
     inboxes = [probe] + [devbatch.DevInbox(rows, G, F, dev, unavail=False) for _ in range(L - 1)]
     settle = devbatch.DevInbox(rows, G, F, dev, unavail=False)
-    SETTLE = 3
+    SETTLE = 8                                # 128 ticks: every follower has acknowledged once, the stream is in steady state
     prev_out = None
     for k in range(SETTLE):
         ic = settle.as_c()
@@ -503,14 +503,16 @@ def run_engine(args):
         # every one of its acks an escape record, and the state right after it is the starting point of every timed pass.
         K2 = int(max(4, min(L, 25)))
         e.restore(); e.checkpoint()                       # (the in-flight table, created by the first compact call, joins the checkpoint)
-        cout0 = compact.CompactOutbox(rows, G, F, esc_cap=1 << 16)
+        ESC_CAP = max(1 << 16, rows * G * F // 16)        # escape records a launch may produce before the dense fallback is needed
+        cout0 = compact.CompactOutbox(rows, G, F, esc_cap=ESC_CAP)
         e.step_compact(compact.encode_inbox(host_inbox(0), None, None), cout0)
         e.checkpoint()
         tags, sent_term = cout0.tags(), cout0.current_term.copy()
         cins, keep = [], []
         couts = []
+        esc_out_max = 0
         for sl in range(NSL):
-            co = compact.CompactOutbox(rows, G, F, esc_cap=1 << 16)
+            co = compact.CompactOutbox(rows, G, F, esc_cap=ESC_CAP)
             for name in co.COLS + ("esc", "counts"):
                 t, v = pinned_like(getattr(co, name)); keep.append(t); setattr(co, name, v)
             couts.append(co)
@@ -520,7 +522,7 @@ def run_engine(args):
                 if len(getattr(ci, name)):
                     t, v = pinned_like(getattr(ci, name)); keep.append(t); setattr(ci, name, v)
             e.step_compact(ci, couts[0])
-            assert int(couts[0].counts[0]) <= couts[0].esc_cap
+            esc_out_max = max(esc_out_max, int(couts[0].counts[0]))
             tags, sent_term = couts[0].tags(), couts[0].current_term.copy()
             cins.append(ci)
         digest_c = e.digest(0, G)
@@ -569,8 +571,10 @@ def run_engine(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(ae, op=dist.ReduceOp.SUM)
+        if esc_out_max > ESC_CAP:
+            raise SystemExit(f"bench.py: a launch produced {esc_out_max} escape records (> {ESC_CAP}): the compact e2e number would need the dense fallback")
         e2e = {"spent": float(t.item()), "h2d": h2d, "d2h": d2h, "acks": float(ae.item()), "launches": n_pass_launch * reps,
-               "launches_per_pass": n_pass_launch, "passes": reps, "exact": e2e_exact, "esc_in": esc_in}
+               "launches_per_pass": n_pass_launch, "passes": reps, "exact": e2e_exact, "esc_in": esc_in, "esc_out_max": esc_out_max}
         del cins, keep, couts
 
         # (B) the DENSE host path of round 1 on a few launches of the same window, for the before / after of the byte cut
@@ -686,7 +690,7 @@ def run_engine(args):
                            "h2d_bytes_per_launch": e2e["h2d"], "d2h_bytes_per_launch": e2e["d2h"],
                            "h2d_bytes_per_ack": e2e["h2d"] / acks_launch, "d2h_bytes_per_ack": e2e["d2h"] / acks_launch,
                            "launches": e2e["launches"], "timed_region_ms": e2e["spent"] * 1e3, "same_end_state_as_device_path": e2e["exact"],
-                           "escape_records_per_launch_up": e2e["esc_in"],
+                           "escape_records_per_launch_up": e2e["esc_in"], "escape_records_per_launch_down_max": e2e["esc_out_max"],
                            "path": "compact (rafting_step_begin_compact / rafting_step_wait_compact)",
                            "note": "wall clock around the compact host path with caller-owned pinned buffers, three launches in flight (H2D / "
                                    "unpack + step + pack kernels / D2H of successive launches overlap); every launch's wire columns cross PCIe up "

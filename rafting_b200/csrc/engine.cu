@@ -340,6 +340,22 @@ static int launch_step(rafting_engine* e, const InboxD& in0, const OutboxD& out,
         classify_kernel<<<(in.n + 255) / 256, 256, 0, st>>>(e->T, in, e->d_perm, e->d_perm_cnt);
         in.perm = e->d_perm; in.perm_cnt = e->d_perm_cnt;
     }
+    // slow classes in their own kernel with their own register cap (RAFTING_SLOW_KERNEL=0 keeps them inside step_kernel;
+    // =2 / =3 pick the other caps compiled in for A/B runs)
+    static const int slowVar = getenv("RAFTING_SLOW_KERNEL") ? atoi(getenv("RAFTING_SLOW_KERNEL")) : 1;
+    if (in.perm && slowVar > 0 && (F == 2 || (F > 2 && F <= 4))) {
+        const uint32_t sb = (in.n + unrolled::SLOW_TPB - 1) / unrolled::SLOW_TPB + (uint32_t)NCLS;
+        if (F == 2) {
+            if (slowVar == 2) unrolled::slow_kernel<2, 6><<<sb, unrolled::SLOW_TPB, 0, st>>>(e->T, in, out, e->d_cfg);
+            else if (slowVar == 3) unrolled::slow_kernel<2, 8><<<sb, unrolled::SLOW_TPB, 0, st>>>(e->T, in, out, e->d_cfg);
+            else unrolled::slow_kernel<2, 4><<<sb, unrolled::SLOW_TPB, 0, st>>>(e->T, in, out, e->d_cfg);
+        } else {
+            if (slowVar == 2) unrolled::slow_kernel<4, 6><<<sb, unrolled::SLOW_TPB, 0, st>>>(e->T, in, out, e->d_cfg);
+            else if (slowVar == 3) unrolled::slow_kernel<4, 8><<<sb, unrolled::SLOW_TPB, 0, st>>>(e->T, in, out, e->d_cfg);
+            else unrolled::slow_kernel<4, 4><<<sb, unrolled::SLOW_TPB, 0, st>>>(e->T, in, out, e->d_cfg);
+        }
+        in.flags |= INBOX_INTERNAL_SLOW_ELSEWHERE;
+    }
     if (F == 1) rc = launch_t<1, 3>(e, in, out, st);
 #ifndef RAFTING_NST2
 #define RAFTING_NST2 3

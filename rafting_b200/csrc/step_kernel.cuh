@@ -147,6 +147,7 @@ struct __align__(16) Stage {             // one staged input row of this block
 // and a chunk stays contiguous for coalescing).
 constexpr int NCLS = 4;
 constexpr uint32_t INBOX_INTERNAL_FAST_ELSEWHERE = 1u << 31;   // InboxD.flags: the steady-leader class runs in pair_kernel
+constexpr uint32_t INBOX_INTERNAL_SLOW_ELSEWHERE = 1u << 30;   // InboxD.flags: the slow classes run in slow_kernel
 __global__ void __launch_bounds__(256) classify_kernel(Tables T, InboxD in, uint32_t* __restrict__ perm, uint32_t* __restrict__ cnt) {
     __shared__ uint32_t wcnt[NCLS][8], base[NCLS];
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;

@@ -1,0 +1,25 @@
+#!/bin/bash
+mkdir -p gpurun_out
+O=gpurun_out
+for v in 0 1 2 3; do
+  RAFTING_SLOW_KERNEL=$v timeout 600 python tools/bench_secondary.py > $O/r2_slow_v$v.jsonl 2> $O/r2_slow_v$v.err
+  python - <<PY
+import json
+for l in open("$O/r2_slow_v$v.jsonl"):
+    try:
+        r=json.loads(l); print("slow variant $v", r["config"], "ms %.4f"%r["kernel_ms_per_step_median"], "frac %.3f"%r["roofline"]["frac"], r["end_state"])
+    except Exception as ex: print("parse", ex)
+PY
+done
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > $O/r2_gputest4.txt; tail -3 $O/r2_gputest4.txt
+timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $O/r2_ref4.json 2> $O/r2_ref4.err
+timeout 1500 python bench.py --steps 20 --warmup 5 > $O/r2_bench4.json 2> $O/r2_bench4.err
+python - <<PY
+import json
+for f in ("r2_ref4","r2_bench4"):
+    try:
+        d=json.load(open("$O/%s.json"%f)); print(f, "value %.4g"%d["value"], "e2e %.4g"%d["e2e"]["value"], "ms/step %.3f"%d["ms_per_step"], {k:v for k,v in d.get("cpu_baseline",{}).items() if k!="sample"})
+        if "roofline" in d: print("  kernel_ms", d["roofline"]["kernel_ms"], "frac", d["roofline"]["frac"], d["clocks"]); print("  e2e", {k:v for k,v in d["e2e"].items() if k!="note"}); print("  sec", [(s["config"], s["kernel_ms_per_step"], s["roofline_frac"]) for s in d.get("secondary_rates",[])])
+    except Exception as ex: print(f, "failed", ex)
+PY
+tail -3 $O/r2_bench4.err
