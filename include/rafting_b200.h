@@ -492,6 +492,11 @@ int rafting_log_term    (rafting_engine_t* e, uint32_t gid, int64_t index, int64
 int rafting_checkpoint(rafting_engine_t* e);
 int rafting_restore   (rafting_engine_t* e);
 int rafting_restore_async(rafting_engine_t* e);   /* the same, enqueued on the step stream without a host synchronisation */
+/* the same state as ONE file that survives the process (planned restart / move of a shard): header + checksummed blocks,
+   written to <path>.tmp, fdatasync'ed and renamed.  Load needs an engine created with the same max_groups / replicas; it
+   verifies every block before touching the tables.  Drains the step stream; RAFTING_E_BUSY while a host step is in flight. */
+int rafting_state_save(rafting_engine_t* e, const char* path);
+int rafting_state_load(rafting_engine_t* e, const char* path);
 
 /* ---- HBM-resident segmented entry buffer with async pinned-host spill (rafting_b200/csrc/seglog.cuh) ----
    Payload side of RaftLog (M/command/RaftLog.java:72-132; RocksLog.java:82-242): newEntry/append ->

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <string>
 #include <vector>
 
 #include "step_kernel.cuh"
@@ -110,6 +111,7 @@ static int dalloc(rafting_engine* e, T** p, size_t count) {
 static void rafting_hostpath_release(rafting_engine* e);
 static void seglog_release(rafting_engine* e);
 static void compact_release(rafting_engine* e);
+static int compact_state(rafting_engine* e);
 static int quiesce_for_table_edit(rafting_engine* e, const char* who);
 extern "C" uint32_t rafting_abi_version(void) { return RAFTING_ABI_VERSION; }
 extern "C" const char* rafting_last_error(void) { return g_err; }
@@ -894,6 +896,96 @@ extern "C" int rafting_restore(rafting_engine_t* e) {
 extern "C" int rafting_restore_async(rafting_engine_t* e) {          // enqueued on the step stream, no host synchronisation
     if (!e) return fail(RAFTING_E_INVAL, "null argument");
     return restore_enqueue(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+// exportable checkpoint: the tables of a shard as ONE file that survives the process.
+// RaftContext.initialize rebuilds a context from StableLock + RaftLog (RaftContext.java:91-113) and starts every group as a
+// Follower; a planned restart of a pump (upgrade, rebalance to another GPU) can instead save the whole shard — roles, timers,
+// Leadership.State, in-flight table — and load it into a fresh engine of the same shape.  Layout: header { magic, version,
+// G, F, term runs, n blocks, total bytes } + { bytes, crc32c } per block + the blocks; written to <path>.tmp, fdatasync'ed,
+// renamed over <path> (a crash leaves the old image or none, never a torn one).
+// ---------------------------------------------------------------------------------------------
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+namespace {
+struct ImgHdr { uint32_t magic, version, G, F, runs, nblocks; uint64_t total; };
+constexpr uint32_t IMG_MAGIC = 0x31474D49u;     // "IMG1"
+uint32_t img_crc_table[256]; bool img_crc_ready = false;
+uint32_t img_crc32c(const void* p, size_t n) {
+    if (!img_crc_ready) {
+        for (uint32_t i = 0; i < 256; i++) { uint32_t v = i; for (int k = 0; k < 8; k++) v = (v & 1) ? (v >> 1) ^ 0x82F63B78u : v >> 1; img_crc_table[i] = v; }
+        img_crc_ready = true;
+    }
+    const uint8_t* b = (const uint8_t*)p; uint32_t c = ~0u;
+    for (size_t i = 0; i < n; i++) c = img_crc_table[(c ^ b[i]) & 0xff] ^ (c >> 8);
+    return ~c;
+}
+bool img_write_all(int fd, const void* p, size_t n) {
+    const uint8_t* b = (const uint8_t*)p;
+    while (n) { const ssize_t w = write(fd, b, n); if (w < 0) { if (errno == EINTR) continue; return false; } b += w; n -= (size_t)w; }
+    return true;
+}
+bool img_read_all(int fd, void* p, size_t n) {
+    uint8_t* b = (uint8_t*)p;
+    while (n) { const ssize_t r = read(fd, b, n); if (r < 0) { if (errno == EINTR) continue; return false; } if (r == 0) return false; b += r; n -= (size_t)r; }
+    return true;
+}
+}  // namespace
+extern "C" int rafting_state_save(rafting_engine_t* e, const char* path) {
+    if (!e || !path) return fail(RAFTING_E_INVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    int rc = quiesce_for_table_edit(e, "rafting_state_save"); if (rc) return rc;
+    std::vector<size_t> ids;
+    for (size_t i = 0; i < e->dev_allocs.size(); i++) if (e->dev_is_state[i]) ids.push_back(i);
+    ImgHdr h; h.magic = IMG_MAGIC; h.version = RAFTING_ABI_VERSION; h.G = e->G; h.F = e->F; h.runs = KRUNS; h.nblocks = (uint32_t)ids.size(); h.total = 0;
+    for (size_t i : ids) h.total += e->dev_bytes[i];
+    std::string tmp = std::string(path) + ".tmp";
+    const int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return fail(RAFTING_E_CUDA, "open %s: %s", tmp.c_str(), strerror(errno));
+    bool ok = img_write_all(fd, &h, sizeof(h));
+    std::vector<uint8_t> buf;
+    for (size_t i : ids) {
+        if (!ok) break;
+        buf.resize(e->dev_bytes[i]);
+        if (cudaMemcpy(buf.data(), e->dev_allocs[i], buf.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { close(fd); unlink(tmp.c_str()); return fail(RAFTING_E_CUDA, "copy of block %zu failed", i); }
+        const uint64_t meta[2] = {(uint64_t)buf.size(), (uint64_t)img_crc32c(buf.data(), buf.size())};
+        ok = img_write_all(fd, meta, sizeof(meta)) && img_write_all(fd, buf.data(), buf.size());
+    }
+    ok = ok && fdatasync(fd) == 0;
+    close(fd);
+    if (!ok || rename(tmp.c_str(), path) != 0) { const int err = errno; unlink(tmp.c_str()); return fail(RAFTING_E_CUDA, "writing %s failed: %s", path, strerror(err)); }
+    return RAFTING_OK;
+}
+extern "C" int rafting_state_load(rafting_engine_t* e, const char* path) {
+    if (!e || !path) return fail(RAFTING_E_INVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    int rc = quiesce_for_table_edit(e, "rafting_state_load"); if (rc) return rc;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(RAFTING_E_INVAL, "open %s: %s", path, strerror(errno));
+    ImgHdr h;
+    if (!img_read_all(fd, &h, sizeof(h)) || h.magic != IMG_MAGIC) { close(fd); return fail(RAFTING_E_INVAL, "%s is not a shard image", path); }
+    if (h.version != RAFTING_ABI_VERSION || h.G != e->G || h.F != e->F || h.runs != (uint32_t)KRUNS) {
+        close(fd); return fail(RAFTING_E_INVAL, "image of a different shape (G %u F %u runs %u abi %u)", h.G, h.F, h.runs, h.version);
+    }
+    // an image taken after the compact path was used carries the in-flight table: create ours before matching blocks
+    std::vector<size_t> ids;
+    for (size_t i = 0; i < e->dev_allocs.size(); i++) if (e->dev_is_state[i]) ids.push_back(i);
+    if (h.nblocks == ids.size() + 2) { rc = compact_state(e); if (rc) { close(fd); return rc; } ids.clear(); for (size_t i = 0; i < e->dev_allocs.size(); i++) if (e->dev_is_state[i]) ids.push_back(i); }
+    if (h.nblocks > ids.size()) { close(fd); return fail(RAFTING_E_INVAL, "image holds %u blocks, the engine %zu", h.nblocks, ids.size()); }
+    // read + verify everything first: a corrupt image must not leave the tables half loaded
+    std::vector<std::vector<uint8_t>> blocks(h.nblocks);
+    for (uint32_t k = 0; k < h.nblocks; k++) {
+        uint64_t meta[2];
+        if (!img_read_all(fd, meta, sizeof(meta)) || meta[0] != e->dev_bytes[ids[k]]) { close(fd); return fail(RAFTING_E_INVAL, "block %u: size mismatch / truncated image", k); }
+        blocks[k].resize(meta[0]);
+        if (!img_read_all(fd, blocks[k].data(), meta[0]) || img_crc32c(blocks[k].data(), meta[0]) != (uint32_t)meta[1]) { close(fd); return fail(RAFTING_E_INVAL, "block %u: checksum mismatch", k); }
+    }
+    close(fd);
+    for (uint32_t k = 0; k < h.nblocks; k++) CU(cudaMemcpy(e->dev_allocs[ids[k]], blocks[k].data(), blocks[k].size(), cudaMemcpyHostToDevice));
+    return RAFTING_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -5,7 +5,7 @@
  * NOT COMPILED IN THIS IMAGE: there is no JDK (no jni.h).  The whole file is guarded so that the
  * build never depends on it; on a box with a JDK:
  *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude \
- *       rafting_b200/csrc/jni/rafting_jni.c -Lrafting_b200 -lrafting_b200 -o librafting_jni.so
+ *       rafting_b200/csrc/jni/rafting_jni.c -Lrafting_b200 -lrafting_b200 -lrafting_durable -lrafting_ingest -o librafting_jni.so
  * The Java side is shown in INTEGRATION.md.
  */
 #if defined(__has_include)
@@ -19,6 +19,8 @@
 #include <string.h>
 
 #include "../../../include/rafting_b200.h"
+#include "../../../include/rafting_durable.h"
+#include "../../../include/rafting_ingest.h"
 
 #define FN(name) Java_io_lubricant_consensus_raft_gpu_NativeEngine_##name
 
@@ -83,5 +85,133 @@ JNIEXPORT void JNICALL FN(allgatherCommit)(JNIEnv* env, jclass k, jlong h, jobje
     int rc = rafting_allgather_commit((rafting_engine_t*)(intptr_t)h,
                                       hostOut ? (int64_t*)(*env)->GetDirectBufferAddress(env, hostOut) : NULL, NULL);
     if (rc) throw_status(env, rc);
+}
+
+/* ---- round 2: the rest of the surface INTEGRATION.md uses -------------------------------------------------------- */
+#define ENG(h) ((rafting_engine_t*)(intptr_t)(h))
+#define BUF(b) ((b) ? (*env)->GetDirectBufferAddress(env, (b)) : NULL)
+#define CHECK(call) do { int rc_ = (call); if (rc_) throw_status(env, rc_); } while (0)
+
+/* restart over a log that spans several terms (INTEGRATION.md §4 "Restart") */
+JNIEXPORT void JNICALL FN(groupOpenBulk)(JNIEnv* env, jclass k, jlong h, jint first, jint count, jobject inits) {
+    CHECK(rafting_group_open_bulk(ENG(h), (uint32_t)first, (uint32_t)count, (const rafting_group_init_t*)BUF(inits)));
+}
+JNIEXPORT void JNICALL FN(groupLoadRuns)(JNIEnv* env, jclass k, jlong h, jint gid, jobject runs, jint n) {
+    CHECK(rafting_group_load_runs(ENG(h), (uint32_t)gid, (const rafting_i64x2_t*)BUF(runs), (uint32_t)n));
+}
+JNIEXPORT void JNICALL FN(leaseRelease)(JNIEnv* env, jclass k, jlong h, jobject leaseBuf) {
+    CHECK(rafting_lease_release(ENG(h), (rafting_lease_t*)BUF(leaseBuf)));
+}
+/* caller-owned pinned buffers (the transport's receive pool): rafting_inbox_t / rafting_outbox_t structs in direct buffers */
+JNIEXPORT void JNICALL FN(stepBeginHost)(JNIEnv* env, jclass k, jlong h, jint slot, jobject inStruct, jobject outStruct) {
+    CHECK(rafting_step_begin_host(ENG(h), (uint32_t)slot, (const rafting_inbox_t*)BUF(inStruct), (const rafting_outbox_t*)BUF(outStruct)));
+}
+JNIEXPORT void JNICALL FN(stepWaitSlot)(JNIEnv* env, jclass k, jlong h, jint slot) { CHECK(rafting_step_wait_slot(ENG(h), (uint32_t)slot)); }
+/* the compact host path: rafting_cinbox_t / rafting_coutbox_t structs in direct buffers */
+JNIEXPORT void JNICALL FN(stepBeginCompact)(JNIEnv* env, jclass k, jlong h, jint slot, jobject cin, jobject cout) {
+    CHECK(rafting_step_begin_compact(ENG(h), (uint32_t)slot, (const rafting_cinbox_t*)BUF(cin), (const rafting_coutbox_t*)BUF(cout)));
+}
+JNIEXPORT void JNICALL FN(stepWaitCompact)(JNIEnv* env, jclass k, jlong h, jint slot) { CHECK(rafting_step_wait_compact(ENG(h), (uint32_t)slot)); }
+JNIEXPORT void JNICALL FN(stepFetchDense)(JNIEnv* env, jclass k, jlong h, jint slot, jobject outStruct) {
+    CHECK(rafting_step_fetch_dense(ENG(h), (uint32_t)slot, (const rafting_outbox_t*)BUF(outStruct)));
+}
+JNIEXPORT void JNICALL FN(checkpoint)(JNIEnv* env, jclass k, jlong h) { CHECK(rafting_checkpoint(ENG(h))); }
+JNIEXPORT void JNICALL FN(restore)(JNIEnv* env, jclass k, jlong h) { CHECK(rafting_restore(ENG(h))); }
+
+/* payload side of RaftLog (GpuRaftLog) */
+JNIEXPORT void JNICALL FN(logConfig)(JNIEnv* env, jclass k, jlong h, jint segBytes, jint hbmSegments, jint ringSlots) {
+    CHECK(rafting_log_config(ENG(h), (uint32_t)segBytes, (uint32_t)hbmSegments, (uint32_t)ringSlots));
+}
+JNIEXPORT jlong JNICALL FN(logStoreOpen)(JNIEnv* env, jclass k, jlong h, jstring path, jint coldMax) {
+    const char* p = (*env)->GetStringUTFChars(env, path, NULL);
+    uint64_t n = 0;
+    int rc = rafting_log_store_open(ENG(h), p, (uint32_t)coldMax, &n);
+    (*env)->ReleaseStringUTFChars(env, path, p);
+    if (rc) throw_status(env, rc);
+    return (jlong)n;
+}
+JNIEXPORT void JNICALL FN(logAppend)(JNIEnv* env, jclass k, jlong h, jobject refs, jint n, jobject blob, jlong blobBytes) {
+    CHECK(rafting_log_append(ENG(h), (const rafting_entry_ref_t*)BUF(refs), (uint32_t)n, BUF(blob), (size_t)blobBytes));
+}
+JNIEXPORT void JNICALL FN(logSync)(JNIEnv* env, jclass k, jlong h) { CHECK(rafting_log_sync(ENG(h))); }
+JNIEXPORT void JNICALL FN(logMark)(JNIEnv* env, jclass k, jlong h, jint gid, jlong lo, jlong hi, jlong epochIndex, jlong epochTerm) {
+    CHECK(rafting_log_mark(ENG(h), (uint32_t)gid, lo, hi, epochIndex, epochTerm));
+}
+JNIEXPORT jint JNICALL FN(logRead)(JNIEnv* env, jclass k, jlong h, jint gid, jlong first, jint maxN, jobject refsOut, jobject blobOut, jlong blobCap) {
+    uint32_t n = 0;
+    CHECK(rafting_log_read(ENG(h), (uint32_t)gid, first, (uint32_t)maxN, (rafting_entry_ref_t*)BUF(refsOut), BUF(blobOut), (size_t)blobCap, &n));
+    return (jint)n;
+}
+JNIEXPORT jint JNICALL FN(logGather)(JNIEnv* env, jclass k, jlong h, jint nRanges, jobject gids, jobject firsts, jobject counts,
+                                     jobject refsOut, jint refsCap, jobject blobOut, jlong blobCap) {
+    uint32_t n = 0; size_t bytes = 0;
+    CHECK(rafting_log_gather(ENG(h), (uint32_t)nRanges, (const uint32_t*)BUF(gids), (const int64_t*)BUF(firsts), (const uint32_t*)BUF(counts),
+                             (rafting_entry_ref_t*)BUF(refsOut), (uint32_t)refsCap, BUF(blobOut), (size_t)blobCap, &n, &bytes));
+    return (jint)n;
+}
+JNIEXPORT void JNICALL FN(logTrim)(JNIEnv* env, jclass k, jlong h, jint first, jint count) {
+    CHECK(rafting_log_trim(ENG(h), (uint32_t)first, (uint32_t)count, NULL, NULL));
+}
+JNIEXPORT jint JNICALL FN(logRecovered)(JNIEnv* env, jclass k, jlong h, jint gid, jobject initOut, jobject runsOut, jint cap) {
+    uint32_t n = 0;
+    CHECK(rafting_log_recovered(ENG(h), (uint32_t)gid, (rafting_group_init_t*)BUF(initOut), (rafting_i64x2_t*)BUF(runsOut), (uint32_t)cap, &n));
+    return (jint)n;
+}
+
+/* ONE JVM owning several shards (ContextManager.java:46): engines[r] becomes rank r of one communicator */
+JNIEXPORT void JNICALL FN(commInitAll)(JNIEnv* env, jclass k, jlongArray handles) {
+    const jsize n = (*env)->GetArrayLength(env, handles);
+    jlong* hs = (*env)->GetLongArrayElements(env, handles, NULL);
+    rafting_engine_t* es[64];
+    for (jsize r = 0; r < n && r < 64; r++) es[r] = ENG(hs[r]);
+    int rc = n <= 64 ? rafting_comm_init_all(es, (int)n) : RAFTING_E_CAPACITY;
+    (*env)->ReleaseLongArrayElements(env, handles, hs, JNI_ABORT);
+    if (rc) throw_status(env, rc);
+}
+JNIEXPORT void JNICALL FN(commInit)(JNIEnv* env, jclass k, jlong h, jint rank, jint world, jobject uid) {
+    CHECK(rafting_comm_init(ENG(h), (int)rank, (int)world, BUF(uid), uid ? (size_t)(*env)->GetDirectBufferCapacity(env, uid) : 0));
+}
+JNIEXPORT void JNICALL FN(allgatherCommitFrom)(JNIEnv* env, jclass k, jlong h, jlong devSrc, jobject hostOut) {
+    CHECK(rafting_allgather_commit_from(ENG(h), (const int64_t*)(intptr_t)devSrc, (int64_t*)BUF(hostOut), NULL));
+}
+
+/* the stable-storage journal: RaftFactory.restoreContext's StableLock (RaftFactory.java:18-36) becomes one journal per shard */
+JNIEXPORT jlong JNICALL FN(journalOpen)(JNIEnv* env, jclass k, jstring dir, jint maxGroups) {
+    const char* d = (*env)->GetStringUTFChars(env, dir, NULL);
+    rafting_journal_t* j = NULL;
+    int rc = rafting_journal_open(d, (uint32_t)maxGroups, &j);
+    (*env)->ReleaseStringUTFChars(env, dir, d);
+    if (rc) { jclass c = (*env)->FindClass(env, "java/io/IOException"); if (c) (*env)->ThrowNew(env, c, rafting_durable_last_error()); return 0; }
+    return (jlong)(intptr_t)j;
+}
+JNIEXPORT void JNICALL FN(journalClose)(JNIEnv* env, jclass k, jlong j) { rafting_journal_close((rafting_journal_t*)(intptr_t)j); }
+JNIEXPORT jlong JNICALL FN(journalCommitStep)(JNIEnv* env, jclass k, jlong j, jobject gids, jint n, jboolean compact, jobject roleWord, jobject currentTerm) {
+    uint64_t recs = 0;
+    int rc = rafting_journal_commit_step((rafting_journal_t*)(intptr_t)j, (const uint32_t*)BUF(gids), (uint32_t)n, compact ? 1 : 0,
+                                         (const uint32_t*)BUF(roleWord), (const int64_t*)BUF(currentTerm), &recs);
+    if (rc) { jclass c = (*env)->FindClass(env, "java/io/IOException"); if (c) (*env)->ThrowNew(env, c, rafting_durable_last_error()); }
+    return (jlong)recs;
+}
+JNIEXPORT void JNICALL FN(journalMilestone)(JNIEnv* env, jclass k, jlong j, jint gid, jlong index, jlong term) {
+    if (rafting_journal_milestone((rafting_journal_t*)(intptr_t)j, (uint32_t)gid, index, term)) {
+        jclass c = (*env)->FindClass(env, "java/io/IOException"); if (c) (*env)->ThrowNew(env, c, rafting_durable_last_error());
+    }
+}
+JNIEXPORT void JNICALL FN(journalRestore)(JNIEnv* env, jclass k, jlong j, jint gid, jobject stableOut) {
+    rafting_journal_restore((rafting_journal_t*)(intptr_t)j, (uint32_t)gid, (rafting_stable_t*)BUF(stableOut));
+}
+JNIEXPORT void JNICALL FN(journalCheckpoint)(JNIEnv* env, jclass k, jlong j) {
+    if (rafting_journal_checkpoint((rafting_journal_t*)(intptr_t)j)) {
+        jclass c = (*env)->FindClass(env, "java/io/IOException"); if (c) (*env)->ThrowNew(env, c, rafting_durable_last_error());
+    }
+}
+
+/* transport framing (include/rafting_ingest.h): cut a receive buffer into frames without one object per frame */
+JNIEXPORT jint JNICALL FN(frameScan)(JNIEnv* env, jclass k, jobject buf, jlong len, jobject framesOut, jint cap, jobject consumedAndFlags) {
+    uint32_t n = 0; size_t used = 0; int transparent = 0;
+    int rc = rafting_frame_scan((const uint8_t*)BUF(buf), (size_t)len, (rafting_frame_t*)BUF(framesOut), (uint32_t)cap, &n, &used, &transparent);
+    int64_t* o = (int64_t*)BUF(consumedAndFlags);
+    if (o) { o[0] = (int64_t)used; o[1] = transparent; o[2] = rc; }
+    return (jint)n;
 }
 #endif /* RAFTING_HAVE_JNI */

@@ -35,7 +35,7 @@ EXPORTS = [
     "rafting_step_begin", "rafting_step_wait", "rafting_step_device", "rafting_state_export",
     "rafting_state_export_bulk", "rafting_state_digest", "rafting_log_term", "rafting_commit_slice",
     "rafting_comm_init", "rafting_comm_init_all", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_allgather_commit_from",
-    "rafting_allgather_commit_all", "rafting_allgather_last", "rafting_restore_async", "rafting_step_device_seq", "rafting_engine_stream",
+    "rafting_allgather_commit_all", "rafting_allgather_last", "rafting_restore_async", "rafting_state_save", "rafting_state_load", "rafting_step_device_seq", "rafting_engine_stream",
     "rafting_engine_counters", "rafting_abi_sizes", "rafting_checkpoint", "rafting_restore",
     "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_step_begin_compact", "rafting_step_wait_compact", "rafting_step_fetch_dense", "rafting_backoff_step", "rafting_allgather_join",
     "rafting_log_config", "rafting_log_append", "rafting_log_read", "rafting_log_gather", "rafting_log_trim", "rafting_log_stats",
@@ -117,6 +117,8 @@ def lib():
         L.rafting_checkpoint.argtypes = [C.c_void_p]
         L.rafting_restore.argtypes = [C.c_void_p]
         L.rafting_restore_async.argtypes = [C.c_void_p]
+        L.rafting_state_save.argtypes = [C.c_void_p, C.c_char_p]
+        L.rafting_state_load.argtypes = [C.c_void_p, C.c_char_p]
         L.rafting_allgather_last.argtypes = [C.c_void_p, C.c_void_p]
         if L.rafting_abi_version() != abi.ABI_VERSION:
             raise RuntimeError("librafting_b200.so ABI version mismatch")
@@ -254,6 +256,12 @@ class Engine:
             _check(lib().rafting_restore(self._h), "rafting_restore")
         else:
             _check(lib().rafting_restore_async(self._h), "rafting_restore_async")
+
+    def state_save(self, path: str):
+        _check(lib().rafting_state_save(self._h, path.encode()), "rafting_state_save")
+
+    def state_load(self, path: str):
+        _check(lib().rafting_state_load(self._h, path.encode()), "rafting_state_load")
 
     def allgather_last(self) -> np.ndarray:
         out = np.zeros(getattr(self, "world", 1) * self.G, dtype=np.int64)

@@ -248,3 +248,33 @@ def test_mixed_churn_parity(engine_mod):
         out = o.step(ib)
         harness.assert_outbox_equal(out, e.step(ib), where=f"mixed step {k}")
     harness.assert_states_equal(o, e, range(0, G, 5), R - 1, where="mixed end")
+
+
+def test_shard_image_survives_the_process(engine_mod, tmp_path):
+    """rafting_state_save writes the whole shard (roles, timers, Leadership.State, run tables) as one
+    checksummed file; a FRESH engine that loads it continues the stream exactly where the first one stopped — every
+    outbox of the following steps equals the oracle's, which never stopped.  A corrupted image is refused untouched."""
+    G, R, rows = 2048, 3, 4
+    cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=rows)
+    e, o = engine_mod.Engine(cfg), binding.Oracle(cfg)
+    init = harness.init_array(G, terms=np.arange(G) % 7)
+    e.open_bulk(0, init), o.open_bulk(0, init)
+    w1 = workload.make_wl(41, 1, G, R - 1); w = workload.make_wl(41, rows, G, R - 1)
+    harness.assert_outbox_equal(harness.elect_all(o, w1), harness.elect_all(e, w1), where="election")
+    prev = harness.run_leader_workload([o, e], w, steps=5)
+    path = str(tmp_path / "shard.img")
+    e.state_save(path)
+    e.close()                                                                  # the process "ends" here
+    e2 = engine_mod.Engine(cfg)
+    bad = str(tmp_path / "bad.img")
+    blob = bytearray(open(path, "rb").read()); blob[len(blob) // 2] ^= 0x40
+    open(bad, "wb").write(bytes(blob))
+    with pytest.raises(engine_mod.RaftingError):
+        e2.state_load(bad)                                                     # checksum mismatch: nothing loaded
+    assert e2.export(5).alive == 0
+    e2.state_load(path)
+    harness.assert_states_equal(o, e2, range(0, G, 97), R - 1, where="after load")
+    harness.run_leader_workload([o, e2], w, steps=4, first_step=5, prevs=prev)
+    harness.assert_states_equal(o, e2, range(0, G, 97), R - 1, where="four steps after the restart")
+    with pytest.raises(engine_mod.RaftingError):
+        engine_mod.Engine(abi.make_cfg(replicas=R, max_groups=G // 2, max_rows=rows)).state_load(path)   # other shape
