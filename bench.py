@@ -507,7 +507,7 @@ def run_engine(args):
         cout0 = compact.CompactOutbox(rows, G, F, esc_cap=ESC_CAP)
         e.step_compact(compact.encode_inbox(host_inbox(0), None, None), cout0)
         e.checkpoint()
-        tags, sent_term = cout0.tags(), cout0.current_term.copy()
+        tags, sent_term, sent_inc = cout0.tags(), cout0.current_term.copy(), cout0.incarnation.copy()
         cins, keep = [], []
         couts = []
         esc_out_max = 0
@@ -517,13 +517,13 @@ def run_engine(args):
                 t, v = pinned_like(getattr(co, name)); keep.append(t); setattr(co, name, v)
             couts.append(co)
         for k in range(1, K2):                            # record pass (untimed): the tags the engine hands out are replayed below
-            ci = compact.encode_inbox(host_inbox(k), tags, sent_term)
+            ci = compact.encode_inbox(host_inbox(k), tags, sent_term, sent_inc)
             for name in ("row_base", "op_c", "ev_c", "esc"):
-                if len(getattr(ci, name)):
+                if getattr(ci, name) is not None and len(getattr(ci, name)):
                     t, v = pinned_like(getattr(ci, name)); keep.append(t); setattr(ci, name, v)
             e.step_compact(ci, couts[0])
             esc_out_max = max(esc_out_max, int(couts[0].counts[0]))
-            tags, sent_term = couts[0].tags(), couts[0].current_term.copy()
+            tags, sent_term, sent_inc = couts[0].tags(), couts[0].current_term.copy(), couts[0].incarnation.copy()
             cins.append(ci)
         digest_c = e.digest(0, G)
         cin_c = [ci.as_c() for ci in cins]

@@ -416,36 +416,40 @@ int rafting_step_wait_slot (rafting_engine_t* e, uint32_t slot);
  *     No free slot (more than 32 RPCs of one lane outstanding): tag 255, and the reply must come back as an escape record.
  *   * dense steps only (no active list), no inbound-request ops (RAFTING_INBOX_NO_REQUESTS is implied): SUBMIT / TIMEOUT
  *     ops, AE / IS acks; vote replies and anything irregular use the escape list.
+ *   * wire words are 32 bits: 4 B per lane slot + 4 B per group row up, 8 B per lane slot + 1 B per group row down.
  * ------------------------------------------------------------------------------------------------------------------- */
-/* ev_c : bits 0..3 kind (RAFTING_EV_NONE / _AE_ACK / _IS_ACK, or 15 = "see the escape list") | 4..5 outcome | 6 success |
+/* ev_c (32 bits per lane slot):
+ *        bits 0..3 kind (RAFTING_EV_NONE / _AE_ACK / _IS_ACK, or 15 = "see the escape list") | 4..5 outcome | 6 success |
  *        7 term-as-sent (RaftResponse.term() == the term the request carried; required for outcome OK, else escape) |
- *        8..15 tag echoed from plan_c | 16..31 now - row_base[row] (ms, unsigned) | 32..63 incarnation
- * op_c : bits 0..31 RAFTING_OP_MAKE(kind, peer, count) with kind NONE / SUBMIT / TIMEOUT | 32..47 now - row_base[row] |
- *        48..63 unavailable-follower mask (lanes 0..15; clusters with more lanes use the dense path)                       */
+ *        8..15 tag echoed from plan_c | 16..31 now - row_base[row] (ms, unsigned)
+ *        The incarnation of the role object that sent the RPC is NOT on the wire: it waits in the in-flight table with the echo
+ *        pair and comes back under the tag (a reply without a tag must be escaped).
+ * op_c (32 bits per group row):
+ *        bits 0..3 kind (NONE / SUBMIT / TIMEOUT) | 4..15 count (1..4095 commands of a SUBMIT) | 16..31 now - row_base[row];
+ *        unavailable-follower masks travel in their own optional column op_unavail (16 bits per group row)                  */
 #define RAFTING_CEV_ESCAPED 15u
-#define RAFTING_CEV_MAKE(kind, outcome, success, term_as_sent, tag, dt, incarnation)                                   \
-    ((uint64_t)(kind) | ((uint64_t)(outcome) << 4) | ((uint64_t)((success) ? 1 : 0) << 6) |                            \
-     ((uint64_t)((term_as_sent) ? 1 : 0) << 7) | ((uint64_t)((tag) & 0xffu) << 8) | ((uint64_t)((dt) & 0xffffu) << 16) | \
-     ((uint64_t)(uint32_t)(incarnation) << 32))
-#define RAFTING_COP_MAKE(op_make, dt, unavail) ((uint64_t)(uint32_t)(op_make) | ((uint64_t)((dt) & 0xffffu) << 32) | ((uint64_t)((unavail) & 0xffffu) << 48))
+#define RAFTING_CEV_MAKE(kind, outcome, success, term_as_sent, tag, dt)                                                \
+    ((uint32_t)(kind) | ((uint32_t)(outcome) << 4) | ((uint32_t)((success) ? 1 : 0) << 6) |                            \
+     ((uint32_t)((term_as_sent) ? 1 : 0) << 7) | ((uint32_t)((tag) & 0xffu) << 8) | ((uint32_t)((dt) & 0xffffu) << 16))
+#define RAFTING_COP_MAKE(kind, count, dt) ((uint32_t)(kind) | ((uint32_t)((count) & 0xfffu) << 4) | ((uint32_t)((dt) & 0xffffu) << 16))
 #define RAFTING_CTAG_NONE 255u
 typedef struct rafting_cesc_in {     /* a lane event in full: overwrites slot (row * G + gid) * F + lane after unpacking */
     uint32_t slot, _pad;
     uint64_t ev_meta;                /* RAFTING_EVM_MAKE(...) */
     int64_t  term, now_ms, epoch_at_send, last_at_send;
 } rafting_cesc_in_t;
-#define RAFTING_CINBOX_HAS_UNAVAIL 1u   /* some op_c carries a non-zero unavailable-follower mask (else the masks are not read) */
 typedef struct rafting_cinbox {
     uint32_t rows, n_esc;
-    uint32_t flags, _pad;
     const int64_t*           row_base;   /* [rows] */
-    const uint64_t*          op_c;       /* [rows][G], may be NULL (no group ops) */
-    const uint64_t*          ev_c;       /* [rows][G][F], may be NULL (no lane events) */
+    const uint32_t*          op_c;       /* [rows][G], may be NULL (no group ops) */
+    const uint16_t*          op_unavail; /* [rows][G] unavailable-follower lanes 0..15 of the op, may be NULL (nobody unavailable) */
+    const uint32_t*          ev_c;       /* [rows][G][F], may be NULL (no lane events) */
     const rafting_cesc_in_t* esc;        /* [n_esc] */
 } rafting_cinbox_t;
-/* plan_c : plan_meta (kind | hb << 4 | count << 16 | incarnation << 32) | bit 6 escaped | bits 8..15 tag.  Not escaped means:
+/* plan_c (32 bits per lane slot): bits 0..3 kind | 4 heartbeat | 6 escaped | 8..15 tag | 16..31 entry count.  Not escaped means:
+ *          the plan's incarnation == incarnation[g] (end of step), and
  *          AE  prevLogIndex = last_entry[g].x - (plan_d & 0xffff), prevLogTerm = current_term[g], lastIndex = prevLogIndex + count,
- *              leaderCommit = commit_index[g] - (plan_d >> 16), epochAtSend = epoch[g].x, incarnation == incarnation[g]
+ *              leaderCommit = commit_index[g] - (plan_d >> 16), epochAtSend = epoch[g].x
  *          IS  (epoch.index, epoch.term) = epoch[g], leaderCommit as above
  *          SKIP_INFLIGHT / UNAVAILABLE: no payload
  * rep_c  : per-event error code of the row's group op (rafting_outbox_t.rep_meta bits 8..15); a row whose op produced a
@@ -453,11 +457,11 @@ typedef struct rafting_cinbox {
 enum { RAFTING_CESC_PLAN = 1, RAFTING_CESC_BALLOT = 2, RAFTING_CESC_REPLY = 3 };
 typedef struct rafting_cesc_out {
     uint32_t kind, slot;             /* PLAN: lane slot; BALLOT / REPLY: row * G + gid */
-    uint64_t meta;                   /* plan_meta (| tag << 8) / ballot_meta / rep_meta */
+    uint64_t meta;                   /* plan_meta | tag << 8 (the full 64-bit word, incarnation included) / ballot_meta / rep_meta */
     int64_t  a, b, c, d, e;          /* PLAN: plan_pp.x, .y, plan_lc.x, .y, plan_epoch; BALLOT: term, last.x, last.y; REPLY: rep_term */
 } rafting_cesc_out_t;
 typedef struct rafting_coutbox {
-    uint64_t* plan_c;                /* [rows][G][F] */
+    uint32_t* plan_c;                /* [rows][G][F] */
     uint32_t* plan_d;                /* [rows][G][F] */
     uint8_t*  rep_c;                 /* [rows][G]    */
     int64_t*  commit_index; int64_t* current_term; uint32_t* role_word; uint32_t* incarnation; uint32_t* err_word;

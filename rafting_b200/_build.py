@@ -12,7 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librafting_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["step_kernel.cuh", "step_body.inc", "seglog.cuh", "handlers.cuh", "tables.cuh", os.path.join("..", "..", "include", "rafting_b200.h")]
+HEADERS = ["step_kernel.cuh", "step_body.inc", "seglog.cuh", "compact.cuh", "pair_kernel.cuh", "handlers.cuh", "tables.cuh",
+           os.path.join("..", "..", "include", "rafting_b200.h")]
 # the synthetic-stream generator (the simulated peers) is NOT part of the product library: tests, bench and the CPU
 # reference arm load it on its own, so a process that times the CPU port never maps librafting_b200.so
 WORKLOAD_LIB = os.path.join(HERE, "librafting_workload.so")
@@ -64,6 +65,23 @@ def build_workload(force: bool = False) -> str:
     return WORKLOAD_LIB
 
 
+FLAGS_LIB = os.path.join(HERE, "librafting_b200_flags.so")
+
+
+def build_flags(force: bool = False) -> str:
+    """The same engine compiled with -DRAFTING_ENABLE_CFG_FLAGS: the device branches of the two opt-in protocol fixes
+    (RAFTING_CFG_STRICT_CANDIDATE_VOTE, RAFTING_CFG_LENIENT_FOLLOWER_COMMIT).  A library of its own: the default build stays
+    byte-identical to the reference-faithful one and rejects a non-zero cfg.flags.  Loaded with RAFTING_B200_LIB=<path>."""
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.join(CSRC, h) for h in ("compact.cuh", "pair_kernel.cuh")]
+    if not force and os.path.exists(FLAGS_LIB) and os.path.getmtime(FLAGS_LIB) > max(os.path.getmtime(d) for d in deps):
+        return FLAGS_LIB
+    cmd = [nvcc()] + NVCC_FLAGS + ["-DRAFTING_ENABLE_CFG_FLAGS"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", FLAGS_LIB, "-ldl"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc (flags build) failed:\n" + (res.stdout + res.stderr)[-4000:])
+    return FLAGS_LIB
+
+
 DURABLE_LIB = os.path.join(HERE, "librafting_durable.so")
 
 
@@ -100,6 +118,7 @@ def build_ingest(force: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_flags(force=True))
     print(build_workload(force=True))
     print(build_durable(force=True))
     print(build_ingest(force=True))

@@ -332,7 +332,6 @@ def leader_of(role_word: int) -> int:
 
 # ---- compact host path (include/rafting_b200.h "COMPACT host path") --------------------------------------------------
 CEV_ESCAPED, CTAG_NONE = 15, 255
-CINBOX_HAS_UNAVAIL = 1
 CESC_PLAN, CESC_BALLOT, CESC_REPLY = 1, 2, 3
 CESC_IN = np.dtype([("slot", "<u4"), ("_pad", "<u4"), ("ev_meta", "<u8"), ("term", "<i8"), ("now_ms", "<i8"),
                     ("epoch_at_send", "<i8"), ("last_at_send", "<i8")])
@@ -341,8 +340,8 @@ assert CESC_IN.itemsize == 48 and CESC_OUT.itemsize == 56
 
 
 class CInboxC(C.Structure):
-    _fields_ = [("rows", C.c_uint32), ("n_esc", C.c_uint32), ("flags", C.c_uint32), ("_pad", C.c_uint32),
-                ("row_base", C.c_void_p), ("op_c", C.c_void_p), ("ev_c", C.c_void_p), ("esc", C.c_void_p)]
+    _fields_ = [("rows", C.c_uint32), ("n_esc", C.c_uint32),
+                ("row_base", C.c_void_p), ("op_c", C.c_void_p), ("op_unavail", C.c_void_p), ("ev_c", C.c_void_p), ("esc", C.c_void_p)]
 
 
 class COutboxC(C.Structure):

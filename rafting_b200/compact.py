@@ -20,18 +20,21 @@ class CompactInbox:
     def __init__(self, rows, n, F):
         self.rows, self.n, self.F = rows, n, F
         self.row_base = np.zeros(rows, dtype=np.int64)
-        self.op_c = np.zeros((rows, n), dtype=np.uint64)
-        self.ev_c = np.zeros((rows, n, F), dtype=np.uint64)
+        self.op_c = np.zeros((rows, n), dtype=np.uint32)
+        self.op_unavail = None                                # [rows, n] uint16 when some follower is unavailable
+        self.ev_c = np.zeros((rows, n, F), dtype=np.uint32)
         self.esc = np.zeros(0, dtype=abi.CESC_IN)
-        self.flags = 0
 
     def nbytes(self):
-        return self.row_base.nbytes + self.op_c.nbytes + self.ev_c.nbytes + self.esc.nbytes
+        return self.row_base.nbytes + sum(a.nbytes for a in (self.op_c, self.op_unavail, self.ev_c) if a is not None) + self.esc.nbytes
 
     def as_c(self) -> abi.CInboxC:
         c = abi.CInboxC()
-        c.rows, c.n_esc, c.flags = self.rows, len(self.esc), self.flags
-        c.row_base, c.op_c, c.ev_c = self.row_base.ctypes.data, self.op_c.ctypes.data, self.ev_c.ctypes.data
+        c.rows, c.n_esc = self.rows, len(self.esc)
+        c.row_base = self.row_base.ctypes.data
+        c.op_c = None if self.op_c is None else self.op_c.ctypes.data
+        c.op_unavail = None if self.op_unavail is None else self.op_unavail.ctypes.data
+        c.ev_c = None if self.ev_c is None else self.ev_c.ctypes.data
         c.esc = self.esc.ctypes.data if len(self.esc) else None
         return c
 
@@ -39,7 +42,7 @@ class CompactInbox:
 class CompactOutbox:
     def __init__(self, rows, n, F, esc_cap=4096):
         self.rows, self.n, self.F, self.esc_cap = rows, n, F, esc_cap
-        self.plan_c = np.zeros((rows, n, F), dtype=np.uint64)
+        self.plan_c = np.zeros((rows, n, F), dtype=np.uint32)
         self.plan_d = np.zeros((rows, n, F), dtype=np.uint32)
         self.rep_c = np.zeros((rows, n), dtype=np.uint8)
         self.commit_index = np.zeros(n, dtype=np.int64)
@@ -66,13 +69,16 @@ class CompactOutbox:
 
     def tags(self) -> np.ndarray:
         """tag of every plan, [rows, n, F] (255 = none)"""
-        return ((self.plan_c >> U64(8)) & U64(0xFF)).astype(np.uint8)
+        return ((self.plan_c >> np.uint32(8)) & np.uint32(0xFF)).astype(np.uint8)
 
 
-def encode_inbox(ib: abi.Inbox, tags: np.ndarray | None, sent_term: np.ndarray | None) -> CompactInbox:
+def encode_inbox(ib: abi.Inbox, tags: np.ndarray | None, sent_term: np.ndarray | None, sent_inc: np.ndarray | None = None) -> CompactInbox:
     """ib: dense host inbox of a NO_REQUESTS step (SUBMIT / TIMEOUT ops, any lane events).
     tags[r, i, f]: the tag the RPC this event answers was sent under (plan_c of the step that emitted it); None = no acks yet.
-    sent_term[i]: the term those RPCs carried (the group's current term when they were planned)."""
+    sent_term[i] / sent_inc[i]: the term those RPCs carried and the incarnation of the role object that sent them (the group's
+    current_term / incarnation columns of the step that planned them).  The incarnation is not on the wire — the engine keeps
+    it with the echo pair under the tag — so a reply whose incarnation differs from sent_inc (a plan that was itself escaped)
+    travels in full."""
     rows, n, F = ib.rows, ib.n, ib.F
     if ib.gids is not None:
         raise ValueError("the compact path is dense (no active list)")
@@ -96,9 +102,12 @@ def encode_inbox(ib: abi.Inbox, tags: np.ndarray | None, sent_term: np.ndarray |
         unav = ib.op_ab["x"].astype(np.uint64) if ib.op_ab is not None else np.zeros((rows, n), np.uint64)
         if (unav > U64(0xFFFF)).any():
             raise ValueError("unavailable mask beyond 16 lanes")
-        c.op_c[:] = (ib.op_meta & U64(0xFFFFFFFF)) | (dt.astype(np.uint64) << U64(32)) | (unav << U64(48))
+        count = (ib.op_meta >> U64(16)) & U64(0xFFFF)
+        if (count > U64(0xFFF)).any():
+            raise ValueError("more than 4095 commands in one SUBMIT: use the dense path for this step")
+        c.op_c[:] = (ok | (count << U64(4)) | (dt.astype(np.uint64) << U64(16))).astype(np.uint32)
         if (unav != 0).any():
-            c.flags |= abi.CINBOX_HAS_UNAVAIL
+            c.op_unavail = unav.astype(np.uint16)
     else:
         c.op_c = None
     if ib.ev_meta is None:
@@ -110,10 +119,11 @@ def encode_inbox(ib: abi.Inbox, tags: np.ndarray | None, sent_term: np.ndarray |
     dt = np.where(ek != 0, ib.ev_tn["y"] - base[:, None, None], 0)
     tg = tags if tags is not None else np.full((rows, n, F), abi.CTAG_NONE, np.uint8)
     term_ok = (ib.ev_tn["x"] == (sent_term[None, :, None] if sent_term is not None else 0))
-    fits = is_ack & (dt >= 0) & (dt <= 0xFFFF) & (tg != abi.CTAG_NONE) & ((outcome != abi.OUT_OK) | term_ok)
+    inc_ok = ((em >> U64(32)) == (sent_inc.astype(np.uint64)[None, :, None] if sent_inc is not None else U64(0)))
+    fits = is_ack & (dt >= 0) & (dt <= 0xFFFF) & (tg != abi.CTAG_NONE) & ((outcome != abi.OUT_OK) | term_ok) & inc_ok
     word = (em & U64(0x7F)) | (np.where(outcome == abi.OUT_OK, 1, 0).astype(np.uint64) << U64(7)) | (tg.astype(np.uint64) << U64(8)) | \
-           (dt.astype(np.uint64) << U64(16)) | (em & U64(0xFFFFFFFF00000000))
-    c.ev_c[:] = np.where(fits, word, np.where(ek != 0, U64(abi.CEV_ESCAPED), U64(0)))
+           (dt.astype(np.uint64) << U64(16))
+    c.ev_c[:] = np.where(fits, word, np.where(ek != 0, U64(abi.CEV_ESCAPED), U64(0))).astype(np.uint32)
     esc_at = np.flatnonzero(((ek != 0) & ~fits).reshape(-1))
     if len(esc_at):
         c.esc = np.zeros(len(esc_at), dtype=abi.CESC_IN)
@@ -130,10 +140,11 @@ def decode_outbox(co: CompactOutbox, G: int | None = None) -> abi.Outbox:
     if int(co.counts[0]) > co.esc_cap:
         raise OverflowError("escape list overflow: fetch the dense outbox (rafting_step_fetch_dense)")
     o = abi.Outbox(rows, n, F, n if G is None else G)
-    pc = co.plan_c
+    pc = co.plan_c.astype(np.uint64)
     kind = (pc & U64(0xF)).astype(np.int64)
     esc = ((pc >> U64(6)) & U64(1)) != 0
-    o.plan_meta[:] = pc & ~U64(0xFF40)                                    # tag and escape bit are wire-only
+    # tag and escape bit are wire-only; a compact plan was sent by the role object that holds the group at the end of the step
+    o.plan_meta[:] = np.where(kind != 0, (pc & U64(0xFFFF001F)) | (co.incarnation.astype(np.uint64)[None, :, None] << U64(32)), U64(0))
     cnt = ((pc >> U64(16)) & U64(0xFFFF)).astype(np.int64)
     dprev = (co.plan_d & np.uint32(0xFFFF)).astype(np.int64)
     dcommit = (co.plan_d >> np.uint32(16)).astype(np.int64)
@@ -153,6 +164,7 @@ def decode_outbox(co: CompactOutbox, G: int | None = None) -> abi.Outbox:
         k, slot = int(r["kind"]), int(r["slot"])
         if k == abi.CESC_PLAN:
             rr, rest = divmod(slot, n * F); i, f = divmod(rest, F)
+            o.plan_meta[rr, i, f] = int(r["meta"]) & ~0xFF40                  # the full plan word of an escaped plan (other incarnation)
             o.plan_pp[rr, i, f] = (r["a"], r["b"]); o.plan_lc[rr, i, f] = (r["c"], r["d"]); o.plan_epoch[rr, i, f] = r["e"]
         elif k == abi.CESC_BALLOT:
             rr, i = divmod(slot, n)

@@ -1,12 +1,12 @@
 // compact.cuh — the compact host path: a third of the dense path's PCIe bytes, losslessly (include/rafting_b200.h,
 // "COMPACT host path").  Two kernels bracket the unchanged step kernel:
 //
-//   unpack_kernel   wire columns (ev_c 8 B / lane slot, op_c 8 B / group row, row_base)  ->  the dense SoA inbox the step kernel
-//                   reads; the (epochAtSend, lastIndexAtSend) pair of every ack comes out of the HBM in-flight table under the
-//                   tag the reply echoes, and the tag's slot is freed
-//   pack_kernel     the dense outbox  ->  plan_c 8 B + plan_d 4 B / lane slot, rep_c 1 B / group row, the per-group columns;
-//                   every AE / IS plan gets a free tag of its (group, follower) lane and parks its echo pair in the table;
-//                   whatever breaks a compact rule goes, in full, to the escape list
+//   unpack_kernel   wire columns (ev_c 4 B / lane slot, op_c 4 B / group row, row_base)  ->  the dense SoA inbox the step kernel
+//                   reads; the (epochAtSend, lastIndexAtSend) pair AND the incarnation of every ack come out of the HBM
+//                   in-flight table under the tag the reply echoes, and the tag's slot is freed
+//   pack_kernel     the dense outbox  ->  plan_c 4 B + plan_d 4 B / lane slot, rep_c 1 B / group row, the per-group columns;
+//                   every AE / IS plan gets a free tag of its (group, follower) lane and parks its echo pair and its
+//                   incarnation in the table; whatever breaks a compact rule goes, in full, to the escape list
 //
 // One thread per (group, follower) walks the rows in order in both kernels, so the tag bitmap of a lane is only ever touched
 // by its own thread, and the three kernels of a step (unpack, step, pack) are ordered on the engine's stream.  What this
@@ -25,15 +25,15 @@ struct InboxW {                                  // writable view of the dense s
 };
 struct CInD {                                    // device view of rafting_cinbox_t
     uint32_t rows, n_esc;
-    const int64_t* row_base; const uint64_t* op_c; const uint64_t* ev_c; const rafting_cesc_in_t* esc;
+    const int64_t* row_base; const uint32_t* op_c; const uint16_t* op_unavail; const uint32_t* ev_c; const rafting_cesc_in_t* esc;
 };
 struct COutD {                                   // device view of rafting_coutbox_t
-    uint64_t* plan_c; uint32_t* plan_d; uint8_t* rep_c;
+    uint32_t* plan_c; uint32_t* plan_d; uint8_t* rep_c;
     int64_t* commit_index; int64_t* current_term; uint32_t* role_word; uint32_t* incarnation; uint32_t* err_word;
     i64x2* last_entry; i64x2* epoch; rafting_cesc_out_t* esc; uint32_t esc_cap; uint32_t* counts;
 };
 
-__global__ void __launch_bounds__(256) unpack_kernel(Tables T, CInD in, InboxW out, i64x2* __restrict__ table, uint32_t* __restrict__ bits) {
+__global__ void __launch_bounds__(256) unpack_kernel(Tables T, CInD in, InboxW out, const i64x2* __restrict__ table, const uint32_t* __restrict__ tinc, uint32_t* __restrict__ bits) {
     const uint32_t GF = T.G * T.F;
     const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     if (t >= GF) return;
@@ -43,15 +43,15 @@ __global__ void __launch_bounds__(256) unpack_kernel(Tables T, CInD in, InboxW o
         uint32_t b = bits[t];
         for (uint32_t r = 0; r < in.rows; r++) {
             const size_t idx = (size_t)r * GF + t;
-            const uint64_t w = in.ev_c[idx];
-            const uint32_t kind = (uint32_t)(w & 0xfu);
+            const uint32_t w = in.ev_c[idx];
+            const uint32_t kind = w & 0xfu;
             uint64_t em = 0;
             if (kind == RAFTING_EV_AE_ACK || kind == RAFTING_EV_IS_ACK) {
-                const uint32_t tag = (uint32_t)(w >> 8) & 0xffu;
-                i64x2 el = {0, 0};
-                if (tag < (uint32_t)CTAGS) { el = table[(size_t)tag * GF + t]; b &= ~(1u << tag); }
-                i64x2 tn; tn.x = ((w >> 7) & 1u) ? term_now : 0; tn.y = in.row_base[r] + (int64_t)((w >> 16) & 0xffffu);
-                em = (w & 0x7full) | (w & 0xffffffff00000000ull);             // kind | outcome | success | incarnation
+                const uint32_t tag = (w >> 8) & 0xffu;
+                i64x2 el = {0, 0}; uint32_t inc = 0;
+                if (tag < (uint32_t)CTAGS) { el = table[(size_t)tag * GF + t]; inc = tinc[(size_t)tag * GF + t]; b &= ~(1u << tag); }
+                i64x2 tn; tn.x = ((w >> 7) & 1u) ? term_now : 0; tn.y = in.row_base[r] + (int64_t)(w >> 16);
+                em = (uint64_t)(w & 0x7fu) | ((uint64_t)inc << 32);         // kind | outcome | success | incarnation (from the table)
                 out.ev_tn[idx] = tn; out.ev_el[idx] = el;
             }
             out.ev_meta[idx] = em;                                          // escaped / empty slots read as "no event" until patched
@@ -61,11 +61,11 @@ __global__ void __launch_bounds__(256) unpack_kernel(Tables T, CInD in, InboxW o
     if (f == 0 && in.op_c) {
         for (uint32_t r = 0; r < in.rows; r++) {
             const size_t gi = (size_t)r * T.G + g;
-            const uint64_t c = in.op_c[gi];
-            out.op_meta[gi] = c & 0xffffffffull;
-            i64x2 nr; nr.x = in.row_base[r] + (int64_t)((c >> 32) & 0xffffu); nr.y = 0;
+            const uint32_t c = in.op_c[gi];
+            out.op_meta[gi] = (uint64_t)RAFTING_OP_MAKE(c & 0xfu, 0u, (c >> 4) & 0xfffu);
+            i64x2 nr; nr.x = in.row_base[r] + (int64_t)(c >> 16); nr.y = 0;
             out.op_nr[gi] = nr;
-            if (out.op_ab) { i64x2 ab; ab.x = (int64_t)((c >> 48) & 0xffffu); ab.y = 0; out.op_ab[gi] = ab; }
+            if (out.op_ab) { i64x2 ab; ab.x = in.op_unavail ? (int64_t)in.op_unavail[gi] : 0; ab.y = 0; out.op_ab[gi] = ab; }
         }
     }
 }
@@ -88,7 +88,7 @@ __device__ __forceinline__ void put_escape(const COutD& o, uint32_t kind, uint32
     }
 }
 
-__global__ void __launch_bounds__(256) pack_kernel(Tables T, uint32_t rows, OutboxD in, COutD out, i64x2* __restrict__ table, uint32_t* __restrict__ bits) {
+__global__ void __launch_bounds__(256) pack_kernel(Tables T, uint32_t rows, OutboxD in, COutD out, i64x2* __restrict__ table, uint32_t* __restrict__ tinc, uint32_t* __restrict__ bits) {
     const uint32_t GF = T.G * T.F;
     const uint32_t t = blockIdx.x * 256u + threadIdx.x;
     if (t >= GF) return;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) pack_kernel(Tables T, uint32_t rows, Outb
         for (uint32_t r = 0; r < rows; r++) {
             const size_t idx = (size_t)r * GF + t;
             const uint64_t pm = in.plan_meta[idx];
-            uint64_t pc = 0; uint32_t pd = 0;
+            uint32_t pc = 0, pd = 0;
             if (pm != 0) {
                 const uint32_t kind = RAFTING_PLM_KIND(pm);
                 const i64x2 pp = in.plan_pp[idx], lc = in.plan_lc[idx];
@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(256) pack_kernel(Tables T, uint32_t rows, Outb
                 uint32_t tag = RAFTING_CTAG_NONE;
                 if (kind == RAFTING_PLAN_AE || kind == RAFTING_PLAN_IS) {
                     const uint32_t fr = ~b;
-                    if (fr) { tag = (uint32_t)__ffs((int)fr) - 1u; b |= 1u << tag; i64x2 v; v.x = pe; v.y = lc.x; table[(size_t)tag * GF + t] = v; }
+                    if (fr) {
+                        tag = (uint32_t)__ffs((int)fr) - 1u; b |= 1u << tag;
+                        i64x2 v; v.x = pe; v.y = lc.x; table[(size_t)tag * GF + t] = v; tinc[(size_t)tag * GF + t] = RAFTING_PLM_INC(pm);
+                    }
                 }
                 const uint64_t dcommit = (uint64_t)commit_end - (uint64_t)lc.y;
                 bool fits = pe == epoch_end.x && RAFTING_PLM_INC(pm) == inc_end;
@@ -122,8 +125,8 @@ __global__ void __launch_bounds__(256) pack_kernel(Tables T, uint32_t rows, Outb
                     fits = fits && pp.x == epoch_end.x && pp.y == epoch_end.y && lc.x == epoch_end.x && dcommit < 65536u;
                     pd = (uint32_t)dcommit << 16;
                 } else fits = fits && pp.x == 0 && pp.y == 0 && lc.x == 0 && lc.y == 0;
-                pc = pm | ((uint64_t)tag << 8);
-                if (!fits) { pc |= 1ull << 6; pd = 0; put_escape(out, RAFTING_CESC_PLAN, (uint32_t)idx, pc, pp.x, pp.y, lc.x, lc.y, pe); }
+                pc = (uint32_t)(pm & 0xffff001full) | (tag << 8);                 // kind | hb | count, + tag
+                if (!fits) { pc |= 1u << 6; pd = 0; put_escape(out, RAFTING_CESC_PLAN, (uint32_t)idx, pm | ((uint64_t)tag << 8), pp.x, pp.y, lc.x, lc.y, pe); }
             }
             out.plan_c[idx] = pc; out.plan_d[idx] = pd;
         }
@@ -149,6 +152,7 @@ __global__ void __launch_bounds__(256) pack_kernel(Tables T, uint32_t rows, Outb
 
 struct CompactState {
     rafting::i64x2* table = nullptr;       // [CTAGS][G * F] (epochAtSend, lastIndexAtSend) of the RPC in flight under that tag
+    uint32_t* tinc = nullptr;               // [CTAGS][G * F] incarnation of the role object that sent it
     uint32_t* bits = nullptr;               // [G * F] tags in use
 };
 static void compact_release(rafting_engine* e) { delete e->compact; e->compact = nullptr; }   // the buffers are in dev_allocs
@@ -158,6 +162,7 @@ static int compact_state(rafting_engine* e) {
     const size_t GF = (size_t)e->G * e->F;
     e->alloc_state = true;                  // protocol state: covered by rafting_checkpoint / rafting_restore
     int rc = dalloc(e, &c->table, GF * rafting::CTAGS);
+    if (!rc) rc = dalloc(e, &c->tinc, GF * rafting::CTAGS);
     if (!rc) rc = dalloc(e, &c->bits, GF);
     e->alloc_state = false;
     if (rc) { delete c; return rc; }
@@ -166,13 +171,14 @@ static int compact_state(rafting_engine* e) {
 }
 
 // byte layout of the two wire blocks of a slot (device copy and — for the small items — a pinned landing block)
-struct CLayout { size_t row_base, op_c, ev_c, esc, in_total; size_t plan_c, plan_d, rep_c, commit, term, role, inc, err, last, epoch, counts, esc_out, out_total, out_dense; };
+struct CLayout { size_t row_base, op_c, op_un, ev_c, esc, in_total; size_t plan_c, plan_d, rep_c, commit, term, role, inc, err, last, epoch, counts, esc_out, out_total, out_dense; };
 static CLayout compact_layout(size_t rows, size_t G, size_t F, size_t n_esc_in, size_t esc_cap) {
     CLayout L; size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
-    L.row_base = take(rows * 8); L.op_c = take(rows * G * 8); L.ev_c = take(rows * G * F * 8); L.esc = take((n_esc_in + 1) * sizeof(rafting_cesc_in_t));
+    L.row_base = take(rows * 8); L.op_c = take(rows * G * 4); L.op_un = take(rows * G * 2); L.ev_c = take(rows * G * F * 4);
+    L.esc = take((n_esc_in + 1) * sizeof(rafting_cesc_in_t));
     L.in_total = o; o = 0;
-    L.plan_c = take(rows * G * F * 8); L.plan_d = take(rows * G * F * 4); L.rep_c = take(rows * G);
+    L.plan_c = take(rows * G * F * 4); L.plan_d = take(rows * G * F * 4); L.rep_c = take(rows * G);
     L.commit = take(G * 8); L.term = take(G * 8); L.role = take(G * 4); L.inc = take(G * 4); L.err = take(G * 4); L.last = take(G * 16); L.epoch = take(G * 16);
     L.counts = take(16);
     L.out_dense = o;                                                          // everything before the escape list travels down every step
@@ -190,6 +196,7 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
         !out->err_word || !out->last_entry || !out->epoch || !out->counts || (out->esc_cap && !out->esc))
         return fail(RAFTING_E_INVAL, "compact outbox: every column is required");
     if (e->F > 16) return fail(RAFTING_E_CAPACITY, "the compact path carries a 16-lane unavailable mask: use the dense path for larger clusters");
+    if (in->op_unavail && !in->op_c) return fail(RAFTING_E_INVAL, "op_unavail without op_c");
     CU(cudaSetDevice(e->cfg.device));
     int rc = hostpath_init(e); if (rc) return rc;
     if ((rc = compact_state(e))) return rc;
@@ -205,10 +212,12 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
         (rc = blk_reserve(S.chout, 256, true))) return rc;
     // ---- H2D: the wire columns as they are ----
     CInD ci; ci.rows = (uint32_t)rows; ci.n_esc = in->n_esc;
-    ci.row_base = (const int64_t*)(S.cin.p + LC.row_base); ci.op_c = nullptr; ci.ev_c = nullptr; ci.esc = (const rafting_cesc_in_t*)(S.cin.p + LC.esc);
+    ci.row_base = (const int64_t*)(S.cin.p + LC.row_base); ci.op_c = nullptr; ci.op_unavail = nullptr; ci.ev_c = nullptr;
+    ci.esc = (const rafting_cesc_in_t*)(S.cin.p + LC.esc);
     CU(cudaMemcpyAsync(S.cin.p + LC.row_base, in->row_base, rows * 8, cudaMemcpyHostToDevice, H->s_h2d));
-    if (in->op_c) { CU(cudaMemcpyAsync(S.cin.p + LC.op_c, in->op_c, rows * G * 8, cudaMemcpyHostToDevice, H->s_h2d)); ci.op_c = (const uint64_t*)(S.cin.p + LC.op_c); }
-    if (in->ev_c) { CU(cudaMemcpyAsync(S.cin.p + LC.ev_c, in->ev_c, rows * G * F * 8, cudaMemcpyHostToDevice, H->s_h2d)); ci.ev_c = (const uint64_t*)(S.cin.p + LC.ev_c); }
+    if (in->op_c) { CU(cudaMemcpyAsync(S.cin.p + LC.op_c, in->op_c, rows * G * 4, cudaMemcpyHostToDevice, H->s_h2d)); ci.op_c = (const uint32_t*)(S.cin.p + LC.op_c); }
+    if (in->op_c && in->op_unavail) { CU(cudaMemcpyAsync(S.cin.p + LC.op_un, in->op_unavail, rows * G * 2, cudaMemcpyHostToDevice, H->s_h2d)); ci.op_unavail = (const uint16_t*)(S.cin.p + LC.op_un); }
+    if (in->ev_c) { CU(cudaMemcpyAsync(S.cin.p + LC.ev_c, in->ev_c, rows * G * F * 4, cudaMemcpyHostToDevice, H->s_h2d)); ci.ev_c = (const uint32_t*)(S.cin.p + LC.ev_c); }
     if (in->n_esc) CU(cudaMemcpyAsync(S.cin.p + LC.esc, in->esc, (size_t)in->n_esc * sizeof(rafting_cesc_in_t), cudaMemcpyHostToDevice, H->s_h2d));
     CU(cudaEventRecord(S.ev_h2d, H->s_h2d));
     // ---- unpack -> step -> pack on the engine's stream ----
@@ -216,7 +225,7 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
     di.rows = (uint32_t)rows; di.n = (uint32_t)G; di.flags = RAFTING_INBOX_NO_REQUESTS;
     if (in->op_c) {
         di.op_meta = (const uint64_t*)(S.din.p + LD.in_off[2]); di.op_nr = (const i64x2*)(S.din.p + LD.in_off[3]);
-        if (in->flags & RAFTING_CINBOX_HAS_UNAVAIL) di.op_ab = (const i64x2*)(S.din.p + LD.in_off[4]);   // else nobody is unavailable
+        if (in->op_unavail) di.op_ab = (const i64x2*)(S.din.p + LD.in_off[4]);   // else nobody is unavailable
     }
     if (in->ev_c || in->n_esc) {
         di.ev_meta = (const uint64_t*)(S.din.p + LD.in_off[8]); di.ev_tn = (const i64x2*)(S.din.p + LD.in_off[9]); di.ev_el = (const i64x2*)(S.din.p + LD.in_off[10]);
@@ -233,7 +242,7 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
     dov.flags = (uint32_t*)(S.dout.p + LD.flags_off);
     if (!in->op_c) { dov.rep_meta = nullptr; dov.rep_term = nullptr; dov.plan_meta = nullptr; dov.plan_pp = nullptr; dov.plan_lc = nullptr; dov.plan_epoch = nullptr; }
     COutD co;
-    co.plan_c = (uint64_t*)(S.cout.p + LC.plan_c); co.plan_d = (uint32_t*)(S.cout.p + LC.plan_d); co.rep_c = (uint8_t*)(S.cout.p + LC.rep_c);
+    co.plan_c = (uint32_t*)(S.cout.p + LC.plan_c); co.plan_d = (uint32_t*)(S.cout.p + LC.plan_d); co.rep_c = (uint8_t*)(S.cout.p + LC.rep_c);
     co.commit_index = (int64_t*)(S.cout.p + LC.commit); co.current_term = (int64_t*)(S.cout.p + LC.term); co.role_word = (uint32_t*)(S.cout.p + LC.role);
     co.incarnation = (uint32_t*)(S.cout.p + LC.inc); co.err_word = (uint32_t*)(S.cout.p + LC.err); co.last_entry = (i64x2*)(S.cout.p + LC.last);
     co.epoch = (i64x2*)(S.cout.p + LC.epoch); co.counts = (uint32_t*)(S.cout.p + LC.counts);
@@ -245,18 +254,18 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
     InboxW dw;                                                                 // unpack writes what the step kernel reads
     dw.op_meta = (uint64_t*)di.op_meta; dw.op_nr = (i64x2*)di.op_nr; dw.op_ab = (i64x2*)di.op_ab;
     dw.ev_meta = (uint64_t*)di.ev_meta; dw.ev_tn = (i64x2*)di.ev_tn; dw.ev_el = (i64x2*)di.ev_el;
-    unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->T, ci, dw, e->compact->table, e->compact->bits);
+    unpack_kernel<<<blocks, 256, 0, e->stream>>>(e->T, ci, dw, e->compact->table, e->compact->tinc, e->compact->bits);
     if (in->ev_c == nullptr && in->n_esc) CU(cudaMemsetAsync((void*)di.ev_meta, 0, rows * G * F * 8, e->stream));
     if (in->n_esc) unpack_escapes_kernel<<<(in->n_esc + 255u) / 256u, 256, 0, e->stream>>>(ci, dw, (uint32_t)(rows * G * F));
     CU(cudaGetLastError());
     rc = launch_step(e, di, dov, e->stream);
     if (rc) { cudaStreamSynchronize(H->s_h2d); return rc; }
-    pack_kernel<<<blocks, 256, 0, e->stream>>>(e->T, (uint32_t)rows, dov, co, e->compact->table, e->compact->bits);
+    pack_kernel<<<blocks, 256, 0, e->stream>>>(e->T, (uint32_t)rows, dov, co, e->compact->table, e->compact->tinc, e->compact->bits);
     CU(cudaGetLastError());
     CU(cudaEventRecord(S.ev_kernel, e->stream));
     // ---- D2H: every wire column + the counters; the escape list only when the counters say it holds something ----
     CU(cudaStreamWaitEvent(H->s_d2h, S.ev_kernel, 0));
-    CU(cudaMemcpyAsync(out->plan_c, co.plan_c, rows * G * F * 8, cudaMemcpyDeviceToHost, H->s_d2h));
+    CU(cudaMemcpyAsync(out->plan_c, co.plan_c, rows * G * F * 4, cudaMemcpyDeviceToHost, H->s_d2h));
     CU(cudaMemcpyAsync(out->plan_d, co.plan_d, rows * G * F * 4, cudaMemcpyDeviceToHost, H->s_d2h));
     CU(cudaMemcpyAsync(out->rep_c, co.rep_c, rows * G, cudaMemcpyDeviceToHost, H->s_d2h));
     CU(cudaMemcpyAsync(out->commit_index, co.commit_index, G * 8, cudaMemcpyDeviceToHost, H->s_d2h));

@@ -973,7 +973,7 @@ extern "C" int rafting_state_load(rafting_engine_t* e, const char* path) {
     // an image taken after the compact path was used carries the in-flight table: create ours before matching blocks
     std::vector<size_t> ids;
     for (size_t i = 0; i < e->dev_allocs.size(); i++) if (e->dev_is_state[i]) ids.push_back(i);
-    if (h.nblocks == ids.size() + 2) { rc = compact_state(e); if (rc) { close(fd); return rc; } ids.clear(); for (size_t i = 0; i < e->dev_allocs.size(); i++) if (e->dev_is_state[i]) ids.push_back(i); }
+    if (h.nblocks == ids.size() + 3) { rc = compact_state(e); if (rc) { close(fd); return rc; } ids.clear(); for (size_t i = 0; i < e->dev_allocs.size(); i++) if (e->dev_is_state[i]) ids.push_back(i); }
     if (h.nblocks > ids.size()) { close(fd); return fail(RAFTING_E_INVAL, "image holds %u blocks, the engine %zu", h.nblocks, ids.size()); }
     // read + verify everything first: a corrupt image must not leave the tables half loaded
     std::vector<std::vector<uint8_t>> blocks(h.nblocks);

@@ -24,7 +24,8 @@ import numpy as np
 from . import abi
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librafting_b200.so")
+# RAFTING_B200_LIB selects another build of the same ABI (the -DRAFTING_ENABLE_CFG_FLAGS library, an A/B variant)
+_LIB_PATH = os.environ.get("RAFTING_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "librafting_b200.so")
 
 STATUS = {0: "OK", -1: "E_INVAL", -2: "E_NOMEM", -3: "E_CUDA", -4: "E_CLOSED", -5: "E_CAPACITY",
           -6: "E_NODEVICE", -7: "E_BUSY", -8: "E_NCCL"}

@@ -74,3 +74,19 @@ def test_random_partitions_engine_in_lock_step(engine_mod, R, pre_vote, seed):
 def _states_equal(c, R):
     for nd in c.nodes:
         harness.assert_states_equal(nd.sut.o, nd.sut.e, range(c.G), R - 1, where=f"node {nd.slot}")
+
+
+def test_opt_in_protocol_fixes_on_the_device_in_lock_step():
+    """The device branches of RAFTING_CFG_STRICT_CANDIDATE_VOTE / _LENIENT_FOLLOWER_COMMIT live in a library of their own
+    (-DRAFTING_ENABLE_CFG_FLAGS; the default build rejects cfg.flags != 0 and keeps its SASS): the unguarded runs that
+    diverge (seed 102) or stall (1030) with the reference's behaviour run on it in lock-step with the oracle and converge."""
+    import os
+    import subprocess
+    import sys
+    from rafting_b200 import _build
+    lib = _build.build_flags()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RAFTING_B200_LIB=lib)
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "run_flagged_cluster.py")], capture_output=True, text=True,
+                         timeout=900, env=env, cwd=root)
+    assert res.returncode == 0 and "FLAGGED-OK" in res.stdout, (res.stdout[-1500:], res.stderr[-3000:])

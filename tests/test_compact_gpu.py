@@ -22,7 +22,7 @@ def _run(G, R, rows, steps, seed, esc_cap=1 << 16, mangle=None):
     w1 = workload.make_wl(seed, 1, G, R - 1)
     w = workload.make_wl(seed, rows, G, R - 1, p_reject_ppm=60_000, p_error_ppm=20_000, p_cancel_ppm=20_000)
     harness.assert_outbox_equal(harness.elect_all(o, w1), harness.elect_all(e, w1), where="election (dense path)")
-    prev, tags, sent_term = None, None, None
+    prev, tags, sent_term, sent_inc = None, None, None, None
     up = down = escapes = 0
     overflows = []
     for k in range(steps):
@@ -30,7 +30,7 @@ def _run(G, R, rows, steps, seed, esc_cap=1 << 16, mangle=None):
         if mangle:
             mangle(k, ib)
         want = o.step(ib, threads=8)
-        cin = compact.encode_inbox(ib, tags, sent_term)
+        cin = compact.encode_inbox(ib, tags, sent_term, sent_inc)
         cout = compact.CompactOutbox(rows, G, R - 1, esc_cap=esc_cap)
         e.step_compact(cin, cout)
         try:
@@ -41,7 +41,7 @@ def _run(G, R, rows, steps, seed, esc_cap=1 << 16, mangle=None):
             overflows.append(k)
         harness.assert_outbox_equal(want, got, where=f"compact step {k}")
         assert np.array_equal(cout.epoch["x"], np.array([0] * G))         # nothing was compacted in this stream
-        prev, tags, sent_term = want, cout.tags(), cout.current_term.copy()
+        prev, tags, sent_term, sent_inc = want, cout.tags(), cout.current_term.copy(), cout.incarnation.copy()
         up += cin.nbytes(); down += cout.nbytes(); escapes += len(cin.esc) + int(cout.counts[0])
     harness.assert_states_equal(o, e, list(range(0, G, max(1, G // 64))) + [G - 1], R - 1, where="compact end")
     return up, down, escapes, ib, cout, overflows
@@ -55,8 +55,8 @@ def test_compact_leader_stream_is_the_dense_step_bit_for_bit():
     assert not overflows
     # the byte cut that motivates the format (dense = 65 B up + 69 B down per ack), on the last, steady-state step
     acks = int(((ib.ev_meta & np.uint64(0xF)) != 0).sum())
-    cin_bytes = rows * 8 + rows * G * 8 + rows * G * (R - 1) * 8
-    assert cin_bytes / acks < 20 and cout.nbytes() / acks < 24, (cin_bytes / acks, cout.nbytes() / acks)
+    cin_bytes = rows * 8 + rows * G * 4 + rows * G * (R - 1) * 4
+    assert cin_bytes / acks < 10 and cout.nbytes() / acks < 16, (cin_bytes / acks, cout.nbytes() / acks)
     assert int(cout.counts[0]) < rows * G // 20                      # steady state: a few per cent of escapes at most
 
 
@@ -84,7 +84,7 @@ def test_compact_escape_overflow_falls_back_to_the_dense_outbox():
     want = o.step(ib)
     # the first replicateLog of a fresh leader sends prevLogIndex 0 / prevLogTerm 0: not compact -> thousands of escapes
     cout = compact.CompactOutbox(rows, G, R - 1, esc_cap=8)
-    e.step_compact(compact.encode_inbox(ib, None, None), cout)
+    e.step_compact(compact.encode_inbox(ib, None, None, None), cout)
     assert int(cout.counts[0]) > 8
     with pytest.raises(OverflowError):
         compact.decode_outbox(cout)
