@@ -416,7 +416,7 @@ int rafting_step_wait_slot (rafting_engine_t* e, uint32_t slot);
  *     No free slot (more than 32 RPCs of one lane outstanding): tag 255, and the reply must come back as an escape record.
  *   * dense steps only (no active list), no inbound-request ops (RAFTING_INBOX_NO_REQUESTS is implied): SUBMIT / TIMEOUT
  *     ops, AE / IS acks; vote replies and anything irregular use the escape list.
- *   * wire words are 32 bits: 4 B per lane slot + 4 B per group row up, 8 B per lane slot + 1 B per group row down.
+ *   * wire words are 32 bits: 4 B per lane slot + 4 B per group row up, 4 B per lane slot + 1 B per group row down.
  * ------------------------------------------------------------------------------------------------------------------- */
 /* ev_c (32 bits per lane slot):
  *        bits 0..3 kind (RAFTING_EV_NONE / _AE_ACK / _IS_ACK, or 15 = "see the escape list") | 4..5 outcome | 6 success |
@@ -432,7 +432,7 @@ int rafting_step_wait_slot (rafting_engine_t* e, uint32_t slot);
     ((uint32_t)(kind) | ((uint32_t)(outcome) << 4) | ((uint32_t)((success) ? 1 : 0) << 6) |                            \
      ((uint32_t)((term_as_sent) ? 1 : 0) << 7) | ((uint32_t)((tag) & 0xffu) << 8) | ((uint32_t)((dt) & 0xffffu) << 16))
 #define RAFTING_COP_MAKE(kind, count, dt) ((uint32_t)(kind) | ((uint32_t)((count) & 0xfffu) << 4) | ((uint32_t)((dt) & 0xffffu) << 16))
-#define RAFTING_CTAG_NONE 255u
+#define RAFTING_CTAG_NONE 63u    /* in ev_c (8-bit field) any value >= 32 means "no tag" */
 typedef struct rafting_cesc_in {     /* a lane event in full: overwrites slot (row * G + gid) * F + lane after unpacking */
     uint32_t slot, _pad;
     uint64_t ev_meta;                /* RAFTING_EVM_MAKE(...) */
@@ -446,23 +446,30 @@ typedef struct rafting_cinbox {
     const uint32_t*          ev_c;       /* [rows][G][F], may be NULL (no lane events) */
     const rafting_cesc_in_t* esc;        /* [n_esc] */
 } rafting_cinbox_t;
-/* plan_c (32 bits per lane slot): bits 0..3 kind | 4 heartbeat | 6 escaped | 8..15 tag | 16..31 entry count.  Not escaped means:
+/* plan_c (ONE 32-bit word per lane slot): bits 0..2 kind | 3 heartbeat | 4 escaped | 5..10 tag (0..31, 63 = none) |
+ *          11..16 entry count (0..50, Leadership.REPLICATE_LIMIT) | 17..24 dprev | 25..31 dcommit.  Not escaped means:
  *          the plan's incarnation == incarnation[g] (end of step), and
- *          AE  prevLogIndex = last_entry[g].x - (plan_d & 0xffff), prevLogTerm = current_term[g], lastIndex = prevLogIndex + count,
- *              leaderCommit = commit_index[g] - (plan_d >> 16), epochAtSend = epoch[g].x
+ *          AE  prevLogIndex = last_entry[g].x - dprev, prevLogTerm = current_term[g], lastIndex = prevLogIndex + count,
+ *              leaderCommit = commit_index[g] - dcommit, epochAtSend = epoch[g].x          (dprev < 256, dcommit < 128)
  *          IS  (epoch.index, epoch.term) = epoch[g], leaderCommit as above
  *          SKIP_INFLIGHT / UNAVAILABLE: no payload
  * rep_c  : per-event error code of the row's group op (rafting_outbox_t.rep_meta bits 8..15); a row whose op produced a
  *          REPLY (inbound requests are not part of compact steps, but the generic handler may answer) is escaped         */
+#define RAFTING_CPLAN_KIND(w)    ((uint32_t)(w) & 7u)
+#define RAFTING_CPLAN_HB(w)      (((uint32_t)(w) >> 3) & 1u)
+#define RAFTING_CPLAN_ESCAPED(w) (((uint32_t)(w) >> 4) & 1u)
+#define RAFTING_CPLAN_TAG(w)     (((uint32_t)(w) >> 5) & 63u)
+#define RAFTING_CPLAN_COUNT(w)   (((uint32_t)(w) >> 11) & 63u)
+#define RAFTING_CPLAN_DPREV(w)   (((uint32_t)(w) >> 17) & 255u)
+#define RAFTING_CPLAN_DCOMMIT(w) (((uint32_t)(w) >> 25) & 127u)
 enum { RAFTING_CESC_PLAN = 1, RAFTING_CESC_BALLOT = 2, RAFTING_CESC_REPLY = 3 };
 typedef struct rafting_cesc_out {
     uint32_t kind, slot;             /* PLAN: lane slot; BALLOT / REPLY: row * G + gid */
-    uint64_t meta;                   /* plan_meta | tag << 8 (the full 64-bit word, incarnation included) / ballot_meta / rep_meta */
+    uint64_t meta;                   /* plan_meta | tag << 8 (the full 64-bit plan word, incarnation included; tag 255 = none) / ballot_meta / rep_meta */
     int64_t  a, b, c, d, e;          /* PLAN: plan_pp.x, .y, plan_lc.x, .y, plan_epoch; BALLOT: term, last.x, last.y; REPLY: rep_term */
 } rafting_cesc_out_t;
 typedef struct rafting_coutbox {
     uint32_t* plan_c;                /* [rows][G][F] */
-    uint32_t* plan_d;                /* [rows][G][F] */
     uint8_t*  rep_c;                 /* [rows][G]    */
     int64_t*  commit_index; int64_t* current_term; uint32_t* role_word; uint32_t* incarnation; uint32_t* err_word;
     rafting_i64x2_t* last_entry;     /* [G] each, as in rafting_outbox_t */

@@ -331,7 +331,7 @@ def leader_of(role_word: int) -> int:
 
 
 # ---- compact host path (include/rafting_b200.h "COMPACT host path") --------------------------------------------------
-CEV_ESCAPED, CTAG_NONE = 15, 255
+CEV_ESCAPED, CTAG_NONE = 15, 63
 CESC_PLAN, CESC_BALLOT, CESC_REPLY = 1, 2, 3
 CESC_IN = np.dtype([("slot", "<u4"), ("_pad", "<u4"), ("ev_meta", "<u8"), ("term", "<i8"), ("now_ms", "<i8"),
                     ("epoch_at_send", "<i8"), ("last_at_send", "<i8")])
@@ -345,7 +345,7 @@ class CInboxC(C.Structure):
 
 
 class COutboxC(C.Structure):
-    _fields_ = [("plan_c", C.c_void_p), ("plan_d", C.c_void_p), ("rep_c", C.c_void_p),
+    _fields_ = [("plan_c", C.c_void_p), ("rep_c", C.c_void_p),
                 ("commit_index", C.c_void_p), ("current_term", C.c_void_p), ("role_word", C.c_void_p), ("incarnation", C.c_void_p),
                 ("err_word", C.c_void_p), ("last_entry", C.c_void_p), ("epoch", C.c_void_p), ("esc", C.c_void_p),
                 ("esc_cap", C.c_uint32), ("_pad", C.c_uint32), ("counts", C.c_void_p)]

@@ -2,7 +2,7 @@
 with the engine — numpy only.
 
   encode_inbox   dense lane events / group ops  ->  ev_c / op_c / row_base (+ escape records for whatever breaks a compact rule)
-  decode_outbox  plan_c / plan_d / rep_c / group columns / escape records  ->  the dense outbox columns
+  decode_outbox  plan_c / rep_c / group columns / escape records  ->  the dense outbox columns
 
 The engine's own unpack / pack kernels (rafting_b200/csrc/compact.cuh) are the inverse of these two; tests/test_compact_gpu.py
 checks that a compact step, decoded, equals the dense step of the oracle bit for bit.
@@ -43,7 +43,6 @@ class CompactOutbox:
     def __init__(self, rows, n, F, esc_cap=4096):
         self.rows, self.n, self.F, self.esc_cap = rows, n, F, esc_cap
         self.plan_c = np.zeros((rows, n, F), dtype=np.uint32)
-        self.plan_d = np.zeros((rows, n, F), dtype=np.uint32)
         self.rep_c = np.zeros((rows, n), dtype=np.uint8)
         self.commit_index = np.zeros(n, dtype=np.int64)
         self.current_term = np.zeros(n, dtype=np.int64)
@@ -55,7 +54,7 @@ class CompactOutbox:
         self.esc = np.zeros(esc_cap, dtype=abi.CESC_OUT)
         self.counts = np.zeros(4, dtype=np.uint32)
 
-    COLS = ("plan_c", "plan_d", "rep_c", "commit_index", "current_term", "role_word", "incarnation", "err_word", "last_entry", "epoch")
+    COLS = ("plan_c", "rep_c", "commit_index", "current_term", "role_word", "incarnation", "err_word", "last_entry", "epoch")
 
     def nbytes(self):
         return sum(getattr(self, c).nbytes for c in self.COLS) + 16
@@ -68,8 +67,8 @@ class CompactOutbox:
         return c
 
     def tags(self) -> np.ndarray:
-        """tag of every plan, [rows, n, F] (255 = none)"""
-        return ((self.plan_c >> np.uint32(8)) & np.uint32(0xFF)).astype(np.uint8)
+        """tag of every plan, [rows, n, F] (abi.CTAG_NONE = none)"""
+        return ((self.plan_c >> np.uint32(5)) & np.uint32(63)).astype(np.uint8)
 
 
 def encode_inbox(ib: abi.Inbox, tags: np.ndarray | None, sent_term: np.ndarray | None, sent_inc: np.ndarray | None = None) -> CompactInbox:
@@ -120,7 +119,7 @@ def encode_inbox(ib: abi.Inbox, tags: np.ndarray | None, sent_term: np.ndarray |
     tg = tags if tags is not None else np.full((rows, n, F), abi.CTAG_NONE, np.uint8)
     term_ok = (ib.ev_tn["x"] == (sent_term[None, :, None] if sent_term is not None else 0))
     inc_ok = ((em >> U64(32)) == (sent_inc.astype(np.uint64)[None, :, None] if sent_inc is not None else U64(0)))
-    fits = is_ack & (dt >= 0) & (dt <= 0xFFFF) & (tg != abi.CTAG_NONE) & ((outcome != abi.OUT_OK) | term_ok) & inc_ok
+    fits = is_ack & (dt >= 0) & (dt <= 0xFFFF) & (tg < 32) & ((outcome != abi.OUT_OK) | term_ok) & inc_ok
     word = (em & U64(0x7F)) | (np.where(outcome == abi.OUT_OK, 1, 0).astype(np.uint64) << U64(7)) | (tg.astype(np.uint64) << U64(8)) | \
            (dt.astype(np.uint64) << U64(16))
     c.ev_c[:] = np.where(fits, word, np.where(ek != 0, U64(abi.CEV_ESCAPED), U64(0))).astype(np.uint32)
@@ -141,13 +140,15 @@ def decode_outbox(co: CompactOutbox, G: int | None = None) -> abi.Outbox:
         raise OverflowError("escape list overflow: fetch the dense outbox (rafting_step_fetch_dense)")
     o = abi.Outbox(rows, n, F, n if G is None else G)
     pc = co.plan_c.astype(np.uint64)
-    kind = (pc & U64(0xF)).astype(np.int64)
-    esc = ((pc >> U64(6)) & U64(1)) != 0
-    # tag and escape bit are wire-only; a compact plan was sent by the role object that holds the group at the end of the step
-    o.plan_meta[:] = np.where(kind != 0, (pc & U64(0xFFFF001F)) | (co.incarnation.astype(np.uint64)[None, :, None] << U64(32)), U64(0))
-    cnt = ((pc >> U64(16)) & U64(0xFFFF)).astype(np.int64)
-    dprev = (co.plan_d & np.uint32(0xFFFF)).astype(np.int64)
-    dcommit = (co.plan_d >> np.uint32(16)).astype(np.int64)
+    kind = (pc & U64(7)).astype(np.int64)
+    hb = (pc >> U64(3)) & U64(1)
+    esc = ((pc >> U64(4)) & U64(1)) != 0
+    cnt = ((pc >> U64(11)) & U64(63)).astype(np.int64)
+    dprev = ((pc >> U64(17)) & U64(255)).astype(np.int64)
+    dcommit = ((pc >> U64(25)) & U64(127)).astype(np.int64)
+    # a compact plan was sent by the role object that holds the group at the end of the step
+    o.plan_meta[:] = np.where(kind != 0, kind.astype(np.uint64) | (hb << U64(4)) | (cnt.astype(np.uint64) << U64(16)) |
+                              (co.incarnation.astype(np.uint64)[None, :, None] << U64(32)), U64(0))
     last_x, term = co.last_entry["x"][None, :, None], co.current_term[None, :, None]
     commit, ep = co.commit_index[None, :, None], co.epoch
     ae, isn = (kind == abi.PLAN_AE) & ~esc, (kind == abi.PLAN_IS) & ~esc
@@ -164,7 +165,7 @@ def decode_outbox(co: CompactOutbox, G: int | None = None) -> abi.Outbox:
         k, slot = int(r["kind"]), int(r["slot"])
         if k == abi.CESC_PLAN:
             rr, rest = divmod(slot, n * F); i, f = divmod(rest, F)
-            o.plan_meta[rr, i, f] = int(r["meta"]) & ~0xFF40                  # the full plan word of an escaped plan (other incarnation)
+            o.plan_meta[rr, i, f] = int(r["meta"]) & ~0xFF00                  # the full plan word of an escaped plan, minus the tag
             o.plan_pp[rr, i, f] = (r["a"], r["b"]); o.plan_lc[rr, i, f] = (r["c"], r["d"]); o.plan_epoch[rr, i, f] = r["e"]
         elif k == abi.CESC_BALLOT:
             rr, i = divmod(slot, n)

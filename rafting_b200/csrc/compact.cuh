@@ -4,7 +4,7 @@
 //   unpack_kernel   wire columns (ev_c 4 B / lane slot, op_c 4 B / group row, row_base)  ->  the dense SoA inbox the step kernel
 //                   reads; the (epochAtSend, lastIndexAtSend) pair AND the incarnation of every ack come out of the HBM
 //                   in-flight table under the tag the reply echoes, and the tag's slot is freed
-//   pack_kernel     the dense outbox  ->  plan_c 4 B + plan_d 4 B / lane slot, rep_c 1 B / group row, the per-group columns;
+//   pack_kernel     the dense outbox  ->  plan_c 4 B / lane slot, rep_c 1 B / group row, the per-group columns;
 //                   every AE / IS plan gets a free tag of its (group, follower) lane and parks its echo pair and its
 //                   incarnation in the table; whatever breaks a compact rule goes, in full, to the escape list
 //
@@ -28,7 +28,7 @@ struct CInD {                                    // device view of rafting_cinbo
     const int64_t* row_base; const uint32_t* op_c; const uint16_t* op_unavail; const uint32_t* ev_c; const rafting_cesc_in_t* esc;
 };
 struct COutD {                                   // device view of rafting_coutbox_t
-    uint32_t* plan_c; uint32_t* plan_d; uint8_t* rep_c;
+    uint32_t* plan_c; uint8_t* rep_c;
     int64_t* commit_index; int64_t* current_term; uint32_t* role_word; uint32_t* incarnation; uint32_t* err_word;
     i64x2* last_entry; i64x2* epoch; rafting_cesc_out_t* esc; uint32_t esc_cap; uint32_t* counts;
 };
@@ -102,9 +102,9 @@ __global__ void __launch_bounds__(256) pack_kernel(Tables T, uint32_t rows, Outb
         for (uint32_t r = 0; r < rows; r++) {
             const size_t idx = (size_t)r * GF + t;
             const uint64_t pm = in.plan_meta[idx];
-            uint32_t pc = 0, pd = 0;
+            uint32_t pc = 0;
             if (pm != 0) {
-                const uint32_t kind = RAFTING_PLM_KIND(pm);
+                const uint32_t kind = RAFTING_PLM_KIND(pm), count = RAFTING_PLM_COUNT(pm);
                 const i64x2 pp = in.plan_pp[idx], lc = in.plan_lc[idx];
                 const int64_t pe = in.plan_epoch[idx];
                 uint32_t tag = RAFTING_CTAG_NONE;
@@ -116,22 +116,22 @@ __global__ void __launch_bounds__(256) pack_kernel(Tables T, uint32_t rows, Outb
                     }
                 }
                 const uint64_t dcommit = (uint64_t)commit_end - (uint64_t)lc.y;
-                bool fits = pe == epoch_end.x && RAFTING_PLM_INC(pm) == inc_end;
+                uint64_t dprev = 0;
+                bool fits = pe == epoch_end.x && RAFTING_PLM_INC(pm) == inc_end && count < 64u;
                 if (kind == RAFTING_PLAN_AE) {
-                    const uint64_t dprev = (uint64_t)last_end.x - (uint64_t)pp.x;
-                    fits = fits && pp.y == term_end && lc.x == (int64_t)((uint64_t)pp.x + RAFTING_PLM_COUNT(pm)) && dprev < 65536u && dcommit < 65536u;
-                    pd = (uint32_t)dprev | ((uint32_t)dcommit << 16);
+                    dprev = (uint64_t)last_end.x - (uint64_t)pp.x;
+                    fits = fits && pp.y == term_end && lc.x == (int64_t)((uint64_t)pp.x + count) && dprev < 256u && dcommit < 128u;
                 } else if (kind == RAFTING_PLAN_IS) {
-                    fits = fits && pp.x == epoch_end.x && pp.y == epoch_end.y && lc.x == epoch_end.x && dcommit < 65536u;
-                    pd = (uint32_t)dcommit << 16;
+                    fits = fits && pp.x == epoch_end.x && pp.y == epoch_end.y && lc.x == epoch_end.x && dcommit < 128u;
                 } else fits = fits && pp.x == 0 && pp.y == 0 && lc.x == 0 && lc.y == 0;
-                pc = (uint32_t)(pm & 0xffff001full) | (tag << 8);                 // kind | hb | count, + tag
-                if (!fits) { pc |= 1u << 6; pd = 0; put_escape(out, RAFTING_CESC_PLAN, (uint32_t)idx, pm | ((uint64_t)tag << 8), pp.x, pp.y, lc.x, lc.y, pe); }
+                pc = kind | ((uint32_t)RAFTING_PLM_HB(pm) << 3) | (tag << 5);
+                if (fits) pc |= (count << 11) | ((uint32_t)dprev << 17) | ((kind == RAFTING_PLAN_AE || kind == RAFTING_PLAN_IS) ? ((uint32_t)dcommit << 25) : 0u);
+                else { pc |= 1u << 4; put_escape(out, RAFTING_CESC_PLAN, (uint32_t)idx, pm | ((uint64_t)(tag == RAFTING_CTAG_NONE ? 255u : tag) << 8), pp.x, pp.y, lc.x, lc.y, pe); }
             }
-            out.plan_c[idx] = pc; out.plan_d[idx] = pd;
+            out.plan_c[idx] = pc;
         }
     } else {
-        for (uint32_t r = 0; r < rows; r++) { const size_t idx = (size_t)r * GF + t; out.plan_c[idx] = 0; out.plan_d[idx] = 0; }
+        for (uint32_t r = 0; r < rows; r++) out.plan_c[(size_t)r * GF + t] = 0;
     }
     bits[t] = b;
     if (f == 0) {
@@ -171,14 +171,14 @@ static int compact_state(rafting_engine* e) {
 }
 
 // byte layout of the two wire blocks of a slot (device copy and — for the small items — a pinned landing block)
-struct CLayout { size_t row_base, op_c, op_un, ev_c, esc, in_total; size_t plan_c, plan_d, rep_c, commit, term, role, inc, err, last, epoch, counts, esc_out, out_total, out_dense; };
+struct CLayout { size_t row_base, op_c, op_un, ev_c, esc, in_total; size_t plan_c, rep_c, commit, term, role, inc, err, last, epoch, counts, esc_out, out_total, out_dense; };
 static CLayout compact_layout(size_t rows, size_t G, size_t F, size_t n_esc_in, size_t esc_cap) {
     CLayout L; size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
     L.row_base = take(rows * 8); L.op_c = take(rows * G * 4); L.op_un = take(rows * G * 2); L.ev_c = take(rows * G * F * 4);
     L.esc = take((n_esc_in + 1) * sizeof(rafting_cesc_in_t));
     L.in_total = o; o = 0;
-    L.plan_c = take(rows * G * F * 4); L.plan_d = take(rows * G * F * 4); L.rep_c = take(rows * G);
+    L.plan_c = take(rows * G * F * 4); L.rep_c = take(rows * G);
     L.commit = take(G * 8); L.term = take(G * 8); L.role = take(G * 4); L.inc = take(G * 4); L.err = take(G * 4); L.last = take(G * 16); L.epoch = take(G * 16);
     L.counts = take(16);
     L.out_dense = o;                                                          // everything before the escape list travels down every step
@@ -192,7 +192,7 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
     if (!e || !in || !out || slot >= RAFTING_HOST_SLOTS) return fail(RAFTING_E_INVAL, "bad argument");
     if (!in->row_base || (!in->op_c && !in->ev_c)) return fail(RAFTING_E_INVAL, "compact inbox needs row_base and at least one of op_c / ev_c");
     if (in->n_esc && !in->esc) return fail(RAFTING_E_INVAL, "n_esc without esc");
-    if (!out->plan_c || !out->plan_d || !out->rep_c || !out->commit_index || !out->current_term || !out->role_word || !out->incarnation ||
+    if (!out->plan_c || !out->rep_c || !out->commit_index || !out->current_term || !out->role_word || !out->incarnation ||
         !out->err_word || !out->last_entry || !out->epoch || !out->counts || (out->esc_cap && !out->esc))
         return fail(RAFTING_E_INVAL, "compact outbox: every column is required");
     if (e->F > 16) return fail(RAFTING_E_CAPACITY, "the compact path carries a 16-lane unavailable mask: use the dense path for larger clusters");
@@ -242,7 +242,7 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
     dov.flags = (uint32_t*)(S.dout.p + LD.flags_off);
     if (!in->op_c) { dov.rep_meta = nullptr; dov.rep_term = nullptr; dov.plan_meta = nullptr; dov.plan_pp = nullptr; dov.plan_lc = nullptr; dov.plan_epoch = nullptr; }
     COutD co;
-    co.plan_c = (uint32_t*)(S.cout.p + LC.plan_c); co.plan_d = (uint32_t*)(S.cout.p + LC.plan_d); co.rep_c = (uint8_t*)(S.cout.p + LC.rep_c);
+    co.plan_c = (uint32_t*)(S.cout.p + LC.plan_c); co.rep_c = (uint8_t*)(S.cout.p + LC.rep_c);
     co.commit_index = (int64_t*)(S.cout.p + LC.commit); co.current_term = (int64_t*)(S.cout.p + LC.term); co.role_word = (uint32_t*)(S.cout.p + LC.role);
     co.incarnation = (uint32_t*)(S.cout.p + LC.inc); co.err_word = (uint32_t*)(S.cout.p + LC.err); co.last_entry = (i64x2*)(S.cout.p + LC.last);
     co.epoch = (i64x2*)(S.cout.p + LC.epoch); co.counts = (uint32_t*)(S.cout.p + LC.counts);
@@ -266,7 +266,6 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
     // ---- D2H: every wire column + the counters; the escape list only when the counters say it holds something ----
     CU(cudaStreamWaitEvent(H->s_d2h, S.ev_kernel, 0));
     CU(cudaMemcpyAsync(out->plan_c, co.plan_c, rows * G * F * 4, cudaMemcpyDeviceToHost, H->s_d2h));
-    CU(cudaMemcpyAsync(out->plan_d, co.plan_d, rows * G * F * 4, cudaMemcpyDeviceToHost, H->s_d2h));
     CU(cudaMemcpyAsync(out->rep_c, co.rep_c, rows * G, cudaMemcpyDeviceToHost, H->s_d2h));
     CU(cudaMemcpyAsync(out->commit_index, co.commit_index, G * 8, cudaMemcpyDeviceToHost, H->s_d2h));
     CU(cudaMemcpyAsync(out->current_term, co.current_term, G * 8, cudaMemcpyDeviceToHost, H->s_d2h));

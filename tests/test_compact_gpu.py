@@ -56,7 +56,7 @@ def test_compact_leader_stream_is_the_dense_step_bit_for_bit():
     # the byte cut that motivates the format (dense = 65 B up + 69 B down per ack), on the last, steady-state step
     acks = int(((ib.ev_meta & np.uint64(0xF)) != 0).sum())
     cin_bytes = rows * 8 + rows * G * 4 + rows * G * (R - 1) * 4
-    assert cin_bytes / acks < 10 and cout.nbytes() / acks < 16, (cin_bytes / acks, cout.nbytes() / acks)
+    assert cin_bytes / acks < 10 and cout.nbytes() / acks < 10, (cin_bytes / acks, cout.nbytes() / acks)
     assert int(cout.counts[0]) < rows * G // 20                      # steady state: a few per cent of escapes at most
 
 
