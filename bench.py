@@ -479,10 +479,11 @@ def run_engine(args):
     # ---- e2e: the same stream through the C-ABI host path, HOST buffers in, HOST buffers out ---------
     e2e = None
     e2e_dense = None
+    e2e_frames = None
     lat_ms = []
     if not args.no_e2e:
         from rafting_b200 import compact
-        NSL = 3                                           # launches in flight on the host path
+        NSL = 4                                           # launches in flight on the host path (RAFTING_HOST_SLOTS)
 
         def pinned_like(a):
             t = torch.empty(a.nbytes, dtype=torch.uint8).pin_memory()
@@ -575,6 +576,64 @@ def run_engine(args):
             raise SystemExit(f"bench.py: a launch produced {esc_out_max} escape records (> {ESC_CAP}): the compact e2e number would need the dense fallback")
         e2e = {"spent": float(t.item()), "h2d": h2d, "d2h": d2h, "acks": float(ae.item()), "launches": n_pass_launch * reps,
                "launches_per_pass": n_pass_launch, "passes": reps, "exact": e2e_exact, "esc_in": esc_in, "esc_out_max": esc_out_max}
+
+        # (A') the same launches arriving as FRAMES (include/rafting_ingest.h): each launch's wire columns sit in ONE
+        # pinned receive buffer as frames of the reference's layout |SOH|TYPE|STX|HEAD_LEN|HEAD|BODY_LEN|BODY|ETX| (type 0x1A, head =
+        # column name); the timed loop cuts the buffer with rafting_frame_scan and hands the body addresses to the engine
+        e2e_frames = None
+        if world == 1:
+            from rafting_b200 import ingest
+            IL = ingest.lib()
+            rx = []
+            for ci in cins:
+                blob = b"".join(ingest.encode(ingest.BATCH, name.encode(), getattr(ci, name).tobytes())
+                                for name in ("row_base", "op_c", "ev_c", "esc") if getattr(ci, name) is not None and len(getattr(ci, name)))
+                tt = torch.frombuffer(bytearray(blob), dtype=torch.uint8).pin_memory()
+                rx.append((tt, tt.data_ptr(), len(blob)))
+            frames = np.zeros(8, dtype=ingest.FRAME)
+            nfr, used, transparent = C.c_uint32(), C.c_size_t(), C.c_int()
+            cinf = [abi.CInboxC() for _ in range(NSL)]
+
+            def frame_pass():
+                for j in range(n_pass_launch):
+                    sl = j % NSL
+                    if j >= NSL:
+                        e.step_wait_compact(sl)
+                    _, base, ln = rx[j]
+                    if IL.rafting_frame_scan(base, ln, frames.ctypes.data, 8, C.byref(nfr), C.byref(used), C.byref(transparent)) or used.value != ln:
+                        raise RuntimeError("frame scan failed")
+                    ci = cinf[sl]
+                    ci.rows, ci.n_esc, ci.op_c, ci.ev_c, ci.esc, ci.op_unavail = rows, 0, None, None, None, None
+                    for fr in frames[:nfr.value]:
+                        head = tt_bytes(base + int(fr["head_off"]), int(fr["head_len"]))
+                        addr = base + int(fr["body_off"])
+                        if head == b"row_base":
+                            ci.row_base = addr
+                        elif head == b"op_c":
+                            ci.op_c = addr
+                        elif head == b"ev_c":
+                            ci.ev_c = addr
+                        elif head == b"esc":
+                            ci.esc, ci.n_esc = addr, int(fr["body_len"]) // abi.CESC_IN.itemsize
+                    e.step_begin_compact(sl, ci, cout_c[sl])
+                for sl in range(NSL):
+                    e.step_wait_compact(sl)
+
+            def tt_bytes(addr, n):
+                return C.string_at(addr, n)
+
+            e.restore(); frame_pass()
+            frames_exact = bool((e.digest(0, G) == digest_c).all())
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                e.restore(sync=False)
+                frame_pass()
+            fspent = time.perf_counter() - t0
+            e2e_frames = {"value": acks_pass * reps / fspent, "unit": "acks/s", "launches": n_pass_launch * reps,
+                          "rx_bytes_per_launch": int(np.mean([r[2] for r in rx])), "same_end_state_as_device_path": frames_exact,
+                          "what": "the compact launches as frames of the reference's wire layout in one pinned receive buffer per launch; "
+                                  "rafting_frame_scan + pointer hand-over inside the timed loop"}
+            del rx
         del cins, keep, couts
 
         # (B) the DENSE host path of round 1 on a few launches of the same window, for the before / after of the byte cut
@@ -698,6 +757,8 @@ def run_engine(args):
                                    "bytes_per_step = per launch x the launches of one step"}
             if e2e_dense:
                 line["e2e_dense_path"] = e2e_dense
+            if e2e_frames:
+                line["e2e_from_frames"] = e2e_frames
             line["commit_latency_ms"] = {"p50": float(np.percentile(lat_ms, 50)), "p99": float(np.percentile(lat_ms, 99)),
                                          "what": "one synchronous launch: host ack in pinned inbox -> commit record readable in pinned outbox"}
         if cpu:
