@@ -18,6 +18,7 @@
 
 namespace rafting {
 
+constexpr uint32_t CESC_INLINE = 256;            // escape records that always travel down with the columns (14 KB)
 constexpr int CTAGS = 32;                        // in-flight slots per (group, follower): IN_FLIGHT_LIMIT is 20 (Leadership.java:11)
 
 struct InboxW {                                  // writable view of the dense staging columns unpack_kernel fills
@@ -275,6 +276,10 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
     CU(cudaMemcpyAsync(out->last_entry, co.last_entry, G * 16, cudaMemcpyDeviceToHost, H->s_d2h));
     CU(cudaMemcpyAsync(out->epoch, co.epoch, G * 16, cudaMemcpyDeviceToHost, H->s_d2h));
     CU(cudaMemcpyAsync(S.chout.p, co.counts, 16, cudaMemcpyDeviceToHost, H->s_d2h));
+    // the first escape records always travel with the columns (a steady-state launch produces a handful): fetching them on
+    // demand at wait time would have to drain the D2H stream, i.e. wait for the copies of every LATER launch as well
+    const uint32_t esc_inline = out->esc_cap < CESC_INLINE ? out->esc_cap : CESC_INLINE;
+    if (esc_inline) CU(cudaMemcpyAsync(out->esc, co.esc, (size_t)esc_inline * sizeof(rafting_cesc_out_t), cudaMemcpyDeviceToHost, H->s_d2h));
     CU(cudaEventRecord(S.ev_done, H->s_d2h));
     S.compact_step = true; S.c_host = *out; S.c_counts_pinned = (uint32_t*)S.chout.p; S.c_esc_dev = co.esc;
     S.dev_out = rafting_outbox_t(); memset(&S.dev_out, 0, sizeof(S.dev_out));
@@ -298,8 +303,9 @@ extern "C" int rafting_step_wait_compact(rafting_engine_t* e, uint32_t slot) {
     S.inflight = false;
     for (int k = 0; k < 4; k++) S.c_host.counts[k] = S.c_counts_pinned[k];
     const uint32_t n = S.c_counts_pinned[0] < S.c_host.esc_cap ? S.c_counts_pinned[0] : S.c_host.esc_cap;
-    if (n) {
-        CU(cudaMemcpyAsync(S.c_host.esc, S.c_esc_dev, (size_t)n * sizeof(rafting_cesc_out_t), cudaMemcpyDeviceToHost, H->s_d2h));
+    if (n > CESC_INLINE) {                                                    // rare: more than the records that travelled with the columns
+        CU(cudaMemcpyAsync(S.c_host.esc + CESC_INLINE, (const rafting_cesc_out_t*)S.c_esc_dev + CESC_INLINE,
+                           (size_t)(n - CESC_INLINE) * sizeof(rafting_cesc_out_t), cudaMemcpyDeviceToHost, H->s_d2h));
         CU(cudaStreamSynchronize(H->s_d2h));
     }
     return RAFTING_OK;
