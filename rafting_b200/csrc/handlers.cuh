@@ -274,24 +274,6 @@ __device__ __forceinline__ int log_up_to_date(const GS& g, int64_t index, int64_
     return index >= g.epochIndex;
 }
 
-// The entry terms of an AppendEntries request live in the step's term pool (global memory).  Walking them one dependent load at
-// a time made a 50-entry request ~50 memory round trips per pass (ncu, config #5: 70 % of slow_kernel's stall samples are
-// long-scoreboard); here eight terms are fetched by independent loads, then handed to fn(i, term) in order; fn returns false
-// to stop (the loops below break early exactly where the serial code did).
-template <typename Fn>
-__device__ __forceinline__ void for_terms(const int64_t* __restrict__ terms, uint32_t n, Fn&& fn) {
-    for (uint32_t base = 0; base < n; base += 8) {
-        int64_t buf[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) buf[k] = (base + k < n) ? __ldg(terms + base + k) : 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (base + k >= n) return;
-            if (!fn(base + (uint32_t)k, buf[k])) return;
-        }
-    }
-}
-
 // Follower.appendEntries body — Follower.java:52-87 + RocksLog.conflict/truncate/append (RocksLog.java:169-225)
 __device__ __noinline__ int follower_append(GS& g, const Ctx& c, RowOut& ro, int peer, int64_t term, int64_t prevIndex,
                                             int64_t prevTerm, int64_t first, uint32_t n, const int64_t* terms,
@@ -308,12 +290,11 @@ __device__ __noinline__ int follower_append(GS& g, const Ctx& c, RowOut& ro, int
         }
         if (n > 0) {
             int64_t conflictIndex = 0;                                       // RocksLog.conflict :199-216
-            for_terms(terms, n, [&](uint32_t i, int64_t ti) {
+            for (uint32_t i = 0; i < n; i++) {
                 int64_t t;
-                if (!term_at(g, c, first + i, t)) return false;
-                if (t != ti) { conflictIndex = first + i; return false; }
-                return true;
-            });
+                if (!term_at(g, c, first + i, t)) break;
+                if (t != terms[i]) { conflictIndex = first + i; break; }
+            }
             const bool nonEmpty = nruns_of(g) > 0;
             const int64_t hiAfter = (conflictIndex != 0 && nonEmpty && g.hi >= conflictIndex) ? conflictIndex - 1 : g.hi;
             const bool emptyAfter = !nonEmpty || hiAfter < g.lo;
@@ -336,10 +317,8 @@ __device__ __noinline__ int follower_append(GS& g, const Ctx& c, RowOut& ro, int
                             }
                         }
                     }
-                    for_terms(terms, n, [&](uint32_t i, int64_t ti) {
-                        if (first + i > prevLogIndex && (!have || ti != lastT)) { runs++; lastT = ti; have = true; }
-                        return true;
-                    });
+                    for (uint32_t i = 0; i < n; i++)
+                        if (first + i > prevLogIndex && (!have || terms[i] != lastT)) { runs++; lastT = terms[i]; have = true; }
                     if (runs > (uint32_t)KRUNS) err = RAFTING_ERR_TERM_RUNS_OVERFLOW;
                 }
             }
@@ -348,13 +327,12 @@ __device__ __noinline__ int follower_append(GS& g, const Ctx& c, RowOut& ro, int
                 if (emptyAfter && first != g.epochIndex + 1) err = RAFTING_ERR_LOG_NOT_FOLLOW_EPOCH;
                 else if (first > prevLogIndex + 1) err = RAFTING_ERR_LOG_NOT_CONTINUOUS;
                 else
-                    for_terms(terms, n, [&](uint32_t i, int64_t ti) {
+                    for (uint32_t i = 0; i < n; i++) {
                         // RocksLog.java:183-191: put everything above prevLogIndex; keys that already
                         // exist there hold the same term (no conflict was found), so only the tail grows
                         const int64_t idx = first + i;
-                        if (idx > prevLogIndex && (nruns_of(g) == 0 || idx > g.hi)) log_append_one(g, c, idx, ti);
-                        return true;
-                    });
+                        if (idx > prevLogIndex && (nruns_of(g) == 0 || idx > g.hi)) log_append_one(g, c, idx, terms[i]);
+                    }
             }
         }
         if (!err && leaderCommit > g.epochIndex && nruns_of(g) > 0) {       // Follower.java:76-82
