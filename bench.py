@@ -512,16 +512,17 @@ def run_engine(args):
         cins, keep = [], []
         couts = []
         esc_out_max = 0
+        # every launch's wire columns live in ONE pinned block per direction, laid out by rafting_compact_layout: one copy up,
+        # one copy down per launch
+        in_off0, out_off = engine.Engine.compact_layout(rows, G, F, 0, ESC_CAP)
         for sl in range(NSL):
-            co = compact.CompactOutbox(rows, G, F, esc_cap=ESC_CAP)
-            for name in co.COLS + ("esc", "counts"):
-                t, v = pinned_like(getattr(co, name)); keep.append(t); setattr(co, name, v)
-            couts.append(co)
+            t = torch.zeros(int(out_off[11]), dtype=torch.uint8).pin_memory(); keep.append(t)
+            couts.append(compact.outbox_in_block(t.numpy(), out_off, rows, G, F, ESC_CAP))
         for k in range(1, K2):                            # record pass (untimed): the tags the engine hands out are replayed below
             ci = compact.encode_inbox(host_inbox(k), tags, sent_term, sent_inc)
-            for name in ("row_base", "op_c", "ev_c", "esc"):
-                if getattr(ci, name) is not None and len(getattr(ci, name)):
-                    t, v = pinned_like(getattr(ci, name)); keep.append(t); setattr(ci, name, v)
+            in_off, _ = engine.Engine.compact_layout(rows, G, F, len(ci.esc), ESC_CAP)
+            t = torch.zeros(int(in_off[5]), dtype=torch.uint8).pin_memory(); keep.append(t)
+            ci = compact.inbox_in_block(t.numpy(), in_off, ci)
             e.step_compact(ci, couts[0])
             esc_out_max = max(esc_out_max, int(couts[0].counts[0]))
             tags, sent_term, sent_inc = couts[0].tags(), couts[0].current_term.copy(), couts[0].incarnation.copy()
@@ -529,7 +530,10 @@ def run_engine(args):
         digest_c = e.digest(0, G)
         cin_c = [ci.as_c() for ci in cins]
         cout_c = [co.as_c() for co in couts]
-        h2d = int(np.mean([ci.nbytes() for ci in cins])); d2h = couts[0].nbytes()
+        # bytes that actually cross PCIe per launch: the single copy up (row_base .. ev_c, or .. the escape records) and the single
+        # copy down (plan_c .. counters + the 256 escape records that always travel with them), alignment padding included
+        h2d = int(np.mean([(in_off0[4] + len(ci.esc) * abi.CESC_IN.itemsize) if len(ci.esc) else (in_off0[3] + ci.ev_c.nbytes) for ci in cins]))
+        d2h = int(out_off[10] + min(ESC_CAP, 256) * abi.CESC_OUT.itemsize)
         esc_in = int(np.mean([len(ci.esc) for ci in cins]))
         acks_pass = sum(acks_per_launch[1:K2])
         n_pass_launch = K2 - 1

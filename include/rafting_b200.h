@@ -402,7 +402,7 @@ int rafting_step_begin_host(rafting_engine_t* e, uint32_t slot /* 0..3 */, const
 int rafting_step_wait_slot (rafting_engine_t* e, uint32_t slot);
 
 /* ---------------------------------------------------------------------------------------------------------------------
- * COMPACT host path (round 2): the same step, a third of the PCIe bytes.
+ * COMPACT host path (round 2): the same step, an eighth of the PCIe bytes.
  *
  * The dense host path moves 65 B up and 69 B down per AppendEntries ack and is PCIe-bound.  Most of those bytes are
  * redundant in leader steady state: every time of a row lies within 65 s of the row's base time; a reply's term is the
@@ -479,6 +479,13 @@ typedef struct rafting_coutbox {
     uint32_t* counts;                /* [4] escape records produced (may exceed esc_cap: then use rafting_step_fetch_dense),
                                         ballots, valid replies, reserved */
 } rafting_coutbox_t;
+/* Byte offsets of the wire columns inside ONE block per direction, as the engine lays them out on the device.  A caller that
+   carves its pinned inbox / outbox out of one block with these offsets gets ONE copy up and ONE copy down per launch instead
+   of one per column (the engine recognises the arrangement from the pointers; any other arrangement works column by column).
+     in_off : row_base, op_c, op_unavail, ev_c, esc, total
+     out_off: plan_c, rep_c, commit_index, current_term, role_word, incarnation, err_word, last_entry, epoch, counts, esc, total */
+int rafting_compact_layout(uint32_t rows, uint32_t max_groups, uint32_t followers, uint32_t n_esc_in, uint32_t esc_cap,
+                           uint64_t in_off[6], uint64_t out_off[12]);
 int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot /* 0..3 */, const rafting_cinbox_t* in_host,
                                const rafting_coutbox_t* out_host);
 int rafting_step_wait_compact (rafting_engine_t* e, uint32_t slot);

@@ -71,6 +71,37 @@ class CompactOutbox:
         return ((self.plan_c >> np.uint32(5)) & np.uint32(63)).astype(np.uint8)
 
 
+def outbox_in_block(block: np.ndarray, out_off, rows: int, n: int, F: int, esc_cap: int) -> CompactOutbox:
+    """A CompactOutbox whose columns are views into ONE (pinned) uint8 block laid out by Engine.compact_layout: the engine then
+    brings a launch's whole outbox down with a single copy."""
+    co = CompactOutbox.__new__(CompactOutbox)
+    co.rows, co.n, co.F, co.esc_cap = rows, n, F, esc_cap
+    spec = (("plan_c", np.uint32, (rows, n, F)), ("rep_c", np.uint8, (rows, n)), ("commit_index", np.int64, (n,)),
+            ("current_term", np.int64, (n,)), ("role_word", np.uint32, (n,)), ("incarnation", np.uint32, (n,)), ("err_word", np.uint32, (n,)),
+            ("last_entry", abi.I64X2, (n,)), ("epoch", abi.I64X2, (n,)), ("counts", np.uint32, (4,)), ("esc", abi.CESC_OUT, (esc_cap,)))
+    for k, (name, dt, shape) in enumerate(spec):
+        cnt = int(np.prod(shape))
+        nbytes = cnt * np.dtype(dt).itemsize
+        setattr(co, name, block[int(out_off[k]):int(out_off[k]) + nbytes].view(dt).reshape(shape))
+    return co
+
+
+def inbox_in_block(block: np.ndarray, in_off, ci: CompactInbox) -> CompactInbox:
+    """Copies an encoded inbox into ONE (pinned) uint8 block laid out by Engine.compact_layout (n_esc_in = len(ci.esc)) and
+    returns the CompactInbox whose columns are views into it: one copy up per launch."""
+    out = CompactInbox.__new__(CompactInbox)
+    out.rows, out.n, out.F = ci.rows, ci.n, ci.F
+    for k, name in enumerate(("row_base", "op_c", "op_unavail", "ev_c", "esc")):
+        a = getattr(ci, name)
+        if a is None or (name == "esc" and len(a) == 0):
+            setattr(out, name, None if name != "esc" else np.zeros(0, dtype=abi.CESC_IN))
+            continue
+        v = block[int(in_off[k]):int(in_off[k]) + a.nbytes].view(a.dtype).reshape(a.shape)
+        v[...] = a
+        setattr(out, name, v)
+    return out
+
+
 def encode_inbox(ib: abi.Inbox, tags: np.ndarray | None, sent_term: np.ndarray | None, sent_inc: np.ndarray | None = None) -> CompactInbox:
     """ib: dense host inbox of a NO_REQUESTS step (SUBMIT / TIMEOUT ops, any lane events).
     tags[r, i, f]: the tag the RPC this event answers was sent under (plan_c of the step that emitted it); None = no acks yet.

@@ -1,4 +1,4 @@
-// compact.cuh — the compact host path: a third of the dense path's PCIe bytes, losslessly (include/rafting_b200.h,
+// compact.cuh — the compact host path: an eighth of the dense path's PCIe bytes, losslessly (include/rafting_b200.h,
 // "COMPACT host path").  Two kernels bracket the unchanged step kernel:
 //
 //   unpack_kernel   wire columns (ev_c 4 B / lane slot, op_c 4 B / group row, row_base)  ->  the dense SoA inbox the step kernel
@@ -188,6 +188,21 @@ static CLayout compact_layout(size_t rows, size_t G, size_t F, size_t n_esc_in, 
     return L;
 }
 
+// Byte offsets of the wire columns inside ONE block per direction, as the engine lays them out on the device.  A caller that
+// allocates its pinned inbox / outbox as one block with these offsets gets ONE copy up and ONE copy down per launch instead of
+// one per column (the engine recognises the layout from the pointers; any other arrangement still works, column by column).
+//   in_off : row_base, op_c, op_unavail, ev_c, esc, total        out_off: plan_c, rep_c, commit_index, current_term, role_word,
+//                                                                          incarnation, err_word, last_entry, epoch, counts, esc, total
+extern "C" int rafting_compact_layout(uint32_t rows, uint32_t G, uint32_t F, uint32_t n_esc_in, uint32_t esc_cap, uint64_t in_off[6], uint64_t out_off[12]) {
+    if (!in_off || !out_off) return fail(RAFTING_E_INVAL, "null argument");
+    const CLayout L = compact_layout(rows, G, F, n_esc_in, esc_cap);
+    const uint64_t i[6] = {L.row_base, L.op_c, L.op_un, L.ev_c, L.esc, L.in_total};
+    const uint64_t o[12] = {L.plan_c, L.rep_c, L.commit, L.term, L.role, L.inc, L.err, L.last, L.epoch, L.counts, L.esc_out, L.out_total};
+    for (int k = 0; k < 6; k++) in_off[k] = i[k];
+    for (int k = 0; k < 12; k++) out_off[k] = o[k];
+    return RAFTING_OK;
+}
+
 extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, const rafting_cinbox_t* in, const rafting_coutbox_t* out) {
     using namespace rafting;
     if (!e || !in || !out || slot >= RAFTING_HOST_SLOTS) return fail(RAFTING_E_INVAL, "bad argument");
@@ -215,11 +230,24 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
     CInD ci; ci.rows = (uint32_t)rows; ci.n_esc = in->n_esc;
     ci.row_base = (const int64_t*)(S.cin.p + LC.row_base); ci.op_c = nullptr; ci.op_unavail = nullptr; ci.ev_c = nullptr;
     ci.esc = (const rafting_cesc_in_t*)(S.cin.p + LC.esc);
-    CU(cudaMemcpyAsync(S.cin.p + LC.row_base, in->row_base, rows * 8, cudaMemcpyHostToDevice, H->s_h2d));
-    if (in->op_c) { CU(cudaMemcpyAsync(S.cin.p + LC.op_c, in->op_c, rows * G * 4, cudaMemcpyHostToDevice, H->s_h2d)); ci.op_c = (const uint32_t*)(S.cin.p + LC.op_c); }
-    if (in->op_c && in->op_unavail) { CU(cudaMemcpyAsync(S.cin.p + LC.op_un, in->op_unavail, rows * G * 2, cudaMemcpyHostToDevice, H->s_h2d)); ci.op_unavail = (const uint16_t*)(S.cin.p + LC.op_un); }
-    if (in->ev_c) { CU(cudaMemcpyAsync(S.cin.p + LC.ev_c, in->ev_c, rows * G * F * 4, cudaMemcpyHostToDevice, H->s_h2d)); ci.ev_c = (const uint32_t*)(S.cin.p + LC.ev_c); }
-    if (in->n_esc) CU(cudaMemcpyAsync(S.cin.p + LC.esc, in->esc, (size_t)in->n_esc * sizeof(rafting_cesc_in_t), cudaMemcpyHostToDevice, H->s_h2d));
+    {
+        const uint8_t* hb = (const uint8_t*)in->row_base - LC.row_base;      // where the block would start on the host
+        const bool one_block = (!in->op_c || (const uint8_t*)in->op_c == hb + LC.op_c) && (!in->op_unavail || (const uint8_t*)in->op_unavail == hb + LC.op_un) &&
+                               (!in->ev_c || (const uint8_t*)in->ev_c == hb + LC.ev_c) && (!in->n_esc || (const uint8_t*)in->esc == hb + LC.esc) &&
+                               in->op_c && in->ev_c;
+        if (one_block) {
+            const size_t span = in->n_esc ? LC.esc + (size_t)in->n_esc * sizeof(rafting_cesc_in_t) : LC.ev_c + rows * G * F * 4;
+            CU(cudaMemcpyAsync(S.cin.p, hb, span, cudaMemcpyHostToDevice, H->s_h2d));
+            ci.op_c = (const uint32_t*)(S.cin.p + LC.op_c); ci.ev_c = (const uint32_t*)(S.cin.p + LC.ev_c);
+            if (in->op_unavail) ci.op_unavail = (const uint16_t*)(S.cin.p + LC.op_un);
+        } else {
+            CU(cudaMemcpyAsync(S.cin.p + LC.row_base, in->row_base, rows * 8, cudaMemcpyHostToDevice, H->s_h2d));
+            if (in->op_c) { CU(cudaMemcpyAsync(S.cin.p + LC.op_c, in->op_c, rows * G * 4, cudaMemcpyHostToDevice, H->s_h2d)); ci.op_c = (const uint32_t*)(S.cin.p + LC.op_c); }
+            if (in->op_c && in->op_unavail) { CU(cudaMemcpyAsync(S.cin.p + LC.op_un, in->op_unavail, rows * G * 2, cudaMemcpyHostToDevice, H->s_h2d)); ci.op_unavail = (const uint16_t*)(S.cin.p + LC.op_un); }
+            if (in->ev_c) { CU(cudaMemcpyAsync(S.cin.p + LC.ev_c, in->ev_c, rows * G * F * 4, cudaMemcpyHostToDevice, H->s_h2d)); ci.ev_c = (const uint32_t*)(S.cin.p + LC.ev_c); }
+            if (in->n_esc) CU(cudaMemcpyAsync(S.cin.p + LC.esc, in->esc, (size_t)in->n_esc * sizeof(rafting_cesc_in_t), cudaMemcpyHostToDevice, H->s_h2d));
+        }
+    }
     CU(cudaEventRecord(S.ev_h2d, H->s_h2d));
     // ---- unpack -> step -> pack on the engine's stream ----
     InboxD di; memset(&di, 0, sizeof(di));
@@ -266,22 +294,36 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
     CU(cudaEventRecord(S.ev_kernel, e->stream));
     // ---- D2H: every wire column + the counters; the escape list only when the counters say it holds something ----
     CU(cudaStreamWaitEvent(H->s_d2h, S.ev_kernel, 0));
-    CU(cudaMemcpyAsync(out->plan_c, co.plan_c, rows * G * F * 4, cudaMemcpyDeviceToHost, H->s_d2h));
-    CU(cudaMemcpyAsync(out->rep_c, co.rep_c, rows * G, cudaMemcpyDeviceToHost, H->s_d2h));
-    CU(cudaMemcpyAsync(out->commit_index, co.commit_index, G * 8, cudaMemcpyDeviceToHost, H->s_d2h));
-    CU(cudaMemcpyAsync(out->current_term, co.current_term, G * 8, cudaMemcpyDeviceToHost, H->s_d2h));
-    CU(cudaMemcpyAsync(out->role_word, co.role_word, G * 4, cudaMemcpyDeviceToHost, H->s_d2h));
-    CU(cudaMemcpyAsync(out->incarnation, co.incarnation, G * 4, cudaMemcpyDeviceToHost, H->s_d2h));
-    CU(cudaMemcpyAsync(out->err_word, co.err_word, G * 4, cudaMemcpyDeviceToHost, H->s_d2h));
-    CU(cudaMemcpyAsync(out->last_entry, co.last_entry, G * 16, cudaMemcpyDeviceToHost, H->s_d2h));
-    CU(cudaMemcpyAsync(out->epoch, co.epoch, G * 16, cudaMemcpyDeviceToHost, H->s_d2h));
-    CU(cudaMemcpyAsync(S.chout.p, co.counts, 16, cudaMemcpyDeviceToHost, H->s_d2h));
-    // the first escape records always travel with the columns (a steady-state launch produces a handful): fetching them on
-    // demand at wait time would have to drain the D2H stream, i.e. wait for the copies of every LATER launch as well
     const uint32_t esc_inline = out->esc_cap < CESC_INLINE ? out->esc_cap : CESC_INLINE;
-    if (esc_inline) CU(cudaMemcpyAsync(out->esc, co.esc, (size_t)esc_inline * sizeof(rafting_cesc_out_t), cudaMemcpyDeviceToHost, H->s_d2h));
+    uint32_t* counts_land = (uint32_t*)S.chout.p;
+    {
+        uint8_t* hb = (uint8_t*)out->plan_c - LC.plan_c;
+        const bool one_block = (uint8_t*)out->rep_c == hb + LC.rep_c && (uint8_t*)out->commit_index == hb + LC.commit && (uint8_t*)out->current_term == hb + LC.term &&
+                               (uint8_t*)out->role_word == hb + LC.role && (uint8_t*)out->incarnation == hb + LC.inc && (uint8_t*)out->err_word == hb + LC.err &&
+                               (uint8_t*)out->last_entry == hb + LC.last && (uint8_t*)out->epoch == hb + LC.epoch && (uint8_t*)out->counts == hb + LC.counts &&
+                               (!out->esc_cap || (uint8_t*)out->esc == hb + LC.esc_out);
+        if (one_block) {
+            // columns, counters and the first escape records: one copy (the counters land in the caller's block directly)
+            CU(cudaMemcpyAsync(hb, S.cout.p, LC.esc_out + (size_t)esc_inline * sizeof(rafting_cesc_out_t), cudaMemcpyDeviceToHost, H->s_d2h));
+            counts_land = out->counts;
+        } else {
+            CU(cudaMemcpyAsync(out->plan_c, co.plan_c, rows * G * F * 4, cudaMemcpyDeviceToHost, H->s_d2h));
+            CU(cudaMemcpyAsync(out->rep_c, co.rep_c, rows * G, cudaMemcpyDeviceToHost, H->s_d2h));
+            CU(cudaMemcpyAsync(out->commit_index, co.commit_index, G * 8, cudaMemcpyDeviceToHost, H->s_d2h));
+            CU(cudaMemcpyAsync(out->current_term, co.current_term, G * 8, cudaMemcpyDeviceToHost, H->s_d2h));
+            CU(cudaMemcpyAsync(out->role_word, co.role_word, G * 4, cudaMemcpyDeviceToHost, H->s_d2h));
+            CU(cudaMemcpyAsync(out->incarnation, co.incarnation, G * 4, cudaMemcpyDeviceToHost, H->s_d2h));
+            CU(cudaMemcpyAsync(out->err_word, co.err_word, G * 4, cudaMemcpyDeviceToHost, H->s_d2h));
+            CU(cudaMemcpyAsync(out->last_entry, co.last_entry, G * 16, cudaMemcpyDeviceToHost, H->s_d2h));
+            CU(cudaMemcpyAsync(out->epoch, co.epoch, G * 16, cudaMemcpyDeviceToHost, H->s_d2h));
+            CU(cudaMemcpyAsync(S.chout.p, co.counts, 16, cudaMemcpyDeviceToHost, H->s_d2h));
+            // the first escape records always travel with the columns (a steady-state launch produces a handful): fetching them
+            // on demand at wait time would have to drain the D2H stream, i.e. wait for the copies of every LATER launch as well
+            if (esc_inline) CU(cudaMemcpyAsync(out->esc, co.esc, (size_t)esc_inline * sizeof(rafting_cesc_out_t), cudaMemcpyDeviceToHost, H->s_d2h));
+        }
+    }
     CU(cudaEventRecord(S.ev_done, H->s_d2h));
-    S.compact_step = true; S.c_host = *out; S.c_counts_pinned = (uint32_t*)S.chout.p; S.c_esc_dev = co.esc;
+    S.compact_step = true; S.c_host = *out; S.c_counts_pinned = counts_land; S.c_esc_dev = co.esc;
     S.dev_out = rafting_outbox_t(); memset(&S.dev_out, 0, sizeof(S.dev_out));
     S.dev_out.rep_meta = dov.rep_meta; S.dev_out.rep_term = dov.rep_term; S.dev_out.plan_meta = dov.plan_meta;
     S.dev_out.plan_pp = (rafting_i64x2_t*)dov.plan_pp; S.dev_out.plan_lc = (rafting_i64x2_t*)dov.plan_lc; S.dev_out.plan_epoch = dov.plan_epoch;
@@ -301,7 +343,7 @@ extern "C" int rafting_step_wait_compact(rafting_engine_t* e, uint32_t slot) {
     if (!S.compact_step) return fail(RAFTING_E_INVAL, "slot %u holds a dense step (use rafting_step_wait_slot)", slot);
     CU(cudaEventSynchronize(S.ev_done));
     S.inflight = false;
-    for (int k = 0; k < 4; k++) S.c_host.counts[k] = S.c_counts_pinned[k];
+    if (S.c_counts_pinned != S.c_host.counts) for (int k = 0; k < 4; k++) S.c_host.counts[k] = S.c_counts_pinned[k];
     const uint32_t n = S.c_counts_pinned[0] < S.c_host.esc_cap ? S.c_counts_pinned[0] : S.c_host.esc_cap;
     if (n > CESC_INLINE) {                                                    // rare: more than the records that travelled with the columns
         CU(cudaMemcpyAsync(S.c_host.esc + CESC_INLINE, (const rafting_cesc_out_t*)S.c_esc_dev + CESC_INLINE,

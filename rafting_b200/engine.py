@@ -38,7 +38,7 @@ EXPORTS = [
     "rafting_comm_init", "rafting_comm_init_all", "rafting_comm_unique_id", "rafting_allgather_commit", "rafting_allgather_commit_from",
     "rafting_allgather_commit_all", "rafting_allgather_last", "rafting_restore_async", "rafting_state_save", "rafting_state_load", "rafting_step_device_seq", "rafting_engine_stream",
     "rafting_engine_counters", "rafting_abi_sizes", "rafting_checkpoint", "rafting_restore",
-    "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_step_begin_compact", "rafting_step_wait_compact", "rafting_step_fetch_dense", "rafting_backoff_step", "rafting_allgather_join",
+    "rafting_step_begin_host", "rafting_step_wait_slot", "rafting_step_begin_compact", "rafting_step_wait_compact", "rafting_step_fetch_dense", "rafting_compact_layout", "rafting_backoff_step", "rafting_allgather_join",
     "rafting_log_config", "rafting_log_append", "rafting_log_read", "rafting_log_gather", "rafting_log_trim", "rafting_log_stats",
     "rafting_log_store_open", "rafting_log_sync", "rafting_log_mark", "rafting_log_recovered", "rafting_log_export_kv", "rafting_log_store_stats",
 ]
@@ -114,6 +114,8 @@ def lib():
         L.rafting_step_wait_slot.argtypes = [C.c_void_p, C.c_uint32]
         L.rafting_step_begin_compact.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.CInboxC), C.POINTER(abi.COutboxC)]
         L.rafting_step_wait_compact.argtypes = [C.c_void_p, C.c_uint32]
+        L.rafting_compact_layout.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64 * 6),
+                                             C.POINTER(C.c_uint64 * 12)]
         L.rafting_step_fetch_dense.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.OutboxC)]
         L.rafting_checkpoint.argtypes = [C.c_void_p]
         L.rafting_restore.argtypes = [C.c_void_p]
@@ -207,7 +209,7 @@ class Engine:
     def step_wait_slot(self, slot: int):
         _check(lib().rafting_step_wait_slot(self._h, slot), "rafting_step_wait_slot")
 
-    # ---- compact host path: a third of the PCIe bytes (include/rafting_b200.h, rafting_b200/compact.py) ----------------
+    # ---- compact host path: an eighth of the PCIe bytes (include/rafting_b200.h, rafting_b200/compact.py) ----------------
     def step_begin_compact(self, slot: int, cin_c: abi.CInboxC, cout_c: abi.COutboxC):
         _check(lib().rafting_step_begin_compact(self._h, slot, C.byref(cin_c), C.byref(cout_c)), "rafting_step_begin_compact")
 
@@ -216,6 +218,13 @@ class Engine:
 
     def step_fetch_dense(self, slot: int, outbox_c: abi.OutboxC):
         _check(lib().rafting_step_fetch_dense(self._h, slot, C.byref(outbox_c)), "rafting_step_fetch_dense")
+
+    @staticmethod
+    def compact_layout(rows: int, G: int, F: int, n_esc_in: int, esc_cap: int):
+        """-> (in_off[6], out_off[12]) byte offsets of the wire columns inside one block per direction (rafting_compact_layout)"""
+        a, b = (C.c_uint64 * 6)(), (C.c_uint64 * 12)()
+        _check(lib().rafting_compact_layout(rows, G, F, n_esc_in, esc_cap, C.byref(a), C.byref(b)), "rafting_compact_layout")
+        return list(a), list(b)
 
     def step_compact(self, cin, cout, slot: int = 0):
         """Synchronous compact step: cin / cout are rafting_b200.compact.CompactInbox / CompactOutbox."""
