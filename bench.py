@@ -532,7 +532,7 @@ def run_engine(args):
         cout_c = [co.as_c() for co in couts]
         # bytes that actually cross PCIe per launch: the single copy up (row_base .. ev_c, or .. the escape records) and the single
         # copy down (plan_c .. counters + the 256 escape records that always travel with them), alignment padding included
-        h2d = int(np.mean([(in_off0[4] + len(ci.esc) * abi.CESC_IN.itemsize) if len(ci.esc) else (in_off0[3] + ci.ev_c.nbytes) for ci in cins]))
+        h2d = int(np.mean([(in_off0[4] + len(ci.esc) * abi.CESC_IN.itemsize) if len(ci.esc) else (in_off0[3] + ci.ev_c.nbytes) for ci in cins]))   # in_off: row_base, op_c, op_unavail, ev_c, esc, total
         d2h = int(out_off[10] + min(ESC_CAP, 256) * abi.CESC_OUT.itemsize)
         esc_in = int(np.mean([len(ci.esc) for ci in cins]))
         acks_pass = sum(acks_per_launch[1:K2])

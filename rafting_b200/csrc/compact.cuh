@@ -176,7 +176,8 @@ struct CLayout { size_t row_base, op_c, op_un, ev_c, esc, in_total; size_t plan_
 static CLayout compact_layout(size_t rows, size_t G, size_t F, size_t n_esc_in, size_t esc_cap) {
     CLayout L; size_t o = 0;
     auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
-    L.row_base = take(rows * 8); L.op_c = take(rows * G * 4); L.op_un = take(rows * G * 2); L.ev_c = take(rows * G * F * 4);
+    // the optional parts come last, so that the single copy of a block-shaped inbox ends where the launch's data ends
+    L.row_base = take(rows * 8); L.op_c = take(rows * G * 4); L.ev_c = take(rows * G * F * 4); L.op_un = take(rows * G * 2);
     L.esc = take((n_esc_in + 1) * sizeof(rafting_cesc_in_t));
     L.in_total = o; o = 0;
     L.plan_c = take(rows * G * F * 4); L.rep_c = take(rows * G);
@@ -236,7 +237,8 @@ extern "C" int rafting_step_begin_compact(rafting_engine_t* e, uint32_t slot, co
                                (!in->ev_c || (const uint8_t*)in->ev_c == hb + LC.ev_c) && (!in->n_esc || (const uint8_t*)in->esc == hb + LC.esc) &&
                                in->op_c && in->ev_c;
         if (one_block) {
-            const size_t span = in->n_esc ? LC.esc + (size_t)in->n_esc * sizeof(rafting_cesc_in_t) : LC.ev_c + rows * G * F * 4;
+            const size_t span = in->n_esc ? LC.esc + (size_t)in->n_esc * sizeof(rafting_cesc_in_t)
+                                : (in->op_unavail ? LC.op_un + rows * G * 2 : LC.ev_c + rows * G * F * 4);
             CU(cudaMemcpyAsync(S.cin.p, hb, span, cudaMemcpyHostToDevice, H->s_h2d));
             ci.op_c = (const uint32_t*)(S.cin.p + LC.op_c); ci.ev_c = (const uint32_t*)(S.cin.p + LC.ev_c);
             if (in->op_unavail) ci.op_unavail = (const uint16_t*)(S.cin.p + LC.op_un);

@@ -29,6 +29,22 @@ def test_null_engine_is_rejected_everywhere():
         lambda: L.rafting_allgather_join(None),
         lambda: L.rafting_log_config(None, 1 << 16, 4, 16),
         lambda: L.rafting_log_append(None, None, 1, None, 0),
+        lambda: L.rafting_lease_release(None, C.byref(lease)),
+        lambda: L.rafting_step_begin_compact(None, 0, C.byref(abi.CInboxC()), C.byref(abi.COutboxC())),
+        lambda: L.rafting_step_wait_compact(None, 0),
+        lambda: L.rafting_step_fetch_dense(None, 0, C.byref(outbox)),
+        lambda: L.rafting_step_device_seq(None, None, None, 1, 0, None),
+        lambda: L.rafting_allgather_commit_from(None, None, None, None),
+        lambda: L.rafting_allgather_commit_all(None, 1, None, None, None),
+        lambda: L.rafting_comm_init_all(None, 1),
+        lambda: L.rafting_allgather_last(None, None),
+        lambda: L.rafting_restore_async(None),
+        lambda: L.rafting_state_save(None, b"/tmp/x"),
+        lambda: L.rafting_state_load(None, b"/tmp/x"),
+        lambda: L.rafting_log_store_open(None, b"/tmp/x", 0, None),
+        lambda: L.rafting_log_sync(None),
+        lambda: L.rafting_log_mark(None, 0, 1, 0, 0, 0),
+        lambda: L.rafting_compact_layout(1, 1, 1, 0, 0, None, None),
     ]
     for k, call in enumerate(calls):
         assert call() == -1, f"call #{k} did not return RAFTING_E_INVAL"
