@@ -1,0 +1,79 @@
+"""The compact wire format is lossless — checked on CPU with a numpy restatement of the engine's unpack / pack kernels
+(tests/compact_model.py) around the oracle: every dense outbox must survive pack -> decode, every dense inbox encode -> unpack,
+through the settling phase (thousands of escapes), steady state (none), unavailable followers, a late reply and a tag shortage."""
+import numpy as np
+
+from oracle import binding
+from rafting_b200 import abi, compact, workload
+from tests import compact_model as model
+from tests import harness
+
+
+def _fields_equal(a: abi.Inbox, b: abi.Inbox):
+    ek = (a.ev_meta & np.uint64(0xF)) != 0
+    assert np.array_equal(a.ev_meta, b.ev_meta)
+    for name in ("ev_tn", "ev_el"):
+        assert np.array_equal(getattr(a, name)[ek], getattr(b, name)[ek]), name
+    ok = (a.op_meta & np.uint64(0xFF)) != 0
+    assert np.array_equal(a.op_meta, b.op_meta) and np.array_equal(a.op_nr["x"][ok], b.op_nr["x"][ok])
+    ua = a.op_ab["x"] if a.op_ab is not None else 0
+    ub = b.op_ab["x"] if b.op_ab is not None else 0
+    assert np.array_equal(np.broadcast_to(ua, a.op_meta.shape), np.broadcast_to(ub, a.op_meta.shape))
+
+
+def test_codec_and_kernel_model_are_lossless_around_the_oracle():
+    G, R, rows = 96, 3, 8
+    F = R - 1
+    cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=rows)
+    o = binding.Oracle(cfg)
+    o.open_bulk(0, harness.init_array(G, terms=np.arange(G) % 7))
+    w1 = workload.make_wl(17, 1, G, F)
+    w = workload.make_wl(17, rows, G, F, p_reject_ppm=60_000, p_error_ppm=30_000, p_cancel_ppm=20_000)
+    harness.elect_all(o, w1)
+    st = model.InFlight(G, F)
+    g_term = np.array([o.export(g).current_term for g in range(G)], dtype=np.int64)
+    prev, tags, sent_term, sent_inc = None, None, None, None
+    escapes_late = 0
+    for k in range(14):
+        ib = workload.leader_inbox_host(w, k, prev)
+        if k % 3 == 2:
+            ib.op_ab["x"][:, ::7] = 2                                  # follower lane 1 unavailable for every seventh group
+        if k == 9:
+            ev = np.argwhere((ib.ev_meta & np.uint64(0xF)) != 0)[0]
+            ib.ev_tn["y"][tuple(ev)] += 80_000                         # a reply 80 s late: escape record
+        ci = compact.encode_inbox(ib, tags, sent_term, sent_inc)
+        back = model.unpack(ci, g_term, st)
+        _fields_equal(ib, back)
+        if k >= 10:
+            escapes_late += len(ci.esc)
+        dense = o.step(ib)
+        epoch = np.zeros(G, dtype=abi.I64X2)
+        for g in range(G):
+            s = o.export(g); epoch[g] = (s.epoch_index, s.epoch_term)
+        co = model.pack(dense, epoch, st, esc_cap=rows * G * F + 2 * rows * G)
+        harness.assert_outbox_equal(dense, compact.decode_outbox(co), where=f"pack -> decode, step {k}")
+        if k >= 10:
+            escapes_late += int(co.counts[0])
+        prev, tags, sent_term, sent_inc = dense, co.tags(), co.current_term.copy(), co.incarnation.copy()
+        g_term = dense.current_term.copy()
+    assert (st.bits != 0).any() and int(np.bitwise_count(st.bits).max()) <= 21          # IN_FLIGHT_LIMIT + 1 RPCs outstanding per lane
+    assert escapes_late < 40                                                      # steady state: only the irregular records
+
+
+def test_a_lane_without_a_free_tag_falls_back_to_escape_records():
+    G, F, rows = 2, 2, 1
+    st = model.InFlight(G, F)
+    st.bits[:] = 0xFFFFFFFF                                                      # every tag of every lane taken
+    dense = abi.Outbox(rows, G, F, G)
+    dense.current_term[:] = 3; dense.incarnation[:] = 5; dense.commit_index[:] = 40; dense.last_entry["x"] = 50; dense.last_entry["y"] = 3
+    dense.plan_meta[0, 0, 0] = abi.PLAN_AE | (2 << 16) | (5 << 32)
+    dense.plan_pp[0, 0, 0] = (45, 3); dense.plan_lc[0, 0, 0] = (47, 38); dense.plan_epoch[0, 0, 0] = 0
+    co = model.pack(dense, np.zeros(G, dtype=abi.I64X2), st, esc_cap=8)
+    assert int(co.tags()[0, 0, 0]) == abi.CTAG_NONE and int(co.counts[0]) == 0  # still a compact plan, just untagged
+    harness.assert_outbox_equal(dense, compact.decode_outbox(co))
+    ib = abi.Inbox(rows, G, F)
+    ib.ack(0, 0, 0, 1000, 5, 3, True, 0, 47)
+    ci = compact.encode_inbox(ib, co.tags(), co.current_term, co.incarnation)
+    assert len(ci.esc) == 1 and int(ci.ev_c[0, 0, 0]) == abi.CEV_ESCAPED          # no tag: the reply carries its echo pair itself
+    back = model.unpack(ci, co.current_term, st)
+    assert tuple(back.ev_el[0, 0, 0]) == (0, 47) and int(back.ev_meta[0, 0, 0]) == int(ib.ev_meta[0, 0, 0])
