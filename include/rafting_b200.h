@@ -417,6 +417,10 @@ int rafting_step_wait_slot (rafting_engine_t* e, uint32_t slot);
  *   * dense steps only (no active list), no inbound-request ops (RAFTING_INBOX_NO_REQUESTS is implied): SUBMIT / TIMEOUT
  *     ops, AE / IS acks; vote replies and anything irregular use the escape list.
  *   * wire words are 32 bits: 4 B per lane slot + 4 B per group row up, 4 B per lane slot + 1 B per group row down.
+ *   * a tag is freed by the compact reply that echoes it (every RPC completes exactly once: reply, error or cancellation,
+ *     Async.java:239-254).  Dense and compact steps can be mixed slot by slot, but the reply to a compact-planned RPC should come
+ *     back through the compact path; if it comes back dense (or never), its tag stays taken and, once a lane has none left,
+ *     that lane's plans are simply untagged (their replies travel as escape records): slower, never wrong.
  * ------------------------------------------------------------------------------------------------------------------- */
 /* ev_c (32 bits per lane slot):
  *        bits 0..3 kind (RAFTING_EV_NONE / _AE_ACK / _IS_ACK, or 15 = "see the escape list") | 4..5 outcome | 6 success |
