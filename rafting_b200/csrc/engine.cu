@@ -474,7 +474,7 @@ static int blk_reserve(Blk& b, size_t bytes, bool pinned) {
     if (b.p) { if (pinned) cudaFreeHost(b.p); else cudaFree(b.p); b.p = nullptr; b.cap = 0; }
     const size_t cap = bytes + bytes / 4 + 4096;
     if (pinned) { CU(cudaHostAlloc((void**)&b.p, cap, cudaHostAllocDefault)); memset(b.p, 0, cap); }
-    else CU(cudaMalloc((void**)&b.p, cap));
+    else { CU(cudaMalloc((void**)&b.p, cap)); CU(cudaMemset(b.p, 0, cap)); }   // column padding and never-written plan fields travel in the one-block D2H copy: defined bytes
     b.cap = cap;
     return 0;
 }
