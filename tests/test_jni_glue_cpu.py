@@ -1,6 +1,7 @@
-"""The JNI glue (rafting_b200/csrc/jni/rafting_jni.c) cannot be built here (no JDK), but it must not rot: it is type-checked
-with gcc against the real C-ABI headers and a stand-in jni.h, and every native method INTEGRATION.md's NativeEngine declares
-must have its Java_..._NativeEngine_<name> definition in the glue."""
+"""The JNI glue (rafting_b200/csrc/jni/rafting_jni.c) cannot be loaded into a JVM here (no JDK), but it must not rot: it is
+type-checked with gcc against the real C-ABI headers and a stand-in jni.h, every native method INTEGRATION.md's NativeEngine
+declares must have its Java_..._NativeEngine_<name> definition in the glue, and the natives are EXECUTED against a stand-in
+JNIEnv (tests/jni_stub/fake_env.c): frame scan and the journal for real, the device natives down their error paths."""
 import os
 import re
 import shutil
@@ -24,3 +25,141 @@ def test_every_native_method_of_the_integration_guide_is_defined():
     declared = set(re.findall(r"static native [\w\[\]]+ (\w+)\(", guide))
     defined = set(re.findall(r"FN\((\w+)\)", open(GLUE).read()))
     assert len(declared) >= 30 and declared <= defined, sorted(declared - defined)
+
+
+# ---- the natives EXECUTED against a stand-in JNIEnv (tests/jni_stub/fake_env.c) -------------------------------------------
+# The glue is compiled with the stand-in jni.h and linked with the in-tree libraries; a fake function table plays the JVM
+# (direct buffers = {addr, cap}, strings = char*, long[] = {n, p}, exceptions recorded).  Host-only natives run for real;
+# the device natives are driven as far as their error path (no GPU on this box -> the status must surface as the exception
+# class INTEGRATION.md promises).
+import ctypes as C  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+PFX = "Java_io_lubricant_consensus_raft_gpu_NativeEngine_"
+
+
+class _Buf(C.Structure):
+    _fields_ = [("addr", C.c_void_p), ("cap", C.c_int64)]
+
+
+class _Longs(C.Structure):
+    _fields_ = [("n", C.c_int32), ("p", C.POINTER(C.c_int64))]
+
+
+def _buf(arr):
+    b = _Buf(arr.ctypes.data, arr.nbytes)
+    b._keep = arr
+    return b
+
+
+@pytest.fixture(scope="module")
+def glue(tmp_path_factory):
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from rafting_b200 import _build
+    _build.build(), _build.build_durable(), _build.build_ingest()
+    libdir = os.path.join(ROOT, "rafting_b200")
+    out = str(tmp_path_factory.mktemp("jni") / "librafting_jni_exec.so")
+    res = subprocess.run(["gcc", "-shared", "-fPIC", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "jni_stub"),
+                          "-I", os.path.join(ROOT, "include"), GLUE, os.path.join(ROOT, "tests", "jni_stub", "fake_env.c"),
+                          "-L", libdir, "-lrafting_b200", "-lrafting_durable", "-lrafting_ingest", f"-Wl,-rpath,{libdir}", "-o", out],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    L = C.CDLL(out)
+    L.fake_env.restype = C.c_void_p
+    L.fake_thrown_class.restype = C.c_char_p
+    L.fake_thrown_message.restype = C.c_char_p
+    L.env = C.c_void_p(L.fake_env())
+    return L
+
+
+def _fn(L, name, restype, *argtypes):
+    f = getattr(L, PFX + name)
+    f.restype = restype
+    f.argtypes = [C.c_void_p, C.c_void_p] + list(argtypes)
+    return lambda *a: f(L.env, None, *a)
+
+
+def test_frame_scan_native_cuts_a_receive_buffer_like_the_c_entry_point(glue):
+    from rafting_b200 import ingest
+    stream = ingest.encode(ingest.ENQ, b"appendEntries:ctx-7", b"\x01\x02\x03", sequence=41) + \
+        ingest.encode(ingest.ACK, b"appendEntries:ctx-7", b"", sequence=41) + \
+        ingest.encode(ingest.SYN, b"node-1")[:9]                                     # a frame cut off mid-way stays unconsumed
+    data = np.frombuffer(stream, dtype=np.uint8).copy()
+    frames = np.zeros(8, dtype=ingest.FRAME)
+    meta = np.zeros(3, dtype=np.int64)
+    glue.fake_reset()
+    n = _fn(glue, "frameScan", C.c_int32, C.POINTER(_Buf), C.c_int64, C.POINTER(_Buf), C.c_int32, C.POINTER(_Buf))(
+        C.byref(_buf(data)), len(data), C.byref(_buf(frames)), 8, C.byref(_buf(meta)))
+    rc, want, used, tr = ingest.scan(stream, cap=8)
+    assert n == 2 == len(want) and meta.tolist() == [used, int(tr), rc] and used == len(stream) - 9
+    assert frames[:2].tobytes() == want.tobytes() and frames["sequence"][0] == 41 and glue.fake_throws() == 0
+
+
+def test_journal_natives_persist_and_restore_through_the_glue(glue, tmp_path):
+    from rafting_b200 import durable
+    jopen = _fn(glue, "journalOpen", C.c_int64, C.c_char_p, C.c_int32)
+    commit = _fn(glue, "journalCommitStep", C.c_int64, C.c_int64, C.POINTER(_Buf), C.c_int32, C.c_uint8, C.POINTER(_Buf), C.POINTER(_Buf))
+    glue.fake_reset()
+    j = jopen(str(tmp_path / "wal").encode(), 8)
+    assert j != 0 and glue.fake_throws() == 0 and glue.fake_balance() == 0          # GetStringUTFChars was released
+    rw = np.zeros(8, dtype=np.uint32)
+    rw[1] = 0 | ((2 + 1) << 8) | (1 << 30)                                            # follower, votedFor slot 2, persist-dirty
+    rw[5] = 2 | ((0 + 1) << 8) | (1 << 30)
+    term = np.arange(8, dtype=np.int64) * 10
+    assert commit(j, None, 8, 0, C.byref(_buf(rw)), C.byref(_buf(term))) == 2
+    _fn(glue, "journalMilestone", None, C.c_int64, C.c_int32, C.c_int64, C.c_int64)(j, 5, 1234, 50)
+    _fn(glue, "journalCheckpoint", None, C.c_int64)(j)
+    st = np.zeros(1, dtype=np.dtype([("term", "<i8"), ("ballot", "<i4"), ("_pad", "<i4"), ("mi", "<i8"), ("mt", "<i8")]))
+    restore = _fn(glue, "journalRestore", None, C.c_int64, C.c_int32, C.POINTER(_Buf))
+    restore(j, 5, C.byref(_buf(st)))
+    assert (st["term"][0], st["ballot"][0], st["mi"][0], st["mt"][0]) == (50, 0, 1234, 50)
+    _fn(glue, "journalClose", None, C.c_int64)(j)
+    assert glue.fake_throws() == 0
+    # a second process (the plain binding) finds what the natives made durable
+    j2 = durable.Journal(str(tmp_path / "wal"), 8)
+    assert (j2.restore(1).term, j2.restore(1).ballot) == (10, 2) and j2.restore(5).milestone_index == 1234
+    j2.close()
+    # failure path: the journal directory cannot be created -> java/io/IOException with the library's message
+    glue.fake_reset()
+    blocker = tmp_path / "file"
+    blocker.write_text("x")
+    assert jopen(str(blocker / "sub").encode(), 8) == 0
+    assert glue.fake_throws() == 1 and glue.fake_thrown_class() == b"java/io/IOException" and glue.fake_thrown_message()
+    assert glue.fake_balance() == 0
+
+
+def test_status_codes_surface_as_the_promised_exception_classes(glue):
+    import torch
+    from rafting_b200 import abi
+    glue.fake_reset()
+    # wrap(): a DirectByteBuffer over native memory
+    raw = np.zeros(64, np.uint8)
+    glue_wrap = getattr(glue, PFX + "wrap")
+    glue_wrap.restype = C.POINTER(_Buf)
+    glue_wrap.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+    b = glue_wrap(glue.env, None, raw.ctypes.data, 64)
+    assert b.contents.addr == raw.ctypes.data and b.contents.cap == 64
+    glue.fake_free_buf(b)
+    # commInitAll over more shards than one process can hold: RAFTING_E_CAPACITY -> RaftException; the long[] is released
+    hs = (C.c_int64 * 65)()
+    longs = _Longs(65, C.cast(hs, C.POINTER(C.c_int64)))
+    _fn(glue, "commInitAll", None, C.POINTER(_Longs))(C.byref(longs))
+    assert glue.fake_throws() == 1 and glue.fake_thrown_class() == b"io/lubricant/consensus/raft/support/RaftException"
+    assert glue.fake_balance() == 0
+    # an invalid configuration -> IllegalArgumentException (checked before any device is touched)
+    glue.fake_reset()
+    cfg = abi.make_cfg(replicas=3, max_groups=16, max_rows=2)
+    cfg.replicas = 99
+    cbuf = _Buf(C.addressof(cfg), C.sizeof(cfg))
+    h = _fn(glue, "create", C.c_int64, C.POINTER(_Buf))(C.byref(cbuf))
+    assert h == 0 and glue.fake_throws() == 1 and glue.fake_thrown_class() == b"java/lang/IllegalArgumentException"
+    if not torch.cuda.is_available():
+        # a valid configuration on a box without a GPU: the CUDA status comes back as RaftException, never as a crash
+        glue.fake_reset()
+        cfg = abi.make_cfg(replicas=3, max_groups=16, max_rows=2)
+        cbuf = _Buf(C.addressof(cfg), C.sizeof(cfg))
+        h = _fn(glue, "create", C.c_int64, C.POINTER(_Buf))(C.byref(cbuf))
+        assert h == 0 and glue.fake_throws() == 1
+        assert glue.fake_thrown_class() == b"io/lubricant/consensus/raft/support/RaftException" and glue.fake_thrown_message()
