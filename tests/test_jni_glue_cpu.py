@@ -36,49 +36,16 @@ import ctypes as C  # noqa: E402
 
 import numpy as np  # noqa: E402
 
-PFX = "Java_io_lubricant_consensus_raft_gpu_NativeEngine_"
-
-
-class _Buf(C.Structure):
-    _fields_ = [("addr", C.c_void_p), ("cap", C.c_int64)]
-
-
-class _Longs(C.Structure):
-    _fields_ = [("n", C.c_int32), ("p", C.POINTER(C.c_int64))]
-
-
-def _buf(arr):
-    b = _Buf(arr.ctypes.data, arr.nbytes)
-    b._keep = arr
-    return b
+from tests import jni_exec  # noqa: E402
+from tests.jni_exec import Buf as _Buf, Longs as _Longs, buf_of_array as _buf, fn as _fn, PFX  # noqa: E402
 
 
 @pytest.fixture(scope="module")
 def glue(tmp_path_factory):
-    if shutil.which("gcc") is None:
+    L = jni_exec.build(str(tmp_path_factory.mktemp("jni")))
+    if L is None:
         pytest.skip("no gcc")
-    from rafting_b200 import _build
-    _build.build(), _build.build_durable(), _build.build_ingest()
-    libdir = os.path.join(ROOT, "rafting_b200")
-    out = str(tmp_path_factory.mktemp("jni") / "librafting_jni_exec.so")
-    res = subprocess.run(["gcc", "-shared", "-fPIC", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "jni_stub"),
-                          "-I", os.path.join(ROOT, "include"), GLUE, os.path.join(ROOT, "tests", "jni_stub", "fake_env.c"),
-                          "-L", libdir, "-lrafting_b200", "-lrafting_durable", "-lrafting_ingest", f"-Wl,-rpath,{libdir}", "-o", out],
-                         capture_output=True, text=True)
-    assert res.returncode == 0, res.stderr[-3000:]
-    L = C.CDLL(out)
-    L.fake_env.restype = C.c_void_p
-    L.fake_thrown_class.restype = C.c_char_p
-    L.fake_thrown_message.restype = C.c_char_p
-    L.env = C.c_void_p(L.fake_env())
     return L
-
-
-def _fn(L, name, restype, *argtypes):
-    f = getattr(L, PFX + name)
-    f.restype = restype
-    f.argtypes = [C.c_void_p, C.c_void_p] + list(argtypes)
-    return lambda *a: f(L.env, None, *a)
 
 
 def test_frame_scan_native_cuts_a_receive_buffer_like_the_c_entry_point(glue):
