@@ -12,8 +12,10 @@
  *             MW 0x95 WaitSnapEvent | PM 0x9E TransSnapEvent          (EventCodec.java:32-41)
  *   SEQUENCE  present for ENQ / ACK only (EventCodec.java:239-244)
  *   HEAD      ENQ / ACK: the scope "<RaftService method name>:<contextId>" (NettyNode.java:55-75); others: the message
- *   BODY      Kryo bytes of the RPC arguments / the RaftResponse — OPAQUE here (kryo 4.0.2 is not in the reference tree);
- *             the pump hands AppendEntries bodies to rafting_log_append and reply bodies to the Java-side decoder
+ *   BODY      Kryo bytes (Serialization.writeObject -> kryo.writeClassAndObject, support/serial/Serialization.java:96-110).
+ *             Request bodies (an Object[] of the RPC arguments, NettyNode.java:55-75) stay OPAQUE here: the pump hands
+ *             AppendEntries bodies to rafting_log_append.  REPLY bodies — one RaftResponse(term, success),
+ *             RaftResponse.java:10-17 — are decoded / encoded by rafting_reply_body_* below (parity UNPINNED, see there)
  *   limits    HEAD_LEN <= 128, BODY_LEN <= 64 MiB (EventCodec.java:25-26); a violation, or a byte other than
  *             SOH/EOT at a frame start, STX after the type, ETX after the body, is the decoder's DecoderException:
  *             RAFTING_E_INVAL, the channel is to be closed (EventCodec.java:326-330)
@@ -72,6 +74,47 @@ int rafting_ctxmap_create (rafting_ctxmap_t** out);
 int rafting_ctxmap_destroy(rafting_ctxmap_t* m);
 int rafting_ctxmap_put    (rafting_ctxmap_t* m, const char* ctx, uint32_t len, uint32_t gid);
 int rafting_ctxmap_get    (const rafting_ctxmap_t* m, const char* ctx, uint32_t len, uint32_t* gid);   /* -1 if unknown */
+
+/* ---- reply bodies: the Kryo bytes of one RaftResponse ----------------------------------------------------------------------
+ * The body of every ACK frame is kryo.writeClassAndObject(RaftResponse) with the reference's Kryo configuration: kryo 4.0.2
+ * (pom.xml:22-26; a dependency, NOT in the reference tree), `new Kryo()` with only the instantiator strategy changed
+ * (Serialization.java:21-26) — so: registration not required, references on, FieldSerializer with variable-length integers.
+ * Kryo 4.0.2's published format for that object is restated here (PARITY UNPINNED: there is no JVM in this image and the
+ * reference's SerializationTest only round-trips, it holds no golden bytes; oracle/java/KryoGen.java prints the vectors
+ * tests/test_ingest_cpu.py would pin against, for a box that has a JDK and the kryo jar):
+ *     01                          class by NAME        (DefaultClassResolver.writeName: varint NAME + 2)
+ *     00                          nameId 0             (first class of this object graph)
+ *     "io.lubricant.consensus.raft.RaftRespons" 'e'|0x80      Output.writeString, ASCII form (1 < length < 64): last byte flagged
+ *     01                          reference marker NOT_NULL   (Kryo.writeReferenceOrNull, first occurrence)
+ *     success  1 byte 00 / 01     FieldSerializer, fields in name order: "success" < "term"
+ *     term     1..9 bytes         Output.writeLong(value, optimizePositive = false): zig-zag, then 7 bits per byte, low first,
+ *                                 bit 7 = "more"; the ninth byte carries 8 bits
+ * 45 .. 53 bytes.  The decoder accepts exactly this shape and nothing else (anything else -> RAFTING_E_INVAL: the pump falls
+ * back to the Java decoder for that frame). */
+#define RAFTING_REPLY_BODY_MAX 53u
+size_t rafting_reply_body_encode(uint8_t* dst, size_t cap, int64_t term, int success);          /* bytes written, 0 = no room */
+int    rafting_reply_body_decode(const uint8_t* body, size_t len, int64_t* term, int* success);
+
+/* One ACK frame of a scanned buffer -> what a lane event needs: the group (scope's context id through the registry), the reply
+ * kind (appendEntries -> RAFTING_EV_AE_ACK, installSnapshot -> _IS_ACK, preVote -> _PV_REPLY, requestVote -> _RV_REPLY), the
+ * frame's sequence (the key of the caller's pending-invocation table, NettyNode.getInvocationIfPresent, NettyNode.java:88-90)
+ * and the decoded RaftResponse.  RAFTING_E_INVAL: not an ACK frame, unknown scope / context, or a body of another shape. */
+int rafting_ack_frame_decode(const uint8_t* buf, const rafting_frame_t* fr, const rafting_ctxmap_t* map, uint32_t* gid,
+                             uint32_t* ev_kind, int32_t* sequence, int64_t* term, int* success);
+
+/* The same for a whole scanned buffer: one record per ACK frame that decodes (frame = its index in `frames`), the others —
+ * requests, handshakes, replies with another body — are skipped and stay with the caller.  out has room for n records. */
+typedef struct rafting_ack_rec {
+    uint32_t gid;
+    uint8_t  kind;            /* RAFTING_EV_*                                                                            */
+    uint8_t  success;
+    uint16_t _pad;
+    int32_t  sequence;
+    uint32_t frame;
+    int64_t  term;
+} rafting_ack_rec_t;        /* 24 bytes */
+int rafting_ack_frames_decode(const uint8_t* buf, const rafting_frame_t* frames, uint32_t n, const rafting_ctxmap_t* map,
+                              rafting_ack_rec_t* out, uint32_t* n_out);
 
 /* ---- engine-to-engine batch records (TYPE 0x1A) ---- */
 typedef struct rafting_batch_rec {

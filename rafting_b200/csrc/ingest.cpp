@@ -112,6 +112,84 @@ extern "C" int rafting_ctxmap_get(const rafting_ctxmap_t* m, const char* ctx, ui
     return RAFTING_OK;
 }
 
+// ---- reply bodies: kryo.writeClassAndObject(RaftResponse) of kryo 4.0.2, restated (see the header; parity unpinned) ----
+static const char RESPONSE_CLASS[] = "io.lubricant.consensus.raft.RaftResponse";      // RaftResponse.java:1,9
+static constexpr size_t RESPONSE_CLASS_LEN = sizeof(RESPONSE_CLASS) - 1;
+static_assert(RESPONSE_CLASS_LEN > 1 && RESPONSE_CLASS_LEN < 64, "Output.writeString takes its ASCII form for 1 < length < 64 only");
+
+extern "C" size_t rafting_reply_body_encode(uint8_t* dst, size_t cap, int64_t term, int success) {
+    uint8_t tmp[RAFTING_REPLY_BODY_MAX];
+    size_t n = 0;
+    tmp[n++] = 0x01;                                        // NAME + 2
+    tmp[n++] = 0x00;                                        // nameId 0
+    memcpy(tmp + n, RESPONSE_CLASS, RESPONSE_CLASS_LEN); n += RESPONSE_CLASS_LEN;
+    tmp[n - 1] |= 0x80;                                     // end of an ASCII string
+    tmp[n++] = 0x01;                                        // NOT_NULL
+    tmp[n++] = success ? 1 : 0;                             // boolean success
+    uint64_t z = ((uint64_t)term << 1) ^ (uint64_t)(term >> 63);      // zig-zag (optimizePositive = false)
+    for (int k = 0; k < 8 && (z >> 7) != 0; k++) { tmp[n++] = (uint8_t)((z & 0x7F) | 0x80); z >>= 7; }
+    tmp[n++] = (uint8_t)z;                                  // the last byte: 7 bits, or all 8 when it is the ninth
+    if (!dst || cap < n) return 0;
+    memcpy(dst, tmp, n);
+    return n;
+}
+
+extern "C" int rafting_reply_body_decode(const uint8_t* body, size_t len, int64_t* term, int* success) {
+    if (!body || !term || !success) return RAFTING_E_INVAL;
+    const size_t fixed = 2 + RESPONSE_CLASS_LEN + 2;
+    if (len < fixed + 1 || len > RAFTING_REPLY_BODY_MAX) return RAFTING_E_INVAL;
+    if (body[0] != 0x01 || body[1] != 0x00) return RAFTING_E_INVAL;
+    if (memcmp(body + 2, RESPONSE_CLASS, RESPONSE_CLASS_LEN - 1) != 0 ||
+        body[2 + RESPONSE_CLASS_LEN - 1] != (uint8_t)(RESPONSE_CLASS[RESPONSE_CLASS_LEN - 1] | 0x80)) return RAFTING_E_INVAL;
+    size_t p = 2 + RESPONSE_CLASS_LEN;
+    if (body[p++] != 0x01) return RAFTING_E_INVAL;          // a back-reference (>= 2) or null (0) cannot open an object graph
+    if (body[p] > 1) return RAFTING_E_INVAL;
+    const int ok = body[p++];
+    uint64_t z = 0; int k = 0;
+    for (;; k++) {
+        if (p >= len) return RAFTING_E_INVAL;               // ran out inside the varlong
+        const uint8_t b = body[p++];
+        if (k == 8) { z |= (uint64_t)b << 56; break; }      // ninth byte: 8 bits, never a continuation flag
+        z |= (uint64_t)(b & 0x7F) << (7 * k);
+        if (!(b & 0x80)) break;
+    }
+    if (p != len) return RAFTING_E_INVAL;                   // trailing bytes: not this object
+    *term = (int64_t)(z >> 1) ^ -(int64_t)(z & 1);
+    *success = ok;
+    return RAFTING_OK;
+}
+
+extern "C" int rafting_ack_frame_decode(const uint8_t* buf, const rafting_frame_t* fr, const rafting_ctxmap_t* map, uint32_t* gid,
+                                        uint32_t* ev_kind, int32_t* sequence, int64_t* term, int* success) {
+    if (!buf || !fr || !map || !gid || !ev_kind || !sequence || !term || !success) return RAFTING_E_INVAL;
+    if (fr->type != RAFTING_FRAME_ACK || !fr->has_sequence) return RAFTING_E_INVAL;
+    uint32_t op = 0, off = 0;
+    const char* head = (const char*)buf + fr->head_off;
+    if (rafting_scope_parse(head, fr->head_len, &op, &off) != RAFTING_OK) return RAFTING_E_INVAL;
+    if (rafting_ctxmap_get(map, head + off, fr->head_len - off, gid) != RAFTING_OK) return RAFTING_E_INVAL;
+    if (rafting_reply_body_decode(buf + fr->body_off, fr->body_len, term, success) != RAFTING_OK) return RAFTING_E_INVAL;
+    *ev_kind = op == RAFTING_OP_AE_REQUEST ? RAFTING_EV_AE_ACK : op == RAFTING_OP_IS_REQUEST ? RAFTING_EV_IS_ACK
+             : op == RAFTING_OP_PREVOTE_REQ ? RAFTING_EV_PV_REPLY : RAFTING_EV_RV_REPLY;
+    *sequence = fr->sequence;
+    return RAFTING_OK;
+}
+
+extern "C" int rafting_ack_frames_decode(const uint8_t* buf, const rafting_frame_t* frames, uint32_t n, const rafting_ctxmap_t* map,
+                                         rafting_ack_rec_t* out, uint32_t* n_out) {
+    if (!buf || (!frames && n) || !map || !out || !n_out) return RAFTING_E_INVAL;
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (frames[i].type != RAFTING_FRAME_ACK) continue;
+        rafting_ack_rec_t r{};
+        uint32_t kind = 0; int ok = 0;
+        if (rafting_ack_frame_decode(buf, frames + i, map, &r.gid, &kind, &r.sequence, &r.term, &ok) != RAFTING_OK) continue;
+        r.kind = (uint8_t)kind; r.success = (uint8_t)ok; r.frame = i;
+        out[k++] = r;
+    }
+    *n_out = k;
+    return RAFTING_OK;
+}
+
 extern "C" int rafting_batch_to_inbox(const rafting_batch_rec_t* recs, uint32_t n, int64_t now_ms, const rafting_inbox_t* in,
                                       uint32_t n_groups, uint32_t F, uint32_t* n_done) {
     if (!recs || !in || !n_done || !in->ev_meta || !in->ev_tn || in->gids) return RAFTING_E_INVAL;

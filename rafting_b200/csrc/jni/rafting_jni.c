@@ -214,4 +214,23 @@ JNIEXPORT jint JNICALL FN(frameScan)(JNIEnv* env, jclass k, jobject buf, jlong l
     if (o) { o[0] = (int64_t)used; o[1] = transparent; o[2] = rc; }
     return (jint)n;
 }
+/* contextId -> gid registry + the reply bodies of a scanned buffer (RaftResponse, Kryo) without one object per frame */
+JNIEXPORT jlong JNICALL FN(ctxmapCreate)(JNIEnv* env, jclass k) {
+    rafting_ctxmap_t* m = NULL;
+    CHECK(rafting_ctxmap_create(&m));
+    return (jlong)(intptr_t)m;
+}
+JNIEXPORT void JNICALL FN(ctxmapPut)(JNIEnv* env, jclass k, jlong m, jstring contextId, jint gid) {
+    const char* c = (*env)->GetStringUTFChars(env, contextId, NULL);
+    int rc = c ? rafting_ctxmap_put((rafting_ctxmap_t*)(intptr_t)m, c, (uint32_t)strlen(c), (uint32_t)gid) : RAFTING_E_NOMEM;
+    if (c) (*env)->ReleaseStringUTFChars(env, contextId, c);
+    if (rc) throw_status(env, rc);
+}
+JNIEXPORT void JNICALL FN(ctxmapDestroy)(JNIEnv* env, jclass k, jlong m) { rafting_ctxmap_destroy((rafting_ctxmap_t*)(intptr_t)m); }
+JNIEXPORT jint JNICALL FN(acksDecode)(JNIEnv* env, jclass k, jobject buf, jobject frames, jint n, jlong m, jobject ackRecsOut) {
+    uint32_t got = 0;
+    CHECK(rafting_ack_frames_decode((const uint8_t*)BUF(buf), (const rafting_frame_t*)BUF(frames), (uint32_t)n,
+                                    (const rafting_ctxmap_t*)(intptr_t)m, (rafting_ack_rec_t*)BUF(ackRecsOut), &got));
+    return (jint)got;
+}
 #endif /* RAFTING_HAVE_JNI */

@@ -18,7 +18,9 @@ FRAME = np.dtype([("type", "u1"), ("has_sequence", "u1"), ("ending", "u1"), ("_p
                   ("head_off", "<u4"), ("head_len", "<u4"), ("body_off", "<u4"), ("body_len", "<u4")])
 BATCH_REC = np.dtype([("gid", "<u4"), ("kind", "u1"), ("lane", "u1"), ("flags", "u1"), ("row", "u1"), ("incarnation", "<u4"),
                       ("_pad", "<u4"), ("term", "<i8"), ("epoch_at_send", "<i8"), ("last_at_send", "<i8")])
-assert FRAME.itemsize == 24 and BATCH_REC.itemsize == 40
+ACK_REC = np.dtype([("gid", "<u4"), ("kind", "u1"), ("success", "u1"), ("_pad", "<u2"), ("sequence", "<i4"), ("frame", "<u4"),
+                    ("term", "<i8")])
+assert FRAME.itemsize == 24 and BATCH_REC.itemsize == 40 and ACK_REC.itemsize == 24
 
 
 def lib():
@@ -37,8 +39,30 @@ def lib():
         L.rafting_ctxmap_get.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.rafting_batch_to_inbox.argtypes = [C.c_void_p, C.c_uint32, C.c_int64, C.POINTER(abi.InboxC), C.c_uint32, C.c_uint32,
                                              C.POINTER(C.c_uint32)]
+        L.rafting_reply_body_encode.restype = C.c_size_t
+        L.rafting_reply_body_encode.argtypes = [C.c_void_p, C.c_size_t, C.c_int64, C.c_int]
+        L.rafting_reply_body_decode.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.rafting_ack_frame_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                               C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.rafting_ack_frames_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         _LIB = L
     return _LIB
+
+
+def reply_body_encode(term: int, success: bool) -> bytes:
+    """The Kryo bytes of RaftResponse(term, success) as the reference's Serialization.writeObject emits them (restated from
+    kryo 4.0.2's format; include/rafting_ingest.h)."""
+    buf = C.create_string_buffer(64)
+    n = lib().rafting_reply_body_encode(buf, len(buf), term, 1 if success else 0)
+    return buf.raw[:n]
+
+
+def reply_body_decode(body: bytes):
+    """-> (term, success) or None when the bytes are not exactly one RaftResponse."""
+    t, ok = C.c_int64(), C.c_int()
+    if lib().rafting_reply_body_decode(body, len(body), C.byref(t), C.byref(ok)) != 0:
+        return None
+    return t.value, bool(ok.value)
 
 
 def encode(ftype: int, head: bytes, body: bytes = b"", sequence: int | None = None, ending: bool = False) -> bytes:
@@ -84,6 +108,30 @@ class CtxMap:
             lib().rafting_ctxmap_destroy(self._h)
         except Exception:
             pass
+
+
+def ack_frame_decode(data: bytes, frame, ctxmap: "CtxMap"):
+    """One scanned ACK frame -> (gid, event kind, sequence, term, success), or None (not an ACK / unknown scope or context /
+    a body that is not one RaftResponse)."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    fr = np.array([frame], dtype=FRAME)
+    gid, kind, seq, term, ok = C.c_uint32(), C.c_uint32(), C.c_int32(), C.c_int64(), C.c_int()
+    if lib().rafting_ack_frame_decode(buf.ctypes.data, fr.ctypes.data, ctxmap._h, C.byref(gid), C.byref(kind), C.byref(seq),
+                                      C.byref(term), C.byref(ok)) != 0:
+        return None
+    return gid.value, kind.value, seq.value, term.value, bool(ok.value)
+
+
+def ack_frames_decode(data: bytes, frames: np.ndarray, ctxmap: "CtxMap") -> np.ndarray:
+    """Every ACK frame of a scanned buffer that decodes -> one ACK_REC (its `frame` = index into `frames`)."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    frames = np.ascontiguousarray(frames, dtype=FRAME)
+    out = np.zeros(max(1, len(frames)), dtype=ACK_REC)
+    n = C.c_uint32()
+    rc = lib().rafting_ack_frames_decode(buf.ctypes.data, frames.ctypes.data, len(frames), ctxmap._h, out.ctypes.data, C.byref(n))
+    if rc:
+        raise ValueError(f"rafting_ack_frames_decode: rc={rc}")
+    return out[:n.value]
 
 
 def batch_to_inbox(recs: np.ndarray, now_ms: int, inbox: abi.Inbox) -> tuple[int, int]:

@@ -1,6 +1,7 @@
 """Transport framing (include/rafting_ingest.h): the reference's EventCodec frame layout
 (transport/EventCodec.java:169-201 encoder, :222-334 decoder) restated in C.  The expected bytes below are written out by
 hand from the layout constants of EventCodec.java:25-41, not produced by the code under test."""
+import os
 import struct
 
 import numpy as np
@@ -109,3 +110,86 @@ def test_batch_records_land_in_the_inbox_columns():
     assert rc == 0 and done == 1 and tuple(ib.ev_el[1, 4, 0]) == (30, 30)
     bad = recs[:1].copy(); bad["gid"] = 16
     assert ingest.batch_to_inbox(bad, 0, ib)[0] == -1
+
+
+# ---- reply bodies: kryo.writeClassAndObject(RaftResponse) restated (parity unpinned: no JVM here; oracle/java/KryoGen.java) ----
+def _kryo_response(term: int, success: bool) -> bytes:
+    """An independent restatement, straight from the format notes in include/rafting_ingest.h."""
+    name = b"io.lubricant.consensus.raft.RaftResponse"
+    out = bytearray([0x01, 0x00]) + name[:-1] + bytes([name[-1] | 0x80]) + bytes([0x01, 1 if success else 0])
+    z = ((term << 1) ^ (term >> 63)) & 0xFFFFFFFFFFFFFFFF
+    for k in range(9):
+        if k == 8:
+            out.append(z & 0xFF)
+            break
+        if z >> 7 == 0:
+            out.append(z)
+            break
+        out.append((z & 0x7F) | 0x80)
+        z >>= 7
+    return bytes(out)
+
+
+def test_reply_body_is_the_kryo_layout_of_a_raft_response():
+    assert ingest.reply_body_encode(5, True) == \
+        b"\x01\x00io.lubricant.consensus.raft.RaftRespons" + bytes([ord("e") | 0x80, 0x01, 0x01, 0x0A])
+    assert ingest.reply_body_encode(0, False)[-3:] == b"\x01\x00\x00" and len(ingest.reply_body_encode(0, False)) == 45
+    assert ingest.reply_body_encode(-1, True)[-1] == 0x01                            # zig-zag: -1 -> 1
+    assert ingest.reply_body_encode(64, True)[-2:] == b"\x80\x01"                     # 128 after zig-zag: two bytes
+    rng = np.random.default_rng(7)
+    terms = [0, 1, -1, 63, 64, -64, -65, 2**31, 2**55, 2**56 - 1, 2**62, 2**63 - 1, -2**63] + \
+        [int(x) for x in rng.integers(-2**63, 2**63 - 1, 200, dtype=np.int64)] + [int(x) for x in rng.integers(0, 1 << 20, 200)]
+    for t in terms:
+        for ok in (False, True):
+            b = ingest.reply_body_encode(t, ok)
+            assert b == _kryo_response(t, ok), (t, ok)
+            assert ingest.reply_body_decode(b) == (t, ok)
+    assert len(ingest.reply_body_encode(-2**63, True)) == 53 == max(len(ingest.reply_body_encode(t, True)) for t in terms)
+
+
+def test_reply_body_decoder_accepts_nothing_but_that_shape():
+    good = ingest.reply_body_encode(1234567, True)
+    assert ingest.reply_body_decode(good) == (1234567, True)
+    for cut in range(len(good)):
+        assert ingest.reply_body_decode(good[:cut]) is None, cut                        # every truncation
+    assert ingest.reply_body_decode(good + b"\x00") is None                             # trailing byte
+    for pos, val in ((0, 0x02), (1, 0x01), (10, ord("X")), (41, ord("e")), (42, 0x02), (42, 0x00), (43, 0x02)):
+        bad = bytearray(good); bad[pos] = val
+        assert ingest.reply_body_decode(bytes(bad)) is None, pos                        # registered id, nameId, class, flag, ref, bool
+    ten = good[:44] + b"\x80" * 9 + b"\x01"
+    assert ingest.reply_body_decode(ten) is None                                        # a varlong never has a tenth byte
+    nine = good[:44] + b"\xff" * 9                                                      # nine bytes: the last carries 8 bits
+    assert ingest.reply_body_decode(nine) == (-2**63, True) and nine == ingest.reply_body_encode(-2**63, True)
+
+
+def test_ack_frames_become_lane_event_fields():
+    cm = ingest.CtxMap()
+    cm.put(b"ctx-7", 7), cm.put(b"ctx-9", 9)
+    kinds = {b"appendEntries": abi.EV_AE_ACK, b"installSnapshot": abi.EV_IS_ACK, b"preVote": abi.EV_PV_REPLY, b"requestVote": abi.EV_RV_REPLY}
+    stream, want = b"", []
+    for i, (m, k) in enumerate(kinds.items()):
+        gid = 7 if i % 2 == 0 else 9
+        stream += ingest.encode(ingest.ACK, m + b":ctx-%d" % gid, ingest.reply_body_encode(100 + i, i % 2 == 1), sequence=1000 + i)
+        want.append((gid, k, 1000 + i, 100 + i, i % 2 == 1))
+    stream += ingest.encode(ingest.ACK, b"appendEntries:nobody", ingest.reply_body_encode(1, True), sequence=1)     # unknown context
+    stream += ingest.encode(ingest.ENQ, b"appendEntries:ctx-7", b"opaque", sequence=2)                                # a request
+    stream += ingest.encode(ingest.ACK, b"appendEntries:ctx-7", b"\x01\x00not-a-response", sequence=3)                # another body
+    rc, frames, used, _ = ingest.scan(stream)
+    assert rc == 0 and used == len(stream) and len(frames) == 7
+    got = [ingest.ack_frame_decode(stream, f, cm) for f in frames]
+    assert got[:4] == want and got[4:] == [None, None, None]
+    recs = ingest.ack_frames_decode(stream, frames, cm)                                 # the whole buffer in one call
+    assert [(int(r["gid"]), int(r["kind"]), int(r["sequence"]), int(r["term"]), bool(r["success"])) for r in recs] == want
+    assert recs["frame"].tolist() == [0, 1, 2, 3]
+
+
+UPSTREAM_KRYO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "upstream_kryo.json")
+
+
+@pytest.mark.skipif(not os.path.exists(UPSTREAM_KRYO), reason="tests/golden/upstream_kryo.json absent: no JDK / kryo jar here (make -C oracle/java kryo)")
+def test_reply_body_matches_the_bytes_the_reference_emits():
+    import json
+    for v in json.load(open(UPSTREAM_KRYO))["vectors"]:
+        want = bytes.fromhex(v["hex"])
+        assert ingest.reply_body_encode(v["term"], v["success"]) == want, v
+        assert ingest.reply_body_decode(want) == (v["term"], v["success"]), v

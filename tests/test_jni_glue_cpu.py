@@ -64,6 +64,27 @@ def test_frame_scan_native_cuts_a_receive_buffer_like_the_c_entry_point(glue):
     assert frames[:2].tobytes() == want.tobytes() and frames["sequence"][0] == 41 and glue.fake_throws() == 0
 
 
+def test_ack_decode_natives_turn_reply_frames_into_records(glue):
+    from rafting_b200 import abi, ingest
+    m = _fn(glue, "ctxmapCreate", C.c_int64)()
+    put = _fn(glue, "ctxmapPut", None, C.c_int64, C.c_char_p, C.c_int32)
+    glue.fake_reset()
+    put(m, b"ctx-3", 3), put(m, b"ctx-4", 4)
+    stream = ingest.encode(ingest.ACK, b"appendEntries:ctx-3", ingest.reply_body_encode(17, True), sequence=5) + \
+        ingest.encode(ingest.ENQ, b"appendEntries:ctx-3", b"opaque", sequence=6) + \
+        ingest.encode(ingest.ACK, b"requestVote:ctx-4", ingest.reply_body_encode(18, False), sequence=7)
+    data = np.frombuffer(stream, dtype=np.uint8).copy()
+    rc, frames, used, _ = ingest.scan(stream)
+    frames = frames.copy()
+    recs = np.zeros(len(frames), dtype=ingest.ACK_REC)
+    n = _fn(glue, "acksDecode", C.c_int32, C.POINTER(_Buf), C.POINTER(_Buf), C.c_int32, C.c_int64, C.POINTER(_Buf))(
+        C.byref(_buf(data)), C.byref(_buf(frames)), len(frames), m, C.byref(_buf(recs)))
+    assert n == 2 and glue.fake_throws() == 0 and glue.fake_balance() == 0
+    assert [(int(r["gid"]), int(r["kind"]), int(r["sequence"]), int(r["term"]), int(r["success"]), int(r["frame"])) for r in recs[:2]] == \
+        [(3, abi.EV_AE_ACK, 5, 17, 1, 0), (4, abi.EV_RV_REPLY, 7, 18, 0, 2)]
+    _fn(glue, "ctxmapDestroy", None, C.c_int64)(m)
+
+
 def test_journal_natives_persist_and_restore_through_the_glue(glue, tmp_path):
     from rafting_b200 import durable
     jopen = _fn(glue, "journalOpen", C.c_int64, C.c_char_p, C.c_int32)
