@@ -3,8 +3,7 @@
 
 #include <string.h>
 
-#include <string>
-#include <unordered_map>
+#include <vector>
 
 namespace {
 constexpr uint8_t SOH = 0x01, STX = 0x02, ETX = 0x03, EOT = 0x04;          // EventCodec.java:29-32
@@ -90,7 +89,48 @@ extern "C" int rafting_scope_parse(const char* head, uint32_t head_len, uint32_t
     return RAFTING_E_INVAL;
 }
 
-struct rafting_ctxmap { std::unordered_map<std::string, uint32_t> m; };
+// contextId -> gid: an open-addressing table over the key bytes (FNV-1a), looked up straight from the receive buffer — no
+// std::string per frame (a lookup per ACK frame is the hot part of rafting_ack_frames_decode).
+struct rafting_ctxmap {
+    struct Slot { uint64_t hash = 0; uint32_t off = 0, len = 0, gid = 0; bool used = false; };
+    std::vector<Slot> slots;
+    std::vector<char> keys;
+    size_t count = 0;
+    static uint64_t fnv(const char* p, uint32_t n) {
+        uint64_t h = 1469598103934665603ull;
+        for (uint32_t i = 0; i < n; i++) { h ^= (uint8_t)p[i]; h *= 1099511628211ull; }
+        return h;
+    }
+    const Slot* find(const char* p, uint32_t n, uint64_t h) const {
+        if (slots.empty()) return nullptr;
+        const size_t mask = slots.size() - 1;
+        for (size_t i = h & mask;; i = (i + 1) & mask) {
+            const Slot& s = slots[i];
+            if (!s.used) return nullptr;
+            if (s.hash == h && s.len == n && (n == 0 || memcmp(keys.data() + s.off, p, n) == 0)) return &s;
+        }
+    }
+    void place(const Slot& s) {
+        const size_t mask = slots.size() - 1;
+        size_t i = s.hash & mask;
+        while (slots[i].used) i = (i + 1) & mask;
+        slots[i] = s;
+    }
+    void grow() {
+        std::vector<Slot> old;
+        old.swap(slots);
+        slots.assign(old.empty() ? 64 : old.size() * 2, Slot());
+        for (const Slot& s : old) if (s.used) place(s);
+    }
+    void put(const char* p, uint32_t n, uint32_t gid) {
+        const uint64_t h = fnv(p, n);
+        if (Slot* s = const_cast<Slot*>(find(p, n, h))) { s->gid = gid; return; }
+        if ((count + 1) * 2 > slots.size()) grow();
+        Slot s; s.hash = h; s.off = (uint32_t)keys.size(); s.len = n; s.gid = gid; s.used = true;
+        keys.insert(keys.end(), p, p + n);
+        place(s); count++;
+    }
+};
 extern "C" int rafting_ctxmap_create(rafting_ctxmap_t** out) {
     if (!out) return RAFTING_E_INVAL;
     try { *out = new rafting_ctxmap(); } catch (...) { return RAFTING_E_NOMEM; }
@@ -99,16 +139,14 @@ extern "C" int rafting_ctxmap_create(rafting_ctxmap_t** out) {
 extern "C" int rafting_ctxmap_destroy(rafting_ctxmap_t* m) { delete m; return RAFTING_OK; }
 extern "C" int rafting_ctxmap_put(rafting_ctxmap_t* m, const char* ctx, uint32_t len, uint32_t gid) {
     if (!m || (!ctx && len)) return RAFTING_E_INVAL;
-    try { m->m[std::string(ctx ? ctx : "", len)] = gid; } catch (...) { return RAFTING_E_NOMEM; }
+    try { m->put(ctx ? ctx : "", len, gid); } catch (...) { return RAFTING_E_NOMEM; }
     return RAFTING_OK;
 }
 extern "C" int rafting_ctxmap_get(const rafting_ctxmap_t* m, const char* ctx, uint32_t len, uint32_t* gid) {
     if (!m || !gid || (!ctx && len)) return RAFTING_E_INVAL;
-    try {
-        auto it = m->m.find(std::string(ctx ? ctx : "", len));
-        if (it == m->m.end()) return RAFTING_E_INVAL;
-        *gid = it->second;
-    } catch (...) { return RAFTING_E_NOMEM; }
+    const rafting_ctxmap::Slot* s = m->find(ctx ? ctx : "", len, rafting_ctxmap::fnv(ctx ? ctx : "", len));
+    if (!s) return RAFTING_E_INVAL;
+    *gid = s->gid;
     return RAFTING_OK;
 }
 

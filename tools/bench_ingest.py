@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""Host-side rates of the transport half (include/rafting_ingest.h), one core, no GPU: cutting a receive buffer of ACK frames
+in the reference's wire layout (EventCodec) and turning them into (gid, kind, sequence, term, success) records
+(rafting_ack_frames_decode: scope -> context registry -> Kryo RaftResponse body).  Prints one JSON line."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rafting_b200 import ingest  # noqa: E402
+
+
+def main(groups=65536, frames_n=400000, reps=7):
+    cm = ingest.CtxMap()
+    for g in range(groups):
+        cm.put(b"ctx-%d" % g, g)
+    rng = np.random.default_rng(1)
+    gids = rng.integers(0, groups, frames_n)
+    stream = b"".join(ingest.encode(ingest.ACK, b"appendEntries:ctx-%d" % g, ingest.reply_body_encode(1000 + i % 7, True), sequence=i)
+                      for i, g in enumerate(gids))
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    frames = np.zeros(frames_n, dtype=ingest.FRAME)
+    recs = np.zeros(frames_n, dtype=ingest.ACK_REC)
+    n, used, tr, m = C.c_uint32(), C.c_size_t(), C.c_int(), C.c_uint32()
+    L = ingest.lib()
+    best = [1e9, 1e9]
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        L.rafting_frame_scan(buf.ctypes.data, len(stream), frames.ctypes.data, frames_n, C.byref(n), C.byref(used), C.byref(tr))
+        t1 = time.perf_counter()
+        L.rafting_ack_frames_decode(buf.ctypes.data, frames.ctypes.data, n.value, cm._h, recs.ctypes.data, C.byref(m))
+        t2 = time.perf_counter()
+        best = [min(best[0], t1 - t0), min(best[1], t2 - t1)]
+    assert n.value == frames_n == m.value and (recs["gid"] == gids).all()
+    print(json.dumps({"what": "ACK frames in the reference's wire layout, one core", "contexts": groups, "frames": frames_n,
+                      "bytes_per_frame": len(stream) / frames_n,
+                      "frame_scan": {"frames_per_s": frames_n / best[0], "GB_per_s": len(stream) / best[0] / 1e9},
+                      "ack_frames_decode": {"acks_per_s": frames_n / best[1]},
+                      "both": {"acks_per_s": frames_n / (best[0] + best[1])}}))
+
+
+if __name__ == "__main__":
+    main()
