@@ -215,14 +215,36 @@ extern "C" int rafting_ack_frame_decode(const uint8_t* buf, const rafting_frame_
 extern "C" int rafting_ack_frames_decode(const uint8_t* buf, const rafting_frame_t* frames, uint32_t n, const rafting_ctxmap_t* map,
                                          rafting_ack_rec_t* out, uint32_t* n_out) {
     if (!buf || (!frames && n) || !map || !out || !n_out) return RAFTING_E_INVAL;
+    // The registry lookup is a random access into a table of one slot per hosted context: frames are taken in blocks, the
+    // scopes of a block are parsed and their slots prefetched first, then looked up and their bodies decoded.
+    constexpr uint32_t BLK = 16;
     uint32_t k = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        if (frames[i].type != RAFTING_FRAME_ACK) continue;
-        rafting_ack_rec_t r{};
-        uint32_t kind = 0; int ok = 0;
-        if (rafting_ack_frame_decode(buf, frames + i, map, &r.gid, &kind, &r.sequence, &r.term, &ok) != RAFTING_OK) continue;
-        r.kind = (uint8_t)kind; r.success = (uint8_t)ok; r.frame = i;
-        out[k++] = r;
+    for (uint32_t base = 0; base < n; base += BLK) {
+        const uint32_t m = n - base < BLK ? n - base : BLK;
+        uint32_t op[BLK], off[BLK]; uint64_t h[BLK]; bool ok[BLK];
+        for (uint32_t j = 0; j < m; j++) {
+            const rafting_frame_t& f = frames[base + j];
+            const char* head = (const char*)buf + f.head_off;
+            ok[j] = f.type == RAFTING_FRAME_ACK && f.has_sequence && rafting_scope_parse(head, f.head_len, &op[j], &off[j]) == RAFTING_OK;
+            if (!ok[j]) continue;
+            h[j] = rafting_ctxmap::fnv(head + off[j], f.head_len - off[j]);
+            if (!map->slots.empty()) __builtin_prefetch(&map->slots[h[j] & (map->slots.size() - 1)]);
+        }
+        for (uint32_t j = 0; j < m; j++) {
+            if (!ok[j]) continue;
+            const rafting_frame_t& f = frames[base + j];
+            const char* head = (const char*)buf + f.head_off;
+            const rafting_ctxmap::Slot* s = map->find(head + off[j], f.head_len - off[j], h[j]);
+            if (!s) continue;
+            rafting_ack_rec_t r{};
+            int success = 0;
+            if (rafting_reply_body_decode(buf + f.body_off, f.body_len, &r.term, &success) != RAFTING_OK) continue;
+            r.gid = s->gid;
+            r.kind = (uint8_t)(op[j] == RAFTING_OP_AE_REQUEST ? RAFTING_EV_AE_ACK : op[j] == RAFTING_OP_IS_REQUEST ? RAFTING_EV_IS_ACK
+                             : op[j] == RAFTING_OP_PREVOTE_REQ ? RAFTING_EV_PV_REPLY : RAFTING_EV_RV_REPLY);
+            r.success = (uint8_t)success; r.sequence = f.sequence; r.frame = base + j;
+            out[k++] = r;
+        }
     }
     *n_out = k;
     return RAFTING_OK;
