@@ -66,7 +66,7 @@ def reply_body_decode(body: bytes):
 
 
 def encode(ftype: int, head: bytes, body: bytes = b"", sequence: int | None = None, ending: bool = False) -> bytes:
-    buf = C.create_string_buffer(16 + len(head) + len(body))
+    buf = C.create_string_buffer(24 + len(head) + len(body))    # 17 bytes of framing at most (sequence + EOT)
     n = lib().rafting_frame_encode(buf, len(buf), ftype, 0 if sequence is None else 1, sequence or 0, head, len(head), body, len(body),
                                    1 if ending else 0)
     if n == 0:

@@ -193,3 +193,36 @@ def test_reply_body_matches_the_bytes_the_reference_emits():
         want = bytes.fromhex(v["hex"])
         assert ingest.reply_body_encode(v["term"], v["success"]) == want, v
         assert ingest.reply_body_decode(want) == (v["term"], v["success"]), v
+
+
+def test_mutated_streams_never_crash_and_never_report_bytes_outside_the_buffer():
+    """Fuzz: valid streams with random byte flips / truncations.  Whatever the scanner reports must lie inside the buffer
+    and inside `consumed`; the ACK decoder must take or refuse each frame without touching anything else (run under
+    ASan / UBSan for profiles/r2_host_sanitizers.txt)."""
+    rng = np.random.default_rng(20260923)
+    cm = ingest.CtxMap()
+    for g in range(32):
+        cm.put(b"c%d" % g, g)
+    methods = [b"appendEntries", b"preVote", b"requestVote", b"installSnapshot", b"bogus"]
+    for trial in range(300):
+        parts = []
+        for i in range(int(rng.integers(1, 12))):
+            t = [ingest.ACK, ingest.ENQ, ingest.SYN, ingest.BATCH][int(rng.integers(0, 4))]
+            head = methods[int(rng.integers(0, 5))] + b":c%d" % int(rng.integers(0, 40))
+            body = ingest.reply_body_encode(int(rng.integers(-2**40, 2**40)), bool(rng.integers(0, 2))) if rng.random() < 0.7 \
+                else bytes(rng.integers(0, 256, int(rng.integers(0, 60)), dtype=np.uint8))
+            parts.append(ingest.encode(t, head, body, sequence=i if t in (ingest.ACK, ingest.ENQ) else None, ending=rng.random() < 0.05))
+        data = bytearray(b"".join(parts))
+        for _ in range(int(rng.integers(0, 4))):
+            data[int(rng.integers(0, len(data)))] = int(rng.integers(0, 256))
+        data = bytes(data[:int(rng.integers(1, len(data) + 1))])
+        rc, frames, used, tr = ingest.scan(data, cap=64)
+        assert rc in (0, -1) and used <= len(data)                                      # RAFTING_OK / RAFTING_E_INVAL
+        for f in frames:
+            assert f["head_off"] + f["head_len"] <= used and f["body_off"] + f["body_len"] <= used
+            assert f["head_len"] <= ingest.MAX_HEAD and f["body_len"] <= ingest.MAX_BODY
+        recs = ingest.ack_frames_decode(data, frames, cm)
+        for r in recs:
+            f = frames[int(r["frame"])]
+            assert f["type"] == ingest.ACK and r["gid"] < 32 and r["kind"] in (abi.EV_AE_ACK, abi.EV_IS_ACK, abi.EV_PV_REPLY, abi.EV_RV_REPLY)
+            assert ingest.reply_body_decode(data[f["body_off"]:f["body_off"] + f["body_len"]]) == (int(r["term"]), bool(r["success"]))
