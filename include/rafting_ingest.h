@@ -24,7 +24,10 @@
  * One extension, used only between two engines: TYPE SUB 0x1A carries a BATCH — one frame per peer and step instead of
  * one frame per group (Leader.java:216 sends one RPC per follower and group).  Its BODY is an array of fixed 40-byte
  * little-endian records (rafting_batch_rec_t); rafting_batch_to_inbox writes reply records straight into the SoA inbox
- * columns of a leased step.  A peer that does not know the type rejects the frame like any unknown type.
+ * columns of a leased step.  A peer that does not know the type rejects the frame like any unknown type.  The same frame
+ * type with HEAD "Q" carries REQUEST records (rafting_req_rec_t, 64 bytes: AppendEntries / InstallSnapshot plans and vote
+ * broadcasts); rafting_outbox_to_requests / rafting_request_to_inbox / rafting_outbox_to_replies are the pump's dispatch loop
+ * in C, checked step by step against the Python pump of tests/cluster_sim.py.
  */
 #ifndef RAFTING_INGEST_H
 #define RAFTING_INGEST_H
@@ -136,6 +139,47 @@ typedef struct rafting_batch_rec {
  * one event per (row, group, lane)). */
 int rafting_batch_to_inbox(const rafting_batch_rec_t* recs, uint32_t n, int64_t now_ms, const rafting_inbox_t* in,
                            uint32_t n_groups, uint32_t F, uint32_t* n_done);
+
+/* ---- engine-to-engine REQUEST records (TYPE 0x1A with HEAD "Q"; reply batches use HEAD "R") -----------------------------
+ * What Leader.replicateLog / Follower.prepareElection / Candidate.startElection send — one RPC per follower and group
+ * (Leader.java:170-216, Follower.java:241-256, Candidate.java:94-110) — as fixed records, one frame per peer and step.
+ * rafting_outbox_to_requests is the pump's dispatch loop in C: it walks a host outbox in the serial
+ * order of the step (row, then group, then lane) and emits one record per AE / IS plan and per lane of a vote broadcast.
+ * An AppendEntries plan does not carry its term (a role object's term is fixed for its lifetime, RaftMember.java:16-26):
+ * the dispatcher remembers (incarnation -> current_term) per group from the end-of-step columns it has seen. */
+typedef struct rafting_req_rec {
+    uint32_t gid;
+    uint8_t  kind;            /* RAFTING_OP_AE_REQUEST / _PREVOTE_REQ / _VOTE_REQ / _IS_REQUEST                          */
+    uint8_t  src_slot;        /* the sending node (the op's `peer` on the receiving side)                                */
+    uint8_t  dst_slot;        /* the node the record goes to: slot of the sender's follower lane                        */
+    uint8_t  row;             /* row of the sender's step                                                                */
+    uint32_t incarnation;     /* of the sending role object; the reply echoes it                                         */
+    uint32_t count;           /* AE: number of entries (their terms / payloads travel beside the record)                */
+    int64_t  term;            /* term argument of the RPC                                                                */
+    int64_t  a, b;            /* AE: prevLogIndex, prevLogTerm | votes: lastLogIndex, lastLogTerm | IS: lastIncluded*   */
+    int64_t  commit;          /* AE: leaderCommit                                                                        */
+    int64_t  epoch, last;     /* AE / IS: (epochAtSend, lastIndexAtSend) — the closure of the reply callback            */
+} rafting_req_rec_t;        /* 64 bytes */
+
+typedef struct rafting_dispatch rafting_dispatch_t;
+int rafting_dispatch_create(uint32_t n_groups, uint32_t F, uint32_t local_slot, rafting_dispatch_t** out);
+int rafting_dispatch_destroy(rafting_dispatch_t* d);
+/* Dense host outbox of `rows` rows -> records (at most cap; RAFTING_E_CAPACITY beyond).  *n_unknown counts AE / IS plans
+ * whose role object's term the dispatcher has never seen (skipped). */
+int rafting_outbox_to_requests(rafting_dispatch_t* d, const rafting_outbox_t* ob, uint32_t rows, rafting_req_rec_t* out,
+                               uint32_t cap, uint32_t* n_out, uint32_t* n_unknown);
+/* Receiving side: one record -> the op slot (row, gid) of a dense host inbox (op_meta / op_nr / op_ab / op_cd / op_e); an AE
+ * record's entry terms are appended to ent_terms at *ent_count.  host_result: RaftContext.installSnapshot's answer for an IS
+ * request (RaftRoutine.java:408-445), ignored otherwise.  RAFTING_E_INVAL: slot taken, gid / row out of range, no room. */
+int rafting_request_to_inbox(const rafting_req_rec_t* r, const int64_t* entry_terms, uint32_t row, int64_t now_ms, int host_result,
+                             const rafting_inbox_t* in, uint32_t n_groups, uint32_t ent_cap, uint32_t* ent_count);
+
+/* After the step: the replies to the requests that were placed.  placed[i] went to row placed_row[i]; a request whose
+ * rep_meta is not valid (the handler threw: no reply leaves, the sender's Async times out — EventLoop semantics) is skipped.
+ * Emits reply records for rafting_batch_to_inbox on the SENDER's side: lane = this node's follower lane there, the echo
+ * fields copied from the request, term = RaftResponse.term().  out has room for n records. */
+int rafting_outbox_to_replies(const rafting_outbox_t* ob, uint32_t n_groups, uint32_t local_slot, const rafting_req_rec_t* placed,
+                              const uint8_t* placed_row, uint32_t n, rafting_batch_rec_t* out, uint32_t* n_out);
 
 #ifdef __cplusplus
 }

@@ -270,3 +270,140 @@ extern "C" int rafting_batch_to_inbox(const rafting_batch_rec_t* recs, uint32_t 
     }
     return RAFTING_OK;
 }
+
+// ---- the pump's dispatch loop in C: outbox -> request records, records -> op slots ----
+struct rafting_dispatch {
+    uint32_t G, F, slot;
+    static constexpr int KEEP = 4;                           // role objects per group whose term is remembered
+    std::vector<uint32_t> inc; std::vector<int64_t> term; std::vector<uint8_t> used, next;
+    int64_t* find(uint32_t g, uint32_t incarnation) {
+        for (int k = 0; k < KEEP; k++) if (used[g * KEEP + k] && inc[g * KEEP + k] == incarnation) return &term[g * KEEP + k];
+        return nullptr;
+    }
+    void learn(uint32_t g, uint32_t incarnation, int64_t t) {
+        if (int64_t* p = find(g, incarnation)) { *p = t; return; }
+        const uint32_t k = g * KEEP + next[g];
+        inc[k] = incarnation; term[k] = t; used[k] = 1; next[g] = (uint8_t)((next[g] + 1) % KEEP);
+    }
+};
+extern "C" int rafting_dispatch_create(uint32_t n_groups, uint32_t F, uint32_t local_slot, rafting_dispatch_t** out) {
+    if (!out || !n_groups || !F || local_slot > F) return RAFTING_E_INVAL;
+    try {
+        auto* d = new rafting_dispatch();
+        d->G = n_groups; d->F = F; d->slot = local_slot;
+        d->inc.assign((size_t)n_groups * rafting_dispatch::KEEP, 0); d->term.assign((size_t)n_groups * rafting_dispatch::KEEP, 0);
+        d->used.assign((size_t)n_groups * rafting_dispatch::KEEP, 0); d->next.assign(n_groups, 0);
+        *out = d;
+    } catch (...) { return RAFTING_E_NOMEM; }
+    return RAFTING_OK;
+}
+extern "C" int rafting_dispatch_destroy(rafting_dispatch_t* d) { delete d; return RAFTING_OK; }
+
+extern "C" int rafting_outbox_to_requests(rafting_dispatch_t* d, const rafting_outbox_t* ob, uint32_t rows, rafting_req_rec_t* out,
+                                          uint32_t cap, uint32_t* n_out, uint32_t* n_unknown) {
+    if (!d || !ob || !out || !n_out || !ob->incarnation || !ob->current_term) return RAFTING_E_INVAL;
+    const uint32_t G = d->G, F = d->F;
+    for (uint32_t g = 0; g < G; g++) d->learn(g, ob->incarnation[g], ob->current_term[g]);
+    uint32_t n = 0, unknown = 0;
+    auto slot_of = [&](uint32_t lane) { return (uint8_t)(lane < d->slot ? lane : lane + 1); };
+    for (uint32_t r = 0; r < rows; r++) {
+        if (ob->plan_meta)
+            for (uint32_t g = 0; g < G; g++)
+                for (uint32_t f = 0; f < F; f++) {
+                    const size_t li = ((size_t)r * G + g) * F + f;
+                    const uint64_t pm = ob->plan_meta[li];
+                    const uint32_t kind = RAFTING_PLM_KIND(pm);
+                    if (kind != RAFTING_PLAN_AE && kind != RAFTING_PLAN_IS) continue;
+                    const int64_t* t = d->find(g, RAFTING_PLM_INC(pm));
+                    if (!t) { unknown++; continue; }
+                    if (n >= cap) { *n_out = n; if (n_unknown) *n_unknown = unknown; return RAFTING_E_CAPACITY; }
+                    rafting_req_rec_t q{};
+                    q.gid = g; q.kind = kind == RAFTING_PLAN_AE ? RAFTING_OP_AE_REQUEST : RAFTING_OP_IS_REQUEST;
+                    q.src_slot = (uint8_t)d->slot; q.dst_slot = slot_of(f); q.row = (uint8_t)r;
+                    q.incarnation = RAFTING_PLM_INC(pm); q.count = kind == RAFTING_PLAN_AE ? RAFTING_PLM_COUNT(pm) : 0;
+                    q.term = *t; q.a = ob->plan_pp[li].x; q.b = ob->plan_pp[li].y;
+                    q.last = ob->plan_lc[li].x; q.commit = kind == RAFTING_PLAN_AE ? ob->plan_lc[li].y : 0;
+                    q.epoch = ob->plan_epoch ? ob->plan_epoch[li] : 0;
+                    out[n++] = q;
+                }
+        if (ob->ballot_meta)
+            for (uint32_t g = 0; g < G; g++) {
+                const size_t gi = (size_t)r * G + g;
+                const uint64_t bm = ob->ballot_meta[gi];
+                const uint32_t kind = (uint32_t)(bm & 0xFu);
+                if (kind == RAFTING_BALLOT_NONE) continue;
+                for (uint32_t f = 0; f < F; f++) {
+                    if (n >= cap) { *n_out = n; if (n_unknown) *n_unknown = unknown; return RAFTING_E_CAPACITY; }
+                    rafting_req_rec_t q{};
+                    q.gid = g; q.kind = kind == RAFTING_BALLOT_PREVOTE ? RAFTING_OP_PREVOTE_REQ : RAFTING_OP_VOTE_REQ;
+                    q.src_slot = (uint8_t)d->slot; q.dst_slot = slot_of(f); q.row = (uint8_t)r;
+                    q.incarnation = (uint32_t)(bm >> 32);
+                    q.term = ob->ballot_term[gi]; q.a = ob->ballot_last[gi].x; q.b = ob->ballot_last[gi].y;
+                    out[n++] = q;
+                }
+            }
+    }
+    *n_out = n; if (n_unknown) *n_unknown = unknown;
+    return RAFTING_OK;
+}
+
+extern "C" int rafting_request_to_inbox(const rafting_req_rec_t* r, const int64_t* entry_terms, uint32_t row, int64_t now_ms,
+                                        int host_result, const rafting_inbox_t* in, uint32_t n_groups, uint32_t ent_cap,
+                                        uint32_t* ent_count) {
+    if (!r || !in || !in->op_meta || !in->op_nr || !in->op_ab || !in->op_cd || in->gids) return RAFTING_E_INVAL;
+    if (r->gid >= n_groups || row >= in->rows) return RAFTING_E_INVAL;
+    if (r->kind != RAFTING_OP_AE_REQUEST && r->kind != RAFTING_OP_PREVOTE_REQ && r->kind != RAFTING_OP_VOTE_REQ &&
+        r->kind != RAFTING_OP_IS_REQUEST) return RAFTING_E_INVAL;
+    const size_t gi = (size_t)row * n_groups + r->gid;
+    uint64_t* om = const_cast<uint64_t*>(in->op_meta);
+    if (RAFTING_OP_KIND(om[gi]) != RAFTING_OP_NONE) return RAFTING_E_INVAL;               // one op per (row, group)
+    rafting_i64x2_t* nr = const_cast<rafting_i64x2_t*>(in->op_nr);
+    rafting_i64x2_t* ab = const_cast<rafting_i64x2_t*>(in->op_ab);
+    rafting_i64x2_t* cd = const_cast<rafting_i64x2_t*>(in->op_cd);
+    uint32_t off = 0, count = 0;
+    int64_t d = 0, e = 0;
+    if (r->kind == RAFTING_OP_AE_REQUEST) {
+        count = r->count;
+        if (count > 0xFFFFu) return RAFTING_E_INVAL;
+        if (count) {
+            if (!ent_count || !in->ent_terms || !entry_terms || (uint64_t)*ent_count + count > ent_cap) return RAFTING_E_INVAL;
+            off = *ent_count;
+            memcpy(const_cast<int64_t*>(in->ent_terms) + off, entry_terms, (size_t)count * 8);
+            *ent_count = off + count;
+        } else if (ent_count) off = *ent_count;
+        d = r->commit; e = r->a + 1;                                                         // entries[0].index = prevLogIndex + 1
+        if (!in->op_e) return RAFTING_E_INVAL;
+    } else if (r->kind == RAFTING_OP_IS_REQUEST) d = host_result ? 1 : 0;
+    om[gi] = (uint64_t)RAFTING_OP_MAKE(r->kind, r->src_slot, count) | ((uint64_t)off << 32);
+    nr[gi].x = now_ms; nr[gi].y = 0;
+    ab[gi].x = r->term; ab[gi].y = r->a;
+    cd[gi].x = r->b; cd[gi].y = d;
+    if (in->op_e) const_cast<int64_t*>(in->op_e)[gi] = e;
+    return RAFTING_OK;
+}
+
+extern "C" int rafting_outbox_to_replies(const rafting_outbox_t* ob, uint32_t n_groups, uint32_t local_slot,
+                                         const rafting_req_rec_t* placed, const uint8_t* placed_row, uint32_t n,
+                                         rafting_batch_rec_t* out, uint32_t* n_out) {
+    if (!ob || !ob->rep_meta || !ob->rep_term || (!placed && n) || (!placed_row && n) || !out || !n_out) return RAFTING_E_INVAL;
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const rafting_req_rec_t& q = placed[i];
+        if (q.gid >= n_groups || q.src_slot == local_slot) return RAFTING_E_INVAL;
+        const size_t gi = (size_t)placed_row[i] * n_groups + q.gid;
+        const uint32_t m = ob->rep_meta[gi];
+        if (!RAFTING_REP_VALID(m)) continue;
+        rafting_batch_rec_t r{};
+        r.gid = q.gid;
+        r.kind = (uint8_t)(q.kind == RAFTING_OP_AE_REQUEST ? RAFTING_EV_AE_ACK : q.kind == RAFTING_OP_IS_REQUEST ? RAFTING_EV_IS_ACK
+                         : q.kind == RAFTING_OP_PREVOTE_REQ ? RAFTING_EV_PV_REPLY : RAFTING_EV_RV_REPLY);
+        r.lane = (uint8_t)(local_slot < q.src_slot ? local_slot : local_slot - 1);      // this node's lane in the sender's numbering
+        r.flags = (uint8_t)(RAFTING_OUT_OK | (RAFTING_REP_SUCCESS(m) << 2));
+        r.incarnation = q.incarnation;
+        r.term = ob->rep_term[gi];
+        r.epoch_at_send = q.epoch; r.last_at_send = q.last;
+        out[k++] = r;
+    }
+    *n_out = k;
+    return RAFTING_OK;
+}

@@ -233,4 +233,32 @@ JNIEXPORT jint JNICALL FN(acksDecode)(JNIEnv* env, jclass k, jobject buf, jobjec
                                     (const rafting_ctxmap_t*)(intptr_t)m, (rafting_ack_rec_t*)BUF(ackRecsOut), &got));
     return (jint)got;
 }
+/* engine-to-engine traffic: the pump's dispatch loop in C (one request / reply batch per peer and step, include/rafting_ingest.h) */
+JNIEXPORT jlong JNICALL FN(dispatchCreate)(JNIEnv* env, jclass k, jint nGroups, jint followers, jint localSlot) {
+    rafting_dispatch_t* d = NULL;
+    CHECK(rafting_dispatch_create((uint32_t)nGroups, (uint32_t)followers, (uint32_t)localSlot, &d));
+    return (jlong)(intptr_t)d;
+}
+JNIEXPORT void JNICALL FN(dispatchDestroy)(JNIEnv* env, jclass k, jlong d) { rafting_dispatch_destroy((rafting_dispatch_t*)(intptr_t)d); }
+JNIEXPORT jint JNICALL FN(outboxToRequests)(JNIEnv* env, jclass k, jlong d, jobject outStruct, jint rows, jobject recsOut, jint cap) {
+    uint32_t n = 0, unknown = 0;
+    CHECK(rafting_outbox_to_requests((rafting_dispatch_t*)(intptr_t)d, (const rafting_outbox_t*)BUF(outStruct), (uint32_t)rows,
+                                     (rafting_req_rec_t*)BUF(recsOut), (uint32_t)cap, &n, &unknown));
+    return (jint)n;
+}
+JNIEXPORT jint JNICALL FN(requestToInbox)(JNIEnv* env, jclass k, jobject rec, jobject entryTerms, jint row, jlong nowMs, jboolean hostResult,
+                                          jobject inStruct, jint nGroups, jint entCap, jint entCount) {
+    uint32_t cnt = (uint32_t)entCount;
+    CHECK(rafting_request_to_inbox((const rafting_req_rec_t*)BUF(rec), (const int64_t*)BUF(entryTerms), (uint32_t)row, nowMs,
+                                   hostResult ? 1 : 0, (const rafting_inbox_t*)BUF(inStruct), (uint32_t)nGroups, (uint32_t)entCap, &cnt));
+    return (jint)cnt;                                       /* the pool's new fill level */
+}
+JNIEXPORT jint JNICALL FN(outboxToReplies)(JNIEnv* env, jclass k, jobject outStruct, jint nGroups, jint localSlot, jobject placed,
+                                           jobject placedRow, jint n, jobject repliesOut) {
+    uint32_t got = 0;
+    CHECK(rafting_outbox_to_replies((const rafting_outbox_t*)BUF(outStruct), (uint32_t)nGroups, (uint32_t)localSlot,
+                                    (const rafting_req_rec_t*)BUF(placed), (const uint8_t*)BUF(placedRow), (uint32_t)n,
+                                    (rafting_batch_rec_t*)BUF(repliesOut), &got));
+    return (jint)got;
+}
 #endif /* RAFTING_HAVE_JNI */

@@ -20,7 +20,9 @@ BATCH_REC = np.dtype([("gid", "<u4"), ("kind", "u1"), ("lane", "u1"), ("flags", 
                       ("_pad", "<u4"), ("term", "<i8"), ("epoch_at_send", "<i8"), ("last_at_send", "<i8")])
 ACK_REC = np.dtype([("gid", "<u4"), ("kind", "u1"), ("success", "u1"), ("_pad", "<u2"), ("sequence", "<i4"), ("frame", "<u4"),
                     ("term", "<i8")])
-assert FRAME.itemsize == 24 and BATCH_REC.itemsize == 40 and ACK_REC.itemsize == 24
+REQ_REC = np.dtype([("gid", "<u4"), ("kind", "u1"), ("src_slot", "u1"), ("dst_slot", "u1"), ("row", "u1"), ("incarnation", "<u4"),
+                    ("count", "<u4"), ("term", "<i8"), ("a", "<i8"), ("b", "<i8"), ("commit", "<i8"), ("epoch", "<i8"), ("last", "<i8")])
+assert FRAME.itemsize == 24 and BATCH_REC.itemsize == 40 and ACK_REC.itemsize == 24 and REQ_REC.itemsize == 64
 
 
 def lib():
@@ -44,6 +46,14 @@ def lib():
         L.rafting_reply_body_decode.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
         L.rafting_ack_frame_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                                C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.rafting_dispatch_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.rafting_dispatch_destroy.argtypes = [C.c_void_p]
+        L.rafting_outbox_to_requests.argtypes = [C.c_void_p, C.POINTER(abi.OutboxC), C.c_uint32, C.c_void_p, C.c_uint32,
+                                                 C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.rafting_request_to_inbox.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int64, C.c_int, C.POINTER(abi.InboxC),
+                                               C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.rafting_outbox_to_replies.argtypes = [C.POINTER(abi.OutboxC), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                C.c_void_p, C.POINTER(C.c_uint32)]
         L.rafting_ack_frames_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         _LIB = L
     return _LIB
@@ -140,3 +150,58 @@ def batch_to_inbox(recs: np.ndarray, now_ms: int, inbox: abi.Inbox) -> tuple[int
     ic = inbox.as_c()
     rc = lib().rafting_batch_to_inbox(recs.ctypes.data, len(recs), now_ms, C.byref(ic), inbox.n, inbox.F, C.byref(done))
     return rc, done.value
+
+
+class Dispatch:
+    """The pump's dispatch loop in C (include/rafting_ingest.h): host outbox -> request records; remembers the term of the
+    role objects (incarnations) it has seen per group."""
+
+    def __init__(self, n_groups: int, F: int, local_slot: int):
+        self._h = C.c_void_p()
+        rc = lib().rafting_dispatch_create(n_groups, F, local_slot, C.byref(self._h))
+        if rc:
+            raise ValueError(f"rafting_dispatch_create: rc={rc}")
+        self.cap = 0
+
+    def requests(self, outbox: abi.Outbox, rows: int, cap: int = 1 << 16):
+        """-> (records, plans skipped because their role object's term is unknown)"""
+        out = np.zeros(cap, dtype=REQ_REC)
+        n, unk = C.c_uint32(), C.c_uint32()
+        oc = outbox.as_c()
+        rc = lib().rafting_outbox_to_requests(self._h, C.byref(oc), rows, out.ctypes.data, cap, C.byref(n), C.byref(unk))
+        if rc:
+            raise ValueError(f"rafting_outbox_to_requests: rc={rc}")
+        return out[:n.value], unk.value
+
+    def __del__(self):
+        try:
+            lib().rafting_dispatch_destroy(self._h)
+        except Exception:
+            pass
+
+
+def request_to_inbox(rec, entry_terms, row: int, now_ms: int, host_result: bool, inbox: abi.Inbox) -> int:
+    """One request record -> the op slot (row, rec.gid) of a dense host inbox; returns the status code."""
+    r = np.array([rec], dtype=REQ_REC)
+    terms = np.ascontiguousarray(entry_terms, dtype=np.int64)
+    ic = inbox.as_c()
+    cnt = C.c_uint32(inbox.ent_count)
+    rc = lib().rafting_request_to_inbox(r.ctypes.data, terms.ctypes.data if len(terms) else None, row, now_ms, 1 if host_result else 0,
+                                        C.byref(ic), inbox.n, len(inbox.ent_terms), C.byref(cnt))
+    if rc == 0:
+        inbox.ent_count = cnt.value
+    return rc
+
+
+def outbox_to_replies(outbox: abi.Outbox, n_groups: int, local_slot: int, placed: np.ndarray, placed_row) -> np.ndarray:
+    """The replies (BATCH_REC, for batch_to_inbox on the sender's side) to the request records placed in this step."""
+    placed = np.ascontiguousarray(placed, dtype=REQ_REC)
+    rows = np.ascontiguousarray(placed_row, dtype=np.uint8)
+    out = np.zeros(max(1, len(placed)), dtype=BATCH_REC)
+    n = C.c_uint32()
+    oc = outbox.as_c()
+    rc = lib().rafting_outbox_to_replies(C.byref(oc), n_groups, local_slot, placed.ctypes.data, rows.ctypes.data, len(placed),
+                                         out.ctypes.data, C.byref(n))
+    if rc:
+        raise ValueError(f"rafting_outbox_to_replies: rc={rc}")
+    return out[:n.value]

@@ -54,7 +54,10 @@ class Node:
 class Cluster:
     def __init__(self, make_sut, G: int = 8, R: int = 3, seed: int = 1, drop_ppm: int = 0, submit_ppm: int = 300_000,
                  heartbeat_ms: int = 50, election_ms: int = 300, compact_every: int = 0, pre_vote: bool = True,
-                 guard_candidate_votes: bool = False, cfg_flags: int = 0):
+                 guard_candidate_votes: bool = False, cfg_flags: int = 0, shadow_native: bool = False):
+        # shadow_native: every step, the C dispatch (rafting_outbox_to_requests) and the C placement (rafting_request_to_inbox)
+        # of include/rafting_ingest.h run beside this file's Python pump and must produce the same records / op columns
+        self.shadow_native = shadow_native
         # see _vote_request_is_unsafe: the reference's Candidate grants votes without the log check
         self.guard_candidate_votes = guard_candidate_votes
         self.compact_every = compact_every       # RaftRoutine.compactLog: checkpoint + RaftLog.flush every N applied entries
@@ -72,6 +75,9 @@ class Cluster:
             init["ballot"] = -1; init["first_index"] = 1; init["now_ms"] = T0
             sut.open_bulk(0, init)
             self.nodes.append(Node(sut, k, G, R))
+            if shadow_native:
+                from rafting_b200 import ingest
+                self.nodes[-1].dispatch = ingest.Dispatch(G, R - 1, k)
         self.tick = 0
         self.inflight = []                       # (deliver_tick, seq, dst_slot, gid, item)
         self.link_clock = defaultdict(int)       # FIFO per (src, dst)
@@ -128,6 +134,11 @@ class Cluster:
         ib = abi.Inbox(ROWS, G, F, ent_cap=ROWS * G * 64, sweep=True)
         ib.row_now[0] = now                                            # fires every due election / keepAlive timer
         placed = {}
+        ib2 = None
+        nd.placed_native = []
+        if self.shadow_native:
+            ib2 = abi.Inbox(ROWS, G, F, ent_cap=ROWS * G * 64, sweep=True)
+            ib2.row_now[0] = now
         for g in range(G):
             q = nd.queue[g]
             # a client command goes to the node that believes it leads the group (RaftStub.submit)
@@ -170,6 +181,8 @@ class Cluster:
                 if it[0] == "op":
                     self._place_op(nd, ib, r, g, now, it[1])
                     placed[(r, g)] = it[1]
+                    if ib2 is not None:
+                        self._place_op_native(nd, ib2, r, g, now, it[1])
                 else:
                     e = it[2]
                     if e["kind"] in (abi.EV_AE_ACK, abi.EV_IS_ACK):
@@ -178,8 +191,34 @@ class Cluster:
                     else:
                         ib.vote_reply(r, g, lane, now, e["inc"], e["term"], e["success"], outcome=e["outcome"],
                                       pre=e["kind"] == abi.EV_PV_REPLY)
+        if ib2 is not None:
+            for col in ("op_meta", "op_nr", "op_ab", "op_cd", "op_e"):
+                assert np.array_equal(getattr(ib, col), getattr(ib2, col)), f"native placement differs in {col} (node {nd.slot}, tick {self.tick})"
+            assert ib.ent_count == ib2.ent_count and np.array_equal(ib.ent_terms[:ib.ent_count], ib2.ent_terms[:ib2.ent_count])
+            self.counts["native_placements_checked"] += len(placed)
         ob = nd.sut.step(ib)
         return ob, placed
+
+    def _place_op_native(self, nd, ib2, r, g, now, op):
+        """The same op through rafting_request_to_inbox (requests) — submits / flushes are not requests and stay in Python."""
+        from rafting_b200 import ingest
+        k = op["kind"]
+        if k in (abi.OP_SUBMIT, abi.OP_FLUSH):
+            return self._place_op(nd, ib2, r, g, now, op)
+        rec = np.zeros(1, dtype=ingest.REQ_REC)[0]
+        rec["gid"], rec["kind"], rec["src_slot"], rec["dst_slot"], rec["incarnation"], rec["term"] = g, k, op["src"], nd.slot, op["inc"], op["term"]
+        terms = []
+        if k == abi.OP_AE_REQUEST:
+            terms = [t for t, _ in op["entries"]]
+            rec["a"], rec["b"], rec["commit"], rec["count"] = op["prev_index"], op["prev_term"], op["leader_commit"], len(terms)
+        elif k == abi.OP_IS_REQUEST:
+            rec["a"], rec["b"] = op["index"], op["index_term"]
+        else:
+            rec["a"], rec["b"] = op["last_index"], op["last_term"]
+        rec["epoch"], rec["last"] = op.get("epoch", 0), op.get("last", 0)
+        rc = ingest.request_to_inbox(rec, terms, r, now, bool(op.get("result", False)), ib2)
+        assert rc == 0, (rc, op)
+        nd.placed_native.append((r, rec.copy()))
 
     @staticmethod
     def _vote_request_is_unsafe(nd, g, op):
@@ -247,8 +286,26 @@ class Cluster:
                 who = self.leaders_by_term[g].setdefault(t, nd.slot)
                 assert who == nd.slot, f"two leaders in term {t} of group {g}: {who} and {nd.slot}"   # election safety
         # row by row, in the serial order of the step: a plan carries the entries the log held when it was made
+        self._sent = [] if self.shadow_native else None              # what this outbox asks the pump to send, in order
+        self._replied = [] if self.shadow_native else None           # the replies this outbox makes the pump send back
         for row in range(ROWS):
             self._dispatch_row(nd, ob, {k: v for k, v in placed.items() if k[0] == row}, row, prev)
+        if self.shadow_native:
+            recs, unknown = nd.dispatch.requests(ob, ROWS)
+            got = [(int(q["row"]), int(q["gid"]), int(q["kind"]), int(q["src_slot"]), int(q["dst_slot"]), int(q["incarnation"]),
+                    int(q["count"]), int(q["term"]), int(q["a"]), int(q["b"]), int(q["commit"]), int(q["epoch"]), int(q["last"]))
+                   for q in recs]
+            assert unknown == 0 and got == self._sent, f"native dispatch differs (node {nd.slot}, tick {self.tick}): " \
+                f"{[x for x in got if x not in self._sent][:3]} vs {[x for x in self._sent if x not in got][:3]}"
+            self.counts["native_requests_checked"] += len(got)
+            from rafting_b200 import ingest
+            order = sorted(range(len(nd.placed_native)), key=lambda i: (nd.placed_native[i][0], int(nd.placed_native[i][1]["gid"])))
+            reps = ingest.outbox_to_replies(ob, G, nd.slot, np.array([nd.placed_native[i][1] for i in order], dtype=ingest.REQ_REC),
+                                            [nd.placed_native[i][0] for i in order]) if order else []
+            got = [(int(q["gid"]), int(q["kind"]), int(q["lane"]), int(q["flags"]), int(q["incarnation"]), int(q["term"]),
+                    int(q["epoch_at_send"]), int(q["last_at_send"])) for q in reps]
+            assert got == self._replied, f"native replies differ (node {nd.slot}, tick {self.tick}): {got[:3]} vs {self._replied[:3]}"
+            self.counts["native_replies_checked"] += len(got)
         # apply committed commands to the file machine (RaftRoutine.commitState -> applyCommand)
         for g in range(G):
             c = int(ob.commit_index[g])
@@ -310,6 +367,9 @@ class Cluster:
             if op["kind"] in (abi.OP_VOTE_REQ, abi.OP_PREVOTE_REQ) and valid and success and prev is not None and \
                     self._vote_request_is_unsafe(nd, g, op):
                 self.counts["votes_granted_to_a_stale_log"] += 1       # the upstream flaw at work (see _vote_request_is_unsafe)
+            if valid and self._replied is not None:
+                self._replied.append((g, ekind, lane, abi.OUT_OK | (4 if success else 0), op["inc"], int(ob.rep_term[r, g]),
+                                      op.get("epoch", 0), op.get("last", 0)))
             if not valid or self._lost(nd.slot, src.slot, g, self.tick, 1):
                 self._timeout_event(src, g, lane, ekind, op["inc"], op.get("epoch", 0), op.get("last", 0))
                 continue
@@ -327,6 +387,10 @@ class Cluster:
             dst = nd.slot_of(f)
             term = nd.inc_term[g].get(inc)
             assert term is not None
+            if self._sent is not None:
+                is_plan = pk[g, f] == abi.PLAN_IS
+                self._sent.append((r, g, abi.OP_IS_REQUEST if is_plan else abi.OP_AE_REQUEST, nd.slot, dst, inc, 0 if is_plan else count,
+                                   term, prev_index, prev_term, 0 if is_plan else commit, epoch, last))
             if pk[g, f] == abi.PLAN_IS:                            # (epoch.index, epoch.term) — Leader.java:172
                 self.counts["is_sent"] += 1
                 if self._lost(nd.slot, dst, g, self.tick, 0):
@@ -352,6 +416,9 @@ class Cluster:
             self.counts["prevote" if pre else "vote"] += 1
             for f in range(F):
                 dst = nd.slot_of(f)
+                if self._sent is not None:
+                    self._sent.append((r, g, abi.OP_PREVOTE_REQ if pre else abi.OP_VOTE_REQ, nd.slot, dst, inc, 0,
+                                       int(ob.ballot_term[r, g]), int(ob.ballot_last[r, g]["x"]), int(ob.ballot_last[r, g]["y"]), 0, 0, 0))
                 if self._lost(nd.slot, dst, g, self.tick, 2 + f):
                     self._timeout_event(nd, g, f, abi.EV_PV_REPLY if pre else abi.EV_RV_REPLY, inc)
                     continue
@@ -403,6 +470,9 @@ class Cluster:
             nd.install[g] = None
         nd.sut, nd.snap = sut, None
         nd.inc_term = [dict() for _ in range(self.G)]
+        if self.shadow_native:
+            from rafting_b200 import ingest
+            nd.dispatch = ingest.Dispatch(self.G, nd.F, slot)
         self.inflight = [m for m in self.inflight if m[2] != slot]     # nothing addressed to the dead process survives
         self.counts["restarts"] += 1
 

@@ -89,11 +89,11 @@ def test_random_partitions_keep_raft_safe(R, pre_vote, seed):
     assert min(len(nd.file[g]) for nd in c.nodes for g in range(c.G)) > (5 if R == 2 else 30)
 
 
-def _jepsen(R, pre_vote, seed, guard, keep=None, flags=0):
+def _jepsen(R, pre_vote, seed, guard, keep=None, flags=0, shadow_native=False):
     import numpy as np
     rng = np.random.default_rng(seed)
     c = Cluster(_oracle, G=4, R=R, seed=seed, drop_ppm=30_000, compact_every=30, pre_vote=pre_vote, guard_candidate_votes=guard,
-                cfg_flags=flags)
+                cfg_flags=flags, shadow_native=shadow_native)
     if keep is not None:
         keep.append(c)
     c.run(80)
@@ -185,3 +185,15 @@ def test_opt_in_fixes_make_the_unguarded_runs_safe_and_live(R, pre_vote, seed):
     from rafting_b200 import abi
     c = _jepsen(R, pre_vote, seed, guard=False, flags=abi.CFG_STRICT_CANDIDATE_VOTE | abi.CFG_LENIENT_FOLLOWER_COMMIT)
     assert c.counts["votes_granted_to_a_stale_log"] == 0 and c.counts["commit_rollback"] == 0
+
+
+@pytest.mark.parametrize("R,pre_vote,seed", [(3, True, 301), (5, False, 302)])
+def test_native_pump_dispatch_matches_the_python_pump_under_partitions(R, pre_vote, seed):
+    """SURVEY §8(f)-2, outbound half: the C dispatch loop (rafting_outbox_to_requests: plans and vote broadcasts -> request
+    records, one batch per peer and step instead of one frame per group) and the C placement (rafting_request_to_inbox:
+    record -> op slot + entry terms) run beside the simulator's Python pump on EVERY step of a Jepsen-style run — elections,
+    heartbeats, appends, compaction, InstallSnapshot, partitions, restarts of role objects — and must emit exactly the same
+    requests in the same order and build exactly the same op columns."""
+    c = _jepsen(R, pre_vote, seed, guard=True, shadow_native=True)
+    assert c.counts["native_requests_checked"] > 2500 and c.counts["native_placements_checked"] > 3000
+    assert c.counts["native_replies_checked"] > 2500 and c.counts["is_sent"] > 0 and c.counts["vote"] > 0

@@ -151,3 +151,56 @@ def test_status_codes_surface_as_the_promised_exception_classes(glue):
         h = _fn(glue, "create", C.c_int64, C.POINTER(_Buf))(C.byref(cbuf))
         assert h == 0 and glue.fake_throws() == 1
         assert glue.fake_thrown_class() == b"io/lubricant/consensus/raft/support/RaftException" and glue.fake_thrown_message()
+
+
+def test_dispatch_natives_turn_an_outbox_into_request_and_reply_records(glue):
+    """outboxToRequests / requestToInbox / outboxToReplies through the glue, against the plain C-ABI binding."""
+    from rafting_b200 import abi, ingest
+    G, F, rows = 4, 2, 2
+    ob = abi.Outbox(rows, G, F, G)
+    ob.incarnation[:] = [5, 6, 7, 8]
+    ob.current_term[:] = [50, 60, 70, 80]
+    ob.plan_meta[1, 2, 0] = abi.PLAN_AE | (3 << 16) | (7 << 32)
+    ob.plan_pp[1, 2, 0] = (100, 69); ob.plan_lc[1, 2, 0] = (103, 99); ob.plan_epoch[1, 2, 0] = 40
+    ob.ballot_meta[0, 1] = abi.BALLOT_VOTE | (6 << 32); ob.ballot_term[0, 1] = 61; ob.ballot_last[0, 1] = (12, 59)
+    glue.fake_reset()
+    d = _fn(glue, "dispatchCreate", C.c_int64, C.c_int32, C.c_int32, C.c_int32)(G, F, 1)
+    recs = np.zeros(16, dtype=ingest.REQ_REC)
+    oc = ob.as_c()
+    n = _fn(glue, "outboxToRequests", C.c_int32, C.c_int64, C.POINTER(_Buf), C.c_int32, C.POINTER(_Buf), C.c_int32)(
+        d, C.byref(jni_exec.buf_of_struct(oc)), rows, C.byref(_buf(recs)), 16)
+    want, unknown = ingest.Dispatch(G, F, 1).requests(ob, rows)
+    assert n == 3 == len(want) and unknown == 0 and recs[:3].tobytes() == want.tobytes() and glue.fake_throws() == 0
+    assert [(int(q["kind"]), int(q["dst_slot"]), int(q["term"])) for q in recs[:3]] == \
+        [(abi.OP_VOTE_REQ, 0, 61), (abi.OP_VOTE_REQ, 2, 61), (abi.OP_AE_REQUEST, 0, 70)]
+    # the AE record lands in a receiver's inbox (node slot 0), its three entry terms appended to the pool
+    ib = abi.Inbox(rows, G, F, ent_cap=64)
+    ic = ib.as_c()
+    terms = np.array([69, 70, 70], dtype=np.int64)
+    cnt = _fn(glue, "requestToInbox", C.c_int32, C.POINTER(_Buf), C.POINTER(_Buf), C.c_int32, C.c_int64, C.c_uint8, C.POINTER(_Buf),
+              C.c_int32, C.c_int32, C.c_int32)(C.byref(_buf(recs[2:3])), C.byref(_buf(terms)), 1, 123456, 0,
+                                               C.byref(jni_exec.buf_of_struct(ic)), G, 64, 0)
+    ref = abi.Inbox(rows, G, F, ent_cap=64)
+    ref.ae_request(1, 2, 123456, 1, 70, 100, 69, [69, 70, 70], 99)
+    assert cnt == 3 and glue.fake_throws() == 0
+    for col in ("op_meta", "op_nr", "op_ab", "op_cd", "op_e"):
+        assert np.array_equal(getattr(ib, col), getattr(ref, col)), col
+    assert np.array_equal(ib.ent_terms[:3], ref.ent_terms[:3])
+    # ... the receiver's step answered it: one reply record for the sender's lane
+    rob = abi.Outbox(rows, G, F, G)
+    rob.rep_meta[1, 2] = 1 | 2; rob.rep_term[1, 2] = 70
+    reps = np.zeros(4, dtype=ingest.BATCH_REC)
+    roc = rob.as_c()
+    prow = np.array([1], dtype=np.uint8)
+    m = _fn(glue, "outboxToReplies", C.c_int32, C.POINTER(_Buf), C.c_int32, C.c_int32, C.POINTER(_Buf), C.POINTER(_Buf), C.c_int32,
+            C.POINTER(_Buf))(C.byref(jni_exec.buf_of_struct(roc)), G, 0, C.byref(_buf(recs[2:3])), C.byref(_buf(prow)), 1, C.byref(_buf(reps)))
+    assert m == 1 and glue.fake_throws() == 0
+    r = reps[0]
+    assert (int(r["gid"]), int(r["kind"]), int(r["lane"]), int(r["flags"]), int(r["incarnation"]), int(r["term"]), int(r["epoch_at_send"]),
+            int(r["last_at_send"])) == (2, abi.EV_AE_ACK, 0, abi.OUT_OK | 4, 7, 70, 40, 103)
+    # capacity error surfaces as RaftException
+    glue.fake_reset()
+    _fn(glue, "outboxToRequests", C.c_int32, C.c_int64, C.POINTER(_Buf), C.c_int32, C.POINTER(_Buf), C.c_int32)(
+        d, C.byref(jni_exec.buf_of_struct(oc)), rows, C.byref(_buf(recs)), 1)
+    assert glue.fake_throws() == 1 and glue.fake_thrown_class() == b"io/lubricant/consensus/raft/support/RaftException"
+    _fn(glue, "dispatchDestroy", None, C.c_int64)(d)
