@@ -181,6 +181,15 @@ int rafting_request_to_inbox(const rafting_req_rec_t* r, const int64_t* entry_te
 int rafting_outbox_to_replies(const rafting_outbox_t* ob, uint32_t n_groups, uint32_t local_slot, const rafting_req_rec_t* placed,
                               const uint8_t* placed_row, uint32_t n, rafting_batch_rec_t* out, uint32_t* n_out);
 
+/* ---- commit records -> apply ranges --------------------------------------------------------------------
+ * What RaftRoutine.commitState hands to applyCommand (RaftRoutine.java:224-306): for every group whose role_word carries the
+ * commit-dirty bit (bit 31) and whose commit_index is ahead of applied[gid], one record (gid, applied + 1 .. commit_index);
+ * applied[gid] is advanced to commit_index.  The caller feeds the ranges to rafting_log_gather and the state machine.
+ * gids == NULL: dense columns (position == gid); otherwise RAFTING_INBOX_COMPACT_GROUPS columns indexed by position. */
+typedef struct rafting_apply_rec { uint32_t gid; uint32_t _pad; int64_t first, last; } rafting_apply_rec_t;   /* 24 bytes */
+int rafting_outbox_apply_ranges(const rafting_outbox_t* ob, const uint32_t* gids, uint32_t n, int64_t* applied, uint32_t n_groups,
+                                rafting_apply_rec_t* out, uint32_t cap, uint32_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

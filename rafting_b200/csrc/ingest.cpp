@@ -407,3 +407,23 @@ extern "C" int rafting_outbox_to_replies(const rafting_outbox_t* ob, uint32_t n_
     *n_out = k;
     return RAFTING_OK;
 }
+
+// commit records -> apply ranges: the scan RaftRoutine.commitState does per context, for the whole shard (RaftRoutine.java:224-306)
+extern "C" int rafting_outbox_apply_ranges(const rafting_outbox_t* ob, const uint32_t* gids, uint32_t n, int64_t* applied,
+                                           uint32_t n_groups, rafting_apply_rec_t* out, uint32_t cap, uint32_t* n_out) {
+    if (!ob || !ob->role_word || !ob->commit_index || !applied || !out || !n_out) return RAFTING_E_INVAL;
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!(ob->role_word[i] & (1u << 31))) continue;                       // commit-dirty: commitIndex moved in this step
+        const uint32_t gid = gids ? gids[i] : i;
+        if (gid >= n_groups) { *n_out = k; return RAFTING_E_INVAL; }
+        const int64_t c = ob->commit_index[i];
+        if (c <= applied[gid]) continue;                                      // a snapshot already moved the machine past it
+        if (k >= cap) { *n_out = k; return RAFTING_E_CAPACITY; }
+        out[k].gid = gid; out[k]._pad = 0; out[k].first = applied[gid] + 1; out[k].last = c;
+        applied[gid] = c;
+        k++;
+    }
+    *n_out = k;
+    return RAFTING_OK;
+}

@@ -261,4 +261,12 @@ JNIEXPORT jint JNICALL FN(outboxToReplies)(JNIEnv* env, jclass k, jobject outStr
                                     (rafting_batch_rec_t*)BUF(repliesOut), &got));
     return (jint)got;
 }
+/* commit records of a step -> (gid, first, last) ranges for RaftMachine.apply; `applied` is the pump's long[G] in a direct buffer */
+JNIEXPORT jint JNICALL FN(applyRanges)(JNIEnv* env, jclass k, jobject outStruct, jobject gids, jint n, jobject applied, jint nGroups,
+                                       jobject rangesOut, jint cap) {
+    uint32_t got = 0;
+    CHECK(rafting_outbox_apply_ranges((const rafting_outbox_t*)BUF(outStruct), (const uint32_t*)BUF(gids), (uint32_t)n, (int64_t*)BUF(applied),
+                                      (uint32_t)nGroups, (rafting_apply_rec_t*)BUF(rangesOut), (uint32_t)cap, &got));
+    return (jint)got;
+}
 #endif /* RAFTING_HAVE_JNI */

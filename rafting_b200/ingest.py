@@ -20,6 +20,7 @@ BATCH_REC = np.dtype([("gid", "<u4"), ("kind", "u1"), ("lane", "u1"), ("flags", 
                       ("_pad", "<u4"), ("term", "<i8"), ("epoch_at_send", "<i8"), ("last_at_send", "<i8")])
 ACK_REC = np.dtype([("gid", "<u4"), ("kind", "u1"), ("success", "u1"), ("_pad", "<u2"), ("sequence", "<i4"), ("frame", "<u4"),
                     ("term", "<i8")])
+APPLY_REC = np.dtype([("gid", "<u4"), ("_pad", "<u4"), ("first", "<i8"), ("last", "<i8")])
 REQ_REC = np.dtype([("gid", "<u4"), ("kind", "u1"), ("src_slot", "u1"), ("dst_slot", "u1"), ("row", "u1"), ("incarnation", "<u4"),
                     ("count", "<u4"), ("term", "<i8"), ("a", "<i8"), ("b", "<i8"), ("commit", "<i8"), ("epoch", "<i8"), ("last", "<i8")])
 assert FRAME.itemsize == 24 and BATCH_REC.itemsize == 40 and ACK_REC.itemsize == 24 and REQ_REC.itemsize == 64
@@ -54,6 +55,8 @@ def lib():
                                                C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.rafting_outbox_to_replies.argtypes = [C.POINTER(abi.OutboxC), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                                 C.c_void_p, C.POINTER(C.c_uint32)]
+        L.rafting_outbox_apply_ranges.argtypes = [C.POINTER(abi.OutboxC), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                  C.c_uint32, C.POINTER(C.c_uint32)]
         L.rafting_ack_frames_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         _LIB = L
     return _LIB
@@ -205,3 +208,18 @@ def outbox_to_replies(outbox: abi.Outbox, n_groups: int, local_slot: int, placed
     if rc:
         raise ValueError(f"rafting_outbox_to_replies: rc={rc}")
     return out[:n.value]
+
+
+def apply_ranges(outbox: abi.Outbox, applied: np.ndarray, gids=None) -> np.ndarray:
+    """Commit records of one step -> (gid, first, last) ranges to apply; advances `applied` (int64 per gid) in place."""
+    assert applied.dtype == np.int64 and applied.flags.c_contiguous
+    n = len(outbox.role_word) if gids is None else len(gids)
+    g = None if gids is None else np.ascontiguousarray(gids, dtype=np.uint32)
+    out = np.zeros(max(1, n), dtype=APPLY_REC)
+    k = C.c_uint32()
+    oc = outbox.as_c()
+    rc = lib().rafting_outbox_apply_ranges(C.byref(oc), None if g is None else g.ctypes.data, n, applied.ctypes.data, len(applied),
+                                           out.ctypes.data, len(out), C.byref(k))
+    if rc:
+        raise ValueError(f"rafting_outbox_apply_ranges: rc={rc}")
+    return out[:k.value]

@@ -307,6 +307,13 @@ class Cluster:
             assert got == self._replied, f"native replies differ (node {nd.slot}, tick {self.tick}): {got[:3]} vs {self._replied[:3]}"
             self.counts["native_replies_checked"] += len(got)
         # apply committed commands to the file machine (RaftRoutine.commitState -> applyCommand)
+        if self.shadow_native:
+            from rafting_b200 import ingest
+            applied = np.array(nd.applied, dtype=np.int64)
+            got = [(int(a["gid"]), int(a["first"]), int(a["last"])) for a in ingest.apply_ranges(ob, applied)]
+            want = [(g, nd.applied[g] + 1, int(ob.commit_index[g])) for g in range(G) if int(ob.commit_index[g]) > nd.applied[g]]
+            assert got == want, f"native apply ranges differ (node {nd.slot}, tick {self.tick}): {got[:3]} vs {want[:3]}"
+            self.counts["native_apply_ranges_checked"] += len(got)
         for g in range(G):
             c = int(ob.commit_index[g])
             while nd.applied[g] < c:

@@ -197,3 +197,4 @@ def test_native_pump_dispatch_matches_the_python_pump_under_partitions(R, pre_vo
     c = _jepsen(R, pre_vote, seed, guard=True, shadow_native=True)
     assert c.counts["native_requests_checked"] > 2500 and c.counts["native_placements_checked"] > 3000
     assert c.counts["native_replies_checked"] > 2500 and c.counts["is_sent"] > 0 and c.counts["vote"] > 0
+    assert c.counts["native_apply_ranges_checked"] > 500          # commit-dirty groups -> (gid, first, last), same as the Python loop

@@ -198,6 +198,17 @@ def test_dispatch_natives_turn_an_outbox_into_request_and_reply_records(glue):
     r = reps[0]
     assert (int(r["gid"]), int(r["kind"]), int(r["lane"]), int(r["flags"]), int(r["incarnation"]), int(r["term"]), int(r["epoch_at_send"]),
             int(r["last_at_send"])) == (2, abi.EV_AE_ACK, 0, abi.OUT_OK | 4, 7, 70, 40, 103)
+    # commit records -> apply ranges
+    cob = abi.Outbox(rows, G, F, G)
+    cob.commit_index[:] = [10, 20, 30, 40]
+    cob.role_word[:] = [1 << 31, 0, 1 << 31, 1 << 31]
+    applied = np.array([4, 0, 30, 35], dtype=np.int64)
+    ranges = np.zeros(4, dtype=ingest.APPLY_REC)
+    coc = cob.as_c()
+    k = _fn(glue, "applyRanges", C.c_int32, C.POINTER(_Buf), C.POINTER(_Buf), C.c_int32, C.POINTER(_Buf), C.c_int32, C.POINTER(_Buf), C.c_int32)(
+        C.byref(jni_exec.buf_of_struct(coc)), None, G, C.byref(_buf(applied)), G, C.byref(_buf(ranges)), 4)
+    assert k == 2 and [(int(a["gid"]), int(a["first"]), int(a["last"])) for a in ranges[:2]] == [(0, 5, 10), (3, 36, 40)]
+    assert applied.tolist() == [10, 0, 30, 40] and glue.fake_throws() == 0
     # capacity error surfaces as RaftException
     glue.fake_reset()
     _fn(glue, "outboxToRequests", C.c_int32, C.c_int64, C.POINTER(_Buf), C.c_int32, C.POINTER(_Buf), C.c_int32)(
