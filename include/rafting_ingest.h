@@ -181,6 +181,28 @@ int rafting_request_to_inbox(const rafting_req_rec_t* r, const int64_t* entry_te
 int rafting_outbox_to_replies(const rafting_outbox_t* ob, uint32_t n_groups, uint32_t local_slot, const rafting_req_rec_t* placed,
                               const uint8_t* placed_row, uint32_t n, rafting_batch_rec_t* out, uint32_t* n_out);
 
+/* ---- replies -> compact wire words (the compact host path of include/rafting_b200.h) -------------------------------------
+ * The pending-invocation table of the pump: what NettyNode keeps per connection as (scope, sequence) -> Invocation
+ * (NettyNode.java:88-90, Async.java) — here (peer, sequence) -> the group, the follower lane, the TAG the plan was sent under
+ * (plan_c bits 5..10; the echo pair and the incarnation wait in the engine's in-flight table under that tag), the term the
+ * request carried, and the echo pair itself for replies that have to travel in full.
+ * rafting_acks_to_cinbox takes the decoded ACK records of one peer (rafting_ack_frames_decode), looks each sequence up and
+ * writes the reply into row `row` of a compact inbox under construction: a 32-bit ev_c word when it fits the compact rules
+ * (an AE / IS ack, tag 0..31, 0 <= now - row_base[row] <= 65535, RaftResponse.term() == the term sent), else the word
+ * RAFTING_CEV_ESCAPED plus one escape record with every field.  A reply whose lane slot in that row is taken is DEFERRED (its
+ * index goes to deferred[], its pending entry stays) — one event per (row, group, lane); an unknown sequence (the invocation
+ * timed out and was removed) is counted and dropped, as the reference drops it (NettyNode.getInvocationIfPresent == null). */
+typedef struct rafting_pending rafting_pending_t;
+int rafting_pending_create(uint32_t capacity_hint, rafting_pending_t** out);
+int rafting_pending_destroy(rafting_pending_t* p);
+int rafting_pending_put(rafting_pending_t* p, uint32_t peer, int32_t sequence, uint32_t gid, uint32_t lane, uint32_t tag /* 0..31 | 63 */,
+                        uint32_t incarnation, int64_t term, int64_t epoch_at_send, int64_t last_at_send);
+int rafting_pending_remove(rafting_pending_t* p, uint32_t peer, int32_t sequence);          /* time-out: RAFTING_E_INVAL if absent */
+uint32_t rafting_pending_size(const rafting_pending_t* p);
+int rafting_acks_to_cinbox(rafting_pending_t* p, uint32_t peer, const rafting_ack_rec_t* acks, uint32_t n, int64_t now_ms, uint32_t row,
+                           const rafting_cinbox_t* cin, uint32_t n_groups, uint32_t F, rafting_cesc_in_t* esc, uint32_t esc_cap,
+                           uint32_t* n_esc /* in/out */, uint32_t* deferred /* [n] */, uint32_t* n_deferred, uint32_t* n_unknown);
+
 /* ---- commit records -> apply ranges --------------------------------------------------------------------
  * What RaftRoutine.commitState hands to applyCommand (RaftRoutine.java:224-306): for every group whose role_word carries the
  * commit-dirty bit (bit 31) and whose commit_index is ahead of applied[gid], one record (gid, applied + 1 .. commit_index);

@@ -269,4 +269,30 @@ JNIEXPORT jint JNICALL FN(applyRanges)(JNIEnv* env, jclass k, jobject outStruct,
                                       (uint32_t)nGroups, (rafting_apply_rec_t*)BUF(rangesOut), (uint32_t)cap, &got));
     return (jint)got;
 }
+/* the pending-invocation table + replies -> compact wire words (what NettyNode.getInvocationIfPresent + the AE-Echo closure do per ack) */
+JNIEXPORT jlong JNICALL FN(pendingCreate)(JNIEnv* env, jclass k, jint capacityHint) {
+    rafting_pending_t* p = NULL;
+    CHECK(rafting_pending_create((uint32_t)capacityHint, &p));
+    return (jlong)(intptr_t)p;
+}
+JNIEXPORT void JNICALL FN(pendingDestroy)(JNIEnv* env, jclass k, jlong p) { rafting_pending_destroy((rafting_pending_t*)(intptr_t)p); }
+JNIEXPORT void JNICALL FN(pendingPut)(JNIEnv* env, jclass k, jlong p, jint peer, jint sequence, jint gid, jint lane, jint tag, jint incarnation,
+                                      jlong term, jlong epochAtSend, jlong lastAtSend) {
+    CHECK(rafting_pending_put((rafting_pending_t*)(intptr_t)p, (uint32_t)peer, sequence, (uint32_t)gid, (uint32_t)lane, (uint32_t)tag,
+                              (uint32_t)incarnation, term, epochAtSend, lastAtSend));
+}
+JNIEXPORT jboolean JNICALL FN(pendingRemove)(JNIEnv* env, jclass k, jlong p, jint peer, jint sequence) {
+    return rafting_pending_remove((rafting_pending_t*)(intptr_t)p, (uint32_t)peer, sequence) == RAFTING_OK;
+}
+/* counters: long[3] in a direct buffer = { escape records used (in/out), deferred acks, unknown sequences } */
+JNIEXPORT void JNICALL FN(acksToCinbox)(JNIEnv* env, jclass k, jlong p, jint peer, jobject acks, jint n, jlong nowMs, jint row, jobject cinStruct,
+                                        jint nGroups, jint followers, jobject esc, jint escCap, jobject deferredOut, jobject counters) {
+    int64_t* c = (int64_t*)BUF(counters);
+    uint32_t nEsc = c ? (uint32_t)c[0] : 0, nDef = 0, nUnknown = 0;
+    int rc = rafting_acks_to_cinbox((rafting_pending_t*)(intptr_t)p, (uint32_t)peer, (const rafting_ack_rec_t*)BUF(acks), (uint32_t)n, nowMs,
+                                    (uint32_t)row, (const rafting_cinbox_t*)BUF(cinStruct), (uint32_t)nGroups, (uint32_t)followers,
+                                    (rafting_cesc_in_t*)BUF(esc), (uint32_t)escCap, &nEsc, (uint32_t*)BUF(deferredOut), &nDef, &nUnknown);
+    if (c) { c[0] = nEsc; c[1] = nDef; c[2] = nUnknown; }
+    if (rc) throw_status(env, rc);
+}
 #endif /* RAFTING_HAVE_JNI */

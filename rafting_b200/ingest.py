@@ -57,6 +57,16 @@ def lib():
                                                 C.c_void_p, C.POINTER(C.c_uint32)]
         L.rafting_outbox_apply_ranges.argtypes = [C.POINTER(abi.OutboxC), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                                   C.c_uint32, C.POINTER(C.c_uint32)]
+        L.rafting_pending_create.argtypes = [C.c_uint32, C.POINTER(C.c_void_p)]
+        L.rafting_pending_destroy.argtypes = [C.c_void_p]
+        L.rafting_pending_put.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64,
+                                          C.c_int64, C.c_int64]
+        L.rafting_pending_remove.argtypes = [C.c_void_p, C.c_uint32, C.c_int32]
+        L.rafting_pending_size.restype = C.c_uint32
+        L.rafting_pending_size.argtypes = [C.c_void_p]
+        L.rafting_acks_to_cinbox.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int64, C.c_uint32, C.POINTER(abi.CInboxC),
+                                             C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p,
+                                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.rafting_ack_frames_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         _LIB = L
     return _LIB
@@ -223,3 +233,41 @@ def apply_ranges(outbox: abi.Outbox, applied: np.ndarray, gids=None) -> np.ndarr
     if rc:
         raise ValueError(f"rafting_outbox_apply_ranges: rc={rc}")
     return out[:k.value]
+
+
+class Pending:
+    """The pump's pending-invocation table: (peer, sequence) -> what the request was sent with (include/rafting_ingest.h)."""
+
+    def __init__(self, capacity_hint: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().rafting_pending_create(capacity_hint, C.byref(self._h))
+        if rc:
+            raise ValueError(f"rafting_pending_create: rc={rc}")
+
+    def put(self, peer, sequence, gid, lane, tag, incarnation, term, epoch_at_send, last_at_send):
+        rc = lib().rafting_pending_put(self._h, peer, sequence, gid, lane, tag, incarnation, term, epoch_at_send, last_at_send)
+        if rc:
+            raise ValueError(f"rafting_pending_put: rc={rc}")
+
+    def remove(self, peer, sequence) -> bool:
+        return lib().rafting_pending_remove(self._h, peer, sequence) == 0
+
+    def __len__(self):
+        return lib().rafting_pending_size(self._h)
+
+    def acks_to_cinbox(self, peer: int, acks: np.ndarray, now_ms: int, row: int, cin, esc: np.ndarray, n_esc: int):
+        """Writes the replies into row `row` of the compact inbox `cin` (rafting_b200.compact.CompactInbox with ev_c allocated);
+        -> (status, escape records used so far, indices of deferred acks, unknown sequences)."""
+        acks = np.ascontiguousarray(acks, dtype=ACK_REC)
+        deferred = np.zeros(max(1, len(acks)), dtype=np.uint32)
+        ne, nd, nu = C.c_uint32(n_esc), C.c_uint32(), C.c_uint32()
+        cc = cin.as_c()
+        rc = lib().rafting_acks_to_cinbox(self._h, peer, acks.ctypes.data, len(acks), now_ms, row, C.byref(cc), cin.n, cin.F,
+                                          esc.ctypes.data, len(esc), C.byref(ne), deferred.ctypes.data, C.byref(nd), C.byref(nu))
+        return rc, ne.value, deferred[:nd.value].copy(), nu.value
+
+    def __del__(self):
+        try:
+            lib().rafting_pending_destroy(self._h)
+        except Exception:
+            pass

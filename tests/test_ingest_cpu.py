@@ -226,3 +226,101 @@ def test_mutated_streams_never_crash_and_never_report_bytes_outside_the_buffer()
             f = frames[int(r["frame"])]
             assert f["type"] == ingest.ACK and r["gid"] < 32 and r["kind"] in (abi.EV_AE_ACK, abi.EV_IS_ACK, abi.EV_PV_REPLY, abi.EV_RV_REPLY)
             assert ingest.reply_body_decode(data[f["body_off"]:f["body_off"] + f["body_len"]]) == (int(r["term"]), bool(r["success"]))
+
+
+def test_replies_become_the_compact_words_the_python_encoder_writes():
+    """ACK records + the pending-invocation table -> ev_c words / escape records of a compact inbox, against
+    rafting_b200.compact.encode_inbox (the encoder the GPU parity tests of the compact path use) on the same events."""
+    from rafting_b200 import compact
+    rng = np.random.default_rng(99)
+    rows, G, F, NPEER = 3, 64, 2, 2
+    sent_term = rng.integers(5, 9, G).astype(np.int64)
+    sent_inc = rng.integers(1, 4, G).astype(np.uint32)
+    base = 1_000_000
+    ib = abi.Inbox(rows, G, F)
+    tags = np.full((rows, G, F), abi.CTAG_NONE, dtype=np.uint8)
+    pend = ingest.Pending()
+    per_call = {}                                                   # (row, peer, now) -> ack records, in arrival order
+    seq = 0
+    for r in range(rows):
+        for g in range(G):
+            for f in range(F):
+                if rng.random() < 0.25:
+                    continue
+                seq += 1
+                kind = [abi.EV_AE_ACK, abi.EV_AE_ACK, abi.EV_IS_ACK, abi.EV_RV_REPLY][int(rng.integers(0, 4))]
+                tag = int(rng.integers(0, 32)) if rng.random() < 0.9 else abi.CTAG_NONE
+                term = int(sent_term[g]) if rng.random() < 0.9 else int(sent_term[g]) + 1          # a newer term: travels in full
+                ok = bool(rng.integers(0, 2))
+                epoch, last = int(rng.integers(0, 50)), int(rng.integers(50, 90))
+                peer = f                                             # lane f <-> one connection
+                now = base + 1000 * r + (0 if peer == 0 else 7)      # the two peers' buffers are drained 7 ms apart
+                # an escaped plan has no tag and may come from another role object: its reply carries that incarnation in full
+                inc = int(sent_inc[g]) if tag != abi.CTAG_NONE else int(sent_inc[g]) + int(rng.integers(0, 2))
+                pend.put(peer, seq, g, f, tag, inc, int(sent_term[g]), epoch, last)
+                rec = np.zeros(1, dtype=ingest.ACK_REC)[0]
+                rec["gid"], rec["kind"], rec["success"], rec["sequence"], rec["term"] = g, kind, ok, seq, term
+                per_call.setdefault((r, peer, now), []).append(rec)
+                tags[r, g, f] = tag
+                if kind in (abi.EV_AE_ACK, abi.EV_IS_ACK):
+                    ib.ack(r, g, f, now, inc, term, ok, epoch, last, snapshot=kind == abi.EV_IS_ACK)
+                else:
+                    ib.vote_reply(r, g, f, now, inc, term, ok)
+                    ib.ev_el[r, g, f] = (epoch, last)
+    want = compact.encode_inbox(ib, tags, sent_term, sent_inc)
+    got = compact.CompactInbox(rows, G, F)
+    esc = np.zeros(rows * G * F, dtype=abi.CESC_IN)
+    n_esc = 0
+    assert len(pend) == seq
+    for (r, peer, now), recs in sorted(per_call.items(), key=lambda kv: kv[0]):
+        got.row_base[r] = base + 1000 * r                            # the row's base: the earliest drain of that row
+        rc, n_esc, deferred, unknown = pend.acks_to_cinbox(peer, np.array(recs, dtype=ingest.ACK_REC), now, r, got, esc, n_esc)
+        assert rc == 0 and len(deferred) == 0 and unknown == 0
+    assert len(pend) == 0                                            # every invocation was completed and removed
+    assert np.array_equal(got.row_base, want.row_base) and np.array_equal(got.ev_c, want.ev_c)
+    a, b = np.sort(esc[:n_esc], order="slot"), np.sort(want.esc, order="slot")
+    assert len(a) == len(b) > 0 and a.tobytes() == b.tobytes()
+    assert ((got.ev_c & 0xF) == abi.CEV_ESCAPED).sum() == n_esc and (got.ev_c != 0).sum() == seq
+    # a second reply for a lane slot that is taken is deferred (its invocation stays pending); an unknown sequence is dropped
+    pend.put(0, 9001, 3, 0, 1, int(sent_inc[3]), int(sent_term[3]), 1, 2)
+    pend.put(0, 9002, 3, 0, 2, int(sent_inc[3]), int(sent_term[3]), 1, 2)
+    two = np.zeros(3, dtype=ingest.ACK_REC)
+    two["gid"], two["kind"], two["success"], two["term"] = 3, abi.EV_AE_ACK, 1, int(sent_term[3])
+    two["sequence"] = [9001, 9002, 7777]
+    fresh = compact.CompactInbox(1, G, F)
+    fresh.row_base[0] = base
+    rc, n2, deferred, unknown = pend.acks_to_cinbox(0, two, base + 5, 0, fresh, esc, 0)
+    assert rc == 0 and n2 == 0 and deferred.tolist() == [1] and unknown == 1 and len(pend) == 1
+    assert fresh.ev_c[0, 3, 0] == (abi.EV_AE_ACK | (1 << 6) | (1 << 7) | (1 << 8) | (5 << 16))
+    assert pend.remove(0, 9002) and not pend.remove(0, 9002) and len(pend) == 0
+
+
+def test_pending_table_behaves_like_a_dict_under_churn():
+    """put / complete / time-out in random order, growth from a tiny table: the open-addressing table (backward-shift deletion)
+    must agree with a dict on every lookup — checked through acks_to_cinbox's "unknown sequence" count."""
+    rng = np.random.default_rng(5)
+    pend, model = ingest.Pending(4), {}
+    G, F = 32, 2
+    from rafting_b200 import compact
+    esc = np.zeros(8, dtype=abi.CESC_IN)
+    for step in range(4000):
+        op = rng.random()
+        peer, seq = int(rng.integers(0, 3)), int(rng.integers(-50, 400))
+        if op < 0.5:
+            g, f = int(rng.integers(0, G)), int(rng.integers(0, F))
+            pend.put(peer, seq, g, f, int(rng.integers(0, 32)), 1, 7, 0, 0)
+            model[(peer, seq)] = (g, f)
+        elif op < 0.75:
+            assert pend.remove(peer, seq) == ((peer, seq) in model)
+            model.pop((peer, seq), None)
+        else:
+            rec = np.zeros(1, dtype=ingest.ACK_REC)
+            known = (peer, seq) in model
+            rec["gid"], rec["kind"], rec["sequence"], rec["term"] = (model[(peer, seq)][0] if known else 0), abi.EV_AE_ACK, seq, 7
+            cin = compact.CompactInbox(1, G, F)
+            rc, _, deferred, unknown = pend.acks_to_cinbox(peer, rec, 10, 0, cin, esc, 0)
+            assert rc == 0 and unknown == (0 if known else 1) and len(deferred) == 0
+            if known:
+                g, f = model.pop((peer, seq))
+                assert cin.ev_c[0, g, f] != 0 and (cin.ev_c != 0).sum() == 1
+        assert len(pend) == len(model)
