@@ -510,7 +510,11 @@ extern "C" int rafting_acks_to_cinbox(rafting_pending_t* p, uint32_t peer, const
     uint32_t* ev = const_cast<uint32_t*>(cin->ev_c);
     const int64_t dt = now_ms - cin->row_base[row];
     uint32_t unknown = 0, nd = 0;
+    constexpr uint32_t AHEAD = 12;                                           // the table is a random access per reply: prefetch ahead
+    const size_t tmask = p->t.empty() ? 0 : p->t.size() - 1;
     for (uint32_t i = 0; i < n; i++) {
+        if (i + AHEAD < n && !p->t.empty())
+            __builtin_prefetch(&p->t[rafting_pending::mix(rafting_pending::key_of(peer, acks[i + AHEAD].sequence)) & tmask]);
         const rafting_ack_rec_t& a = acks[i];
         rafting_pending::E* e = p->find(rafting_pending::key_of(peer, a.sequence));
         if (!e || e->gid != a.gid) { unknown++; continue; }                  // timed out earlier, or a sequence of another scope
