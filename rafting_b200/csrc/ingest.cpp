@@ -302,6 +302,8 @@ extern "C" int rafting_dispatch_destroy(rafting_dispatch_t* d) { delete d; retur
 extern "C" int rafting_outbox_to_requests(rafting_dispatch_t* d, const rafting_outbox_t* ob, uint32_t rows, rafting_req_rec_t* out,
                                           uint32_t cap, uint32_t* n_out, uint32_t* n_unknown) {
     if (!d || !ob || !out || !n_out || !ob->incarnation || !ob->current_term) return RAFTING_E_INVAL;
+    if (ob->plan_meta && (!ob->plan_pp || !ob->plan_lc)) return RAFTING_E_INVAL;
+    if (ob->ballot_meta && (!ob->ballot_term || !ob->ballot_last)) return RAFTING_E_INVAL;
     const uint32_t G = d->G, F = d->F;
     for (uint32_t g = 0; g < G; g++) d->learn(g, ob->incarnation[g], ob->current_term[g]);
     uint32_t n = 0, unknown = 0;
@@ -364,7 +366,7 @@ extern "C" int rafting_request_to_inbox(const rafting_req_rec_t* r, const int64_
     int64_t d = 0, e = 0;
     if (r->kind == RAFTING_OP_AE_REQUEST) {
         count = r->count;
-        if (count > 0xFFFFu) return RAFTING_E_INVAL;
+        if (count > 0xFFFFu || !in->op_e) return RAFTING_E_INVAL;               // checked before anything is written
         if (count) {
             if (!ent_count || !in->ent_terms || !entry_terms || (uint64_t)*ent_count + count > ent_cap) return RAFTING_E_INVAL;
             off = *ent_count;
@@ -372,7 +374,6 @@ extern "C" int rafting_request_to_inbox(const rafting_req_rec_t* r, const int64_
             *ent_count = off + count;
         } else if (ent_count) off = *ent_count;
         d = r->commit; e = r->a + 1;                                                         // entries[0].index = prevLogIndex + 1
-        if (!in->op_e) return RAFTING_E_INVAL;
     } else if (r->kind == RAFTING_OP_IS_REQUEST) d = host_result ? 1 : 0;
     om[gi] = (uint64_t)RAFTING_OP_MAKE(r->kind, r->src_slot, count) | ((uint64_t)off << 32);
     nr[gi].x = now_ms; nr[gi].y = 0;
