@@ -77,3 +77,83 @@ def test_a_lane_without_a_free_tag_falls_back_to_escape_records():
     assert len(ci.esc) == 1 and int(ci.ev_c[0, 0, 0]) == abi.CEV_ESCAPED          # no tag: the reply carries its echo pair itself
     back = model.unpack(ci, co.current_term, st)
     assert tuple(back.ev_el[0, 0, 0]) == (0, 47) and int(back.ev_meta[0, 0, 0]) == int(ib.ev_meta[0, 0, 0])
+
+
+def test_reference_format_reply_frames_reach_the_compact_inbox_through_the_native_chain():
+    """SURVEY §8(f)-2 end to end on the host, on the real leader stream: every reply of the stream travels as ONE frame of the
+    reference's wire layout (EventCodec framing, scope head, Kryo RaftResponse body, sequence), and the native chain —
+    rafting_frame_scan -> rafting_ack_frames_decode -> rafting_acks_to_cinbox with the pending table filled when the plans left
+    — must build the compact inbox compact.encode_inbox builds from the same dense events, word for word and escape record
+    for escape record (the encoder the GPU parity tests of the compact path feed the engine with)."""
+    from rafting_b200 import ingest
+    G, R, rows = 64, 3, 6
+    F = R - 1
+    cfg = abi.make_cfg(replicas=R, max_groups=G, max_rows=rows)
+    o = binding.Oracle(cfg)
+    o.open_bulk(0, harness.init_array(G, terms=np.arange(G) % 7))
+    w1 = workload.make_wl(23, 1, G, F)
+    w = workload.make_wl(23, rows, G, F, p_reject_ppm=80_000, p_error_ppm=0, p_cancel_ppm=0)   # rejections, no transport errors: every event is a frame
+    harness.elect_all(o, w1)
+    st = model.InFlight(G, F)
+    cm = ingest.CtxMap()
+    for g in range(G):
+        cm.put(b"ctx-%d" % g, g)
+    pend = ingest.Pending()
+    seq_of = {}                                                                      # (row, g, f) of the planning step -> sequence
+    next_seq = [1] * F
+    prev, tags, sent_term, sent_inc = None, None, None, None
+    frames_total = words = escapes = 0
+    for k in range(10):
+        ib = workload.leader_inbox_host(w, k, prev)
+        ek = (ib.ev_meta & np.uint64(0xF)).astype(np.int64)
+        if k in (4, 7):
+            for ev in np.argwhere(ek != 0)[:3]:
+                ib.ev_tn["y"][tuple(ev)] += 80_000                                   # replies 80 s late: they travel as escape records
+        if prev is not None:
+            want = compact.encode_inbox(ib, tags, sent_term, sent_inc)
+            got = compact.CompactInbox(rows, G, F)
+            got.row_base[:] = want.row_base                                         # the pump's clock: the first drain of each row
+            esc = np.zeros(rows * G * F, dtype=abi.CESC_IN)
+            n_esc = 0
+            for r in range(rows):
+                for f in range(F):                                                   # one connection per follower lane
+                    at = [(g, int(ib.ev_tn["y"][r, g, f])) for g in range(G) if ek[r, g, f] != 0]
+                    for now in sorted(set(t for _, t in at)):                        # one receive buffer per (connection, drain time)
+                        buf = b""
+                        for g, t in at:
+                            if t != now:
+                                continue
+                            assert (int(ib.ev_meta[r, g, f]) >> 4) & 3 == abi.OUT_OK
+                            method = b"installSnapshot" if ek[r, g, f] == abi.EV_IS_ACK else b"appendEntries"
+                            body = ingest.reply_body_encode(int(ib.ev_tn["x"][r, g, f]), bool((int(ib.ev_meta[r, g, f]) >> 6) & 1))
+                            buf += ingest.encode(ingest.ACK, method + b":ctx-%d" % g, body, sequence=seq_of[(r, g, f)])
+                        rc, frames, used, _ = ingest.scan(buf, cap=G + 1)
+                        assert rc == 0 and used == len(buf)
+                        acks = ingest.ack_frames_decode(buf, frames, cm)
+                        assert len(acks) == len(frames)
+                        frames_total += len(frames)
+                        rc, n_esc, deferred, unknown = pend.acks_to_cinbox(f, acks, now, r, got, esc, n_esc)
+                        assert rc == 0 and len(deferred) == 0 and unknown == 0
+            assert np.array_equal(got.ev_c, want.ev_c), f"step {k}: ev_c words differ"
+            a, b = np.sort(esc[:n_esc], order="slot"), np.sort(want.esc, order="slot")
+            assert a.tobytes() == b.tobytes(), f"step {k}: escape records differ"
+            words += int(((got.ev_c & 0xF) != 0).sum()) - n_esc
+            escapes += n_esc
+            assert len(pend) == 0                                                    # every plan of the previous step was answered
+        dense = o.step(ib)
+        epoch = np.zeros(G, dtype=abi.I64X2)
+        for g in range(G):
+            s = o.export(g); epoch[g] = (s.epoch_index, s.epoch_term)
+        co = model.pack(dense, epoch, st, esc_cap=rows * G * F + 2 * rows * G)
+        model.unpack(compact.encode_inbox(ib, tags, sent_term, sent_inc), dense.current_term, st) if prev is not None else None   # frees the tags
+        prev, tags, sent_term, sent_inc = dense, co.tags(), co.current_term.copy(), co.incarnation.copy()
+        # the plans leave: remember what each was sent with, under the sequence of its connection
+        seq_of = {}
+        pk = (dense.plan_meta & np.uint64(0xF)).astype(np.int64)
+        for r, g, f in np.argwhere((pk == abi.PLAN_AE) | (pk == abi.PLAN_IS)):
+            r, g, f = int(r), int(g), int(f)
+            seq_of[(r, g, f)] = next_seq[f]
+            pend.put(f, next_seq[f], g, f, int(tags[r, g, f]), int(dense.plan_meta[r, g, f]) >> 32, int(sent_term[g]),
+                     int(dense.plan_epoch[r, g, f]), int(dense.plan_lc[r, g, f]["x"]))
+            next_seq[f] += 1
+    assert frames_total > 3000 and words > 2500 and escapes == 6
