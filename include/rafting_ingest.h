@@ -195,13 +195,21 @@ int rafting_outbox_to_replies(const rafting_outbox_t* ob, uint32_t n_groups, uin
 typedef struct rafting_pending rafting_pending_t;
 int rafting_pending_create(uint32_t capacity_hint, rafting_pending_t** out);
 int rafting_pending_destroy(rafting_pending_t* p);
-int rafting_pending_put(rafting_pending_t* p, uint32_t peer, int32_t sequence, uint32_t gid, uint32_t lane, uint32_t tag /* 0..31 | 63 */,
-                        uint32_t incarnation, int64_t term, int64_t epoch_at_send, int64_t last_at_send);
+int rafting_pending_put(rafting_pending_t* p, uint32_t peer, int32_t sequence, uint32_t ev_kind /* RAFTING_EV_* of the reply */, uint32_t gid,
+                        uint32_t lane, uint32_t tag /* 0..31 | 63 */, uint32_t incarnation, int64_t term, int64_t epoch_at_send,
+                        int64_t last_at_send);
 int rafting_pending_remove(rafting_pending_t* p, uint32_t peer, int32_t sequence);          /* time-out: RAFTING_E_INVAL if absent */
 uint32_t rafting_pending_size(const rafting_pending_t* p);
 int rafting_acks_to_cinbox(rafting_pending_t* p, uint32_t peer, const rafting_ack_rec_t* acks, uint32_t n, int64_t now_ms, uint32_t row,
                            const rafting_cinbox_t* cin, uint32_t n_groups, uint32_t F, rafting_cesc_in_t* esc, uint32_t esc_cap,
                            uint32_t* n_esc /* in/out */, uint32_t* deferred /* [n] */, uint32_t* n_deferred, uint32_t* n_unknown);
+
+/* Invocations that completed WITHOUT a reply — the Async timed out or was cancelled (Async.java:239-254: outcome ERROR /
+ * CANCELED; Leader's callback then runs statFailure) — written the same way: the ev_c word carries the outcome and the tag
+ * (success 0), or an escape record when the plan had no tag / the time offset does not fit.  Same deferral rule. */
+int rafting_failures_to_cinbox(rafting_pending_t* p, uint32_t peer, const int32_t* sequences, uint32_t n, uint32_t outcome, int64_t now_ms,
+                               uint32_t row, const rafting_cinbox_t* cin, uint32_t n_groups, uint32_t F, rafting_cesc_in_t* esc,
+                               uint32_t esc_cap, uint32_t* n_esc, uint32_t* deferred, uint32_t* n_deferred, uint32_t* n_unknown);
 
 /* ---- commit records -> apply ranges --------------------------------------------------------------------
  * What RaftRoutine.commitState hands to applyCommand (RaftRoutine.java:224-306): for every group whose role_word carries the

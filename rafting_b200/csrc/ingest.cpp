@@ -431,7 +431,7 @@ extern "C" int rafting_outbox_apply_ranges(const rafting_outbox_t* ob, const uin
 
 // ---- the pending-invocation table and replies -> compact wire words ----
 struct rafting_pending {
-    struct E { uint64_t key; uint32_t gid; uint8_t lane, tag, used, _p; uint32_t inc; int64_t term, epoch, last; };
+    struct E { uint64_t key; uint32_t gid; uint8_t lane, tag, used, kind; uint32_t inc; int64_t term, epoch, last; };
     std::vector<E> t;
     size_t count = 0;
     static uint64_t mix(uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; return x ^ (x >> 33); }
@@ -478,9 +478,10 @@ extern "C" int rafting_pending_create(uint32_t capacity_hint, rafting_pending_t*
 }
 extern "C" int rafting_pending_destroy(rafting_pending_t* p) { delete p; return RAFTING_OK; }
 extern "C" uint32_t rafting_pending_size(const rafting_pending_t* p) { return p ? (uint32_t)p->count : 0; }
-extern "C" int rafting_pending_put(rafting_pending_t* p, uint32_t peer, int32_t sequence, uint32_t gid, uint32_t lane, uint32_t tag,
-                                   uint32_t incarnation, int64_t term, int64_t epoch_at_send, int64_t last_at_send) {
-    if (!p || lane > 255 || (tag > 31 && tag != RAFTING_CTAG_NONE)) return RAFTING_E_INVAL;
+extern "C" int rafting_pending_put(rafting_pending_t* p, uint32_t peer, int32_t sequence, uint32_t ev_kind, uint32_t gid, uint32_t lane,
+                                   uint32_t tag, uint32_t incarnation, int64_t term, int64_t epoch_at_send, int64_t last_at_send) {
+    if (!p || lane > 255 || (tag > 31 && tag != RAFTING_CTAG_NONE) || ev_kind == RAFTING_EV_NONE || ev_kind > RAFTING_EV_RV_REPLY)
+        return RAFTING_E_INVAL;
     const uint64_t key = rafting_pending::key_of(peer, sequence);
     try {
         rafting_pending::E* e = p->find(key);
@@ -490,7 +491,7 @@ extern "C" int rafting_pending_put(rafting_pending_t* p, uint32_t peer, int32_t 
             p->place(n); p->count++;
             e = p->find(key);
         }
-        e->gid = gid; e->lane = (uint8_t)lane; e->tag = (uint8_t)tag; e->inc = incarnation; e->term = term;
+        e->gid = gid; e->lane = (uint8_t)lane; e->tag = (uint8_t)tag; e->kind = (uint8_t)ev_kind; e->inc = incarnation; e->term = term;
         e->epoch = epoch_at_send; e->last = last_at_send;
     } catch (...) { return RAFTING_E_NOMEM; }
     return RAFTING_OK;
@@ -518,7 +519,7 @@ extern "C" int rafting_acks_to_cinbox(rafting_pending_t* p, uint32_t peer, const
             __builtin_prefetch(&p->t[rafting_pending::mix(rafting_pending::key_of(peer, acks[i + AHEAD].sequence)) & tmask]);
         const rafting_ack_rec_t& a = acks[i];
         rafting_pending::E* e = p->find(rafting_pending::key_of(peer, a.sequence));
-        if (!e || e->gid != a.gid) { unknown++; continue; }                  // timed out earlier, or a sequence of another scope
+        if (!e || e->gid != a.gid || e->kind != a.kind) { unknown++; continue; }   // timed out earlier, or a sequence of another scope
         if (e->gid >= n_groups || e->lane >= F) return RAFTING_E_INVAL;
         const size_t li = ((size_t)row * n_groups + e->gid) * F + e->lane;
         if (ev[li] != 0) { deferred[nd++] = i; continue; }                    // one event per (row, group, lane)
@@ -533,6 +534,40 @@ extern "C" int rafting_acks_to_cinbox(rafting_pending_t* p, uint32_t peer, const
             x.slot = (uint32_t)li;
             x.ev_meta = RAFTING_EVM_MAKE(a.kind, RAFTING_OUT_OK, a.success ? 1 : 0, e->inc);
             x.term = a.term; x.now_ms = now_ms; x.epoch_at_send = e->epoch; x.last_at_send = e->last;
+            ev[li] = RAFTING_CEV_ESCAPED;
+        }
+        p->erase(e);
+    }
+    *n_deferred = nd;
+    if (n_unknown) *n_unknown = unknown;
+    return RAFTING_OK;
+}
+
+extern "C" int rafting_failures_to_cinbox(rafting_pending_t* p, uint32_t peer, const int32_t* sequences, uint32_t n, uint32_t outcome,
+                                          int64_t now_ms, uint32_t row, const rafting_cinbox_t* cin, uint32_t n_groups, uint32_t F,
+                                          rafting_cesc_in_t* esc, uint32_t esc_cap, uint32_t* n_esc, uint32_t* deferred,
+                                          uint32_t* n_deferred, uint32_t* n_unknown) {
+    if (!p || (!sequences && n) || !cin || !cin->ev_c || !cin->row_base || !n_esc || !n_deferred || (!deferred && n) || row >= cin->rows ||
+        (outcome != RAFTING_OUT_ERROR && outcome != RAFTING_OUT_CANCELED)) return RAFTING_E_INVAL;
+    uint32_t* ev = const_cast<uint32_t*>(cin->ev_c);
+    const int64_t dt = now_ms - cin->row_base[row];
+    uint32_t unknown = 0, nd = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        rafting_pending::E* e = p->find(rafting_pending::key_of(peer, sequences[i]));
+        if (!e) { unknown++; continue; }
+        if (e->gid >= n_groups || e->lane >= F) return RAFTING_E_INVAL;
+        const size_t li = ((size_t)row * n_groups + e->gid) * F + e->lane;
+        if (ev[li] != 0) { deferred[nd++] = i; continue; }
+        const bool is_ack = e->kind == RAFTING_EV_AE_ACK || e->kind == RAFTING_EV_IS_ACK;
+        if (is_ack && e->tag < 32 && dt >= 0 && dt <= 0xFFFF) {
+            ev[li] = RAFTING_CEV_MAKE(e->kind, outcome, 0, 0, e->tag, (uint32_t)dt);
+        } else {
+            if (!esc || *n_esc >= esc_cap) { *n_deferred = nd; if (n_unknown) *n_unknown = unknown; return RAFTING_E_CAPACITY; }
+            rafting_cesc_in_t& x = esc[(*n_esc)++];
+            memset(&x, 0, sizeof(x));
+            x.slot = (uint32_t)li;
+            x.ev_meta = RAFTING_EVM_MAKE(e->kind, outcome, 0, e->inc);
+            x.term = 0; x.now_ms = now_ms; x.epoch_at_send = e->epoch; x.last_at_send = e->last;
             ev[li] = RAFTING_CEV_ESCAPED;
         }
         p->erase(e);

@@ -276,10 +276,23 @@ JNIEXPORT jlong JNICALL FN(pendingCreate)(JNIEnv* env, jclass k, jint capacityHi
     return (jlong)(intptr_t)p;
 }
 JNIEXPORT void JNICALL FN(pendingDestroy)(JNIEnv* env, jclass k, jlong p) { rafting_pending_destroy((rafting_pending_t*)(intptr_t)p); }
-JNIEXPORT void JNICALL FN(pendingPut)(JNIEnv* env, jclass k, jlong p, jint peer, jint sequence, jint gid, jint lane, jint tag, jint incarnation,
-                                      jlong term, jlong epochAtSend, jlong lastAtSend) {
-    CHECK(rafting_pending_put((rafting_pending_t*)(intptr_t)p, (uint32_t)peer, sequence, (uint32_t)gid, (uint32_t)lane, (uint32_t)tag,
-                              (uint32_t)incarnation, term, epochAtSend, lastAtSend));
+JNIEXPORT void JNICALL FN(pendingPut)(JNIEnv* env, jclass k, jlong p, jint peer, jint sequence, jint evKind, jint gid, jint lane, jint tag,
+                                      jint incarnation, jlong term, jlong epochAtSend, jlong lastAtSend) {
+    CHECK(rafting_pending_put((rafting_pending_t*)(intptr_t)p, (uint32_t)peer, sequence, (uint32_t)evKind, (uint32_t)gid, (uint32_t)lane,
+                              (uint32_t)tag, (uint32_t)incarnation, term, epochAtSend, lastAtSend));
+}
+/* timed-out / cancelled invocations -> the same row; counters as in acksToCinbox */
+JNIEXPORT void JNICALL FN(failuresToCinbox)(JNIEnv* env, jclass k, jlong p, jint peer, jobject sequences, jint n, jint outcome, jlong nowMs, jint row,
+                                            jobject cinStruct, jint nGroups, jint followers, jobject esc, jint escCap, jobject deferredOut,
+                                            jobject counters) {
+    int64_t* c = (int64_t*)BUF(counters);
+    uint32_t nEsc = c ? (uint32_t)c[0] : 0, nDef = 0, nUnknown = 0;
+    int rc = rafting_failures_to_cinbox((rafting_pending_t*)(intptr_t)p, (uint32_t)peer, (const int32_t*)BUF(sequences), (uint32_t)n,
+                                        (uint32_t)outcome, nowMs, (uint32_t)row, (const rafting_cinbox_t*)BUF(cinStruct), (uint32_t)nGroups,
+                                        (uint32_t)followers, (rafting_cesc_in_t*)BUF(esc), (uint32_t)escCap, &nEsc, (uint32_t*)BUF(deferredOut),
+                                        &nDef, &nUnknown);
+    if (c) { c[0] = nEsc; c[1] = nDef; c[2] = nUnknown; }
+    if (rc) throw_status(env, rc);
 }
 JNIEXPORT jboolean JNICALL FN(pendingRemove)(JNIEnv* env, jclass k, jlong p, jint peer, jint sequence) {
     return rafting_pending_remove((rafting_pending_t*)(intptr_t)p, (uint32_t)peer, sequence) == RAFTING_OK;

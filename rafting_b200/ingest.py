@@ -59,8 +59,11 @@ def lib():
                                                   C.c_uint32, C.POINTER(C.c_uint32)]
         L.rafting_pending_create.argtypes = [C.c_uint32, C.POINTER(C.c_void_p)]
         L.rafting_pending_destroy.argtypes = [C.c_void_p]
-        L.rafting_pending_put.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64,
-                                          C.c_int64, C.c_int64]
+        L.rafting_pending_put.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                          C.c_int64, C.c_int64, C.c_int64]
+        L.rafting_failures_to_cinbox.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int64, C.c_uint32,
+                                                 C.POINTER(abi.CInboxC), C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32),
+                                                 C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.rafting_pending_remove.argtypes = [C.c_void_p, C.c_uint32, C.c_int32]
         L.rafting_pending_size.restype = C.c_uint32
         L.rafting_pending_size.argtypes = [C.c_void_p]
@@ -244,8 +247,8 @@ class Pending:
         if rc:
             raise ValueError(f"rafting_pending_create: rc={rc}")
 
-    def put(self, peer, sequence, gid, lane, tag, incarnation, term, epoch_at_send, last_at_send):
-        rc = lib().rafting_pending_put(self._h, peer, sequence, gid, lane, tag, incarnation, term, epoch_at_send, last_at_send)
+    def put(self, peer, sequence, ev_kind, gid, lane, tag, incarnation, term, epoch_at_send, last_at_send):
+        rc = lib().rafting_pending_put(self._h, peer, sequence, ev_kind, gid, lane, tag, incarnation, term, epoch_at_send, last_at_send)
         if rc:
             raise ValueError(f"rafting_pending_put: rc={rc}")
 
@@ -264,6 +267,16 @@ class Pending:
         cc = cin.as_c()
         rc = lib().rafting_acks_to_cinbox(self._h, peer, acks.ctypes.data, len(acks), now_ms, row, C.byref(cc), cin.n, cin.F,
                                           esc.ctypes.data, len(esc), C.byref(ne), deferred.ctypes.data, C.byref(nd), C.byref(nu))
+        return rc, ne.value, deferred[:nd.value].copy(), nu.value
+
+    def failures_to_cinbox(self, peer: int, sequences, outcome: int, now_ms: int, row: int, cin, esc: np.ndarray, n_esc: int):
+        """Invocations that timed out (OUT_ERROR) / were cancelled (OUT_CANCELED): same contract as acks_to_cinbox."""
+        seqs = np.ascontiguousarray(sequences, dtype=np.int32)
+        deferred = np.zeros(max(1, len(seqs)), dtype=np.uint32)
+        ne, nd, nu = C.c_uint32(n_esc), C.c_uint32(), C.c_uint32()
+        cc = cin.as_c()
+        rc = lib().rafting_failures_to_cinbox(self._h, peer, seqs.ctypes.data, len(seqs), outcome, now_ms, row, C.byref(cc), cin.n, cin.F,
+                                              esc.ctypes.data, len(esc), C.byref(ne), deferred.ctypes.data, C.byref(nd), C.byref(nu))
         return rc, ne.value, deferred[:nd.value].copy(), nu.value
 
     def __del__(self):

@@ -92,7 +92,7 @@ def test_reference_format_reply_frames_reach_the_compact_inbox_through_the_nativ
     o = binding.Oracle(cfg)
     o.open_bulk(0, harness.init_array(G, terms=np.arange(G) % 7))
     w1 = workload.make_wl(23, 1, G, F)
-    w = workload.make_wl(23, rows, G, F, p_reject_ppm=80_000, p_error_ppm=0, p_cancel_ppm=0)   # rejections, no transport errors: every event is a frame
+    w = workload.make_wl(23, rows, G, F, p_reject_ppm=80_000, p_error_ppm=30_000, p_cancel_ppm=20_000)   # rejections, time-outs, cancellations
     harness.elect_all(o, w1)
     st = model.InFlight(G, F)
     cm = ingest.CtxMap()
@@ -102,7 +102,7 @@ def test_reference_format_reply_frames_reach_the_compact_inbox_through_the_nativ
     seq_of = {}                                                                      # (row, g, f) of the planning step -> sequence
     next_seq = [1] * F
     prev, tags, sent_term, sent_inc = None, None, None, None
-    frames_total = words = escapes = 0
+    frames_total = words = escapes = failures = 0
     for k in range(10):
         ib = workload.leader_inbox_host(w, k, prev)
         ek = (ib.ev_meta & np.uint64(0xF)).astype(np.int64)
@@ -120,10 +120,14 @@ def test_reference_format_reply_frames_reach_the_compact_inbox_through_the_nativ
                     at = [(g, int(ib.ev_tn["y"][r, g, f])) for g in range(G) if ek[r, g, f] != 0]
                     for now in sorted(set(t for _, t in at)):                        # one receive buffer per (connection, drain time)
                         buf = b""
+                        failed = {abi.OUT_ERROR: [], abi.OUT_CANCELED: []}
                         for g, t in at:
                             if t != now:
                                 continue
-                            assert (int(ib.ev_meta[r, g, f]) >> 4) & 3 == abi.OUT_OK
+                            outcome = (int(ib.ev_meta[r, g, f]) >> 4) & 3
+                            if outcome != abi.OUT_OK:                                # no frame: the invocation's Async failed
+                                failed[outcome].append(seq_of[(r, g, f)])
+                                continue
                             method = b"installSnapshot" if ek[r, g, f] == abi.EV_IS_ACK else b"appendEntries"
                             body = ingest.reply_body_encode(int(ib.ev_tn["x"][r, g, f]), bool((int(ib.ev_meta[r, g, f]) >> 6) & 1))
                             buf += ingest.encode(ingest.ACK, method + b":ctx-%d" % g, body, sequence=seq_of[(r, g, f)])
@@ -134,6 +138,10 @@ def test_reference_format_reply_frames_reach_the_compact_inbox_through_the_nativ
                         frames_total += len(frames)
                         rc, n_esc, deferred, unknown = pend.acks_to_cinbox(f, acks, now, r, got, esc, n_esc)
                         assert rc == 0 and len(deferred) == 0 and unknown == 0
+                        for outcome, seqs in failed.items():
+                            rc, n_esc, deferred, unknown = pend.failures_to_cinbox(f, seqs, outcome, now, r, got, esc, n_esc)
+                            assert rc == 0 and len(deferred) == 0 and unknown == 0
+                            failures += len(seqs)
             assert np.array_equal(got.ev_c, want.ev_c), f"step {k}: ev_c words differ"
             a, b = np.sort(esc[:n_esc], order="slot"), np.sort(want.esc, order="slot")
             assert a.tobytes() == b.tobytes(), f"step {k}: escape records differ"
@@ -153,7 +161,8 @@ def test_reference_format_reply_frames_reach_the_compact_inbox_through_the_nativ
         for r, g, f in np.argwhere((pk == abi.PLAN_AE) | (pk == abi.PLAN_IS)):
             r, g, f = int(r), int(g), int(f)
             seq_of[(r, g, f)] = next_seq[f]
-            pend.put(f, next_seq[f], g, f, int(tags[r, g, f]), int(dense.plan_meta[r, g, f]) >> 32, int(sent_term[g]),
+            pend.put(f, next_seq[f], abi.EV_IS_ACK if pk[r, g, f] == abi.PLAN_IS else abi.EV_AE_ACK, g, f, int(tags[r, g, f]),
+                     int(dense.plan_meta[r, g, f]) >> 32, int(sent_term[g]),
                      int(dense.plan_epoch[r, g, f]), int(dense.plan_lc[r, g, f]["x"]))
             next_seq[f] += 1
-    assert frames_total > 3000 and words > 2500 and escapes == 6
+    assert frames_total > 3000 and words > 2500 and escapes >= 6 and failures > 100

@@ -257,7 +257,7 @@ def test_replies_become_the_compact_words_the_python_encoder_writes():
                 now = base + 1000 * r + (0 if peer == 0 else 7)      # the two peers' buffers are drained 7 ms apart
                 # an escaped plan has no tag and may come from another role object: its reply carries that incarnation in full
                 inc = int(sent_inc[g]) if tag != abi.CTAG_NONE else int(sent_inc[g]) + int(rng.integers(0, 2))
-                pend.put(peer, seq, g, f, tag, inc, int(sent_term[g]), epoch, last)
+                pend.put(peer, seq, kind, g, f, tag, inc, int(sent_term[g]), epoch, last)
                 rec = np.zeros(1, dtype=ingest.ACK_REC)[0]
                 rec["gid"], rec["kind"], rec["success"], rec["sequence"], rec["term"] = g, kind, ok, seq, term
                 per_call.setdefault((r, peer, now), []).append(rec)
@@ -282,8 +282,8 @@ def test_replies_become_the_compact_words_the_python_encoder_writes():
     assert len(a) == len(b) > 0 and a.tobytes() == b.tobytes()
     assert ((got.ev_c & 0xF) == abi.CEV_ESCAPED).sum() == n_esc and (got.ev_c != 0).sum() == seq
     # a second reply for a lane slot that is taken is deferred (its invocation stays pending); an unknown sequence is dropped
-    pend.put(0, 9001, 3, 0, 1, int(sent_inc[3]), int(sent_term[3]), 1, 2)
-    pend.put(0, 9002, 3, 0, 2, int(sent_inc[3]), int(sent_term[3]), 1, 2)
+    pend.put(0, 9001, abi.EV_AE_ACK, 3, 0, 1, int(sent_inc[3]), int(sent_term[3]), 1, 2)
+    pend.put(0, 9002, abi.EV_AE_ACK, 3, 0, 2, int(sent_inc[3]), int(sent_term[3]), 1, 2)
     two = np.zeros(3, dtype=ingest.ACK_REC)
     two["gid"], two["kind"], two["success"], two["term"] = 3, abi.EV_AE_ACK, 1, int(sent_term[3])
     two["sequence"] = [9001, 9002, 7777]
@@ -308,7 +308,7 @@ def test_pending_table_behaves_like_a_dict_under_churn():
         peer, seq = int(rng.integers(0, 3)), int(rng.integers(-50, 400))
         if op < 0.5:
             g, f = int(rng.integers(0, G)), int(rng.integers(0, F))
-            pend.put(peer, seq, g, f, int(rng.integers(0, 32)), 1, 7, 0, 0)
+            pend.put(peer, seq, abi.EV_AE_ACK, g, f, int(rng.integers(0, 32)), 1, 7, 0, 0)
             model[(peer, seq)] = (g, f)
         elif op < 0.75:
             assert pend.remove(peer, seq) == ((peer, seq) in model)

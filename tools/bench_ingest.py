@@ -51,7 +51,7 @@ def main(groups=65536, frames_n=400000, reps=7):
         pend = ingest.Pending(n_slots)
         hp = pend._h
         for sq, slot in enumerate(order):
-            L.rafting_pending_put(hp, 0, sq, int(slot) // Fl, int(slot) % Fl, sq % 32, 1, 7, 0, 0)
+            L.rafting_pending_put(hp, 0, sq, _abi.EV_AE_ACK, int(slot) // Fl, int(slot) % Fl, sq % 32, 1, 7, 0, 0)
         cin = compact.CompactInbox(1, groups, Fl)
         cin.row_base[0] = 5
         cc = cin.as_c()
