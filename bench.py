@@ -63,6 +63,9 @@ def parse():
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-secondary", action="store_true", help="skip the vote / follower-request rates (configs #3, #5)")
     p.add_argument("--no-bind", action="store_true", help="do not bind the process to the GPU's NUMA node")
+    p.add_argument("--log-appends", action="store_true",
+                   help="experiment (SURVEY 8(f)-1): a second host thread appends entry payloads to the HBM entry buffer "
+                        "(rafting_log_append, its own stream) during the whole timed region; the line gains run.log_appends")
     return p.parse_args()
 
 
@@ -436,6 +439,37 @@ def run_engine(args):
 
     sampler = ClockSampler(local); sampler.start()
     warm()
+    appender = None
+    if args.log_appends:
+        import threading
+        e.log_config(segment_bytes=1 << 22, hbm_segments=1024, ring_slots=64)        # 4 GiB arena: no spill during the run
+        n_ref, payload = 16384, 256
+        a_refs = np.zeros(n_ref, dtype=engine.Engine.ENTRY_REF)
+        a_refs["gid"] = np.arange(n_ref, dtype=np.uint32) % G
+        a_refs["len"] = payload
+        a_refs["term"] = 1
+        a_refs["blob_off"] = np.arange(n_ref, dtype=np.uint64) * payload
+        a_blob = np.random.default_rng(5).integers(0, 256, size=n_ref * payload, dtype=np.uint8)
+        a_state = {"stop": False, "calls": 0, "bytes": 0, "rc": 0, "t0": 0.0, "t1": 0.0}
+
+        def _append_loop():
+            torch.cuda.set_device(local)
+            Lb = engine.lib()
+            idx = 1
+            a_state["t0"] = time.perf_counter()
+            while not a_state["stop"]:
+                a_refs["index"] = idx
+                rc = Lb.rafting_log_append(e._h, a_refs.ctypes.data, n_ref, a_blob.ctypes.data, a_blob.nbytes)
+                if rc:
+                    a_state["rc"] = rc
+                    break
+                idx += 1
+                a_state["calls"] += 1
+                a_state["bytes"] += a_blob.nbytes
+            a_state["t1"] = time.perf_counter()
+        appender = threading.Thread(target=_append_loop, daemon=True)
+        appender.start()
+        time.sleep(0.05)
     sampler.armed = True
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(ext)
@@ -444,6 +478,14 @@ def run_engine(args):
     e.allgather_join()                      # the timed region ends when the last summary has been gathered
     ev1.record(ext)
     torch.cuda.synchronize(); barrier()
+    log_appends = None
+    if appender is not None:
+        a_state["stop"] = True
+        appender.join(timeout=30)
+        secs = max(1e-9, a_state["t1"] - a_state["t0"])
+        log_appends = {"calls": a_state["calls"], "payload_bytes": a_state["bytes"], "GB_per_s": a_state["bytes"] / secs / 1e9,
+                       "status": a_state["rc"], "records_per_call": n_ref, "payload": payload,
+                       "what": "rafting_log_append from a second host thread during the whole timed region (entry buffer's own stream)"}
     sampler.armed = False                   # clocks are sampled only while the GPU is under the timed load
     total_ms = ev0.elapsed_time(ev1)
     digest_b = e.digest(0, G)
@@ -731,6 +773,8 @@ def run_engine(args):
             "collective": ("ncclAllGather of commitIndex[G/N] after every launch, source = the launch's outbox commit column, on its "
                            "own stream; the step stream waits for the gather issued one launch earlier") if world > 1 else "none (1 GPU)",
             "bit_exact_replay": replay_ok, "host_placement": placement}
+        if log_appends is not None:
+            run["log_appends"] = log_appends
         if world > 1:
             cfgd["gather_verified"] = gather_ok            # SURVEY §8(d) #4's pass criterion, checked on every rank
         line = {
