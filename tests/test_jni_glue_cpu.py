@@ -215,3 +215,41 @@ def test_dispatch_natives_turn_an_outbox_into_request_and_reply_records(glue):
         d, C.byref(jni_exec.buf_of_struct(oc)), rows, C.byref(_buf(recs)), 1)
     assert glue.fake_throws() == 1 and glue.fake_thrown_class() == b"io/lubricant/consensus/raft/support/RaftException"
     _fn(glue, "dispatchDestroy", None, C.c_int64)(d)
+
+
+# ---- the Java declarations against the glue's C signatures, native by native ---------------------------------------------------
+JAVA = os.path.join(ROOT, "rafting_b200", "java", "io", "lubricant", "consensus", "raft", "gpu", "NativeEngine.java")
+_JTYPE = {"long": "jlong", "int": "jint", "boolean": "jboolean", "void": "void", "ByteBuffer": "jobject", "String": "jstring",
+          "long[]": "jlongArray"}
+
+
+def _java_natives(text):
+    out = {}
+    for ret, name, params in re.findall(r"static native ([\w\[\]]+)\s+(\w+)\(([^)]*)\)", text, re.S):
+        types = [" ".join(p.split()[:-1]) for p in (q.strip() for q in params.split(",")) if p]
+        out[name] = (_JTYPE[ret], [_JTYPE[t] for t in types])
+    return out
+
+
+def _glue_natives(text):
+    out = {}
+    for ret, name, params in re.findall(r"JNIEXPORT (\w+) JNICALL FN\((\w+)\)\(([^)]*)\)", text, re.S):
+        ps = [" ".join(p.split()[:-1]) for p in (q.strip() for q in params.split(","))]
+        assert ps[:2] == ["JNIEnv*", "jclass"], (name, ps[:2])
+        out[name] = (ret, ps[2:])
+    return out
+
+
+def test_java_declarations_match_the_glue_signatures():
+    """A JNI mismatch (a missing argument, an int where the glue takes a jlong) is undefined behaviour that no compiler sees:
+    NativeEngine.java and rafting_jni.c are compared native by native — same set, same return type, same argument types in
+    the same order — and the listing in INTEGRATION.md must be the file's."""
+    java = _java_natives(open(JAVA).read())
+    glue = _glue_natives(open(GLUE).read())
+    assert set(java) == set(glue), (sorted(set(java) - set(glue)), sorted(set(glue) - set(java)))
+    for name in sorted(java):
+        assert java[name] == glue[name], f"{name}: Java {java[name]} vs glue {glue[name]}"
+    assert len(java) >= 50
+    guide = _java_natives(open(os.path.join(ROOT, "INTEGRATION.md")).read())
+    assert guide == java
+    assert "package io.lubricant.consensus.raft.gpu;" in open(JAVA).read()
