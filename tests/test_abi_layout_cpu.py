@@ -61,3 +61,14 @@ def test_every_mirror_has_the_layout_the_headers_compile_to(tmp_path):
         assert got[cname] == (size,), f"sizeof({cname}) = {got[cname][0]}, the mirror has {size}"
         for n, off, sz in fields:
             assert got[f"{cname}.{n}"] == (off, sz), f"{cname}.{n}: C (offset, size) = {got[f'{cname}.{n}']}, mirror = {(off, sz)}"
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="no gcc")
+def test_generated_java_layout_constants_are_current():
+    """rafting_b200/java/.../Layout.java (offsets the Java side uses on direct ByteBuffers) is generated from the headers by
+    tools/gen_java_layout.py; a header change without regenerating it fails here."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_java_layout", os.path.join(ROOT, "tools", "gen_java_layout.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    assert open(gen.OUT).read() == gen.generate(), "run `python tools/gen_java_layout.py`"
