@@ -211,6 +211,30 @@ int rafting_failures_to_cinbox(rafting_pending_t* p, uint32_t peer, const int32_
                                uint32_t row, const rafting_cinbox_t* cin, uint32_t n_groups, uint32_t F, rafting_cesc_in_t* esc,
                                uint32_t esc_cap, uint32_t* n_esc, uint32_t* deferred, uint32_t* n_deferred, uint32_t* n_unknown);
 
+/* ---- the inbox builder: what the event loops' queues become (dense / leased path) -------------------------------------------
+ * The reference queues work per context on its event loop (EventLoop.java:87-101): replies hop back with execute(urgent),
+ * inbound requests and RaftStub.submit are queued behind them.  The builder keeps one FIFO per group — requests (records +
+ * entry terms), replies (batch records) and submits (placed at the FRONT: RaftStub.process runs before what is already
+ * queued for the tick) — and turns them into the rows of one dense step: row 0 is the sweep row (row_now[0] = now fires the
+ * due timers); per group the queue is drained in order, an op taking the op slot of the row AFTER the cursor's row, a lane
+ * event the slot of its lane in the cursor's row when that slot lies behind the cursor, else in the next row; what does not
+ * fit into `rows` rows stays queued for the next step (one op per (row, group), one event per (row, group, lane), the serial
+ * order of the step == arrival order).  tests/cluster_sim.py holds the same rule in Python; the two are compared on every
+ * step of randomized cluster runs. */
+typedef struct rafting_builder rafting_builder_t;
+int rafting_builder_create(uint32_t n_groups, uint32_t F, rafting_builder_t** out);
+int rafting_builder_destroy(rafting_builder_t* b);
+int rafting_builder_push_submit (rafting_builder_t* b, uint32_t gid, uint32_t count, uint32_t unavailable_mask);
+int rafting_builder_push_request(rafting_builder_t* b, const rafting_req_rec_t* r, const int64_t* entry_terms);
+int rafting_builder_push_reply  (rafting_builder_t* b, const rafting_batch_rec_t* r);
+int rafting_builder_clear_group (rafting_builder_t* b, uint32_t gid);
+uint32_t rafting_builder_pending(const rafting_builder_t* b);
+/* in: a dense host inbox with row_now, all op_* and ev_* columns and ent_terms[ent_cap]; the builder zeroes and fills it.
+ * placed / placed_row / is_submit: what went in, in (group, row) order — requests for rafting_outbox_to_replies, submits
+ * (kind RAFTING_OP_SUBMIT, count) so that the caller can store the payloads of accepted commands. */
+int rafting_builder_build(rafting_builder_t* b, int64_t now_ms, const rafting_inbox_t* in, uint32_t ent_cap, uint32_t* ent_count,
+                          rafting_req_rec_t* placed, uint8_t* placed_row, uint32_t placed_cap, uint32_t* n_placed);
+
 /* ---- commit records -> apply ranges --------------------------------------------------------------------
  * What RaftRoutine.commitState hands to applyCommand (RaftRoutine.java:224-306): for every group whose role_word carries the
  * commit-dirty bit (bit 31) and whose commit_index is ahead of applied[gid], one record (gid, applied + 1 .. commit_index);

@@ -3,6 +3,7 @@
 
 #include <string.h>
 
+#include <deque>
 #include <vector>
 
 namespace {
@@ -574,5 +575,122 @@ extern "C" int rafting_failures_to_cinbox(rafting_pending_t* p, uint32_t peer, c
     }
     *n_deferred = nd;
     if (n_unknown) *n_unknown = unknown;
+    return RAFTING_OK;
+}
+
+// ---- the inbox builder: per-group FIFOs -> the rows of one dense step (the placement rule of tests/cluster_sim.py) ----
+struct rafting_builder {
+    struct Item { uint8_t is_event; rafting_req_rec_t req; rafting_batch_rec_t rep; std::vector<int64_t> terms; };
+    uint32_t G, F;
+    std::vector<std::deque<Item>> q;
+    size_t pending = 0;
+};
+extern "C" int rafting_builder_create(uint32_t n_groups, uint32_t F, rafting_builder_t** out) {
+    if (!out || !n_groups || !F || F > 255) return RAFTING_E_INVAL;
+    try { auto* b = new rafting_builder(); b->G = n_groups; b->F = F; b->q.resize(n_groups); *out = b; } catch (...) { return RAFTING_E_NOMEM; }
+    return RAFTING_OK;
+}
+extern "C" int rafting_builder_destroy(rafting_builder_t* b) { delete b; return RAFTING_OK; }
+extern "C" uint32_t rafting_builder_pending(const rafting_builder_t* b) { return b ? (uint32_t)b->pending : 0; }
+extern "C" int rafting_builder_clear_group(rafting_builder_t* b, uint32_t gid) {
+    if (!b || gid >= b->G) return RAFTING_E_INVAL;
+    b->pending -= b->q[gid].size(); b->q[gid].clear();
+    return RAFTING_OK;
+}
+extern "C" int rafting_builder_push_submit(rafting_builder_t* b, uint32_t gid, uint32_t count, uint32_t unavailable_mask) {
+    if (!b || gid >= b->G || count == 0 || count > 0xFFFFu) return RAFTING_E_INVAL;
+    try {
+        rafting_builder::Item it{}; it.is_event = 0;
+        it.req.gid = gid; it.req.kind = RAFTING_OP_SUBMIT; it.req.count = count; it.req.a = (int64_t)unavailable_mask;
+        b->q[gid].push_front(std::move(it)); b->pending++;
+    } catch (...) { return RAFTING_E_NOMEM; }
+    return RAFTING_OK;
+}
+extern "C" int rafting_builder_push_request(rafting_builder_t* b, const rafting_req_rec_t* r, const int64_t* entry_terms) {
+    if (!b || !r || r->gid >= b->G) return RAFTING_E_INVAL;
+    if (r->kind != RAFTING_OP_AE_REQUEST && r->kind != RAFTING_OP_PREVOTE_REQ && r->kind != RAFTING_OP_VOTE_REQ) return RAFTING_E_INVAL;
+    if (r->kind == RAFTING_OP_AE_REQUEST && (r->count > 0xFFFFu || (r->count && !entry_terms))) return RAFTING_E_INVAL;
+    try {
+        rafting_builder::Item it{}; it.is_event = 0; it.req = *r;
+        if (r->kind == RAFTING_OP_AE_REQUEST && r->count) it.terms.assign(entry_terms, entry_terms + r->count);
+        b->q[r->gid].push_back(std::move(it)); b->pending++;
+    } catch (...) { return RAFTING_E_NOMEM; }
+    return RAFTING_OK;
+}
+extern "C" int rafting_builder_push_reply(rafting_builder_t* b, const rafting_batch_rec_t* r) {
+    if (!b || !r || r->gid >= b->G || r->lane >= b->F || r->kind == RAFTING_EV_NONE || r->kind > RAFTING_EV_RV_REPLY) return RAFTING_E_INVAL;
+    try {
+        rafting_builder::Item it{}; it.is_event = 1; it.rep = *r;
+        b->q[r->gid].push_back(std::move(it)); b->pending++;
+    } catch (...) { return RAFTING_E_NOMEM; }
+    return RAFTING_OK;
+}
+
+extern "C" int rafting_builder_build(rafting_builder_t* b, int64_t now_ms, const rafting_inbox_t* in, uint32_t ent_cap, uint32_t* ent_count,
+                                     rafting_req_rec_t* placed, uint8_t* placed_row, uint32_t placed_cap, uint32_t* n_placed) {
+    if (!b || !in || !in->row_now || !in->op_meta || !in->op_nr || !in->op_ab || !in->op_cd || !in->op_e || !in->ev_meta || !in->ev_tn ||
+        !in->ev_el || in->gids || !ent_count || !n_placed || (!placed && placed_cap) || (!placed_row && placed_cap) || in->rows < 2 ||
+        (ent_cap && !in->ent_terms)) return RAFTING_E_INVAL;
+    const uint32_t G = b->G, F = b->F, rows = in->rows;
+    const size_t ng = (size_t)rows * G, nl = ng * F;
+    uint64_t* om = const_cast<uint64_t*>(in->op_meta);
+    rafting_i64x2_t* nr = const_cast<rafting_i64x2_t*>(in->op_nr);
+    rafting_i64x2_t* ab = const_cast<rafting_i64x2_t*>(in->op_ab);
+    rafting_i64x2_t* cd = const_cast<rafting_i64x2_t*>(in->op_cd);
+    int64_t* oe = const_cast<int64_t*>(in->op_e);
+    uint64_t* em = const_cast<uint64_t*>(in->ev_meta);
+    rafting_i64x2_t* tn = const_cast<rafting_i64x2_t*>(in->ev_tn);
+    rafting_i64x2_t* el = const_cast<rafting_i64x2_t*>(in->ev_el);
+    memset(om, 0, ng * 8); memset(nr, 0, ng * 16); memset(ab, 0, ng * 16); memset(cd, 0, ng * 16); memset(oe, 0, ng * 8);
+    memset(em, 0, nl * 8); memset(tn, 0, nl * 16); memset(el, 0, nl * 16);
+    int64_t* rn = const_cast<int64_t*>(in->row_now);
+    memset(rn, 0, (size_t)rows * 8);
+    rn[0] = now_ms;                                                         // the sweep row: every due election / keepAlive timer
+    uint32_t ents = 0, np = 0;
+    for (uint32_t g = 0; g < G; g++) {
+        auto& q = b->q[g];
+        uint32_t cursor = 0;                                                // position r * (F + 1) + (0 = op | 1 + lane)
+        while (!q.empty()) {
+            rafting_builder::Item& it = q.front();
+            uint32_t r, pos;
+            if (!it.is_event) { r = cursor / (F + 1) + 1; pos = r * (F + 1); }
+            else {
+                r = cursor / (F + 1); pos = r * (F + 1) + 1 + it.rep.lane;
+                if (pos <= cursor) { r += 1; pos += F + 1; }
+            }
+            if (r >= rows) break;                                           // stays queued for the next step
+            if (!it.is_event && np >= placed_cap) break;                    // the caller's list of placed ops is full: next step
+            const size_t gi = (size_t)r * G + g;
+            if (!it.is_event) {
+                const rafting_req_rec_t& x = it.req;
+                uint32_t off = 0, count = 0;
+                int64_t a = 0, bb = 0, c = 0, d = 0, e = 0;
+                if (x.kind == RAFTING_OP_SUBMIT) { count = x.count; a = x.a; }
+                else {
+                    a = x.term; bb = x.a; c = x.b;
+                    if (x.kind == RAFTING_OP_AE_REQUEST) {
+                        count = x.count; off = ents;
+                        if ((uint64_t)ents + count > ent_cap) break;       // no room for the entry terms in this step: next step
+                        if (count) memcpy(const_cast<int64_t*>(in->ent_terms) + ents, it.terms.data(), (size_t)count * 8);
+                        ents += count;
+                        d = x.commit; e = x.a + 1;
+                    }
+                }
+                placed[np] = x; placed_row[np] = (uint8_t)r;
+                np++;
+                om[gi] = (uint64_t)RAFTING_OP_MAKE(x.kind, x.kind == RAFTING_OP_SUBMIT ? 0 : x.src_slot, count) | ((uint64_t)off << 32);
+                nr[gi].x = now_ms; nr[gi].y = 0; ab[gi].x = a; ab[gi].y = bb; cd[gi].x = c; cd[gi].y = d; oe[gi] = e;
+            } else {
+                const rafting_batch_rec_t& x = it.rep;
+                const size_t li = gi * F + x.lane;
+                em[li] = RAFTING_EVM_MAKE(x.kind, x.flags & 3u, (x.flags >> 2) & 1u, x.incarnation);
+                tn[li].x = x.term; tn[li].y = now_ms;
+                if (x.kind == RAFTING_EV_AE_ACK || x.kind == RAFTING_EV_IS_ACK) { el[li].x = x.epoch_at_send; el[li].y = x.last_at_send; }
+            }
+            cursor = pos;
+            q.pop_front(); b->pending--;
+        }
+    }
+    *ent_count = ents; *n_placed = np;
     return RAFTING_OK;
 }

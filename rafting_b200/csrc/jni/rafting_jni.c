@@ -308,4 +308,33 @@ JNIEXPORT void JNICALL FN(acksToCinbox)(JNIEnv* env, jclass k, jlong p, jint pee
     if (c) { c[0] = nEsc; c[1] = nDef; c[2] = nUnknown; }
     if (rc) throw_status(env, rc);
 }
+/* the inbox builder: per-group FIFOs of requests / replies / submits -> the rows of one dense step */
+JNIEXPORT jlong JNICALL FN(builderCreate)(JNIEnv* env, jclass k, jint nGroups, jint followers) {
+    rafting_builder_t* b = NULL;
+    CHECK(rafting_builder_create((uint32_t)nGroups, (uint32_t)followers, &b));
+    return (jlong)(intptr_t)b;
+}
+JNIEXPORT void JNICALL FN(builderDestroy)(JNIEnv* env, jclass k, jlong b) { rafting_builder_destroy((rafting_builder_t*)(intptr_t)b); }
+JNIEXPORT void JNICALL FN(builderPushSubmit)(JNIEnv* env, jclass k, jlong b, jint gid, jint count, jint unavailableMask) {
+    CHECK(rafting_builder_push_submit((rafting_builder_t*)(intptr_t)b, (uint32_t)gid, (uint32_t)count, (uint32_t)unavailableMask));
+}
+JNIEXPORT void JNICALL FN(builderPushRequest)(JNIEnv* env, jclass k, jlong b, jobject rec, jobject entryTerms) {
+    CHECK(rafting_builder_push_request((rafting_builder_t*)(intptr_t)b, (const rafting_req_rec_t*)BUF(rec), (const int64_t*)BUF(entryTerms)));
+}
+JNIEXPORT void JNICALL FN(builderPushReply)(JNIEnv* env, jclass k, jlong b, jobject rec) {
+    CHECK(rafting_builder_push_reply((rafting_builder_t*)(intptr_t)b, (const rafting_batch_rec_t*)BUF(rec)));
+}
+JNIEXPORT void JNICALL FN(builderClearGroup)(JNIEnv* env, jclass k, jlong b, jint gid) {
+    CHECK(rafting_builder_clear_group((rafting_builder_t*)(intptr_t)b, (uint32_t)gid));
+}
+/* returns the number of ops placed; counters: long[2] = { entry terms used, items still queued } */
+JNIEXPORT jint JNICALL FN(builderBuild)(JNIEnv* env, jclass k, jlong b, jlong nowMs, jobject inStruct, jint entCap, jobject placedOut, jobject placedRowOut,
+                                        jint placedCap, jobject counters) {
+    uint32_t ents = 0, n = 0;
+    CHECK(rafting_builder_build((rafting_builder_t*)(intptr_t)b, nowMs, (const rafting_inbox_t*)BUF(inStruct), (uint32_t)entCap, &ents,
+                                (rafting_req_rec_t*)BUF(placedOut), (uint8_t*)BUF(placedRowOut), (uint32_t)placedCap, &n));
+    int64_t* c = (int64_t*)BUF(counters);
+    if (c) { c[0] = ents; c[1] = rafting_builder_pending((const rafting_builder_t*)(intptr_t)b); }
+    return (jint)n;
+}
 #endif /* RAFTING_HAVE_JNI */

@@ -70,6 +70,16 @@ def lib():
         L.rafting_acks_to_cinbox.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int64, C.c_uint32, C.POINTER(abi.CInboxC),
                                              C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p,
                                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.rafting_builder_create.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.rafting_builder_destroy.argtypes = [C.c_void_p]
+        L.rafting_builder_push_submit.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.rafting_builder_push_request.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.rafting_builder_push_reply.argtypes = [C.c_void_p, C.c_void_p]
+        L.rafting_builder_clear_group.argtypes = [C.c_void_p, C.c_uint32]
+        L.rafting_builder_pending.restype = C.c_uint32
+        L.rafting_builder_pending.argtypes = [C.c_void_p]
+        L.rafting_builder_build.argtypes = [C.c_void_p, C.c_int64, C.POINTER(abi.InboxC), C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p,
+                                            C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.rafting_ack_frames_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         _LIB = L
     return _LIB
@@ -282,5 +292,59 @@ class Pending:
     def __del__(self):
         try:
             lib().rafting_pending_destroy(self._h)
+        except Exception:
+            pass
+
+
+class Builder:
+    """Per-group FIFOs of requests / replies / submits -> the rows of one dense step (include/rafting_ingest.h)."""
+
+    def __init__(self, n_groups: int, F: int):
+        self._h = C.c_void_p()
+        rc = lib().rafting_builder_create(n_groups, F, C.byref(self._h))
+        if rc:
+            raise ValueError(f"rafting_builder_create: rc={rc}")
+        self.G, self.F = n_groups, F
+
+    def push_submit(self, gid, count, unavailable_mask=0):
+        rc = lib().rafting_builder_push_submit(self._h, gid, count, unavailable_mask)
+        if rc:
+            raise ValueError(f"rafting_builder_push_submit: rc={rc}")
+
+    def push_request(self, rec, entry_terms=()):
+        r = np.array([rec], dtype=REQ_REC)
+        t = np.ascontiguousarray(entry_terms, dtype=np.int64)
+        rc = lib().rafting_builder_push_request(self._h, r.ctypes.data, t.ctypes.data if len(t) else None)
+        if rc:
+            raise ValueError(f"rafting_builder_push_request: rc={rc}")
+
+    def push_reply(self, rec):
+        r = np.array([rec], dtype=BATCH_REC)
+        rc = lib().rafting_builder_push_reply(self._h, r.ctypes.data)
+        if rc:
+            raise ValueError(f"rafting_builder_push_reply: rc={rc}")
+
+    def clear_group(self, gid):
+        lib().rafting_builder_clear_group(self._h, gid)
+
+    def __len__(self):
+        return lib().rafting_builder_pending(self._h)
+
+    def build(self, now_ms: int, inbox: abi.Inbox, placed_cap: int = 4096):
+        """Fills `inbox` (dense, sweep row, every column allocated); -> (placed records, their rows)."""
+        placed = np.zeros(placed_cap, dtype=REQ_REC)
+        rows = np.zeros(placed_cap, dtype=np.uint8)
+        ic = inbox.as_c()
+        cnt, n = C.c_uint32(), C.c_uint32()
+        rc = lib().rafting_builder_build(self._h, now_ms, C.byref(ic), len(inbox.ent_terms), C.byref(cnt), placed.ctypes.data,
+                                         rows.ctypes.data, placed_cap, C.byref(n))
+        if rc:
+            raise ValueError(f"rafting_builder_build: rc={rc}")
+        inbox.ent_count = cnt.value
+        return placed[:n.value], rows[:n.value]
+
+    def __del__(self):
+        try:
+            lib().rafting_builder_destroy(self._h)
         except Exception:
             pass

@@ -65,6 +65,13 @@ final class NativeEngine {
     static native boolean pendingRemove(long p, int peer, int sequence);                         // the invocation timed out
     static native void acksToCinbox(long p, int peer, ByteBuffer ackRecs, int n, long nowMs, int row, ByteBuffer cinStruct, int nGroups, int followers,
                                     ByteBuffer esc, int escCap, ByteBuffer deferredOut, ByteBuffer counters);   // replies -> ev_c words / escape records
+    static native long builderCreate(int nGroups, int followers);                                // the event loops' queues: per-group FIFOs -> rows of a step
+    static native void builderDestroy(long b);
+    static native void builderPushSubmit(long b, int gid, int count, int unavailableMask);       // RaftStub.submit: to the FRONT of the group's queue
+    static native void builderPushRequest(long b, ByteBuffer reqRec, ByteBuffer entryTerms);     // an inbound appendEntries / preVote / requestVote
+    static native void builderPushReply(long b, ByteBuffer replyRec);                            // a reply (or a failed invocation) for one follower lane
+    static native void builderClearGroup(long b, int gid);
+    static native int  builderBuild(long b, long nowMs, ByteBuffer inStruct, int entCap, ByteBuffer placedOut, ByteBuffer placedRowOut, int placedCap, ByteBuffer counters);
     static native int  applyRanges(ByteBuffer outStruct, ByteBuffer gids, int n, ByteBuffer applied, int nGroups, ByteBuffer rangesOut, int cap);   // commit-dirty groups -> (gid, first, last)
     static native long dispatchCreate(int nGroups, int followers, int localSlot);                // engine-to-engine peers: the dispatch loop of §4 in C
     static native void dispatchDestroy(long d);

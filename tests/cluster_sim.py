@@ -58,6 +58,9 @@ class Cluster:
         # shadow_native: every step, the C dispatch (rafting_outbox_to_requests) and the C placement (rafting_request_to_inbox)
         # of include/rafting_ingest.h run beside this file's Python pump and must produce the same records / op columns
         self.shadow_native = shadow_native
+        # with shadow_native and neither compaction nor the vote guard (both are host-side decisions made while placing), the C
+        # inbox builder (rafting_builder_*) receives every queue item this file queues and must build the identical inbox
+        self.shadow_builder = shadow_native and not compact_every and not guard_candidate_votes
         # see _vote_request_is_unsafe: the reference's Candidate grants votes without the log check
         self.guard_candidate_votes = guard_candidate_votes
         self.compact_every = compact_every       # RaftRoutine.compactLog: checkpoint + RaftLog.flush every N applied entries
@@ -78,6 +81,7 @@ class Cluster:
             if shadow_native:
                 from rafting_b200 import ingest
                 self.nodes[-1].dispatch = ingest.Dispatch(G, R - 1, k)
+                self.nodes[-1].builder = ingest.Builder(G, R - 1) if self.shadow_builder else None
         self.tick = 0
         self.inflight = []                       # (deliver_tick, seq, dst_slot, gid, item)
         self.link_clock = defaultdict(int)       # FIFO per (src, dst)
@@ -120,6 +124,8 @@ class Cluster:
         self.inflight = [m for m in self.inflight if m[0] > self.tick]
         for _, _, dst, gid, item in sorted(due, key=lambda m: (m[0], m[1])):
             self.nodes[dst].queue[gid].append(item)
+            if self.shadow_native and self.shadow_builder:
+                self._push_native(self.nodes[dst], gid, item)
         outs = []
         for nd in self.nodes:
             outs.append(self._step_node(nd, now, submit))
@@ -145,6 +151,8 @@ class Cluster:
             if submit and nd.snap is not None and (int(nd.snap.role_word[g]) & 3) == abi.ROLE_LEADER \
                     and self._rand(0x5B, nd.slot, g, self.tick) % 1_000_000 < self.submit_ppm:
                 q.appendleft(("op", dict(kind=abi.OP_SUBMIT, count=1 + self._rand(0x5C, nd.slot, g, self.tick) % 3)))
+                if self.shadow_native and self.shadow_builder:
+                    nd.builder.push_submit(g, q[0][1]["count"])
             if self.compact_every and nd.snap is not None and nd.install[g] is None:
                 done = nd.snapshot[g][0] if nd.snapshot[g] else 0
                 if nd.applied[g] - done >= self.compact_every:
@@ -191,6 +199,17 @@ class Cluster:
                     else:
                         ib.vote_reply(r, g, lane, now, e["inc"], e["term"], e["success"], outcome=e["outcome"],
                                       pre=e["kind"] == abi.EV_PV_REPLY)
+        if self.shadow_native and self.shadow_builder:
+            ib3 = abi.Inbox(ROWS, G, F, ent_cap=ROWS * G * 64, sweep=True)
+            placed3, rows3 = nd.builder.build(now, ib3)
+            for col in ("row_now", "op_meta", "op_nr", "op_ab", "op_cd", "op_e", "ev_meta", "ev_tn", "ev_el"):
+                assert np.array_equal(getattr(ib, col), getattr(ib3, col)), f"native builder differs in {col} (node {nd.slot}, tick {self.tick})"
+            assert ib.ent_count == ib3.ent_count and np.array_equal(ib.ent_terms[:ib.ent_count], ib3.ent_terms[:ib3.ent_count])
+            assert len(nd.builder) == sum(len(q) for q in nd.queue), "the two sets of queues hold different leftovers"
+            assert sorted((int(r), int(q["gid"]), int(q["kind"])) for q, r in zip(placed3, rows3)) == \
+                sorted((r, g, op["kind"]) for (r, g), op in placed.items())
+            self.counts["native_builds_checked"] += 1
+            self.counts["native_build_items"] += int((ib.op_meta != 0).sum()) + int(((ib.ev_meta & np.uint64(0xF)) != 0).sum())
         if ib2 is not None:
             for col in ("op_meta", "op_nr", "op_ab", "op_cd", "op_e"):
                 assert np.array_equal(getattr(ib, col), getattr(ib2, col)), f"native placement differs in {col} (node {nd.slot}, tick {self.tick})"
@@ -198,6 +217,31 @@ class Cluster:
             self.counts["native_placements_checked"] += len(placed)
         ob = nd.sut.step(ib)
         return ob, placed
+
+    def _push_native(self, nd, gid, item):
+        """A queue item of this file -> the C builder's queue: requests as rafting_req_rec_t (+ entry terms), lane events as
+        rafting_batch_rec_t."""
+        from rafting_b200 import ingest
+        if item[0] == "op":
+            op = item[1]
+            k = op["kind"]
+            assert k in (abi.OP_AE_REQUEST, abi.OP_PREVOTE_REQ, abi.OP_VOTE_REQ), k
+            rec = np.zeros(1, dtype=ingest.REQ_REC)[0]
+            rec["gid"], rec["kind"], rec["src_slot"], rec["dst_slot"], rec["incarnation"], rec["term"] = gid, k, op["src"], nd.slot, op["inc"], op["term"]
+            terms = []
+            if k == abi.OP_AE_REQUEST:
+                terms = [t for t, _ in op["entries"]]
+                rec["a"], rec["b"], rec["commit"], rec["count"] = op["prev_index"], op["prev_term"], op["leader_commit"], len(terms)
+                rec["epoch"], rec["last"] = op.get("epoch", 0), op.get("last", 0)
+            else:
+                rec["a"], rec["b"] = op["last_index"], op["last_term"]
+            nd.builder.push_request(rec, terms)
+        else:
+            _, lane, e = item
+            rec = np.zeros(1, dtype=ingest.BATCH_REC)[0]
+            rec["gid"], rec["kind"], rec["lane"], rec["flags"] = gid, e["kind"], lane, e["outcome"] | (4 if e["success"] else 0)
+            rec["incarnation"], rec["term"], rec["epoch_at_send"], rec["last_at_send"] = e["inc"], e["term"], e["epoch"], e["last"]
+            nd.builder.push_reply(rec)
 
     def _place_op_native(self, nd, ib2, r, g, now, op):
         """The same op through rafting_request_to_inbox (requests) — submits / flushes are not requests and stay in Python."""
@@ -474,6 +518,8 @@ class Cluster:
             if len(runs) > 1:
                 sut.load_runs(g, runs)
             nd.queue[g].clear()
+            if self.shadow_native and self.shadow_builder:
+                nd.builder.clear_group(g)
             nd.install[g] = None
         nd.sut, nd.snap = sut, None
         nd.inc_term = [dict() for _ in range(self.G)]

@@ -198,3 +198,24 @@ def test_native_pump_dispatch_matches_the_python_pump_under_partitions(R, pre_vo
     assert c.counts["native_requests_checked"] > 2500 and c.counts["native_placements_checked"] > 3000
     assert c.counts["native_replies_checked"] > 2500 and c.counts["is_sent"] > 0 and c.counts["vote"] > 0
     assert c.counts["native_apply_ranges_checked"] > 500          # commit-dirty groups -> (gid, first, last), same as the Python loop
+
+
+@pytest.mark.parametrize("R,pre_vote,seed", [(3, True, 401), (5, False, 402), (3, False, 403)])
+def test_native_inbox_builder_matches_the_python_queues(R, pre_vote, seed):
+    """The third phase of the pump in C — rafting_builder_*: per-group FIFOs of requests, replies and submits -> the rows of a
+    step — receives every item the simulator queues (lossy links, partitions, time-outs, leader changes) and must build the
+    identical inbox, column for column, and keep the identical leftovers, on every step.  (Runs without compaction and without
+    the vote guard: both are host-side decisions taken while placing, outside the builder; safety is not asserted here.)"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    c = Cluster(_oracle, G=5, R=R, seed=seed, drop_ppm=30_000, pre_vote=pre_vote, shadow_native=True)
+    assert c.shadow_builder
+    c.run(60)
+    for phase in range(6):
+        k = int(rng.integers(0, (R - 1) // 2 + 1))
+        c.cut = set(int(x) for x in rng.choice(R, size=k, replace=False))
+        c.run(40)
+    c.cut = set()
+    c.run(100)
+    assert c.counts["native_builds_checked"] == R * c.tick and c.counts["native_build_items"] > 2500
+    assert c.counts["native_requests_checked"] > 800 and c.counts["native_replies_checked"] > 600

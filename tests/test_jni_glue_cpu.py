@@ -253,3 +253,32 @@ def test_java_declarations_match_the_glue_signatures():
     guide = _java_natives(open(os.path.join(ROOT, "INTEGRATION.md")).read())
     assert guide == java
     assert "package io.lubricant.consensus.raft.gpu;" in open(JAVA).read()
+
+
+def test_builder_natives_fill_an_inbox_like_the_c_entry_points(glue):
+    from rafting_b200 import abi, ingest
+    G, F, rows = 4, 2, 4
+    glue.fake_reset()
+    b = _fn(glue, "builderCreate", C.c_int64, C.c_int32, C.c_int32)(G, F)
+    ref = ingest.Builder(G, F)
+    req = np.zeros(1, dtype=ingest.REQ_REC)
+    req["gid"], req["kind"], req["src_slot"], req["term"], req["a"], req["b"], req["commit"], req["count"] = 2, abi.OP_AE_REQUEST, 1, 9, 40, 8, 39, 2
+    terms = np.array([9, 9], dtype=np.int64)
+    rep = np.zeros(1, dtype=ingest.BATCH_REC)
+    rep["gid"], rep["kind"], rep["lane"], rep["flags"], rep["incarnation"], rep["term"], rep["epoch_at_send"], rep["last_at_send"] = 2, abi.EV_AE_ACK, 1, 4, 3, 9, 0, 41
+    _fn(glue, "builderPushRequest", None, C.c_int64, C.POINTER(_Buf), C.POINTER(_Buf))(b, C.byref(_buf(req)), C.byref(_buf(terms)))
+    _fn(glue, "builderPushReply", None, C.c_int64, C.POINTER(_Buf))(b, C.byref(_buf(rep)))
+    _fn(glue, "builderPushSubmit", None, C.c_int64, C.c_int32, C.c_int32, C.c_int32)(b, 2, 3, 0)
+    ref.push_request(req[0], terms), ref.push_reply(rep[0]), ref.push_submit(2, 3)
+    got, want = (abi.Inbox(rows, G, F, ent_cap=16, sweep=True) for _ in range(2))
+    gc = got.as_c()
+    placed, prow, counters = np.zeros(8, dtype=ingest.REQ_REC), np.zeros(8, dtype=np.uint8), np.zeros(2, dtype=np.int64)
+    n = _fn(glue, "builderBuild", C.c_int32, C.c_int64, C.c_int64, C.POINTER(_Buf), C.c_int32, C.POINTER(_Buf), C.POINTER(_Buf), C.c_int32,
+            C.POINTER(_Buf))(b, 5000, C.byref(jni_exec.buf_of_struct(gc)), 16, C.byref(_buf(placed)), C.byref(_buf(prow)), 8, C.byref(_buf(counters)))
+    wp, wr = ref.build(5000, want)
+    assert n == 2 == len(wp) and counters.tolist() == [2, 0] and glue.fake_throws() == 0
+    assert placed[:2].tobytes() == wp.tobytes() and prow[:2].tolist() == wr.tolist() == [1, 2]     # the submit leads, then the request
+    for col in ("row_now", "op_meta", "op_nr", "op_ab", "op_cd", "op_e", "ev_meta", "ev_tn", "ev_el"):
+        assert np.array_equal(getattr(got, col), getattr(want, col)), col
+    assert got.ev_meta[2, 2, 1] != 0 and np.array_equal(got.ent_terms[:2], [9, 9])                  # the reply follows the request's row
+    _fn(glue, "builderDestroy", None, C.c_int64)(b)
