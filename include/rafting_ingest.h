@@ -28,6 +28,11 @@
  * type with HEAD "Q" carries REQUEST records (rafting_req_rec_t, 64 bytes: AppendEntries / InstallSnapshot plans and vote
  * broadcasts); rafting_outbox_to_requests / rafting_request_to_inbox / rafting_outbox_to_replies are the pump's dispatch loop
  * in C, checked step by step against the Python pump of tests/cluster_sim.py.
+ *
+ * Threading: every object of this header (context registry, pending table, builder, dispatcher) belongs to ONE pump thread —
+ * the one that owns the engine shard; none of them locks.  The stateless functions (frame scan / encode,
+ * reply bodies, record <-> column conversions) may be called from any thread on disjoint buffers.  Status codes are
+ * rafting_b200.h's; no function throws across the ABI.
  */
 #ifndef RAFTING_INGEST_H
 #define RAFTING_INGEST_H
